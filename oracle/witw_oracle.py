@@ -1,0 +1,236 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU oracle for the WITW cross-view retrieval hot path.
+
+A restatement (torch-CPU / numpy, fp32 like the reference, plus an fp64 fused form)
+of the seven reference functions on the path.  It is the
+checker for the CUDA kernels and the "port" CPU baseline of bench.py; it is never
+on the product path.  Parity of this file against the real reference is pinned by
+tests/test_oracle_golden.py using fixtures in tests/golden/ that were produced by
+tests/golden/make_golden.py from the unmodified reference (imported from
+/root/reference in the build container).
+
+Every function cites the reference lines it restates (paths relative to
+/root/reference).  The heavy library calls are the same ones the reference makes
+(F.conv2d, argmax, linalg.norm, advanced indexing) so CPU timings of this port are
+representative of the reference's own PyTorch-CPU path.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+# model/cvig_fov.py:19-22 (Globals)
+SURFACE_H = 128
+SURFACE_W = 512
+OVERHEAD = 256
+
+
+# --------------------------------------------------------------------------- a2 grid
+def polar_grid(h_s=SURFACE_H, w_s=SURFACE_W, s_o=OVERHEAD):
+    """Sample coordinates of the polar transform, float64 [h_s, w_s] each.
+
+    model/cvig_fov.py:197-201: meshgrid over (w_s, h_s); radius (s_o/2)*(h_s-1-yy)/h_s;
+    yy_o = s_o/2 + r*cos(2*pi*xx/w_s); xx_o = s_o/2 - r*sin(2*pi*xx/w_s).
+    Evaluation order of the float64 products is kept: ((s_o/2)*(h_s-1-yy))/h_s * trig.
+    """
+    cols, rows = np.meshgrid(range(w_s), range(h_s))
+    half = s_o / 2
+    radial = half * (h_s - 1 - rows) / h_s
+    ang = 2 * math.pi * cols / w_s
+    y_src = half + radial * np.cos(ang)
+    x_src = half - radial * np.sin(ang)
+    return x_src, y_src
+
+
+# --------------------------------------------------------------------------- a1 LUT
+def bilinear_lut(x, y, src_h, src_w):
+    """Clipped tap indices and fp32 weights for bilinear sampling at (x, y).
+
+    model/cvig_fov.py:163-181.  floor, +1, then clip all four integer coordinates to
+    the image; the weights are formed in float64 from the *clipped* integers and only
+    then rounded to fp32 (torch.FloatTensor).  Returns int arrays x0,x1,y0,y1 and fp32
+    arrays wa,wb,wc,wd, each shaped like x.
+    """
+    x = np.asarray(x)
+    y = np.asarray(y)
+    assert x.shape == y.shape
+    x_lo = np.floor(x).astype(int)
+    y_lo = np.floor(y).astype(int)
+    x_hi = x_lo + 1
+    y_hi = y_lo + 1
+    x_lo = np.clip(x_lo, 0, src_w - 1)
+    x_hi = np.clip(x_hi, 0, src_w - 1)
+    y_lo = np.clip(y_lo, 0, src_h - 1)
+    y_hi = np.clip(y_hi, 0, src_h - 1)
+    w_a = ((x_hi - x) * (y_hi - y)).astype(np.float32)
+    w_b = ((x_hi - x) * (y - y_lo)).astype(np.float32)
+    w_c = ((x - x_lo) * (y_hi - y)).astype(np.float32)
+    w_d = ((x - x_lo) * (y - y_lo)).astype(np.float32)
+    return (x_lo, x_hi, y_lo, y_hi), (w_a, w_b, w_c, w_d)
+
+
+def bilinear_interpolate(im, x, y):
+    """model/cvig_fov.py:156-183.  im [C,H,W] fp32 -> [C,h,w] fp32.
+
+    Blend order of line 183 is kept: ((wa*Ia + wb*Ib) + wc*Ic) + wd*Id, every
+    product and sum rounded to fp32 separately.
+    """
+    (x_lo, x_hi, y_lo, y_hi), (w_a, w_b, w_c, w_d) = bilinear_lut(x, y, im.shape[1], im.shape[2])
+    t_a = im[:, y_lo, x_lo]
+    t_b = im[:, y_hi, x_lo]
+    t_c = im[:, y_lo, x_hi]
+    t_d = im[:, y_hi, x_hi]
+    w_a, w_b, w_c, w_d = (torch.from_numpy(w).unsqueeze(0) for w in (w_a, w_b, w_c, w_d))
+    return w_a * t_a + w_b * t_b + w_c * t_c + w_d * t_d
+
+
+def polar_transform(overhead, h_s=SURFACE_H, w_s=SURFACE_W, s_o=OVERHEAD):
+    """model/cvig_fov.py:186-209 on one tile [C,s_o,s_o] -> [C,h_s,w_s]."""
+    x_src, y_src = polar_grid(h_s, w_s, s_o)
+    return bilinear_interpolate(overhead, x_src, y_src)
+
+
+# --------------------------------------------------------------------------- a3
+def correlation_scores(overhead_embed, surface_embed):
+    """Un-normalised circular cross-correlation, fp32 [G,Q,W].
+
+    model/cvig_fov.py:299-312: wrap-pad the gallery width by sw-1 columns, conv2d
+    with the queries as filters; output height is 1 and is squeezed.
+    """
+    sw = surface_embed.shape[3]
+    wrapped = torch.cat((overhead_embed, overhead_embed[:, :, :, : sw - 1]), dim=3)
+    return F.conv2d(wrapped, surface_embed, stride=1).squeeze(-2)
+
+
+def correlation(overhead_embed, surface_embed):
+    """model/cvig_fov.py:297-315: argmax over the azimuth shift, int64 [G,Q], first max wins."""
+    return torch.argmax(correlation_scores(overhead_embed, surface_embed), dim=-1)
+
+
+# --------------------------------------------------------------------------- a4
+def crop_overhead(overhead_embed, orientation, surface_width):
+    """model/cvig_fov.py:318-343: out[g,q,c,h,k] = ov[g,c,h,(k+ori[g,q]) % W], k < surface_width."""
+    n_g, n_q = orientation.shape
+    c, h, w = overhead_embed.shape[1:]
+    col = (torch.arange(w).view(1, 1, w) + orientation.unsqueeze(-1)) % w          # [G,Q,W]
+    col = col.view(n_g, n_q, 1, 1, w).expand(n_g, n_q, c, h, w)
+    tiled = overhead_embed.unsqueeze(1).expand(n_g, n_q, c, h, w)
+    return torch.gather(tiled, 4, col)[..., :surface_width]
+
+
+# --------------------------------------------------------------------------- a5
+def l2_distance(overhead_cropped, surface_embed):
+    """model/cvig_fov.py:346-363: L2-normalise both sides over (C,H,sw); 2*(1 - dot). No epsilon."""
+    n_g, n_q = overhead_cropped.shape[:2]
+    o = overhead_cropped.reshape(n_g, n_q, -1)
+    o = o / torch.linalg.norm(o, ord=2, dim=-1, keepdim=True)
+    s = surface_embed.reshape(n_q, -1)
+    s = s / torch.linalg.norm(s, ord=2, dim=-1, keepdim=True)
+    return 2 * (1 - torch.sum(o * s.unsqueeze(0), dim=2))
+
+
+def match(overhead_embed, surface_embed):
+    """a3 -> a4 -> a5 chained exactly as the callers do (cvig_fov.py:547-549). Returns (orientation, distance)."""
+    ori = correlation(overhead_embed, surface_embed)
+    crop = crop_overhead(overhead_embed, ori, surface_embed.shape[3])
+    return ori, l2_distance(crop, surface_embed)
+
+
+# --------------------------------------------------------------------------- a6 / a7
+def rank_loop(overhead_embed, surface_embed, query_indices=None):
+    """model/cvig_fov.py:543-552.  One query at a time against the whole gallery;
+    rank = #{g : d[g] <= d[idx]} (ties and self count; NaN compares false)."""
+    count = surface_embed.size(0)
+    idxs = range(count) if query_indices is None else query_indices
+    ranks = np.zeros([len(idxs)], dtype=int)
+    for n, idx in enumerate(idxs):
+        one = surface_embed[idx : idx + 1]
+        _, dist = match(overhead_embed, one)
+        dist = dist.squeeze()
+        ranks[n] = torch.sum(torch.le(dist, dist[idx])).item()
+    return ranks
+
+
+def baseline_rank_loop(overhead_embed, surface_embed):
+    """model/cvig_baseline.py:453-460.  Plain Euclidean distance on [N,D] embeddings, same rank rule."""
+    count = surface_embed.size(0)
+    ranks = np.zeros([count], dtype=int)
+    for idx in range(count):
+        diff = overhead_embed - surface_embed[idx : idx + 1]
+        dist = torch.pow(torch.sum(torch.pow(diff, 2), dim=1), 0.5)
+        ranks[idx] = torch.sum(torch.le(dist, dist[idx])).item()
+    return ranks
+
+
+def recall_from_ranks(ranks):
+    """model/cvig_fov.py:553-558 (= cvig_baseline.py:461-466).  Percentages, mean and median rank."""
+    ranks = np.asarray(ranks)
+    count = ranks.shape[0]
+    return {
+        "top_one": np.sum(ranks <= 1) / count * 100,
+        "top_five": np.sum(ranks <= 5) / count * 100,
+        "top_ten": np.sum(ranks <= 10) / count * 100,
+        "top_percent": np.sum(ranks * 100 <= count) / count * 100,
+        "mean": np.mean(ranks),
+        "median": np.median(ranks),
+        "count": count,
+    }
+
+
+# --------------------------------------------------------------------------- heatmap caller
+def heatmap_scores(overhead_embed, surface_embed, output_width_max=64):
+    """tools/heatmap/heatmap.py:171-177: one query vs. many tiles -> (degrees, dissimilarity, score)."""
+    ori, dist = match(overhead_embed, surface_embed)
+    degrees = torch.squeeze(ori) * 360 / output_width_max - 180
+    dist = torch.squeeze(dist)
+    return degrees, dist, torch.exp(10.0 * (1.0 - dist))
+
+
+# --------------------------------------------------------------------------- fused identity, fp64
+def fused_fp64(overhead_embed, surface_embed):
+    """The algebraic identity the CUDA kernels implement, in float64:
+
+        s* = argmax_s corr[g,q,s]
+        d  = 2 - 2*corr[g,q,s*] / ( sqrt(sum_{k<sw} colE[g,(s*+k)%W]) * ||su_q|| )
+
+    Used to adjudicate tolerance questions (which of two fp32 answers is nearer the truth)
+    and as an independent cross-check of the restatement above.  Returns (corr [G,Q,W] f64,
+    orientation int64 [G,Q], distance f64 [G,Q]).
+    """
+    ov = overhead_embed.double()
+    su = surface_embed.double()
+    n_g, c, h, w = ov.shape
+    n_q, _, _, sw = su.shape
+    shift = (torch.arange(w).view(w, 1) + torch.arange(sw).view(1, sw)) % w      # [W, sw]
+    windows = ov[:, :, :, shift]                                                # [G,C,H,W,sw]
+    corr = torch.einsum("gchsk,qchk->gqs", windows, su)
+    ori = torch.argmax(corr, dim=-1)
+    col_energy = (ov * ov).sum(dim=(1, 2))                                      # [G,W]
+    crop_energy = col_energy[:, shift].sum(-1)                                  # [G,W]
+    qn = su.reshape(n_q, -1).norm(dim=1)
+    best = torch.gather(corr, 2, ori.unsqueeze(-1)).squeeze(-1)
+    cn = torch.sqrt(torch.gather(crop_energy.unsqueeze(1).expand(n_g, n_q, w), 2, ori.unsqueeze(-1)).squeeze(-1))
+    dist = 2 - 2 * best / (cn * qn.unsqueeze(0))
+    return corr, ori, dist
+
+
+# --------------------------------------------------------------------------- synthetic data
+def synth_features(n_gallery, n_query, fov=360, c=16, h=4, w=64, noise=0.5, seed=1234, planted=True):
+    """Synthetic feature maps of the BASELINE shapes.
+
+    Gallery ~ N(0,1)*0.06 (the scale random-init FOV_DSM emits).  With ``planted`` the first
+    min(G,Q) queries are the matching gallery item rolled by a per-query azimuth, cropped to
+    the field of view and perturbed with noise, so recall is non-degenerate.
+    Returns (overhead_embed [G,c,h,w], surface_embed [Q,c,h,sw], planted_shift int64 [Q]).
+    """
+    sw = int(fov / 360 * 512) // 8
+    gen = torch.Generator().manual_seed(seed)
+    ov = torch.randn(n_gallery, c, h, w, generator=gen) * 0.06
+    su = torch.randn(n_query, c, h, sw, generator=gen) * 0.06
+    shifts = torch.randint(0, w, (n_query,), generator=gen)
+    if planted:
+        n = min(n_gallery, n_query)
+        cols = (shifts[:n].view(n, 1) + torch.arange(sw).view(1, sw)) % w     # [n, sw]
+        picked = torch.gather(ov[:n], 3, cols.view(n, 1, 1, sw).expand(n, c, h, sw))
+        su[:n] = picked + noise * su[:n]
+    return ov, su, shifts

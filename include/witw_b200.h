@@ -1,0 +1,169 @@
+/* witw_b200.h -- C ABI of libwitw_b200.so: B200 (sm_100a) kernels for the WITW
+ * cross-view retrieval hot path.
+ *
+ * The reference (IQTLabs/WITW) has no FFI: its hot path is six Python functions in
+ * model/cvig_fov.py (byte-identical copies in model/cvig_semantic.py) plus the rank
+ * loop of test().  This header is the boundary a binding for that path uses; each
+ * entry point names the reference code it replaces (paths relative to the reference
+ * repository root).  The Python binding (ctypes) is witw_b200/_lib.py, and
+ * witw_b200/ops.py mirrors the reference's function names and signatures.
+ *
+ * Conventions
+ *   - every function returns 0 (WITW_OK) or a negative WITW_ERR_* code; the message
+ *     is available from witw_last_error() (thread-local)
+ *   - pointers named *_dev are device pointers on the current CUDA device, all
+ *     others are host pointers; tensors are dense, row-major, in the reference's
+ *     layouts (NCHW features, [gallery, query] matrices)
+ *   - no function allocates device memory; sizes of operand/workspace buffers are
+ *     returned by the *_bytes queries and the caller owns the buffers
+ *   - work is enqueued on `stream` (a cudaStream_t) and not synchronised
+ *   - there is no CPU fallback: without an sm_100 device every compute call fails
+ */
+#ifndef WITW_B200_H
+#define WITW_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* witw_stream_t; /* cudaStream_t */
+
+#define WITW_OK 0
+#define WITW_ERR_INVALID (-1)     /* bad argument (shape, null pointer, alignment) */
+#define WITW_ERR_UNSUPPORTED (-2) /* valid request outside what the kernels cover */
+#define WITW_ERR_CUDA (-3)        /* CUDA runtime / driver error */
+#define WITW_ERR_DEVICE (-4)      /* no sm_100 device */
+
+const char* witw_last_error(void);
+int witw_version(void);
+/* 0 when the current device is compute capability 10.x, WITW_ERR_DEVICE otherwise */
+int witw_device_check(void);
+
+/* ------------------------------------------------------------------------------------------
+ * K1  polar transform            replaces model/cvig_fov.py:156-209
+ *                                (bilinear_interpolate + PolarTransform.__call__)
+ * ------------------------------------------------------------------------------------------ */
+
+/* Host, float64.  Sample coordinates of PolarTransform (cvig_fov.py:197-201) for an
+ * [h_s, w_s] panorama-aligned image resampled from an [s_o, s_o] tile.  x, y: [h_s*w_s]. */
+int witw_polar_grid(int h_s, int w_s, int s_o, double* x, double* y);
+
+/* Host.  Tap indices and fp32 weights of bilinear_interpolate (cvig_fov.py:163-181):
+ * floor, +1, clip all four to the image, weights from the clipped integers in float64,
+ * rounded to fp32.  idx4: [n][4] = x0,x1,y0,y1;  w4: [n][4] = wa,wb,wc,wd. */
+int witw_bilinear_lut(const double* x, const double* y, int64_t n, int src_h, int src_w,
+                      int32_t* idx4, float* w4);
+
+/* Device.  dst[i, p] = wa*src[i,y0,x0] + wb*src[i,y1,x0] + wc*src[i,y0,x1] + wd*src[i,y1,x1]
+ * (cvig_fov.py:173-183, same order, every product and sum rounded to fp32) for n_img
+ * planes [src_h, src_w] and n_out sample points.  Bit-exact with the reference; generic
+ * geometry.  This is what the bilinear_interpolate drop-in calls. */
+int witw_bilinear_gather_f32(const float* src_dev, float* dst_dev, const int32_t* idx4_dev,
+                             const float* w4_dev, int64_t n_img, int src_h, int src_w,
+                             int64_t n_out, witw_stream_t stream);
+
+/* Fast polar resample: shared-memory staged quadrants, register-resident sample table.
+ * A plan holds the packed table for one geometry; build it once on the host, copy it to
+ * the device, pass both copies.  Weights are (1-fx, fx) x (1-fy, fy) with fx, fy the
+ * float64 fractions rounded to fp32, i.e. within 2^-24 absolute of the reference's
+ * weights; pixels whose taps the reference clips are patched with the exact formula. */
+size_t witw_polar_plan_bytes(int h_s, int w_s, int s_o);
+int witw_polar_plan_build(int h_s, int w_s, int s_o, void* plan_host);
+int witw_polar_resample_f32(const float* src_dev, float* dst_dev, int64_t n_img,
+                            const void* plan_host, const void* plan_dev, witw_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K2/K3  orientation-searched distance       replaces model/cvig_fov.py:297-363
+ *        (correlation -> crop_overhead -> l2_distance)
+ *
+ *   corr[g,q,s] = sum_{c,h,k<sw} ov[g,c,h,(s+k)%W] * su[q,c,h,k]
+ *   ori[g,q]    = argmax_s corr[g,q,s]                (first maximum)
+ *   dist[g,q]   = 2 - 2*corr[g,q,ori] / (||crop(ov_g, ori)|| * ||su_q||)
+ *
+ * CH = C*H feature rows of W (gallery) / sw (query) columns.
+ * ------------------------------------------------------------------------------------------ */
+
+/* Exact fp32 path on CUDA cores; any CH, W <= 128, 1 <= sw <= W.  Outputs are optional
+ * (NULL to skip): dist [G,Q] fp32, ori [G,Q] int64, corr [G,Q,W] fp32. */
+int witw_match_f32(const float* ov_dev, const float* su_dev, int64_t G, int64_t Q, int CH, int W,
+                   int sw, float* dist_dev, int64_t* ori_dev, float* corr_dev,
+                   witw_stream_t stream);
+
+/* Same, for explicit (gallery, query) index pairs: pair p compares ov[pair_g[p]] with
+ * su[pair_q[p]].  dist/ori: [n_pairs].  Used for the true-match distances of the rank
+ * evaluation and for fp32 re-checks of tensor-core results. */
+int witw_match_pairs_f32(const float* ov_dev, const float* su_dev, const int64_t* pair_g_dev,
+                         const int64_t* pair_q_dev, int64_t n_pairs, int CH, int W, int sw,
+                         float* dist_dev, int64_t* ori_dev, witw_stream_t stream);
+
+/* Standalone a4 (cvig_fov.py:318-343): out[g,q,ch,k] = ov[g,ch,(k+ori[g,q])%W], k<sw. */
+int witw_crop_gather_f32(const float* ov_dev, const int64_t* ori_dev, float* out_dev, int64_t G,
+                         int64_t Q, int CH, int W, int sw, witw_stream_t stream);
+
+/* Standalone a5 (cvig_fov.py:346-363): crop [G,Q,K], su [Q,K] -> dist [G,Q]. */
+int witw_l2_distance_f32(const float* crop_dev, const float* su_dev, float* dist_dev, int64_t G,
+                         int64_t Q, int64_t K, witw_stream_t stream);
+
+/* Tensor-core path (tcgen05, bf16 operands, fp32 accumulation in TMEM); W must be 64.
+ * gallery_prep writes the gallery operand (pre-shifted 16-byte rows that a no-swizzle UMMA
+ * descriptor reads as the Hankel matrix of all 64 azimuth shifts) and the table
+ * crop_inv_norm[g,s] = 1/||crop(ov_g,s)|| (fp32, from the fp32 inputs).  query_prep writes
+ * the bf16 query operand [Q, CH*sw_pad] and q_inv_norm[q]. */
+size_t witw_gallery_operand_bytes(int64_t G, int CH, int sw);
+size_t witw_query_operand_bytes(int64_t Q, int CH, int sw);
+int witw_gallery_prep(const float* ov_dev, int64_t G, int CH, int W, int sw, void* gal_op_dev,
+                      float* crop_inv_norm_dev /* [G_pad4,64], G_pad4 = G rounded up to 4 */,
+                      witw_stream_t stream);
+int witw_query_prep(const float* su_dev, int64_t Q, int CH, int sw, void* qry_op_dev,
+                    float* q_inv_norm_dev /* [Q] */, witw_stream_t stream);
+
+/* One sweep of Q queries over G gallery items.  Optional outputs (NULL to skip):
+ *   dist [G,Q] fp32, ori [G,Q] uint8
+ *   rank_count [Q] int32 += #{g : dist[g,q] <= d_true[q]}   (needs d_true [Q]; the rank rule
+ *        of cvig_fov.py:552; the caller zeroes rank_count, shards add into it)
+ *   topk_dist/topk_idx [n_slots,Q,topk]: per-query k smallest (distance, gallery index +
+ *        g_index_offset) candidates of each of n_slots gallery slices, ascending; n_slots from
+ *        witw_match_tc_topk_slots(); merge them with witw_topk_merge(). topk <= 16.
+ */
+int witw_match_tc_topk_slots(int64_t G, int64_t Q);
+int witw_match_tc(const void* gal_op_dev, const float* crop_inv_norm_dev, const void* qry_op_dev,
+                  const float* q_inv_norm_dev, int64_t G, int64_t Q, int CH, int sw,
+                  float* dist_dev, uint8_t* ori_dev, const float* d_true_dev,
+                  int32_t* rank_count_dev, int topk, float* topk_dist_dev, int32_t* topk_idx_dev,
+                  int32_t g_index_offset, witw_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K4  rank / top-k               replaces model/cvig_fov.py:550-552 and
+ *                                model/cvig_baseline.py:456-460
+ * ------------------------------------------------------------------------------------------ */
+
+/* ranks[q] = #{g : dist[g,q] <= dist[true_idx[q], q]} over a materialised [G,Q] matrix
+ * (true_idx NULL = identity).  NaN compares false, ties and the match itself count. */
+int witw_rank_from_dist_f32(const float* dist_dev, int64_t G, int64_t Q,
+                            const int64_t* true_idx_dev, int64_t* ranks_dev,
+                            witw_stream_t stream);
+
+/* Baseline variant (cvig_baseline.py:458-460): Euclidean distance between [N,D] gallery and
+ * [Q,D] query embeddings, then the same rank rule.  dist_dev optional [N,Q]. */
+int witw_l2_rank_f32(const float* ov_dev, const float* su_dev, int64_t N, int64_t Q, int64_t D,
+                     const int64_t* true_idx_dev, float* dist_dev, int64_t* ranks_dev,
+                     witw_stream_t stream);
+
+/* Per query (column) the k smallest distances of dist [G,Q], ascending, ties by lower
+ * gallery index; idx gets g + g_index_offset.  k <= 128.  out: [Q,k]. */
+int witw_topk_from_dist_f32(const float* dist_dev, int64_t G, int64_t Q, int k,
+                            float* topk_dist_dev, int32_t* topk_idx_dev, int32_t g_index_offset,
+                            witw_stream_t stream);
+
+/* Merge n_lists sorted candidate lists per query ([n_lists,Q,k] each) into one [Q,k]. */
+int witw_topk_merge(const float* cand_dist_dev, const int32_t* cand_idx_dev, int n_lists,
+                    int64_t Q, int k, float* topk_dist_dev, int32_t* topk_idx_dev,
+                    witw_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WITW_B200_H */

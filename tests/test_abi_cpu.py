@@ -1,0 +1,136 @@
+"""CPU-side checks of the C ABI and host logic (no GPU needed)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import witw_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "witw_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(witw_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from witw_b200 import _lib
+
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    names = _declared_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), "missing export " + n
+    # the ctypes table covers exactly the header
+    assert sorted(_lib.SIGNATURES) == names
+    assert _lib.load().witw_version() >= 100
+
+
+def test_host_grid_and_lut_match_oracle():
+    from witw_b200 import _lib, ops
+
+    x, y = ops.polar_grid()
+    xr, yr = O.polar_grid()
+    assert np.array_equal(x, xr) and np.array_equal(y, yr)
+    n = x.size
+    idx = np.empty((n, 4), np.int32)
+    w = np.empty((n, 4), np.float32)
+    _lib.call("witw_bilinear_lut", x.ctypes.data, y.ctypes.data, n, 256, 256, idx.ctypes.data, w.ctypes.data)
+    (x0, x1, y0, y1), ws = O.bilinear_lut(xr, yr, 256, 256)
+    for col, ref in enumerate((x0, x1, y0, y1)):
+        assert np.array_equal(idx[:, col].reshape(x.shape), ref)
+    for col, ref in enumerate(ws):
+        assert np.array_equal(w[:, col].reshape(x.shape), ref)
+
+
+def test_polar_plan_structure():
+    from witw_b200 import _lib
+
+    lib = _lib.load()
+    nbytes = lib.witw_polar_plan_bytes(128, 512, 256)
+    assert nbytes > 3 * 4 * 65536 // 2
+    buf = np.zeros(nbytes, np.uint8)
+    _lib.call("witw_polar_plan_build", 128, 512, 256, buf.ctypes.data)
+    hdr = buf[:64].view(np.int32)
+    assert hdr[1:4].tolist() == [128, 512, 256]
+    assert hdr[12] == 2  # the two clip-quirk pixels are the only exceptions
+    # fractions reproduce the float64 grid: fx = fp32(x - floor(x))
+    x, y = O.polar_grid()
+    lut_off = int(buf[52:56].view(np.uint32)[0])
+    fx = buf[lut_off: lut_off + 4 * 65536].view(np.float32).reshape(4, 16, 1024)
+    q, i, t = 2, 5, 777
+    lin = i * 1024 + t
+    row, col = lin // 128, q * 128 + lin % 128
+    assert fx[q, i, t] == np.float32(x[row, col] - np.floor(x[row, col]))
+    # unsupported geometry is refused, not approximated
+    assert lib.witw_polar_plan_bytes(100, 300, 256) == 0
+    assert "outside" in _lib.last_error()
+
+
+def test_operand_size_queries():
+    from witw_b200 import _lib
+
+    lib = _lib.load()
+    # 360 deg: 30 blocks of 128 B per (item pair, feature row) -> 120 KB per item
+    assert lib.witw_gallery_operand_bytes(10000, 64, 64) == 5000 * 64 * 30 * 128
+    assert lib.witw_gallery_operand_bytes(10000, 64, 16) == 5000 * 64 * 18 * 128
+    assert lib.witw_query_operand_bytes(10000, 64, 64) == 10000 * 4096 * 2
+    assert lib.witw_query_operand_bytes(10, 64, 12) == 10 * 64 * 16 * 2
+    assert lib.witw_gallery_operand_bytes(8, 3, 16) == 0  # CH not a multiple of 64/sw_pad
+    assert 1 <= lib.witw_match_tc_topk_slots(10000, 10000) <= 64
+
+
+def test_no_cpu_fallback():
+    import witw_b200 as W
+
+    ov, su, _ = O.synth_features(4, 4)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        W.match(ov, su)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        W.correlation(ov, su)
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            W.PolarTransform()({"overhead": torch.zeros(3, 256, 256)})
+
+
+def test_recall_from_ranks_matches_oracle():
+    import witw_b200 as W
+
+    ranks = np.array([1, 1, 2, 7, 11, 300, 5, 1, 3, 64])
+    a, b = W.recall_from_ranks(torch.from_numpy(ranks)), O.recall_from_ranks(ranks)
+    assert a.keys() == b.keys()
+    for k in a:
+        assert a[k] == b[k]
+
+
+def test_install_rebinds_and_restores():
+    import types
+
+    import witw_b200 as W
+
+    mod = types.ModuleType("fake_cvig")
+    for n in ("bilinear_interpolate", "PolarTransform", "correlation", "crop_overhead", "l2_distance"):
+        setattr(mod, n, object())
+    orig = W.install(mod)
+    assert mod.correlation is W.correlation and mod.PolarTransform is W.PolarTransform
+    assert hasattr(mod, "evaluate_ranks") and set(orig) >= {"correlation", "l2_distance"}
+    W.uninstall(mod)
+    assert mod.correlation is orig["correlation"] and not hasattr(mod, "evaluate_ranks")
+    with pytest.raises(AttributeError):
+        W.install(types.ModuleType("not_cvig"))
+
+
+def test_shard_bounds_partition():
+    import witw_b200 as W
+
+    for n, p in ((10, 4), (1000000, 8), (3, 8), (0, 2)):
+        spans = [W.shard_bounds(n, p, r) for r in range(p)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(p - 1))
+        sizes = [b - a for a, b in spans]
+        assert max(sizes) - min(sizes) <= 1

@@ -1,0 +1,221 @@
+"""GPU parity tests (run with -m gpu on the B200 box): CUDA path through the C ABI vs the
+golden vectors frozen from the reference and vs the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import witw_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def W():
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    import witw_b200
+
+    from witw_b200 import _lib
+
+    _lib.call("witw_device_check")
+    return witw_b200
+
+
+def t(a):
+    return torch.from_numpy(np.ascontiguousarray(a))
+
+
+def cu(a):
+    return (t(a) if isinstance(a, np.ndarray) else a).cuda()
+
+
+# ------------------------------------------------------------------ K1
+def test_polar_exact_kernel_bit_exact(W, golden):
+    g = golden("polar")
+    out = W.polar_transform(cu(g["tile"]), exact=True)
+    assert torch.equal(out.cpu(), t(g["polar"]))
+
+
+def test_polar_fast_kernel(W, golden):
+    g = golden("polar")
+    ref = t(g["polar"])
+    out = W.polar_transform(cu(g["tile"])).cpu()
+    assert out.shape == ref.shape and out.dtype == torch.float32
+    # weights are within 2^-24 of the reference's, |tile| < 6: a few fp32 ulps of the tile's scale
+    err = (out - ref).abs().max().item()
+    assert err <= 4e-6, err
+    assert float(out[:, 0, 0].abs().max()) == 0.0 and float(out[:, 0, 384].abs().max()) == 0.0
+    rel = ((out - ref).abs() / ref.abs().clamp_min(1e-2)).max().item()
+    assert rel <= 1e-3
+
+
+def test_polar_fast_kernel_many_planes(W):
+    # more planes than persistent CTAs x pipeline stages: exercises the TMA ring wrap-around and batch layout
+    gen = torch.Generator().manual_seed(3)
+    tiles = torch.randn(70, 5, 256, 256, generator=gen)
+    out = W.polar_transform(tiles.cuda())
+    exact = W.polar_transform(tiles.cuda(), exact=True)
+    assert out.shape == (70, 5, 128, 512)
+    assert (out - exact).abs().max().item() <= 4e-6
+    for n, c in ((0, 0), (33, 2), (69, 4)):
+        assert torch.equal(exact[n, c].cpu(), O.polar_transform(tiles[n, c: c + 1])[0])
+
+
+def test_polar_transform_dropin_contract(W, golden):
+    g = golden("polar")
+    data = {"overhead": cu(g["tile"]), "surface": 7}
+    out = W.PolarTransform(exact=True)(data)
+    assert out is data and out["surface"] == 7 and torch.equal(out["polar"].cpu(), t(g["polar"]))
+    cpu = W.PolarTransform(exact=True)({"overhead": t(g["tile"])})  # CPU in -> CPU out, computed on the GPU
+    assert not cpu["polar"].is_cuda and torch.equal(cpu["polar"], t(g["polar"]))
+
+
+def test_bilinear_interpolate_generic_bit_exact(W, golden):
+    g = golden("bilinear")
+    out = W.bilinear_interpolate(cu(g["im"]), g["x"], g["y"])
+    assert torch.equal(out.cpu(), t(g["out"]))
+
+
+# ------------------------------------------------------------------ K2/K3, exact fp32 path
+CASES = ["fov360", "fov90", "fov70", "fov180", "fov6", "ties", "zeronorm", "c8h2"]
+
+
+def _check_match(ori, dist, corr64, ref_ori, ref_dist, atol):
+    """orientation must agree except where the two candidate shifts tie to round-off; distance within atol."""
+    ori, dist = ori.cpu(), dist.cpu()
+    assert ori.dtype == torch.int64 and dist.dtype == torch.float32
+    diff = ori != ref_ori
+    if diff.any():
+        a = torch.gather(corr64, 2, ori.unsqueeze(-1)).squeeze(-1)
+        b = torch.gather(corr64, 2, ref_ori.unsqueeze(-1)).squeeze(-1)
+        scale = corr64.abs().amax(-1)
+        assert bool((((a - b).abs() <= 1e-5 * scale) | ~diff).all()), "orientation differs beyond a round-off tie"
+    assert torch.equal(torch.isnan(dist), torch.isnan(ref_dist))
+    ok = ~torch.isnan(ref_dist) & ~diff
+    assert (dist[ok] - ref_dist[ok]).abs().max().item() <= atol
+    return int(diff.sum())
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_match_fp32_vs_golden(W, golden, name):
+    g = golden("match")
+    ov, su = t(g[name + "_ov"]), t(g[name + "_su"])
+    ori, dist = W.match(ov.cuda(), su.cuda(), path="fp32")
+    corr64 = O.fused_fp64(ov, su)[0]
+    flips = _check_match(ori, dist, corr64, t(g[name + "_ori"]), t(g[name + "_dist"]), atol=5e-6)
+    if name == "ties":
+        assert flips == 0 and torch.equal(ori.cpu()[2], torch.zeros(6, dtype=torch.int64))
+    assert torch.equal(W.correlation(ov.cuda(), su.cuda(), path="fp32"), ori)
+    sc = W.correlation_scores(ov.cuda(), su.cuda()).cpu()
+    ref_sc = O.correlation_scores(ov, su)
+    assert torch.allclose(sc, ref_sc, rtol=0, atol=2e-5 * float(ref_sc.abs().max()) + 1e-12, equal_nan=True)
+
+
+@pytest.mark.parametrize("name", ["fov90", "ties"])
+def test_crop_and_l2_standalone(W, golden, name):
+    g = golden("match")
+    ov, su, ori = t(g[name + "_ov"]), t(g[name + "_su"]), t(g[name + "_ori"])
+    crop = W.crop_overhead(ov.cuda(), ori.cuda(), su.shape[3])
+    assert tuple(crop.shape) == (ov.shape[0], su.shape[0], 16, 4, su.shape[3])
+    assert torch.equal(crop.cpu(), t(g[name + "_crop"]))          # a pure gather: bit-exact
+    dist = W.l2_distance(crop, su.cuda())
+    assert torch.allclose(dist.cpu(), t(g[name + "_dist"]), rtol=0, atol=3e-6)
+
+
+def test_match_pairs_and_ragged_tiles(W):
+    ov, su, sh = O.synth_features(37, 45, fov=90, noise=2.0, seed=5)   # not multiples of the 4x32 CTA tile
+    ori, dist = W.match(ov.cuda(), su.cuda(), path="fp32")
+    ref_ori, ref = O.match(ov, su)
+    _check_match(ori, dist, O.fused_fp64(ov, su)[0], ref_ori, ref, atol=5e-6)
+    idx = torch.arange(37).flip(0)
+    d, o = W.true_match_distances(ov.cuda(), su[:37].cuda(), idx.cuda())
+    assert torch.allclose(d.cpu(), ref[idx, torch.arange(37)], rtol=0, atol=5e-6)
+    assert torch.equal(o.cpu(), ref_ori[idx, torch.arange(37)])
+
+
+def test_empty_inputs(W):
+    ov, su, _ = O.synth_features(4, 3)
+    o, d = W.match(ov[:0].cuda(), su.cuda(), path="fp32")
+    assert tuple(o.shape) == (0, 3) and tuple(d.shape) == (0, 3)
+    o, d = W.match(ov.cuda(), su[:0].cuda(), path="fp32")
+    assert tuple(o.shape) == (4, 0)
+    assert tuple(W.rank_from_distances(torch.zeros(0, 5).cuda()).shape) == (5,)
+
+
+def test_errors(W):
+    ov, su, _ = O.synth_features(4, 3)
+    with pytest.raises(RuntimeError):
+        W.match(ov.cuda(), su[:, :8].cuda())                      # channel mismatch (conv2d raises in the reference)
+    x = ov.cuda().requires_grad_(True)
+    with pytest.raises(RuntimeError, match="forward-only"):
+        W.match(x, su.cuda())
+    with torch.no_grad():
+        W.match(x, su.cuda(), path="fp32")
+    with pytest.raises(W.WitwError):
+        W.match(torch.zeros(2, 16, 4, 48).cuda(), torch.zeros(2, 16, 4, 8).cuda(), path="tc")   # W != 64
+
+
+# ------------------------------------------------------------------ K4
+@pytest.mark.parametrize("name", ["r360", "r90"])
+def test_evaluate_ranks_fp32_vs_golden(W, golden, name):
+    g = golden("ranks")
+    ranks = W.evaluate_ranks(cu(g[name + "_ov"]), cu(g[name + "_su"]), path="fp32")
+    assert ranks.dtype == torch.int64
+    assert np.array_equal(ranks.cpu().numpy(), g[name + "_ranks"])
+    rec = W.recall_from_ranks(ranks)
+    assert rec == O.recall_from_ranks(g[name + "_ranks"])
+
+
+def test_rank_from_distances_and_topk(W):
+    gen = torch.Generator().manual_seed(9)
+    for (G, Q) in ((1000, 516), (257, 33), (5, 4)):
+        d = torch.rand(G, Q, generator=gen)
+        d[G // 2, :] = d[0, :]                 # exact ties
+        d[min(3, G - 1), 1] = float("nan")     # NaN compares false
+        true_idx = torch.randint(0, G, (Q,), generator=gen)
+        thr = d[true_idx, torch.arange(Q)]
+        want = (d <= thr.unsqueeze(0)).sum(0)
+        assert torch.equal(W.rank_from_distances(d.cuda(), true_idx.cuda()).cpu(), want)
+        k = min(7, G)
+        dd = torch.where(torch.isnan(d), torch.full_like(d, float("inf")), d)
+        td, ti = W.topk_from_distances(d.cuda(), k)
+        ref_d = torch.sort(dd.t(), dim=1, stable=True)
+        assert torch.equal(td.cpu(), ref_d.values[:, :k])
+        assert torch.equal(ti.cpu().long(), ref_d.indices[:, :k])
+
+
+def test_baseline_ranks_vs_golden(W, golden):
+    g = golden("baseline")
+    ranks, dist = W.baseline_ranks(cu(g["ov"].astype(np.float32)), cu(g["su"].astype(np.float32)), return_distances=True)
+    ov, su = t(g["ov"].astype(np.float32)), t(g["su"].astype(np.float32))
+    ref = torch.cdist(ov.double(), su.double())
+    assert torch.allclose(dist.cpu().double(), ref, rtol=1e-6)
+    # rank ties at fp32 round-off aside, the counts are the reference's
+    assert np.array_equal(ranks.cpu().numpy(), g["ranks"])
+
+
+def test_heatmap_scores(W):
+    ov, su, _ = O.synth_features(50, 1, fov=70, noise=0.5, seed=2)
+    deg, dis, score = W.heatmap_scores(ov.cuda(), su.cuda(), path="fp32")
+    rdeg, rdis, rscore = O.heatmap_scores(ov, su)
+    assert torch.equal(deg.cpu(), rdeg) and torch.allclose(dis.cpu(), rdis, atol=5e-6) and torch.allclose(score.cpu(), rscore, rtol=1e-4)
+
+
+def test_install_on_namespace_runs_rank_loop(W, golden):
+    """The reference's rank-loop body (cvig_fov.py:545-552) runs unchanged on the rebound names."""
+    import types
+
+    cvig = types.ModuleType("cvig_like")
+    for n in ("bilinear_interpolate", "PolarTransform", "correlation", "crop_overhead", "l2_distance"):
+        setattr(cvig, n, None)
+    W.install(cvig)
+    g = golden("ranks")
+    overhead_embed, surface_embed = cu(g["r90_ov"]), cu(g["r90_su"])
+    count = surface_embed.size(0)
+    ranks = np.zeros([count], dtype=int)
+    for idx in range(count):
+        this_surface_embed = torch.unsqueeze(surface_embed[idx, :], 0)
+        orientation_estimate = cvig.correlation(overhead_embed, this_surface_embed)
+        overhead_cropped_all = cvig.crop_overhead(overhead_embed, orientation_estimate, this_surface_embed.shape[3])
+        distances = torch.squeeze(cvig.l2_distance(overhead_cropped_all, this_surface_embed))
+        ranks[idx] = torch.sum(torch.le(distances, distances[idx])).item()
+    assert np.array_equal(ranks, g["r90_ranks"])

@@ -1,0 +1,79 @@
+"""ctypes binding of libwitw_b200.so (C ABI declared in include/witw_b200.h).
+
+There is no fallback: if the shared library is missing or a call fails, an exception is
+raised.  Build the library with ``python -c "import __graft_entry__ as g; g.build()"`` or
+``make -C witw_b200/csrc``.
+"""
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_uint8, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libwitw_b200.so")
+
+_lib = None
+
+# name -> (restype, argtypes); must list every symbol include/witw_b200.h declares
+SIGNATURES = {
+    "witw_last_error": (c_char_p, []),
+    "witw_version": (c_int, []),
+    "witw_device_check": (c_int, []),
+    "witw_polar_grid": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p]),
+    "witw_bilinear_lut": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
+    "witw_bilinear_gather_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int64, c_void_p]),
+    "witw_polar_plan_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "witw_polar_plan_build": (c_int, [c_int, c_int, c_int, c_void_p]),
+    "witw_polar_resample_f32": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "witw_match_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "witw_match_pairs_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "witw_crop_gather_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p]),
+    "witw_l2_distance_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
+    "witw_gallery_operand_bytes": (c_size_t, [c_int64, c_int, c_int]),
+    "witw_query_operand_bytes": (c_size_t, [c_int64, c_int, c_int]),
+    "witw_gallery_prep": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "witw_query_prep": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "witw_match_tc_topk_slots": (c_int, [c_int64, c_int64]),
+    "witw_match_tc": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p,
+                              c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int32, c_void_p]),
+    "witw_rank_from_dist_f32": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
+    "witw_l2_rank_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "witw_topk_from_dist_f32": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_int32, c_void_p]),
+    "witw_topk_merge": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
+}
+
+
+class WitwError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library once; raise if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise ImportError(
+            "witw_b200: %s is missing -- build it with `make -C witw_b200/csrc` "
+            "(there is no CPU or PyTorch fallback for the hot path)" % LIB_PATH
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def last_error():
+    return load().witw_last_error().decode("utf-8", "replace")
+
+
+def check(rc, what=""):
+    if rc != 0:
+        raise WitwError("%s failed (%d): %s" % (what or "libwitw_b200 call", rc, last_error()))
+
+
+def call(name, *args):
+    """Call a C-ABI function that returns a status code and raise on failure."""
+    check(getattr(load(), name)(*args), name)

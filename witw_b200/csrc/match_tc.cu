@@ -1,0 +1,646 @@
+// K2/K3 -- orientation-searched distance on the 5th-generation tensor cores (tcgen05).
+// Replaces the correlation -> crop_overhead -> l2_distance chain of model/cvig_fov.py:297-363
+// for whole-gallery sweeps, fused with the rank counting of model/cvig_fov.py:552.
+//
+// GEMM view:  D[q, (g,s)] = sum_{ch,k} su[q,ch,k] * ov[g,ch,(s+k) % 64]
+//   M = queries (plain K-major bf16 tile, TMA, 128B swizzle)
+//   N = (gallery item, azimuth shift): for one item the B operand is the 64 x K Hankel matrix
+//       of its feature rows.  It is never materialised: gallery_prep stores, per pair of items
+//       and feature row, "blocks" of 8 rows x 16 bytes
+//            block b, row r  =  v_{r%2}[4b + r/2 .. 4b + r/2 + 7]        (v = row, circular)
+//       and a NO-SWIZZLE K-major UMMA descriptor with SBO = 128 B (next 8 N-rows = next block)
+//       and LBO = 256 B (next 8 K-columns = two blocks on) makes N-row n = 2s + item read
+//       v_item[s + k]: overlapping addresses give all 64 shifts of two items from 30 blocks
+//       (3.75 KB) instead of a 16 KB expanded tile.
+//   K = (feature row, column) = CH * sw_pad, fp32 accumulation in TMEM.
+// The shifts of one (query, item) pair sit in 64 TMEM columns of one lane, so the epilogue's
+// argmax over the shift is register-local: tcgen05.ld, running max, then
+//   dist = 2 - 2 * corr_max * crop_inv_norm[g, s*] * q_inv_norm[q]
+// and, optionally, the rank count against the true-match distance and a per-query top-k.
+//
+// cta_group::2 (default): a CTA pair computes a 256-query x 4-item tile per accumulator stage
+// (UMMA 256x256x16); each CTA stages its own 128 queries and 2 items.  Warp roles per CTA:
+// 0 TMA producer, 1 MMA issuer (leader) / full-barrier relay (peer), 2 TMEM allocator,
+// 4-7 epilogue.  Two accumulator stages (2 x 256 TMEM columns) overlap epilogue and MMA.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cstdlib>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace witw {
+
+void* get_encode_tiled();  // polar.cu
+
+constexpr int kTcThreads = 256;
+constexpr int kTcMaxStages = 8;
+constexpr int kABytes = 128 * 128;  // 128 queries x 64 bf16
+constexpr int kW = 64;              // azimuth columns of the gallery feature map
+
+struct TcGeom {
+  int sw_pad;   // 16, 32 or 64: query columns padded with zeros
+  int nkap;     // K=16 steps per feature row  = sw_pad / 16
+  int cpb;      // feature rows per 64-wide K block = 64 / sw_pad
+  int bpc;      // 128-byte blocks stored per (item pair, feature row)
+  int sbo, lbo; // B descriptor strides in bytes
+  int kstep;    // bytes between consecutive K=16 steps of one feature row
+  int b_bytes;  // B bytes per K block per CTA
+  int kblocks;  // CH * sw_pad / 64
+};
+
+static bool full_b_layout() {
+  static int v = -1;
+  if (v < 0) { const char* e = std::getenv("WITW_TC_FULL_B"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
+static int cta_group_mode() {
+  static int v = -1;
+  if (v < 0) { const char* e = std::getenv("WITW_TC_CG"); v = (e && e[0] == '1') ? 1 : 2; }
+  return v;
+}
+
+static bool make_geom(int CH, int sw, TcGeom* g) {
+  if (sw < 1 || sw > 64 || CH < 1) return false;
+  g->sw_pad = sw <= 16 ? 16 : (sw <= 32 ? 32 : 64);
+  g->nkap = g->sw_pad / 16;
+  g->cpb = 64 / g->sw_pad;
+  if (CH % g->cpb != 0) return false;
+  if (full_b_layout()) {  // debug layout: every (t,u,kappa) block stored separately
+    g->bpc = 32 * g->nkap; g->sbo = 128; g->lbo = 16 * 128; g->kstep = 32 * 128;
+  } else {                // Hankel layout: block index t + 2u + 4kappa
+    g->bpc = 18 + 4 * (g->nkap - 1); g->sbo = 128; g->lbo = 256; g->kstep = 512;
+  }
+  g->b_bytes = g->cpb * g->bpc * 128;
+  g->kblocks = CH * g->sw_pad / 64;
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------
+// operand preparation
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gallery_blocks_kernel(const float* __restrict__ ov, int64_t G, int CH, int bpc, int full, int nkap,
+                      uint4* __restrict__ out, int64_t n_chunks) {
+  // one thread per 16-byte row of a block: (pair, ch, b, r)
+  const int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= n_chunks) return;
+  const int r = (int)(id & 7);
+  const int64_t blk = id >> 3;
+  const int b = (int)(blk % bpc);
+  const int64_t pc = blk / bpc;
+  const int ch = (int)(pc % CH);
+  const int64_t pair = pc / CH;
+  int vb = b;  // virtual Hankel block index t + 2u + 4kappa
+  if (full) { const int t = b & 15, u = (b >> 4) & 1, kap = b >> 5; vb = t + 2 * u + 4 * kap; }
+  const int64_t item = 2 * pair + (r & 1);
+  const int start = 4 * vb + (r >> 1);
+  uint32_t w[4] = {0, 0, 0, 0};
+  if (item < G) {
+    const float* row = ov + (item * CH + ch) * kW;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __nv_bfloat162 p = __floats2bfloat162_rn(row[(start + 2 * j) & 63], row[(start + 2 * j + 1) & 63]);
+      w[j] = *reinterpret_cast<const uint32_t*>(&p);
+    }
+  }
+  out[id] = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+__global__ void __launch_bounds__(64)
+crop_norm_kernel(const float* __restrict__ ov, int64_t G, int CH, int sw, float* __restrict__ crop_inv_norm) {
+  __shared__ float col_e[kW];
+  const int64_t g = blockIdx.x;
+  const int j = threadIdx.x;
+  float e = 0.f;
+  if (g < G)
+    for (int ch = 0; ch < CH; ++ch) { const float v = ov[(g * CH + ch) * kW + j]; e = fmaf(v, v, e); }
+  col_e[j] = e;
+  __syncthreads();
+  float c = 0.f;
+  for (int k = 0; k < sw; ++k) c += col_e[(j + k) & 63];
+  crop_inv_norm[g * kW + j] = g < G ? 1.0f / sqrtf(c) : 0.f;
+}
+
+__global__ void __launch_bounds__(128)
+query_prep_kernel(const float* __restrict__ su, int64_t Q, int CH, int sw, int sw_pad, __nv_bfloat16* __restrict__ out,
+                  float* __restrict__ q_inv_norm) {
+  __shared__ float red[4];
+  const int64_t q = blockIdx.x;
+  const float* src = su + q * CH * sw;
+  __nv_bfloat16* dst = out + q * CH * sw_pad;
+  float e = 0.f;
+  for (int i = threadIdx.x; i < CH * sw_pad; i += blockDim.x) {
+    const int ch = i / sw_pad, k = i - ch * sw_pad;
+    const float v = k < sw ? src[ch * sw + k] : 0.f;
+    e = fmaf(v, v, e);
+    dst[i] = __float2bfloat16_rn(v);
+  }
+  for (int m = 16; m > 0; m >>= 1) e += __shfl_xor_sync(0xffffffffu, e, m);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = e;
+  __syncthreads();
+  if (threadIdx.x == 0) q_inv_norm[q] = 1.0f / sqrtf(red[0] + red[1] + red[2] + red[3]);
+}
+
+// ------------------------------------------------------------------------------------------
+// PTX helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t s2u(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ int g_tc_timeout_flag = 0;
+
+__device__ __forceinline__ void bar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!done && spin > (1u << 26)) {  // a protocol bug must not hang the GPU: fail the launch instead
+      g_tc_timeout_flag = 1;
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void bar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bar_arrive_local(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void bar_arrive_cluster(uint32_t local_bar, uint32_t cta_rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_bar), "r"(cta_rank));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+__device__ __forceinline__ void tma_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <int CG>
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (CG == 1) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+template <int CG>
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  if constexpr (CG == 1) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+  } else {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((uint16_t)3)
+                 : "memory");
+  }
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// 64-bit shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout, version 1)
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+  d |= (uint64_t)(layout_type & 7u) << 61;
+  return d;
+}
+
+constexpr int kTopkMax = 16;
+
+struct TcParams {
+  const unsigned char* gal_op;   // [pairs][CH][bpc][8][8] bf16
+  const float* crop_inv_norm;    // [G_pad4][64]
+  const float* q_inv_norm;       // [Q]
+  float* dist;                   // [G][Q] or null
+  uint8_t* ori;                  // [G][Q] or null
+  const float* d_true;           // [Q] or null
+  int32_t* rank_count;           // [Q] or null
+  float* topk_dist;              // [n_chunks][Q][topk] or null
+  int32_t* topk_idx;
+  int64_t G, Q;
+  int topk;
+  int32_t g_offset;
+  int n_qtiles, n_chunks, groups_per_chunk, n_groups;
+  int kblocks, cpb, bpc, nkap;
+  int sbo, lbo, kstep, b_bytes;
+  int64_t pair_bytes;            // CH * bpc * 128
+  int n_stages;                  // depth of the operand ring (<= kTcMaxStages)
+};
+
+template <int CG>
+__global__ void __launch_bounds__(kTcThreads, 1)
+match_tc_kernel(const __grid_constant__ CUtensorMap q_map, const TcParams P) {
+  constexpr int UM = 128 * CG;           // UMMA M
+  constexpr int UN = 128 * CG;           // UMMA N  (= accumulator columns per stage)
+  constexpr int IG = 2 * CG;             // gallery items per group
+  constexpr uint32_t kTmemCols = 2 * UN;
+  constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(UN >> 3) << 17) | ((uint32_t)(UM >> 4) << 24);
+
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const uint32_t b_stride = (uint32_t)((P.b_bytes + 127) & ~127);
+  unsigned char* a_base = smem;                                 // kTcStages * 16 KB, 1024-aligned
+  const uint32_t kTcStages = (uint32_t)P.n_stages;
+  unsigned char* b_base = smem + kTcStages * kABytes;           // n_stages * b_stride
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_base + kTcStages * b_stride);
+  uint64_t* full = bars;                         // [n_stages]
+  uint64_t* empty = bars + kTcMaxStages;         // [n_stages]
+  uint64_t* peer_full = bars + 2 * kTcMaxStages; // [n_stages]  (leader only)
+  uint64_t* tmem_full = bars + 3 * kTcMaxStages; // [2]
+  uint64_t* tmem_empty = tmem_full + 2;       // [2]          (leader only)
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t cta_rank = 0;
+  if constexpr (CG == 2) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
+  const bool leader = cta_rank == 0;
+  const int unit = blockIdx.x / CG, n_units = gridDim.x / CG;
+  const int n_items = P.n_chunks * P.n_qtiles;
+
+  if (warp == 0 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&q_map) : "memory");
+  if (warp == 1 && lane == 0) {
+    if (s2u(smem) & 1023u) __trap();  // SWIZZLE_128B operand tiles need a 1024-byte aligned base
+    for (uint32_t s = 0; s < kTcStages; ++s) {
+      bar_init(s2u(&full[s]), 1);
+      bar_init(s2u(&empty[s]), 1);
+      bar_init(s2u(&peer_full[s]), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      bar_init(s2u(&tmem_full[a]), 1);
+      bar_init(s2u(&tmem_empty[a]), 4 * CG);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    if constexpr (CG == 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s2u(tmem_holder)), "r"(kTmemCols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s2u(tmem_holder)), "r"(kTmemCols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+  }
+  tc_fence_before();
+  if constexpr (CG == 2) {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  } else {
+    __syncthreads();
+  }
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    // ===================== TMA producer (one lane) =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int item = unit; item < n_items; item += n_units) {
+        const int chunk = item / P.n_qtiles, qt = item - chunk * P.n_qtiles;
+        const int q_row0 = qt * UM + (int)cta_rank * 128;
+        const int grp0 = chunk * P.groups_per_chunk;
+        const int grp1 = min(grp0 + P.groups_per_chunk, P.n_groups);
+        for (int grp = grp0; grp < grp1; ++grp) {
+          const unsigned char* pair_ptr = P.gal_op + ((int64_t)grp * CG + cta_rank) * P.pair_bytes;
+          for (int kb = 0; kb < P.kblocks; ++kb, ++it) {
+            const uint32_t s = it % kTcStages, ph = (it / kTcStages) & 1;
+            bar_wait(s2u(&empty[s]), ph ^ 1);
+            bar_expect_tx(s2u(&full[s]), (uint32_t)(kABytes + P.b_bytes));
+            tma_2d(s2u(a_base + s * kABytes), &q_map, s2u(&full[s]), kb * 64, q_row0);
+            bulk_1d(s2u(b_base + s * b_stride), pair_ptr + (int64_t)kb * P.b_bytes, (uint32_t)P.b_bytes, s2u(&full[s]));
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader) {
+      // ===================== MMA issuer (one lane of the leader CTA) =====================
+      if (lane == 0) {
+        uint32_t it = 0, acc_it = 0;
+        for (int item = unit; item < n_items; item += n_units) {
+          const int chunk = item / P.n_qtiles;
+          const int grp0 = chunk * P.groups_per_chunk;
+          const int grp1 = min(grp0 + P.groups_per_chunk, P.n_groups);
+          for (int grp = grp0; grp < grp1; ++grp, ++acc_it) {
+            const uint32_t acc = acc_it & 1, acc_ph = (acc_it >> 1) & 1;
+            bar_wait(s2u(&tmem_empty[acc]), acc_ph ^ 1);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + acc * UN;
+            for (int kb = 0; kb < P.kblocks; ++kb, ++it) {
+              const uint32_t s = it % kTcStages, ph = (it / kTcStages) & 1;
+              bar_wait(s2u(&full[s]), ph);
+              if constexpr (CG == 2) bar_wait(s2u(&peer_full[s]), ph);
+              tc_fence_after();
+              const uint32_t a_addr = s2u(a_base + s * kABytes);
+              const uint32_t b_addr = s2u(b_base + s * b_stride);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {  // four K=16 steps of the 64-wide K block
+                const int c_in = j / P.nkap, kap = j - c_in * P.nkap;
+                const uint64_t da = make_desc(a_addr + j * 32, 16, 1024, 2 /*SWIZZLE_128B*/);
+                const uint64_t db = make_desc(b_addr + c_in * P.bpc * 128 + kap * P.kstep, P.lbo, P.sbo, 0 /*no swizzle*/);
+                umma_bf16<CG>(tmem_d, da, db, kIdesc, (kb | j) != 0 ? 1u : 0u);
+              }
+              umma_commit<CG>(s2u(&empty[s]));  // frees the stage in both CTAs when the MMAs retire
+            }
+            umma_commit<CG>(s2u(&tmem_full[acc]));
+          }
+        }
+      }
+    } else if constexpr (CG == 2) {
+      // ===================== peer CTA: relay "my operands have landed" to the leader =====================
+      if (lane == 0) {
+        uint32_t it = 0;
+        for (int item = unit; item < n_items; item += n_units) {
+          const int chunk = item / P.n_qtiles;
+          const int grp0 = chunk * P.groups_per_chunk;
+          const int grp1 = min(grp0 + P.groups_per_chunk, P.n_groups);
+          const uint32_t total = (uint32_t)(grp1 - grp0) * (uint32_t)P.kblocks;
+          for (uint32_t i = 0; i < total; ++i, ++it) {
+            const uint32_t s = it % kTcStages, ph = (it / kTcStages) & 1;
+            bar_wait(s2u(&full[s]), ph);
+            bar_arrive_cluster(s2u(&peer_full[s]), 0);
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: 4 warps = 128 TMEM lanes = 128 queries =====================
+    const int wq = warp & 3;
+    const int row = wq * 32 + lane;
+    const uint32_t lane_field = (uint32_t)(wq * 32) << 16;
+    uint32_t acc_it = 0;
+    for (int item = unit; item < n_items; item += n_units) {
+      const int chunk = item / P.n_qtiles, qt = item - chunk * P.n_qtiles;
+      const int64_t q = (int64_t)qt * UM + cta_rank * 128 + row;
+      const bool q_ok = q < P.Q;
+      const float qin = q_ok ? P.q_inv_norm[q] : 0.f;
+      const float dtrue = (q_ok && P.d_true) ? P.d_true[q] : __int_as_float(0x7fc00000);
+      int cnt = 0;
+      float td[kTopkMax];
+      int32_t ti[kTopkMax];
+#pragma unroll
+      for (int j = 0; j < kTopkMax; ++j) { td[j] = __int_as_float(0x7f800000); ti[j] = -1; }
+      const int grp0 = chunk * P.groups_per_chunk;
+      const int grp1 = min(grp0 + P.groups_per_chunk, P.n_groups);
+      for (int grp = grp0; grp < grp1; ++grp, ++acc_it) {
+        const uint32_t acc = acc_it & 1, acc_ph = (acc_it >> 1) & 1;
+        bar_wait(s2u(&tmem_full[acc]), acc_ph);
+        tc_fence_after();
+        float best[IG];
+        int arg[IG];
+#pragma unroll
+        for (int i = 0; i < IG; ++i) { best[i] = -__int_as_float(0x7f800000); arg[i] = 0; }
+#pragma unroll
+        for (int c = 0; c < UN / 32; ++c) {  // 32 columns = 16 shifts x 2 items
+          uint32_t v[32];
+          tmem_ld32(tmem_base + lane_field + acc * UN + c * 32, v);
+          tmem_ld_wait();
+          const int h = c >> 2;              // which CTA's item pair these columns belong to
+          const int s0 = (c & 3) * 16;
+#pragma unroll
+          for (int ds = 0; ds < 16; ++ds) {
+#pragma unroll
+            for (int gi = 0; gi < 2; ++gi) {
+              const float x = __uint_as_float(v[2 * ds + gi]);
+              const int i = 2 * h + gi;
+              if (x > best[i]) { best[i] = x; arg[i] = s0 + ds; }  // strict '>' in ascending shift order: first maximum
+            }
+          }
+        }
+        // accumulator stage is drained into registers: hand it back to the MMA issuer
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (CG == 1 || leader) bar_arrive_local(s2u(&tmem_empty[acc]));
+          else bar_arrive_cluster(s2u(&tmem_empty[acc]), 0);
+        }
+#pragma unroll
+        for (int i = 0; i < IG; ++i) {
+          const int64_t g = (int64_t)grp * IG + i;
+          if (g < P.G && q_ok) {
+            const float cin = P.crop_inv_norm[g * kW + arg[i]];
+            const float d = 2.0f * (1.0f - best[i] * cin * qin);
+            if (P.dist) P.dist[g * P.Q + q] = d;
+            if (P.ori) P.ori[g * P.Q + q] = (uint8_t)arg[i];
+            cnt += (d <= dtrue) ? 1 : 0;
+            if (P.topk > 0 && d < td[kTopkMax - 1]) {
+              // insertion into the ascending register list (strict '<': earlier index wins ties)
+              float cd = d;
+              int32_t ci = (int32_t)g + P.g_offset;
+#pragma unroll
+              for (int j = 0; j < kTopkMax; ++j) {
+                if (cd < td[j]) {
+                  const float t0 = td[j]; const int32_t t1 = ti[j];
+                  td[j] = cd; ti[j] = ci; cd = t0; ci = t1;
+                }
+              }
+            }
+          }
+        }
+      }
+      if (q_ok) {
+        if (P.rank_count && cnt) atomicAdd(P.rank_count + q, cnt);
+        if (P.topk > 0) {
+          float* od = P.topk_dist + ((int64_t)chunk * P.Q + q) * P.topk;
+          int32_t* oi = P.topk_idx + ((int64_t)chunk * P.Q + q) * P.topk;
+#pragma unroll
+          for (int j = 0; j < kTopkMax; ++j)
+            if (j < P.topk) { od[j] = td[j]; oi[j] = ti[j]; }
+        }
+      }
+    }
+  }
+
+  // ===================== teardown =====================
+  tc_fence_before();
+  if constexpr (CG == 2) {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  } else {
+    __syncthreads();
+  }
+  if (warp == 2) {
+    tc_fence_after();
+    if constexpr (CG == 1)
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+// Work split shared by the kernel launch and witw_match_tc_topk_slots().
+struct TcSchedule { int cg, n_units, n_qtiles, n_groups, groups_per_chunk, n_chunks; };
+
+static TcSchedule make_schedule(int64_t G, int64_t Q) {
+  TcSchedule s;
+  s.cg = cta_group_mode();
+  s.n_units = std::max(1, sm_count() / s.cg);
+  const int64_t tq = 128 * s.cg, ig = 2 * s.cg;
+  s.n_qtiles = (int)ceil_div<int64_t>(std::max<int64_t>(Q, 1), tq);
+  s.n_groups = (int)ceil_div<int64_t>(std::max<int64_t>(G, 1), ig);
+  // about 32 work items per unit for balance, chunks of at least 4 groups, at most 64 chunks
+  // (the top-k merge takes up to 64 candidate lists)
+  int64_t want_chunks = ceil_div<int64_t>((int64_t)s.n_units * 32, s.n_qtiles);
+  want_chunks = std::max<int64_t>(1, std::min<int64_t>(want_chunks, 64));
+  want_chunks = std::min<int64_t>(want_chunks, ceil_div<int64_t>(s.n_groups, 4));
+  s.groups_per_chunk = (int)ceil_div<int64_t>(s.n_groups, std::max<int64_t>(want_chunks, 1));
+  s.n_chunks = (int)ceil_div<int64_t>(s.n_groups, s.groups_per_chunk);
+  return s;
+}
+
+}  // namespace witw
+
+using namespace witw;
+
+extern "C" size_t witw_gallery_operand_bytes(int64_t G, int CH, int sw) {
+  TcGeom g;
+  if (G < 0 || !make_geom(CH, sw, &g)) { set_error(WITW_ERR_UNSUPPORTED, "witw_gallery_operand_bytes: unsupported CH=%d sw=%d", CH, sw); return 0; }
+  const int64_t pairs = ceil_div<int64_t>(G, 4) * 2;
+  return (size_t)std::max<int64_t>(pairs, 2) * CH * g.bpc * 128;
+}
+
+extern "C" size_t witw_query_operand_bytes(int64_t Q, int CH, int sw) {
+  TcGeom g;
+  if (Q < 0 || !make_geom(CH, sw, &g)) { set_error(WITW_ERR_UNSUPPORTED, "witw_query_operand_bytes: unsupported CH=%d sw=%d", CH, sw); return 0; }
+  return (size_t)std::max<int64_t>(Q, 1) * CH * g.sw_pad * 2;
+}
+
+extern "C" int witw_gallery_prep(const float* ov, int64_t G, int CH, int W, int sw, void* gal_op, float* crop_inv_norm,
+                                 witw_stream_t stream) {
+  TcGeom g;
+  WITW_REQUIRE(W == kW, WITW_ERR_UNSUPPORTED, "witw_gallery_prep: the tensor-core path needs W == 64 (got %d)", W);
+  WITW_REQUIRE(G >= 0 && make_geom(CH, sw, &g), WITW_ERR_UNSUPPORTED, "witw_gallery_prep: unsupported CH=%d sw=%d", CH, sw);
+  if (G == 0) return WITW_OK;
+  WITW_REQUIRE(ov && gal_op && crop_inv_norm, WITW_ERR_INVALID, "witw_gallery_prep: null pointer");
+  WITW_REQUIRE(((uintptr_t)gal_op & 127) == 0, WITW_ERR_INVALID, "witw_gallery_prep: operand buffer must be 128-byte aligned");
+  const int64_t g4 = ceil_div<int64_t>(G, 4) * 4;
+  const int64_t n_chunks = (g4 / 2) * CH * g.bpc * 8;
+  gallery_blocks_kernel<<<(unsigned)ceil_div<int64_t>(n_chunks, 256), 256, 0, as_stream(stream)>>>(
+      ov, G, CH, g.bpc, full_b_layout() ? 1 : 0, g.nkap, reinterpret_cast<uint4*>(gal_op), n_chunks);
+  WITW_LAUNCH_CHECK();
+  crop_norm_kernel<<<(unsigned)g4, 64, 0, as_stream(stream)>>>(ov, G, CH, sw, crop_inv_norm);
+  WITW_LAUNCH_CHECK();
+  return WITW_OK;
+}
+
+extern "C" int witw_query_prep(const float* su, int64_t Q, int CH, int sw, void* qry_op, float* q_inv_norm, witw_stream_t stream) {
+  TcGeom g;
+  WITW_REQUIRE(Q >= 0 && make_geom(CH, sw, &g), WITW_ERR_UNSUPPORTED, "witw_query_prep: unsupported CH=%d sw=%d", CH, sw);
+  if (Q == 0) return WITW_OK;
+  WITW_REQUIRE(su && qry_op && q_inv_norm, WITW_ERR_INVALID, "witw_query_prep: null pointer");
+  WITW_REQUIRE(Q < (1ll << 31), WITW_ERR_INVALID, "witw_query_prep: too many queries");
+  query_prep_kernel<<<(unsigned)Q, 128, 0, as_stream(stream)>>>(su, Q, CH, sw, g.sw_pad, reinterpret_cast<__nv_bfloat16*>(qry_op), q_inv_norm);
+  WITW_LAUNCH_CHECK();
+  return WITW_OK;
+}
+
+extern "C" int witw_match_tc_topk_slots(int64_t G, int64_t Q) { return make_schedule(G, Q).n_chunks; }
+
+extern "C" int witw_match_tc(const void* gal_op, const float* crop_inv_norm, const void* qry_op, const float* q_inv_norm, int64_t G,
+                             int64_t Q, int CH, int sw, float* dist, uint8_t* ori, const float* d_true, int32_t* rank_count,
+                             int topk, float* topk_dist, int32_t* topk_idx, int32_t g_offset, witw_stream_t stream) {
+  TcGeom geo;
+  WITW_REQUIRE(G >= 0 && Q >= 0 && make_geom(CH, sw, &geo), WITW_ERR_UNSUPPORTED, "witw_match_tc: unsupported CH=%d sw=%d", CH, sw);
+  if (G == 0 || Q == 0) return WITW_OK;
+  WITW_REQUIRE(gal_op && crop_inv_norm && qry_op && q_inv_norm, WITW_ERR_INVALID, "witw_match_tc: null operand");
+  WITW_REQUIRE(topk >= 0 && topk <= kTopkMax, WITW_ERR_UNSUPPORTED, "witw_match_tc: fused top-k supports k <= %d (got %d)", kTopkMax, topk);
+  WITW_REQUIRE(topk == 0 || (topk_dist && topk_idx), WITW_ERR_INVALID, "witw_match_tc: top-k buffers missing");
+  WITW_REQUIRE(!rank_count || d_true, WITW_ERR_INVALID, "witw_match_tc: rank_count needs d_true");
+  WITW_REQUIRE(G < (1ll << 31) && Q < (1ll << 31), WITW_ERR_INVALID, "witw_match_tc: sizes exceed 2^31");
+  WITW_REQUIRE(((uintptr_t)qry_op & 15) == 0 && ((uintptr_t)gal_op & 15) == 0, WITW_ERR_INVALID, "witw_match_tc: operands must be 16-byte aligned");
+  int rc = witw_device_check();
+  if (rc != WITW_OK) return rc;
+
+  const TcSchedule sch = make_schedule(G, Q);
+  typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  auto encode = reinterpret_cast<EncodeTiledFn>(get_encode_tiled());
+  WITW_REQUIRE(encode != nullptr, WITW_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  const int64_t ktot = (int64_t)CH * geo.sw_pad;
+  CUtensorMap qmap;
+  const cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)Q};
+  const cuuint64_t strides[1] = {(cuuint64_t)ktot * 2};
+  const cuuint32_t box[2] = {64, 128};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult cr = encode(&qmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(qry_op), dims, strides, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  WITW_REQUIRE(cr == CUDA_SUCCESS, WITW_ERR_CUDA, "cuTensorMapEncodeTiled(query operand) failed with CUresult %d", (int)cr);
+
+  TcParams P;
+  std::memset(&P, 0, sizeof(P));
+  P.gal_op = reinterpret_cast<const unsigned char*>(gal_op);
+  P.crop_inv_norm = crop_inv_norm; P.q_inv_norm = q_inv_norm;
+  P.dist = dist; P.ori = ori; P.d_true = d_true; P.rank_count = rank_count;
+  P.topk_dist = topk_dist; P.topk_idx = topk_idx; P.G = G; P.Q = Q; P.topk = topk; P.g_offset = g_offset;
+  P.n_qtiles = sch.n_qtiles; P.n_chunks = sch.n_chunks; P.groups_per_chunk = sch.groups_per_chunk; P.n_groups = sch.n_groups;
+  P.kblocks = geo.kblocks; P.cpb = geo.cpb; P.bpc = geo.bpc; P.nkap = geo.nkap;
+  P.sbo = geo.sbo; P.lbo = geo.lbo; P.kstep = geo.kstep; P.b_bytes = geo.b_bytes;
+  P.pair_bytes = (int64_t)CH * geo.bpc * 128;
+
+  const uint32_t b_stride = (uint32_t)((geo.b_bytes + 127) & ~127);
+  const size_t fixed = (3 * kTcMaxStages + 4) * 8 + 16;
+  int n_stages = (int)std::min<size_t>(kTcMaxStages, (227 * 1024 - fixed) / (kABytes + b_stride));
+  WITW_REQUIRE(n_stages >= 2, WITW_ERR_UNSUPPORTED, "witw_match_tc: operand stage of %u bytes does not fit shared memory twice", kABytes + b_stride);
+  P.n_stages = n_stages;
+  const size_t smem = (size_t)n_stages * (kABytes + b_stride) + fixed;
+  const int n_items = sch.n_chunks * sch.n_qtiles;
+  const int units = std::min(sch.n_units, n_items);
+  cudaLaunchConfig_t cfg;
+  std::memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(units * sch.cg));
+  cfg.blockDim = dim3(kTcThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = as_stream(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)sch.cg;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (sch.cg == 2) {
+    WITW_CUDA(cudaFuncSetAttribute(match_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    WITW_CUDA(cudaLaunchKernelEx(&cfg, match_tc_kernel<2>, qmap, P));
+  } else {
+    WITW_CUDA(cudaFuncSetAttribute(match_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    WITW_CUDA(cudaLaunchKernelEx(&cfg, match_tc_kernel<1>, qmap, P));
+  }
+  WITW_LAUNCH_CHECK();
+  return WITW_OK;
+}

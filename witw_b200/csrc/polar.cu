@@ -1,0 +1,438 @@
+// K1 -- aerial polar transform (bilinear resample of overhead tiles into panorama-aligned
+// polar images).  Replaces model/cvig_fov.py:156-209 (bilinear_interpolate + PolarTransform).
+//
+// Two device paths:
+//   * witw_bilinear_gather_f32: generic geometry, taps and fp32 weights from a host-built
+//     float64 table (exactly the reference's arithmetic) -> bit-exact with the reference.
+//   * witw_polar_resample_f32: the throughput path.  One persistent CTA per SM, pinned to one
+//     azimuth quadrant.  The quadrant's source window (a 132x129-float box, 1.6 % larger
+//     than the pixels it needs) is streamed through a 3-stage TMA ring in shared memory;
+//     each of the 1024 threads keeps the sample table of its 16 output pixels in registers
+//     for the whole launch (no table traffic), gathers 4 taps per pixel from shared memory
+//     and stores with lanes on consecutive output columns (128-byte coalesced rows).
+//     HBM traffic is the algorithmic minimum: every source byte is read once (plus the box
+//     margin), every output byte written once.
+#include <cuda.h>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+
+namespace witw {
+
+// ------------------------------------------------------------------------------------------
+// host side: grid and table (float64, mirrors the reference's evaluation order)
+// ------------------------------------------------------------------------------------------
+static void polar_grid_host(int h_s, int w_s, int s_o, double* x, double* y) {
+  const double half = s_o / 2.0;  // cvig_fov.py:198 (s_o/2) is a true division in Python 3
+  const double two_pi = 2 * 3.141592653589793;  // math.pi
+  for (int r = 0; r < h_s; ++r) {
+    // (s_o/2) * (h_s - 1 - yy) / h_s : product first, then the division (left to right)
+    const double radial = half * (double)(h_s - 1 - r) / (double)h_s;
+    for (int c = 0; c < w_s; ++c) {
+      const double ang = two_pi * (double)c / (double)w_s;
+      y[(size_t)r * w_s + c] = half + radial * std::cos(ang);
+      x[(size_t)r * w_s + c] = half - radial * std::sin(ang);
+    }
+  }
+}
+
+static inline int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+static void bilinear_lut_host(const double* x, const double* y, int64_t n, int src_h, int src_w,
+                              int32_t* idx4, float* w4) {
+  for (int64_t i = 0; i < n; ++i) {
+    int x0 = (int)std::floor(x[i]), y0 = (int)std::floor(y[i]);
+    int x1 = x0 + 1, y1 = y0 + 1;
+    x0 = clampi(x0, 0, src_w - 1);
+    x1 = clampi(x1, 0, src_w - 1);
+    y0 = clampi(y0, 0, src_h - 1);
+    y1 = clampi(y1, 0, src_h - 1);
+    idx4[4 * i + 0] = x0;
+    idx4[4 * i + 1] = x1;
+    idx4[4 * i + 2] = y0;
+    idx4[4 * i + 3] = y1;
+    // float64 products of the clipped differences, then one rounding to fp32 (cvig_fov.py:178-181)
+    w4[4 * i + 0] = (float)(((double)x1 - x[i]) * ((double)y1 - y[i]));
+    w4[4 * i + 1] = (float)(((double)x1 - x[i]) * (y[i] - (double)y0));
+    w4[4 * i + 2] = (float)((x[i] - (double)x0) * ((double)y1 - y[i]));
+    w4[4 * i + 3] = (float)((x[i] - (double)x0) * (y[i] - (double)y0));
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// generic gather kernel (bit-exact path)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bilinear_gather_kernel(const float* __restrict__ src,
+                                                              float* __restrict__ dst,
+                                                              const int4* __restrict__ idx4,
+                                                              const float4* __restrict__ w4,
+                                                              int64_t n_img, int src_h, int src_w,
+                                                              int64_t n_out, int img_per_block) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_out) return;
+  const int4 t = idx4[p];  // x0, x1, y0, y1
+  const float4 w = w4[p];  // wa, wb, wc, wd
+  const int oa = t.z * src_w + t.x, ob = t.w * src_w + t.x, oc = t.z * src_w + t.y, od = t.w * src_w + t.y;
+  const int64_t plane = (int64_t)src_h * src_w;
+  const int64_t i0 = (int64_t)blockIdx.y * img_per_block;
+  const int64_t i1 = min(i0 + img_per_block, n_img);
+  for (int64_t i = i0; i < i1; ++i) {
+    const float* s = src + i * plane;
+    const float a = __ldg(s + oa), b = __ldg(s + ob), c = __ldg(s + oc), d = __ldg(s + od);
+    // ((wa*Ia + wb*Ib) + wc*Ic) + wd*Id, no contraction (cvig_fov.py:183)
+    float r = __fadd_rn(__fmul_rn(w.x, a), __fmul_rn(w.y, b));
+    r = __fadd_rn(r, __fmul_rn(w.z, c));
+    r = __fadd_rn(r, __fmul_rn(w.w, d));
+    dst[i * n_out + p] = r;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// fast path: plan
+// ------------------------------------------------------------------------------------------
+constexpr int kPolarThreads = 1024;
+constexpr int kPolarPx = 16;  // output pixels per thread per quadrant
+constexpr int kBoxW = 132;    // floats per staged source row (multiple of 4: TMA inner box is 16-byte granular)
+constexpr int kBoxH = 129;
+constexpr int kPolarStages = 3;
+constexpr uint32_t kPlanMagic = 0x57495031u;  // "WIP1"
+
+struct PolarException {  // a pixel whose taps the reference clips: patched with the exact formula
+  int32_t pix;           // row * w_s + col
+  int32_t x0, x1, y0, y1;
+  float w[4];
+};
+
+struct PolarPlanHeader {
+  uint32_t magic;
+  int32_t h_s, w_s, s_o;
+  int32_t box_x0[4], box_y0[4];
+  int32_t n_exc;
+  uint32_t lut_off;  // byte offset of the register table: float fx[4][PX][1024], float fy[..], uint32 off2[4][PX/2][1024]
+                     // (off2 packs the 16-bit box offsets of pixels 2i and 2i+1)
+  uint32_t exc_off;  // byte offset of PolarException[n_exc]
+  uint32_t total_bytes;
+};
+
+static bool polar_fast_supported(int h_s, int w_s, int s_o) {
+  if (w_s % 128 != 0 || s_o < 8 || h_s < 1) return false;
+  return (int64_t)h_s * (w_s / 4) == (int64_t)kPolarThreads * kPolarPx;
+}
+
+// Builds header + tables into `out` (may be null to only count).  Returns bytes, 0 if unsupported.
+static size_t polar_plan_build_host(int h_s, int w_s, int s_o, void* out) {
+  if (!polar_fast_supported(h_s, w_s, s_o)) return 0;
+  const int64_t n = (int64_t)h_s * w_s;
+  std::vector<double> x(n), y(n);
+  polar_grid_host(h_s, w_s, s_o, x.data(), y.data());
+  std::vector<int32_t> idx(4 * n);
+  std::vector<float> w(4 * n);
+  bilinear_lut_host(x.data(), y.data(), n, s_o, s_o, idx.data(), w.data());
+  const int qw = w_s / 4;
+  std::vector<PolarException> exc;
+  std::vector<char> is_exc(n, 0);
+  int bx0[4], by0[4], bx1[4], by1[4];
+  for (int q = 0; q < 4; ++q) { bx0[q] = by0[q] = 1 << 30; bx1[q] = by1[q] = -(1 << 30); }
+  for (int64_t p = 0; p < n; ++p) {
+    const int fx0 = (int)std::floor(x[p]), fy0 = (int)std::floor(y[p]);
+    const bool clipped = idx[4 * p] != fx0 || idx[4 * p + 1] != fx0 + 1 || idx[4 * p + 2] != fy0 || idx[4 * p + 3] != fy0 + 1;
+    if (clipped) {
+      PolarException e;
+      e.pix = (int32_t)p;
+      e.x0 = idx[4 * p]; e.x1 = idx[4 * p + 1]; e.y0 = idx[4 * p + 2]; e.y1 = idx[4 * p + 3];
+      for (int k = 0; k < 4; ++k) e.w[k] = w[4 * p + k];
+      exc.push_back(e);
+      is_exc[p] = 1;
+      continue;
+    }
+    const int q = (int)((p % w_s) / qw);
+    bx0[q] = std::min(bx0[q], fx0); bx1[q] = std::max(bx1[q], fx0 + 1);
+    by0[q] = std::min(by0[q], fy0); by1[q] = std::max(by1[q], fy0 + 1);
+  }
+  for (int q = 0; q < 4; ++q)
+    if (bx1[q] - bx0[q] + 1 > kBoxW || by1[q] - by0[q] + 1 > kBoxH) return 0;
+  const size_t lut_elems = (size_t)4 * kPolarPx * kPolarThreads;
+  PolarPlanHeader h;
+  std::memset(&h, 0, sizeof(h));
+  h.magic = kPlanMagic; h.h_s = h_s; h.w_s = w_s; h.s_o = s_o;
+  for (int q = 0; q < 4; ++q) { h.box_x0[q] = bx0[q]; h.box_y0[q] = by0[q]; }
+  h.n_exc = (int32_t)exc.size();
+  h.lut_off = 256;
+  h.exc_off = (uint32_t)(h.lut_off + 3 * lut_elems * 4);
+  h.total_bytes = (uint32_t)(h.exc_off + std::max<size_t>(exc.size(), 1) * sizeof(PolarException));
+  if (out == nullptr) return h.total_bytes;
+  char* base = (char*)out;
+  std::memset(base, 0, h.total_bytes);
+  std::memcpy(base, &h, sizeof(h));
+  float* fx = (float*)(base + h.lut_off);
+  float* fy = fx + lut_elems;
+  uint32_t* off = (uint32_t*)(fy + lut_elems);
+  for (int q = 0; q < 4; ++q)
+    for (int i = 0; i < kPolarPx; ++i)
+      for (int t = 0; t < kPolarThreads; ++t) {
+        const int lin = i * kPolarThreads + t;  // pixel index inside the quadrant, row-major [h_s][qw]
+        const int row = lin / qw, col = q * qw + lin % qw;
+        const int64_t p = (int64_t)row * w_s + col;
+        const size_t o = ((size_t)q * kPolarPx + i) * kPolarThreads + t;
+        const size_t o2 = ((size_t)q * (kPolarPx / 2) + i / 2) * kPolarThreads + t;
+        const int sh = (i & 1) * 16;
+        if (is_exc[p]) { fx[o] = 0.f; fy[o] = 0.f; continue; }  // offset 0, patched afterwards
+        const int fx0 = (int)std::floor(x[p]), fy0 = (int)std::floor(y[p]);
+        fx[o] = (float)(x[p] - (double)fx0);
+        fy[o] = (float)(y[p] - (double)fy0);
+        off[o2] |= (uint32_t)((fy0 - by0[q]) * kBoxW + (fx0 - bx0[q])) << sh;
+      }
+  if (!exc.empty()) std::memcpy(base + h.exc_off, exc.data(), exc.size() * sizeof(PolarException));
+  return h.total_bytes;
+}
+
+// ------------------------------------------------------------------------------------------
+// fast path: kernel
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+struct PolarQuadBoxes { int x0[4], y0[4]; };
+
+__global__ void __launch_bounds__(kPolarThreads, 1)
+polar_quadrant_kernel(const __grid_constant__ CUtensorMap src_map, float* __restrict__ dst, int n_img,
+                      const float* __restrict__ lut_fx, const float* __restrict__ lut_fy,
+                      const uint32_t* __restrict__ lut_off, PolarQuadBoxes boxes, int h_s, int w_s) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr uint32_t kStageBytes = kBoxW * kBoxH * 4;
+  constexpr uint32_t kStageStride = (kStageBytes + 127) & ~127u;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + kPolarStages * kStageStride);
+
+  const int tid = threadIdx.x;
+  const int q = blockIdx.x & 3;
+  const int worker = blockIdx.x >> 2, n_workers = gridDim.x >> 2;
+  const int qw = w_s >> 2;
+
+  // this thread's 16 sample points stay in registers for the whole launch
+  float fx[kPolarPx], fy[kPolarPx];
+  uint32_t off2[kPolarPx / 2];
+#pragma unroll
+  for (int i = 0; i < kPolarPx; ++i) {
+    const size_t o = ((size_t)q * kPolarPx + i) * kPolarThreads + tid;
+    fx[i] = lut_fx[o];
+    fy[i] = lut_fy[o];
+  }
+#pragma unroll
+  for (int i = 0; i < kPolarPx / 2; ++i) off2[i] = lut_off[((size_t)q * (kPolarPx / 2) + i) * kPolarThreads + tid];
+  // output offset of pixel i: rows advance by kPolarThreads/qw per i
+  const int rows_per_i = kPolarThreads / qw;
+  const size_t out_base = (size_t)(tid / qw) * w_s + (size_t)q * qw + (tid % qw);
+  const size_t out_step = (size_t)rows_per_i * w_s;
+  const size_t plane_out = (size_t)h_s * w_s;
+
+  if (tid == 0) {
+    for (int s = 0; s < kPolarStages; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const int bx = q == 0 ? boxes.x0[0] : (q == 1 ? boxes.x0[1] : (q == 2 ? boxes.x0[2] : boxes.x0[3]));
+  const int by = q == 0 ? boxes.y0[0] : (q == 1 ? boxes.y0[1] : (q == 2 ? boxes.y0[2] : boxes.y0[3]));
+  if (tid == 0) {
+    for (int s = 0; s < kPolarStages; ++s) {
+      const int it = worker + s * n_workers;
+      if (it < n_img) {
+        mbar_expect_tx(&full[s], kStageBytes);
+        tma_load_3d(smem_raw + s * kStageStride, &src_map, &full[s], bx, by, it);
+      }
+    }
+  }
+
+  int j = 0;
+  for (int it = worker; it < n_img; it += n_workers, ++j) {
+    const int s = j % kPolarStages;
+    mbar_wait(&full[s], (uint32_t)((j / kPolarStages) & 1));
+    const float* tile = reinterpret_cast<const float*>(smem_raw + s * kStageStride);
+    float* o = dst + (size_t)it * plane_out + out_base;
+#pragma unroll
+    for (int b = 0; b < kPolarPx; b += 4) {  // batches of 4 pixels bound the live registers (1024 threads -> 64 regs each)
+      float r[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = b + u;
+        const float* p = tile + ((off2[i >> 1] >> ((i & 1) * 16)) & 0xffffu);
+        const float ia = p[0], ic = p[1], ib = p[kBoxW], id = p[kBoxW + 1];
+        // the four weights are recomputed per plane on purpose: hoisting them out of the plane loop
+        // would cost 64 more registers per thread (the empty asm makes fxi/fyi opaque to LICM)
+        float fxi = fx[i], fyi = fy[i];
+        asm volatile("" : "+f"(fxi), "+f"(fyi));
+        const float ax = 1.0f - fxi, ay = 1.0f - fyi;
+        // reference order (cvig_fov.py:178-183): wa=(x1-x)(y1-y) wb=(x1-x)(y-y0) wc=(x-x0)(y1-y) wd=(x-x0)(y-y0)
+        float t = __fadd_rn(__fmul_rn(__fmul_rn(ax, ay), ia), __fmul_rn(__fmul_rn(ax, fyi), ib));
+        t = __fadd_rn(t, __fmul_rn(__fmul_rn(fxi, ay), ic));
+        r[u] = __fadd_rn(t, __fmul_rn(__fmul_rn(fxi, fyi), id));
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) __stcs(o + (b + u) * out_step, r[u]);
+      asm volatile("" ::: "memory");
+    }
+    __syncthreads();  // every thread is done with stage s
+    if (tid == 0) {
+      const int nxt = it + kPolarStages * n_workers;
+      if (nxt < n_img) {
+        mbar_expect_tx(&full[s], kStageBytes);
+        tma_load_3d(smem_raw + s * kStageStride, &src_map, &full[s], bx, by, nxt);
+      }
+    }
+  }
+}
+
+__global__ void polar_exception_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t n_img,
+                                       const PolarException* __restrict__ exc, int n_exc, int s_o, int64_t plane_out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_img * n_exc) return;
+  const int64_t img = i / n_exc;
+  const PolarException e = exc[i % n_exc];
+  const float* s = src + img * (int64_t)s_o * s_o;
+  const float a = s[e.y0 * s_o + e.x0], b = s[e.y1 * s_o + e.x0], c = s[e.y0 * s_o + e.x1], d = s[e.y1 * s_o + e.x1];
+  float r = __fadd_rn(__fmul_rn(e.w[0], a), __fmul_rn(e.w[1], b));
+  r = __fadd_rn(r, __fmul_rn(e.w[2], c));
+  r = __fadd_rn(r, __fmul_rn(e.w[3], d));
+  dst[img * plane_out + e.pix] = r;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+void* get_encode_tiled() {
+  static void* fn = nullptr;
+  if (fn == nullptr) {
+    cudaDriverEntryPointQueryResult qres;
+    void* f = nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = f;
+  }
+  return fn;
+}
+
+}  // namespace witw
+
+using namespace witw;
+
+extern "C" int witw_polar_grid(int h_s, int w_s, int s_o, double* x, double* y) {
+  WITW_REQUIRE(h_s > 0 && w_s > 0 && s_o > 0 && x && y, WITW_ERR_INVALID, "witw_polar_grid: bad arguments");
+  polar_grid_host(h_s, w_s, s_o, x, y);
+  return WITW_OK;
+}
+
+extern "C" int witw_bilinear_lut(const double* x, const double* y, int64_t n, int src_h, int src_w, int32_t* idx4,
+                                 float* w4) {
+  WITW_REQUIRE(x && y && idx4 && w4 && n >= 0 && src_h > 0 && src_w > 0, WITW_ERR_INVALID, "witw_bilinear_lut: bad arguments");
+  bilinear_lut_host(x, y, n, src_h, src_w, idx4, w4);
+  return WITW_OK;
+}
+
+extern "C" int witw_bilinear_gather_f32(const float* src, float* dst, const int32_t* idx4, const float* w4, int64_t n_img,
+                                        int src_h, int src_w, int64_t n_out, witw_stream_t stream) {
+  WITW_REQUIRE(src && dst && idx4 && w4, WITW_ERR_INVALID, "witw_bilinear_gather_f32: null pointer");
+  WITW_REQUIRE(n_img >= 0 && n_out >= 0 && src_h > 0 && src_w > 0 && (int64_t)src_h * src_w < (1ll << 31), WITW_ERR_INVALID,
+               "witw_bilinear_gather_f32: bad shape");
+  if (n_img == 0 || n_out == 0) return WITW_OK;
+  const int64_t bx = ceil_div<int64_t>(n_out, 256);
+  // enough blocks in y to fill the machine a few times over, each looping over a run of planes
+  int64_t by = std::min<int64_t>(n_img, std::max<int64_t>(1, (int64_t)sm_count() * 16 / bx));
+  by = std::min<int64_t>(by, 65535);
+  const int per = (int)ceil_div<int64_t>(n_img, by);
+  by = ceil_div<int64_t>(n_img, per);
+  WITW_REQUIRE(bx < (1ll << 31), WITW_ERR_INVALID, "witw_bilinear_gather_f32: too many sample points");
+  bilinear_gather_kernel<<<dim3((unsigned)bx, (unsigned)by), 256, 0, as_stream(stream)>>>(
+      src, dst, reinterpret_cast<const int4*>(idx4), reinterpret_cast<const float4*>(w4), n_img, src_h, src_w, n_out, per);
+  WITW_LAUNCH_CHECK();
+  return WITW_OK;
+}
+
+extern "C" size_t witw_polar_plan_bytes(int h_s, int w_s, int s_o) {
+  const size_t b = polar_plan_build_host(h_s, w_s, s_o, nullptr);
+  if (b == 0) set_error(WITW_ERR_UNSUPPORTED, "witw_polar_plan: geometry %dx%d from %d is outside the staged fast path", h_s, w_s, s_o);
+  return b;
+}
+
+extern "C" int witw_polar_plan_build(int h_s, int w_s, int s_o, void* plan_host) {
+  WITW_REQUIRE(plan_host, WITW_ERR_INVALID, "witw_polar_plan_build: null plan");
+  const size_t b = polar_plan_build_host(h_s, w_s, s_o, plan_host);
+  WITW_REQUIRE(b != 0, WITW_ERR_UNSUPPORTED, "witw_polar_plan_build: geometry %dx%d from %d is outside the staged fast path", h_s, w_s, s_o);
+  return WITW_OK;
+}
+
+extern "C" int witw_polar_resample_f32(const float* src, float* dst, int64_t n_img, const void* plan_host,
+                                       const void* plan_dev, witw_stream_t stream) {
+  WITW_REQUIRE(src && dst && plan_host && plan_dev, WITW_ERR_INVALID, "witw_polar_resample_f32: null pointer");
+  PolarPlanHeader h;
+  std::memcpy(&h, plan_host, sizeof(h));
+  WITW_REQUIRE(h.magic == kPlanMagic, WITW_ERR_INVALID, "witw_polar_resample_f32: plan_host is not a polar plan");
+  WITW_REQUIRE(n_img >= 0 && n_img < (1ll << 31), WITW_ERR_INVALID, "witw_polar_resample_f32: bad n_img");
+  WITW_REQUIRE(((uintptr_t)src & 15) == 0, WITW_ERR_INVALID, "witw_polar_resample_f32: src must be 16-byte aligned");
+  if (n_img == 0) return WITW_OK;
+  int rc = witw_device_check();
+  if (rc != WITW_OK) return rc;
+
+  auto encode = reinterpret_cast<EncodeTiledFn>(get_encode_tiled());
+  WITW_REQUIRE(encode != nullptr, WITW_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  CUtensorMap map;
+  const cuuint64_t dims[3] = {(cuuint64_t)h.s_o, (cuuint64_t)h.s_o, (cuuint64_t)n_img};
+  const cuuint64_t strides[2] = {(cuuint64_t)h.s_o * 4, (cuuint64_t)h.s_o * h.s_o * 4};
+  const cuuint32_t box[3] = {kBoxW, kBoxH, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  CUresult cr = encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(src), dims, strides, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  WITW_REQUIRE(cr == CUDA_SUCCESS, WITW_ERR_CUDA, "cuTensorMapEncodeTiled(polar source) failed with CUresult %d", (int)cr);
+
+  constexpr uint32_t kStageBytes = kBoxW * kBoxH * 4;
+  constexpr uint32_t kStageStride = (kStageBytes + 127) & ~127u;
+  const size_t smem = (size_t)kPolarStages * kStageStride + kPolarStages * sizeof(uint64_t);
+  static bool attr_set = false;
+  if (!attr_set) {
+    WITW_CUDA(cudaFuncSetAttribute(polar_quadrant_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  const char* pd = (const char*)plan_dev;
+  const size_t lut_elems = (size_t)4 * kPolarPx * kPolarThreads;
+  const float* fx = (const float*)(pd + h.lut_off);
+  const float* fy = fx + lut_elems;
+  const uint32_t* off = (const uint32_t*)(fy + lut_elems);
+  PolarQuadBoxes boxes;
+  for (int q = 0; q < 4; ++q) { boxes.x0[q] = h.box_x0[q]; boxes.y0[q] = h.box_y0[q]; }
+  int grid = (sm_count() / 4) * 4;
+  if ((int64_t)grid > 4 * n_img) grid = (int)(4 * n_img);
+  polar_quadrant_kernel<<<grid, kPolarThreads, smem, as_stream(stream)>>>(map, dst, (int)n_img, fx, fy, off, boxes, h.h_s, h.w_s);
+  WITW_LAUNCH_CHECK();
+  if (h.n_exc > 0) {
+    const int64_t n = n_img * h.n_exc;
+    polar_exception_kernel<<<(unsigned)ceil_div<int64_t>(n, 256), 256, 0, as_stream(stream)>>>(
+        src, dst, n_img, (const PolarException*)(pd + h.exc_off), h.n_exc, h.s_o, (int64_t)h.h_s * h.w_s);
+    WITW_LAUNCH_CHECK();
+  }
+  return WITW_OK;
+}

@@ -1,0 +1,245 @@
+// K4 -- rank by counting and top-k over a materialised [gallery, query] distance matrix,
+// plus the baseline Euclidean variant.  Replaces the per-query body of the rank loops in
+// model/cvig_fov.py:550-552 and model/cvig_baseline.py:458-460:
+//     rank[q] = #{ g : d[g,q] <= d[true(q), q] }     (ties and the match itself count,
+//                                                     NaN compares false)
+// HBM-bound: 4*G*Q bytes read once.  Columns are queries, so a warp reads 32 (or 128 with
+// float4) consecutive queries of one gallery row per request; counts stay in registers and
+// leave the SM as one atomic per (query, gallery slice).
+#include "common.cuh"
+
+namespace witw {
+
+constexpr int kRankThreads = 128;
+
+// float4 path: Q % 4 == 0, 16-byte aligned base
+__global__ void __launch_bounds__(kRankThreads)
+rank_count_vec4_kernel(const float* __restrict__ dist, int64_t G, int64_t Q, const int64_t* __restrict__ true_idx,
+                       unsigned long long* __restrict__ ranks, int64_t rows_per_block) {
+  const int64_t q4 = (int64_t)blockIdx.x * kRankThreads + threadIdx.x;  // index of a group of 4 queries
+  if (q4 * 4 >= Q) return;
+  const int64_t q = q4 * 4;
+  float thr[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int64_t t = true_idx ? true_idx[q + j] : (q + j);
+    thr[j] = (t >= 0 && t < G) ? dist[t * Q + q + j] : __int_as_float(0x7fc00000);  // NaN: nothing counts
+  }
+  const int64_t g0 = (int64_t)blockIdx.y * rows_per_block;
+  const int64_t g1 = min(g0 + rows_per_block, G);
+  unsigned c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+  const float4* p = reinterpret_cast<const float4*>(dist + q);
+  const int64_t stride4 = Q >> 2;
+  int64_t g = g0;
+  for (; g + 4 <= g1; g += 4) {  // 4 independent 16-byte loads in flight per thread
+    const float4 a = __ldcs(p + g * stride4), b = __ldcs(p + (g + 1) * stride4);
+    const float4 c = __ldcs(p + (g + 2) * stride4), d = __ldcs(p + (g + 3) * stride4);
+    c0 += (a.x <= thr[0]) + (b.x <= thr[0]) + (c.x <= thr[0]) + (d.x <= thr[0]);
+    c1 += (a.y <= thr[1]) + (b.y <= thr[1]) + (c.y <= thr[1]) + (d.y <= thr[1]);
+    c2 += (a.z <= thr[2]) + (b.z <= thr[2]) + (c.z <= thr[2]) + (d.z <= thr[2]);
+    c3 += (a.w <= thr[3]) + (b.w <= thr[3]) + (c.w <= thr[3]) + (d.w <= thr[3]);
+  }
+  for (; g < g1; ++g) {
+    const float4 a = __ldcs(p + g * stride4);
+    c0 += (a.x <= thr[0]);
+    c1 += (a.y <= thr[1]);
+    c2 += (a.z <= thr[2]);
+    c3 += (a.w <= thr[3]);
+  }
+  if (c0) atomicAdd(ranks + q, (unsigned long long)c0);
+  if (c1) atomicAdd(ranks + q + 1, (unsigned long long)c1);
+  if (c2) atomicAdd(ranks + q + 2, (unsigned long long)c2);
+  if (c3) atomicAdd(ranks + q + 3, (unsigned long long)c3);
+}
+
+__global__ void __launch_bounds__(kRankThreads)
+rank_count_scalar_kernel(const float* __restrict__ dist, int64_t G, int64_t Q, const int64_t* __restrict__ true_idx,
+                         unsigned long long* __restrict__ ranks, int64_t rows_per_block) {
+  const int64_t q = (int64_t)blockIdx.x * kRankThreads + threadIdx.x;
+  if (q >= Q) return;
+  const int64_t t = true_idx ? true_idx[q] : q;
+  const float thr = (t >= 0 && t < G) ? dist[t * Q + q] : __int_as_float(0x7fc00000);
+  const int64_t g0 = (int64_t)blockIdx.y * rows_per_block;
+  const int64_t g1 = min(g0 + rows_per_block, G);
+  unsigned c = 0;
+  for (int64_t g = g0; g < g1; ++g) c += (__ldcs(dist + g * Q + q) <= thr);
+  if (c) atomicAdd(ranks + q, (unsigned long long)c);
+}
+
+// Euclidean distance matrix of the baseline model: one warp per (gallery row, 8 queries held in shared memory)
+constexpr int kL2QT = 8;
+__global__ void __launch_bounds__(256)
+l2_dist_kernel(const float* __restrict__ ov, const float* __restrict__ su, int64_t N, int64_t Q, int64_t D,
+               float* __restrict__ dist) {
+  extern __shared__ float sq[];  // kL2QT * D
+  const int64_t q0 = (int64_t)blockIdx.x * kL2QT;
+  for (int64_t i = threadIdx.x; i < kL2QT * D; i += blockDim.x) {
+    const int64_t q = q0 + i / D;
+    sq[i] = q < Q ? su[q * D + i % D] : 0.f;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int64_t n = (int64_t)blockIdx.y * 8 + warp; n < N; n += (int64_t)gridDim.y * 8) {
+    float acc[kL2QT];
+#pragma unroll
+    for (int j = 0; j < kL2QT; ++j) acc[j] = 0.f;
+    const float* o = ov + n * D;
+    for (int64_t d = lane; d < D; d += 32) {
+      const float v = o[d];
+#pragma unroll
+      for (int j = 0; j < kL2QT; ++j) {
+        const float t = v - sq[j * D + d];
+        acc[j] = fmaf(t, t, acc[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kL2QT; ++j) {
+      float a = acc[j];
+      for (int m = 16; m > 0; m >>= 1) a += __shfl_xor_sync(0xffffffffu, a, m);
+      if (lane == 0 && q0 + j < Q) dist[n * Q + q0 + j] = sqrtf(a);  // pow(sum, 0.5)
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// top-k: one thread per query column keeps an ascending list of k (distance, index) in shared
+// memory, laid out [k][threads] so a warp's accesses to one list slot hit 32 different banks.
+// ------------------------------------------------------------------------------------------
+constexpr int kTopkThreads = 64;
+
+__global__ void __launch_bounds__(kTopkThreads)
+topk_columns_kernel(const float* __restrict__ dist, int64_t G, int64_t Q, int k, float* __restrict__ out_d,
+                    int32_t* __restrict__ out_i, int32_t g_offset) {
+  extern __shared__ unsigned char raw[];
+  float* ld = reinterpret_cast<float*>(raw);                       // [k][kTopkThreads]
+  int32_t* li = reinterpret_cast<int32_t*>(ld + (size_t)k * kTopkThreads);
+  const int t = threadIdx.x;
+  const int64_t q = (int64_t)blockIdx.x * kTopkThreads + t;
+  const float inf = __int_as_float(0x7f800000);
+  for (int j = 0; j < k; ++j) { ld[j * kTopkThreads + t] = inf; li[j * kTopkThreads + t] = -1; }
+  if (q < Q) {
+    float worst = inf;
+    int filled = 0;
+    for (int64_t g = 0; g < G; ++g) {
+      const float d = __ldcs(dist + g * Q + q);
+      // strict '<' keeps the earlier (lower) gallery index on ties; NaN never enters
+      if (d < worst || (filled < k && d <= inf && d == d)) {
+        int j = filled < k ? filled : k - 1;
+        while (j > 0 && ld[(j - 1) * kTopkThreads + t] > d) {
+          ld[j * kTopkThreads + t] = ld[(j - 1) * kTopkThreads + t];
+          li[j * kTopkThreads + t] = li[(j - 1) * kTopkThreads + t];
+          --j;
+        }
+        ld[j * kTopkThreads + t] = d;
+        li[j * kTopkThreads + t] = (int32_t)g + g_offset;
+        if (filled < k) ++filled;
+        if (filled == k) worst = ld[(k - 1) * kTopkThreads + t];
+      }
+    }
+    for (int j = 0; j < k; ++j) {
+      out_d[q * k + j] = ld[j * kTopkThreads + t];
+      out_i[q * k + j] = li[j * kTopkThreads + t];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128)
+topk_merge_kernel(const float* __restrict__ cd, const int32_t* __restrict__ ci, int n_lists, int64_t Q, int k,
+                  float* __restrict__ out_d, int32_t* __restrict__ out_i) {
+  // thread per query; repeated selection of the smallest head among n_lists sorted lists.
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= Q) return;
+  constexpr int kMaxLists = 64;
+  unsigned char head[kMaxLists];
+  for (int l = 0; l < n_lists; ++l) head[l] = 0;
+  const float inf = __int_as_float(0x7f800000);
+  for (int j = 0; j < k; ++j) {
+    float best = inf;
+    int32_t best_i = -1;
+    int best_l = -1;
+    for (int l = 0; l < n_lists; ++l) {
+      if (head[l] >= k) continue;
+      const size_t o = ((size_t)l * Q + q) * k + head[l];
+      const float d = cd[o];
+      const int32_t i = ci[o];
+      if (i < 0) continue;  // exhausted list (padding)
+      if (best_l < 0 || d < best || (d == best && i < best_i)) { best = d; best_i = i; best_l = l; }
+    }
+    if (best_l >= 0) ++head[best_l];
+    out_d[q * k + j] = best_l >= 0 ? best : inf;
+    out_i[q * k + j] = best_i;
+  }
+}
+
+}  // namespace witw
+
+using namespace witw;
+
+extern "C" int witw_rank_from_dist_f32(const float* dist, int64_t G, int64_t Q, const int64_t* true_idx, int64_t* ranks,
+                                       witw_stream_t stream) {
+  WITW_REQUIRE(G >= 0 && Q >= 0, WITW_ERR_INVALID, "witw_rank_from_dist_f32: bad shape");
+  if (Q == 0) return WITW_OK;
+  WITW_REQUIRE(ranks && (dist || G == 0), WITW_ERR_INVALID, "witw_rank_from_dist_f32: null pointer");
+  WITW_CUDA(cudaMemsetAsync(ranks, 0, sizeof(int64_t) * Q, as_stream(stream)));
+  if (G == 0) return WITW_OK;
+  const bool vec = (Q % 4 == 0) && (((uintptr_t)dist & 15) == 0);
+  const int64_t cols = vec ? Q / 4 : Q;
+  const int64_t bx = ceil_div<int64_t>(cols, kRankThreads);
+  // slice the gallery so the grid is a few waves of the machine
+  int64_t by = std::max<int64_t>(1, std::min<int64_t>(ceil_div<int64_t>(G, 64), (int64_t)sm_count() * 16 / bx));
+  by = std::min<int64_t>(by, 65535);
+  const int64_t rows = ceil_div<int64_t>(G, by);
+  by = ceil_div<int64_t>(G, rows);
+  WITW_REQUIRE(bx < (1ll << 31), WITW_ERR_INVALID, "witw_rank_from_dist_f32: too many queries");
+  auto* r = reinterpret_cast<unsigned long long*>(ranks);
+  if (vec)
+    rank_count_vec4_kernel<<<dim3((unsigned)bx, (unsigned)by), kRankThreads, 0, as_stream(stream)>>>(dist, G, Q, true_idx, r, rows);
+  else
+    rank_count_scalar_kernel<<<dim3((unsigned)bx, (unsigned)by), kRankThreads, 0, as_stream(stream)>>>(dist, G, Q, true_idx, r, rows);
+  WITW_LAUNCH_CHECK();
+  return WITW_OK;
+}
+
+extern "C" int witw_l2_rank_f32(const float* ov, const float* su, int64_t N, int64_t Q, int64_t D, const int64_t* true_idx,
+                                float* dist, int64_t* ranks, witw_stream_t stream) {
+  WITW_REQUIRE(N >= 0 && Q >= 0 && D > 0, WITW_ERR_INVALID, "witw_l2_rank_f32: bad shape");
+  if (Q == 0) return WITW_OK;
+  WITW_REQUIRE(dist != nullptr, WITW_ERR_INVALID, "witw_l2_rank_f32: dist_dev [N,Q] is required (it is the workspace the ranks are counted from)");
+  WITW_REQUIRE((ov && su) || N == 0, WITW_ERR_INVALID, "witw_l2_rank_f32: null input");
+  const size_t smem = sizeof(float) * kL2QT * (size_t)D;
+  WITW_REQUIRE(smem <= 200 * 1024, WITW_ERR_UNSUPPORTED, "witw_l2_rank_f32: embedding dimension %lld too large", (long long)D);
+  if (N > 0) {
+    WITW_CUDA(cudaFuncSetAttribute(l2_dist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t bx = ceil_div<int64_t>(Q, kL2QT);
+    int64_t by = std::max<int64_t>(1, std::min<int64_t>(ceil_div<int64_t>(N, 8), (int64_t)sm_count() * 8 / bx));
+    by = std::min<int64_t>(by, 65535);
+    WITW_REQUIRE(bx < (1ll << 31), WITW_ERR_INVALID, "witw_l2_rank_f32: too many queries");
+    l2_dist_kernel<<<dim3((unsigned)bx, (unsigned)by), 256, smem, as_stream(stream)>>>(ov, su, N, Q, D, dist);
+    WITW_LAUNCH_CHECK();
+  }
+  if (ranks != nullptr) return witw_rank_from_dist_f32(dist, N, Q, true_idx, ranks, stream);
+  return WITW_OK;
+}
+
+extern "C" int witw_topk_from_dist_f32(const float* dist, int64_t G, int64_t Q, int k, float* topk_dist, int32_t* topk_idx,
+                                       int32_t g_offset, witw_stream_t stream) {
+  WITW_REQUIRE(G >= 0 && Q >= 0 && k > 0 && k <= 128, WITW_ERR_INVALID, "witw_topk_from_dist_f32: bad shape (k must be 1..128)");
+  if (Q == 0) return WITW_OK;
+  WITW_REQUIRE(topk_dist && topk_idx && (dist || G == 0), WITW_ERR_INVALID, "witw_topk_from_dist_f32: null pointer");
+  const size_t smem = (size_t)k * kTopkThreads * 8;
+  WITW_CUDA(cudaFuncSetAttribute(topk_columns_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  topk_columns_kernel<<<(unsigned)ceil_div<int64_t>(Q, kTopkThreads), kTopkThreads, smem, as_stream(stream)>>>(dist, G, Q, k, topk_dist,
+                                                                                                          topk_idx, g_offset);
+  WITW_LAUNCH_CHECK();
+  return WITW_OK;
+}
+
+extern "C" int witw_topk_merge(const float* cand_dist, const int32_t* cand_idx, int n_lists, int64_t Q, int k, float* topk_dist,
+                               int32_t* topk_idx, witw_stream_t stream) {
+  WITW_REQUIRE(n_lists > 0 && n_lists <= 64 && Q >= 0 && k > 0 && k <= 128, WITW_ERR_INVALID, "witw_topk_merge: bad shape (n_lists 1..64, k 1..128)");
+  if (Q == 0) return WITW_OK;
+  WITW_REQUIRE(cand_dist && cand_idx && topk_dist && topk_idx, WITW_ERR_INVALID, "witw_topk_merge: null pointer");
+  topk_merge_kernel<<<(unsigned)ceil_div<int64_t>(Q, 128), 128, 0, as_stream(stream)>>>(cand_dist, cand_idx, n_lists, Q, k, topk_dist, topk_idx);
+  WITW_LAUNCH_CHECK();
+  return WITW_OK;
+}

@@ -1,0 +1,47 @@
+"""Drop-in installation onto the reference's modules.
+
+The reference has no plugin mechanism: train()/test() in model/cvig_fov.py and
+tools/heatmap/heatmap.py look up ``correlation``, ``crop_overhead``, ``l2_distance``,
+``PolarTransform`` and ``bilinear_interpolate`` as module attributes at call time
+(cvig_fov.py:396, 450-453, 500, 537-538, 547-549; heatmap.py:106, 172-175).  Rebinding those
+attributes on the imported module therefore swaps the hot path for every caller:
+
+    import cvig_fov, witw_b200
+    witw_b200.install(cvig_fov)        # cvig_fov.test() now runs the B200 kernels
+"""
+from . import ops
+
+_REBOUND = ("bilinear_interpolate", "PolarTransform", "correlation", "crop_overhead", "l2_distance")
+_ADDED = ("match", "evaluate_ranks", "recall_from_ranks", "heatmap_scores", "polar_transform")
+
+
+def install(module):
+    """Rebind the hot-path names of a reference module (cvig_fov / cvig_semantic) to witw_b200.
+
+    Returns the dict of replaced originals (also kept on the module as ``_witw_b200_originals``).
+    """
+    originals = {}
+    for name in _REBOUND:
+        if not hasattr(module, name):
+            raise AttributeError("install: %s has no attribute %r -- not a WITW cvig module?" % (getattr(module, "__name__", module), name))
+        originals[name] = getattr(module, name)
+        setattr(module, name, getattr(ops, name))
+    for name in _ADDED:
+        if hasattr(module, name):
+            originals[name] = getattr(module, name)
+        setattr(module, name, getattr(ops, name))
+    module._witw_b200_originals = originals
+    return originals
+
+
+def uninstall(module):
+    """Undo install()."""
+    originals = getattr(module, "_witw_b200_originals", None)
+    if originals is None:
+        return
+    for name in _REBOUND + _ADDED:
+        if name in originals:
+            setattr(module, name, originals[name])
+        elif hasattr(module, name):
+            delattr(module, name)
+    del module._witw_b200_originals

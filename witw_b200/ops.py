@@ -1,0 +1,491 @@
+"""Host-side mirror of the reference's hot-path functions, calling libwitw_b200.so.
+
+Same names, argument meaning, tensor layouts and return types as model/cvig_fov.py
+(= model/cvig_semantic.py) of IQTLabs/WITW:
+
+    bilinear_interpolate   cvig_fov.py:156-183
+    PolarTransform         cvig_fov.py:186-209
+    correlation            cvig_fov.py:297-315
+    crop_overhead          cvig_fov.py:318-343
+    l2_distance            cvig_fov.py:346-363
+
+plus the fused forms the reference spells as a Python loop:
+
+    match                  correlation -> crop_overhead -> l2_distance   (cvig_fov.py:547-549)
+    evaluate_ranks         the rank loop of test()                       (cvig_fov.py:543-552)
+    recall_from_ranks      the thresholds that follow                    (cvig_fov.py:553-558)
+    baseline_ranks         cvig_baseline.py:453-460
+    heatmap_scores         tools/heatmap/heatmap.py:171-177
+
+Everything runs on the CUDA device of its inputs; there is no CPU fallback.  These are
+forward-only kernels: tensors that require grad under an enabled grad mode are refused
+rather than silently detached (train() in the reference back-propagates through
+crop_overhead / l2_distance).
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+
+# model/cvig_fov.py:19-22
+SURFACE_HEIGHT_MAX = 128
+SURFACE_WIDTH_MAX = 512
+OVERHEAD_SIZE = 256
+
+# problems with at least this many (gallery, query) pairs go to the tensor-core kernel
+TC_MIN_PAIRS = 1 << 16
+
+
+# ----------------------------------------------------------------------------- helpers
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _need_cuda(name, *tensors):
+    for t in tensors:
+        if not isinstance(t, torch.Tensor):
+            raise TypeError("%s: expected torch tensors, got %r" % (name, type(t)))
+        if not t.is_cuda:
+            raise RuntimeError(
+                "%s: tensor is on %s; witw_b200 runs on a CUDA (sm_100a) device only and has no CPU fallback" % (name, t.device)
+            )
+        if t.requires_grad and torch.is_grad_enabled():
+            raise RuntimeError(
+                "%s: forward-only kernel got a tensor that requires grad; wrap the call in torch.no_grad() "
+                "(training through crop_overhead/l2_distance is not covered by witw_b200)" % name
+            )
+    dev = tensors[0].device
+    for t in tensors[1:]:
+        if t.device != dev:
+            raise RuntimeError("%s: tensors are on different devices (%s vs %s)" % (name, dev, t.device))
+    return dev
+
+
+def _f32c(t):
+    """fp32, contiguous view/copy of a feature tensor (bf16/fp16 inputs are widened)."""
+    if t.dtype not in (torch.float32, torch.bfloat16, torch.float16):
+        raise TypeError("witw_b200: unsupported dtype %s (fp32, or bf16/fp16 widened to fp32)" % t.dtype)
+    return t.detach().to(torch.float32).contiguous()
+
+
+def _feature_dims(name, overhead_embed, surface_embed):
+    if overhead_embed.dim() != 4 or surface_embed.dim() != 4:
+        raise ValueError("%s: expected [G,C,H,W] and [Q,C,H,sw] feature maps" % name)
+    g, c, h, w = overhead_embed.shape
+    q, sc, sh, sw = surface_embed.shape
+    if (c, h) != (sc, sh):
+        # F.conv2d in the reference raises on a channel mismatch and yields an empty/garbage map on a height mismatch
+        raise RuntimeError("%s: feature maps disagree in (C,H): %s vs %s" % (name, (c, h), (sc, sh)))
+    if sw > w:
+        raise RuntimeError("%s: query width %d exceeds gallery width %d" % (name, sw, w))
+    return g, q, c * h, w, sw
+
+
+# ----------------------------------------------------------------------------- K1
+_lut_cache = {}
+_plan_cache = {}
+
+
+def _gather_lut(x, y, src_h, src_w, device):
+    """Device copies of the reference's tap indices / weights for sample points (x, y)."""
+    x = np.ascontiguousarray(np.asarray(x, dtype=np.float64))
+    y = np.ascontiguousarray(np.asarray(y, dtype=np.float64))
+    n = x.size
+    idx = np.empty((n, 4), dtype=np.int32)
+    w = np.empty((n, 4), dtype=np.float32)
+    _lib.call("witw_bilinear_lut", x.ctypes.data, y.ctypes.data, n, src_h, src_w, idx.ctypes.data, w.ctypes.data)
+    return torch.from_numpy(idx).to(device), torch.from_numpy(w).to(device)
+
+
+def bilinear_interpolate(im, x, y):
+    """Drop-in for cvig_fov.py:156-183.  im [C,H,W] (or [N,C,H,W]) on CUDA, x/y float arrays [h,w].
+
+    Returns [C,h,w] (or [N,C,h,w]) fp32, bit-identical to the reference: taps and weights come
+    from the same float64 arithmetic, the blend keeps the reference's order with no FMA contraction.
+    """
+    x = np.asarray(x)
+    y = np.asarray(y)
+    assert x.shape == y.shape
+    dev = _need_cuda("bilinear_interpolate", im)
+    src = _f32c(im)
+    lead = src.shape[:-2]
+    src_h, src_w = src.shape[-2:]
+    with torch.cuda.device(dev):
+        idx, w = _gather_lut(x, y, src_h, src_w, dev)
+        n_img = int(np.prod(lead)) if len(lead) else 1
+        out = torch.empty(tuple(lead) + tuple(x.shape), dtype=torch.float32, device=dev)
+        _lib.call("witw_bilinear_gather_f32", src.data_ptr(), out.data_ptr(), idx.data_ptr(), w.data_ptr(),
+                  n_img, src_h, src_w, x.size, _stream())
+    return out
+
+
+def polar_grid(h_s=SURFACE_HEIGHT_MAX, w_s=SURFACE_WIDTH_MAX, s_o=OVERHEAD_SIZE):
+    """Sample coordinates of cvig_fov.py:197-201 as float64 arrays (x, y) of shape [h_s, w_s]."""
+    x = np.empty((h_s, w_s), dtype=np.float64)
+    y = np.empty((h_s, w_s), dtype=np.float64)
+    _lib.call("witw_polar_grid", h_s, w_s, s_o, x.ctypes.data, y.ctypes.data)
+    return x, y
+
+
+def _polar_plan(h_s, w_s, s_o, device):
+    key = (h_s, w_s, s_o, str(device))
+    if key not in _plan_cache:
+        nbytes = _lib.load().witw_polar_plan_bytes(h_s, w_s, s_o)
+        if nbytes == 0:
+            _plan_cache[key] = None
+        else:
+            host = np.zeros(nbytes, dtype=np.uint8)
+            _lib.call("witw_polar_plan_build", h_s, w_s, s_o, host.ctypes.data)
+            _plan_cache[key] = (host, torch.from_numpy(host).to(device))
+    return _plan_cache[key]
+
+
+def polar_transform(overhead, h_s=SURFACE_HEIGHT_MAX, w_s=SURFACE_WIDTH_MAX, s_o=OVERHEAD_SIZE, exact=False):
+    """Batched polar transform: overhead [...,s_o,s_o] on CUDA -> [...,h_s,w_s] fp32.
+
+    exact=False: the staged throughput kernel (weights within 2^-24 of the reference's);
+    exact=True, or a geometry outside the staged kernel: the bit-exact gather kernel.
+    """
+    dev = _need_cuda("polar_transform", overhead)
+    src = _f32c(overhead)
+    if src.shape[-1] != s_o or src.shape[-2] != s_o:
+        raise ValueError("polar_transform: expected %dx%d tiles, got %s" % (s_o, s_o, tuple(src.shape[-2:])))
+    lead = tuple(src.shape[:-2])
+    n_img = int(np.prod(lead)) if len(lead) else 1
+    out = torch.empty(lead + (h_s, w_s), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        plan = None if exact else _polar_plan(h_s, w_s, s_o, dev)
+        if plan is None:
+            key = ("grid", h_s, w_s, s_o, str(dev))
+            if key not in _lut_cache:
+                gx, gy = polar_grid(h_s, w_s, s_o)
+                _lut_cache[key] = _gather_lut(gx, gy, s_o, s_o, dev)
+            idx, w = _lut_cache[key]
+            _lib.call("witw_bilinear_gather_f32", src.data_ptr(), out.data_ptr(), idx.data_ptr(), w.data_ptr(),
+                      n_img, s_o, s_o, h_s * w_s, _stream())
+        else:
+            host, devplan = plan
+            _lib.call("witw_polar_resample_f32", src.data_ptr(), out.data_ptr(), n_img, host.ctypes.data,
+                      devplan.data_ptr(), _stream())
+    return out
+
+
+class PolarTransform(object):
+    """Drop-in for cvig_fov.py:186-209: ``data['polar'] = polar(data['overhead'])``, other keys kept.
+
+    The reference runs this per sample on CPU inside DataLoader workers.  Here the work is done
+    on the GPU: a CUDA tensor (single tile [C,256,256] or a batch [N,C,256,256]) is transformed in
+    place on its device; a CPU tensor is copied to ``device`` (default: current CUDA device),
+    transformed there and returned on the CPU so the reference's call sites keep working
+    (this needs CUDA in the calling process, i.e. num_workers=0 or a spawn context).
+    """
+
+    def __init__(self, device=None, exact=False, h_s=SURFACE_HEIGHT_MAX, w_s=SURFACE_WIDTH_MAX, s_o=OVERHEAD_SIZE):
+        self.device = device
+        self.exact = exact
+        self.geom = (h_s, w_s, s_o)
+
+    def __call__(self, data):
+        tile = data["overhead"]
+        if tile.is_cuda:
+            data["polar"] = polar_transform(tile, *self.geom, exact=self.exact)
+        else:
+            if not torch.cuda.is_available():
+                raise RuntimeError("PolarTransform: no CUDA device; witw_b200 has no CPU fallback")
+            dev = torch.device(self.device) if self.device is not None else torch.device("cuda", torch.cuda.current_device())
+            data["polar"] = polar_transform(tile.to(dev, non_blocking=True), *self.geom, exact=self.exact).to(tile.device)
+        return data
+
+
+# ----------------------------------------------------------------------------- K2/K3
+class GalleryIndex(object):
+    """Gallery feature maps prepared for the tensor-core sweep (bf16 Hankel blocks + crop norms).
+
+    Built once per (gallery, query width); reused for every query batch.  ``g_offset`` is the
+    global index of the first item when the gallery is one shard of a larger one.
+    """
+
+    def __init__(self, overhead_embed, surface_width, g_offset=0, keep_fp32=True):
+        dev = _need_cuda("GalleryIndex", overhead_embed)
+        if overhead_embed.dim() != 4:
+            raise ValueError("GalleryIndex: expected [G,C,H,W]")
+        g, c, h, w = overhead_embed.shape
+        self.device, self.G, self.CH, self.W, self.sw = dev, g, c * h, w, int(surface_width)
+        self.C, self.H = c, h
+        self.g_offset = int(g_offset)
+        ov = _f32c(overhead_embed)
+        self.ov = ov if keep_fp32 else None
+        with torch.cuda.device(dev):
+            nbytes = _lib.load().witw_gallery_operand_bytes(g, self.CH, self.sw)
+            if nbytes == 0 or w != 64:
+                raise _lib.WitwError("GalleryIndex: " + (_lib.last_error() if w == 64 else "tensor-core path needs W == 64, got %d" % w))
+            self.operand = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            g4 = (g + 3) // 4 * 4
+            self.crop_inv_norm = torch.empty(max(g4, 4) * 64, dtype=torch.float32, device=dev)
+            _lib.call("witw_gallery_prep", ov.data_ptr(), g, self.CH, w, self.sw, self.operand.data_ptr(),
+                      self.crop_inv_norm.data_ptr(), _stream())
+
+
+class QueryBatch(object):
+    """Query feature maps prepared for the tensor-core sweep (bf16 [Q, CH*sw_pad] + inverse norms)."""
+
+    def __init__(self, surface_embed, keep_fp32=True):
+        dev = _need_cuda("QueryBatch", surface_embed)
+        q, c, h, sw = surface_embed.shape
+        self.device, self.Q, self.CH, self.sw = dev, q, c * h, sw
+        su = _f32c(surface_embed)
+        self.su = su if keep_fp32 else None
+        with torch.cuda.device(dev):
+            nbytes = _lib.load().witw_query_operand_bytes(q, self.CH, sw)
+            if nbytes == 0:
+                raise _lib.WitwError("QueryBatch: " + _lib.last_error())
+            self.operand = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            self.inv_norm = torch.empty(max(q, 1), dtype=torch.float32, device=dev)
+            _lib.call("witw_query_prep", su.data_ptr(), q, self.CH, sw, self.operand.data_ptr(), self.inv_norm.data_ptr(), _stream())
+
+
+def tc_supported(ch, w, sw):
+    """Shapes the tcgen05 kernel covers: 64 azimuth columns, K = CH*sw_pad a multiple of 64."""
+    if w != 64 or sw < 1 or sw > 64:
+        return False
+    sw_pad = 16 if sw <= 16 else (32 if sw <= 32 else 64)
+    return ch % (64 // sw_pad) == 0
+
+
+def _pick_path(path, g, q, ch, w, sw):
+    if path == "auto":
+        return "tc" if (tc_supported(ch, w, sw) and g * q >= TC_MIN_PAIRS) else "fp32"
+    if path not in ("tc", "fp32"):
+        raise ValueError("path must be 'auto', 'tc' or 'fp32'")
+    if path == "tc" and not tc_supported(ch, w, sw):
+        raise _lib.WitwError("tensor-core path does not cover CH=%d W=%d sw=%d" % (ch, w, sw))
+    return path
+
+
+def sweep_tc(gallery, queries, want_dist=False, want_ori=False, d_true=None, rank_count=None, topk=0):
+    """One tensor-core sweep of a QueryBatch over a GalleryIndex.  Returns a dict with the requested outputs."""
+    if gallery.CH != queries.CH or gallery.sw != queries.sw or gallery.device != queries.device:
+        raise ValueError("sweep_tc: gallery and queries disagree (CH %d/%d, sw %d/%d)" % (gallery.CH, queries.CH, gallery.sw, queries.sw))
+    dev, g, q = gallery.device, gallery.G, queries.Q
+    out = {}
+    with torch.cuda.device(dev):
+        dist = torch.empty((g, q), dtype=torch.float32, device=dev) if want_dist else None
+        ori = torch.empty((g, q), dtype=torch.uint8, device=dev) if want_ori else None
+        tk_d = tk_i = None
+        slots = 0
+        if topk:
+            slots = _lib.load().witw_match_tc_topk_slots(g, q)
+            tk_d = torch.empty((slots, q, topk), dtype=torch.float32, device=dev)
+            tk_i = torch.empty((slots, q, topk), dtype=torch.int32, device=dev)
+        if g > 0 and q > 0:
+            _lib.call("witw_match_tc", gallery.operand.data_ptr(), gallery.crop_inv_norm.data_ptr(), queries.operand.data_ptr(),
+                      queries.inv_norm.data_ptr(), g, q, gallery.CH, gallery.sw, _ptr(dist), _ptr(ori), _ptr(d_true),
+                      _ptr(rank_count), int(topk), _ptr(tk_d), _ptr(tk_i), gallery.g_offset, _stream())
+        if topk:
+            fin_d = torch.empty((q, topk), dtype=torch.float32, device=dev)
+            fin_i = torch.empty((q, topk), dtype=torch.int32, device=dev)
+            if q > 0:
+                _lib.call("witw_topk_merge", tk_d.data_ptr(), tk_i.data_ptr(), slots, q, int(topk), fin_d.data_ptr(), fin_i.data_ptr(), _stream())
+            out["topk_dist"], out["topk_idx"] = fin_d, fin_i
+    out["dist"], out["ori"] = dist, ori
+    return out
+
+
+def match(overhead_embed, surface_embed, path="auto"):
+    """(orientation int64 [G,Q], distance fp32 [G,Q]) = a3 -> a4 -> a5 fused (cvig_fov.py:547-549).
+
+    path 'fp32': exact fp32 kernel; 'tc': tcgen05 bf16 x bf16 -> fp32; 'auto': by problem size.
+    """
+    dev = _need_cuda("match", overhead_embed, surface_embed)
+    g, q, ch, w, sw = _feature_dims("match", overhead_embed, surface_embed)
+    which = _pick_path(path, g, q, ch, w, sw)
+    if which == "tc":
+        res = sweep_tc(GalleryIndex(overhead_embed, sw, keep_fp32=False), QueryBatch(surface_embed, keep_fp32=False),
+                       want_dist=True, want_ori=True)
+        return res["ori"].to(torch.int64), res["dist"]
+    ov, su = _f32c(overhead_embed), _f32c(surface_embed)
+    with torch.cuda.device(dev):
+        dist = torch.empty((g, q), dtype=torch.float32, device=dev)
+        ori = torch.empty((g, q), dtype=torch.int64, device=dev)
+        _lib.call("witw_match_f32", ov.data_ptr(), su.data_ptr(), g, q, ch, w, sw, dist.data_ptr(), ori.data_ptr(), 0, _stream())
+    return ori, dist
+
+
+def correlation_scores(overhead_embed, surface_embed):
+    """Un-normalised circular cross-correlation fp32 [G,Q,W] (the conv2d output of cvig_fov.py:308), exact path."""
+    dev = _need_cuda("correlation_scores", overhead_embed, surface_embed)
+    g, q, ch, w, sw = _feature_dims("correlation_scores", overhead_embed, surface_embed)
+    ov, su = _f32c(overhead_embed), _f32c(surface_embed)
+    with torch.cuda.device(dev):
+        corr = torch.empty((g, q, w), dtype=torch.float32, device=dev)
+        _lib.call("witw_match_f32", ov.data_ptr(), su.data_ptr(), g, q, ch, w, sw, 0, 0, corr.data_ptr(), _stream())
+    return corr
+
+
+def correlation(overhead_embed, surface_embed, path="auto"):
+    """Drop-in for cvig_fov.py:297-315: orientation int64 [batch_overhead, batch_surface]."""
+    return match(overhead_embed, surface_embed, path=path)[0]
+
+
+def crop_overhead(overhead_embed, orientation, surface_width):
+    """Drop-in for cvig_fov.py:318-343: [G,Q,C,H,surface_width], rolled by the orientation and cropped.
+
+    The device is taken from the inputs (the reference reads a module-level ``device`` global).
+    """
+    dev = _need_cuda("crop_overhead", overhead_embed, orientation)
+    g, c, h, w = overhead_embed.shape
+    if orientation.dim() != 2 or orientation.shape[0] != g:
+        raise ValueError("crop_overhead: orientation must be [G,Q]")
+    q = orientation.shape[1]
+    sw = int(surface_width)
+    ov = _f32c(overhead_embed)
+    ori = orientation.detach().to(torch.int64).contiguous()
+    with torch.cuda.device(dev):
+        out = torch.empty((g, q, c, h, sw), dtype=torch.float32, device=dev)
+        _lib.call("witw_crop_gather_f32", ov.data_ptr(), ori.data_ptr(), out.data_ptr(), g, q, c * h, w, sw, _stream())
+    return out
+
+
+def l2_distance(overhead_cropped, surface_embed):
+    """Drop-in for cvig_fov.py:346-363: chord distance fp32 [G,Q] of the L2-normalised maps (no epsilon)."""
+    dev = _need_cuda("l2_distance", overhead_cropped, surface_embed)
+    g, q = overhead_cropped.shape[:2]
+    k = int(np.prod(overhead_cropped.shape[2:]))
+    if surface_embed.shape[0] != q or int(np.prod(surface_embed.shape[1:])) != k:
+        raise RuntimeError("l2_distance: shapes %s and %s do not broadcast" % (tuple(overhead_cropped.shape), tuple(surface_embed.shape)))
+    crop, su = _f32c(overhead_cropped), _f32c(surface_embed)
+    with torch.cuda.device(dev):
+        dist = torch.empty((g, q), dtype=torch.float32, device=dev)
+        _lib.call("witw_l2_distance_f32", crop.data_ptr(), su.data_ptr(), dist.data_ptr(), g, q, k, _stream())
+    return dist
+
+
+# ----------------------------------------------------------------------------- K4
+def true_match_distances(overhead_embed, surface_embed, true_idx=None):
+    """Exact fp32 (distance [Q], orientation [Q]) of each query against its matching gallery item."""
+    dev = _need_cuda("true_match_distances", overhead_embed, surface_embed)
+    g, q, ch, w, sw = _feature_dims("true_match_distances", overhead_embed, surface_embed)
+    ov, su = _f32c(overhead_embed), _f32c(surface_embed)
+    with torch.cuda.device(dev):
+        pq = torch.arange(q, dtype=torch.int64, device=dev)
+        pg = pq if true_idx is None else true_idx.to(dev, torch.int64).contiguous()
+        if q and (int(pg.max()) >= g or int(pg.min()) < 0):
+            raise IndexError("true_match_distances: true index outside the gallery")
+        d = torch.empty(q, dtype=torch.float32, device=dev)
+        o = torch.empty(q, dtype=torch.int64, device=dev)
+        _lib.call("witw_match_pairs_f32", ov.data_ptr(), su.data_ptr(), pg.data_ptr(), pq.data_ptr(), q, ch, w, sw,
+                  d.data_ptr(), o.data_ptr(), _stream())
+    return d, o
+
+
+def rank_from_distances(distances, true_idx=None):
+    """ranks int64 [Q] from a materialised [G,Q] matrix: #{g: d[g,q] <= d[true(q),q]} (cvig_fov.py:550-552)."""
+    dev = _need_cuda("rank_from_distances", distances)
+    g, q = distances.shape
+    d = _f32c(distances)
+    with torch.cuda.device(dev):
+        ranks = torch.empty(q, dtype=torch.int64, device=dev)
+        ti = None if true_idx is None else true_idx.to(dev, torch.int64).contiguous()
+        _lib.call("witw_rank_from_dist_f32", d.data_ptr(), g, q, _ptr(ti), ranks.data_ptr(), _stream())
+    return ranks
+
+
+def topk_from_distances(distances, k, g_offset=0):
+    """(dist fp32 [Q,k], idx int32 [Q,k]): the k nearest gallery items of every query column, ascending."""
+    dev = _need_cuda("topk_from_distances", distances)
+    g, q = distances.shape
+    d = _f32c(distances)
+    with torch.cuda.device(dev):
+        td = torch.empty((q, k), dtype=torch.float32, device=dev)
+        ti = torch.empty((q, k), dtype=torch.int32, device=dev)
+        _lib.call("witw_topk_from_dist_f32", d.data_ptr(), g, q, int(k), td.data_ptr(), ti.data_ptr(), int(g_offset), _stream())
+    return td, ti
+
+
+def evaluate_ranks(overhead_embed, surface_embed, true_idx=None, path="auto", topk=0):
+    """The rank loop of test() (cvig_fov.py:543-552) as one call: ranks int64 [count] on the device.
+
+    Query i matches gallery item i (or true_idx[i]).  The true-match distances are computed in
+    exact fp32; on the tensor-core path the gallery sweep counts d[g,q] <= d_true[q] in the GEMM
+    epilogue without materialising the [G,Q] matrix.  With topk > 0 also returns
+    (topk_dist [Q,k], topk_idx [Q,k]).
+    """
+    dev = _need_cuda("evaluate_ranks", overhead_embed, surface_embed)
+    g, q, ch, w, sw = _feature_dims("evaluate_ranks", overhead_embed, surface_embed)
+    if true_idx is None and q > g:
+        raise ValueError("evaluate_ranks: %d queries but only %d gallery items and no true_idx" % (q, g))
+    which = _pick_path(path, g, q, ch, w, sw)
+    if which == "fp32":
+        _, dist = match(overhead_embed, surface_embed, path="fp32")
+        ranks = rank_from_distances(dist, true_idx)
+        if topk:
+            return (ranks,) + topk_from_distances(dist, topk)
+        return ranks
+    gallery = GalleryIndex(overhead_embed, sw)
+    queries = QueryBatch(surface_embed)
+    return evaluate_ranks_prepared(gallery, queries, true_idx=true_idx, topk=topk)
+
+
+def evaluate_ranks_prepared(gallery, queries, true_idx=None, topk=0, d_true=None):
+    """evaluate_ranks on prepared operands (tensor-core path)."""
+    dev = gallery.device
+    with torch.cuda.device(dev):
+        if d_true is None:
+            if gallery.ov is None or queries.su is None:
+                raise ValueError("evaluate_ranks_prepared: fp32 features were dropped; pass d_true")
+            ov4 = gallery.ov.view(gallery.G, gallery.C, gallery.H, gallery.W)
+            su4 = queries.su.view(queries.Q, gallery.C, gallery.H, queries.sw)
+            d_true, _ = true_match_distances(ov4, su4, true_idx)
+        counts = torch.zeros(max(queries.Q, 1), dtype=torch.int32, device=dev)
+        res = sweep_tc(gallery, queries, d_true=d_true, rank_count=counts, topk=topk)
+        ranks = counts[: queries.Q].to(torch.int64)
+    if topk:
+        return ranks, res["topk_dist"], res["topk_idx"]
+    return ranks
+
+
+def baseline_ranks(overhead_embed, surface_embed, true_idx=None, return_distances=False):
+    """cvig_baseline.py:453-460: Euclidean distances of [N,D] embeddings and the same rank rule."""
+    dev = _need_cuda("baseline_ranks", overhead_embed, surface_embed)
+    if overhead_embed.dim() != 2 or surface_embed.dim() != 2 or overhead_embed.shape[1] != surface_embed.shape[1]:
+        raise ValueError("baseline_ranks: expected [N,D] and [Q,D]")
+    n, d = overhead_embed.shape
+    q = surface_embed.shape[0]
+    ov, su = _f32c(overhead_embed), _f32c(surface_embed)
+    with torch.cuda.device(dev):
+        dist = torch.empty((n, q), dtype=torch.float32, device=dev)
+        ranks = torch.empty(q, dtype=torch.int64, device=dev)
+        ti = None if true_idx is None else true_idx.to(dev, torch.int64).contiguous()
+        _lib.call("witw_l2_rank_f32", ov.data_ptr(), su.data_ptr(), n, q, d, _ptr(ti), dist.data_ptr(), ranks.data_ptr(), _stream())
+    return (ranks, dist) if return_distances else ranks
+
+
+def recall_from_ranks(ranks):
+    """cvig_fov.py:553-558: top-1/5/10/1 % (percent), mean and median rank.  Host arithmetic on the D2H'd ranks."""
+    if isinstance(ranks, torch.Tensor):
+        ranks = ranks.detach().cpu().numpy()
+    ranks = np.asarray(ranks)
+    count = ranks.shape[0]
+    return {
+        "top_one": np.sum(ranks <= 1) / count * 100,
+        "top_five": np.sum(ranks <= 5) / count * 100,
+        "top_ten": np.sum(ranks <= 10) / count * 100,
+        "top_percent": np.sum(ranks * 100 <= count) / count * 100,
+        "mean": np.mean(ranks),
+        "median": np.median(ranks),
+        "count": count,
+    }
+
+
+def heatmap_scores(overhead_embed, surface_embed, output_width_max=64, path="auto"):
+    """tools/heatmap/heatmap.py:171-177: one photo against many tiles -> (orientation degrees, dissimilarity, score)."""
+    ori, dist = match(overhead_embed, surface_embed, path=path)
+    orientations = torch.squeeze(ori) * 360 / output_width_max - 180
+    dist = torch.squeeze(dist)
+    return orientations, dist, torch.exp(10.0 * (1.0 - dist))

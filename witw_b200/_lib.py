@@ -34,7 +34,7 @@ SIGNATURES = {
     "witw_query_prep": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "witw_match_tc_topk_slots": (c_int, [c_int64, c_int64]),
     "witw_match_tc": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p,
-                              c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int32, c_void_p]),
+                              c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int32, c_void_p]),
     "witw_rank_from_dist_f32": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
     "witw_l2_rank_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "witw_topk_from_dist_f32": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_int32, c_void_p]),

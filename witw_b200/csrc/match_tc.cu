@@ -252,6 +252,7 @@ struct TcParams {
   float* dist;                   // [G][Q] or null
   uint8_t* ori;                  // [G][Q] or null
   const float* d_true;           // [Q] or null
+  const int32_t* true_idx;       // [Q] global gallery index of each query's match, or null
   int32_t* rank_count;           // [Q] or null
   float* topk_dist;              // [n_chunks][Q][topk] or null
   int32_t* topk_idx;
@@ -410,6 +411,9 @@ match_tc_kernel(const __grid_constant__ CUtensorMap q_map, const TcParams P) {
       const bool q_ok = q < P.Q;
       const float qin = q_ok ? P.q_inv_norm[q] : 0.f;
       const float dtrue = (q_ok && P.d_true) ? P.d_true[q] : __int_as_float(0x7fc00000);
+      // the match itself always counts (d[idx] <= d[idx] in cvig_fov.py:552) unless its distance is NaN;
+      // deciding it from the bf16 distance against the fp32 threshold would be a coin flip
+      const int32_t self_g = (q_ok && P.true_idx) ? P.true_idx[q] - P.g_offset : -1;
       int cnt = 0;
       float td[kTopkMax];
       int32_t ti[kTopkMax];
@@ -457,7 +461,7 @@ match_tc_kernel(const __grid_constant__ CUtensorMap q_map, const TcParams P) {
             const float d = 2.0f * (1.0f - best[i] * cin * qin);
             if (P.dist) P.dist[g * P.Q + q] = d;
             if (P.ori) P.ori[g * P.Q + q] = (uint8_t)arg[i];
-            cnt += (d <= dtrue) ? 1 : 0;
+            cnt += ((int32_t)g == self_g ? (dtrue == dtrue) : (d <= dtrue)) ? 1 : 0;
             if (P.topk > 0 && d < td[kTopkMax - 1]) {
               // insertion into the ascending register list (strict '<': earlier index wins ties)
               float cd = d;
@@ -571,8 +575,8 @@ extern "C" int witw_query_prep(const float* su, int64_t Q, int CH, int sw, void*
 extern "C" int witw_match_tc_topk_slots(int64_t G, int64_t Q) { return make_schedule(G, Q).n_chunks; }
 
 extern "C" int witw_match_tc(const void* gal_op, const float* crop_inv_norm, const void* qry_op, const float* q_inv_norm, int64_t G,
-                             int64_t Q, int CH, int sw, float* dist, uint8_t* ori, const float* d_true, int32_t* rank_count,
-                             int topk, float* topk_dist, int32_t* topk_idx, int32_t g_offset, witw_stream_t stream) {
+                             int64_t Q, int CH, int sw, float* dist, uint8_t* ori, const float* d_true, const int32_t* true_idx,
+                             int32_t* rank_count, int topk, float* topk_dist, int32_t* topk_idx, int32_t g_offset, witw_stream_t stream) {
   TcGeom geo;
   WITW_REQUIRE(G >= 0 && Q >= 0 && make_geom(CH, sw, &geo), WITW_ERR_UNSUPPORTED, "witw_match_tc: unsupported CH=%d sw=%d", CH, sw);
   if (G == 0 || Q == 0) return WITW_OK;
@@ -606,7 +610,7 @@ extern "C" int witw_match_tc(const void* gal_op, const float* crop_inv_norm, con
   std::memset(&P, 0, sizeof(P));
   P.gal_op = reinterpret_cast<const unsigned char*>(gal_op);
   P.crop_inv_norm = crop_inv_norm; P.q_inv_norm = q_inv_norm;
-  P.dist = dist; P.ori = ori; P.d_true = d_true; P.rank_count = rank_count;
+  P.dist = dist; P.ori = ori; P.d_true = d_true; P.true_idx = true_idx; P.rank_count = rank_count;
   P.topk_dist = topk_dist; P.topk_idx = topk_idx; P.G = G; P.Q = Q; P.topk = topk; P.g_offset = g_offset;
   P.n_qtiles = sch.n_qtiles; P.n_chunks = sch.n_chunks; P.groups_per_chunk = sch.groups_per_chunk; P.n_groups = sch.n_groups;
   P.kblocks = geo.kblocks; P.cpb = geo.cpb; P.bpc = geo.bpc; P.nkap = geo.nkap;

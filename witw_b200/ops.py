@@ -268,8 +268,10 @@ def _pick_path(path, g, q, ch, w, sw):
     return path
 
 
-def sweep_tc(gallery, queries, want_dist=False, want_ori=False, d_true=None, rank_count=None, topk=0):
-    """One tensor-core sweep of a QueryBatch over a GalleryIndex.  Returns a dict with the requested outputs."""
+def sweep_tc(gallery, queries, want_dist=False, want_ori=False, d_true=None, true_idx=None, rank_count=None, topk=0, events=None):
+    """One tensor-core sweep of a QueryBatch over a GalleryIndex.  Returns a dict with the requested outputs.
+
+    events: optional (start, end) torch.cuda.Event pair recorded around the sweep kernel alone (bench.py's roofline timer)."""
     if gallery.CH != queries.CH or gallery.sw != queries.sw or gallery.device != queries.device:
         raise ValueError("sweep_tc: gallery and queries disagree (CH %d/%d, sw %d/%d)" % (gallery.CH, queries.CH, gallery.sw, queries.sw))
     dev, g, q = gallery.device, gallery.G, queries.Q
@@ -284,9 +286,13 @@ def sweep_tc(gallery, queries, want_dist=False, want_ori=False, d_true=None, ran
             tk_d = torch.empty((slots, q, topk), dtype=torch.float32, device=dev)
             tk_i = torch.empty((slots, q, topk), dtype=torch.int32, device=dev)
         if g > 0 and q > 0:
+            if events is not None:
+                events[0].record()
             _lib.call("witw_match_tc", gallery.operand.data_ptr(), gallery.crop_inv_norm.data_ptr(), queries.operand.data_ptr(),
                       queries.inv_norm.data_ptr(), g, q, gallery.CH, gallery.sw, _ptr(dist), _ptr(ori), _ptr(d_true),
-                      _ptr(rank_count), int(topk), _ptr(tk_d), _ptr(tk_i), gallery.g_offset, _stream())
+                      _ptr(true_idx), _ptr(rank_count), int(topk), _ptr(tk_d), _ptr(tk_i), gallery.g_offset, _stream())
+            if events is not None:
+                events[1].record()
         if topk:
             fin_d = torch.empty((q, topk), dtype=torch.float32, device=dev)
             fin_i = torch.empty((q, topk), dtype=torch.int32, device=dev)
@@ -432,7 +438,7 @@ def evaluate_ranks(overhead_embed, surface_embed, true_idx=None, path="auto", to
     return evaluate_ranks_prepared(gallery, queries, true_idx=true_idx, topk=topk)
 
 
-def evaluate_ranks_prepared(gallery, queries, true_idx=None, topk=0, d_true=None):
+def evaluate_ranks_prepared(gallery, queries, true_idx=None, topk=0, d_true=None, events=None):
     """evaluate_ranks on prepared operands (tensor-core path)."""
     dev = gallery.device
     with torch.cuda.device(dev):
@@ -443,7 +449,11 @@ def evaluate_ranks_prepared(gallery, queries, true_idx=None, topk=0, d_true=None
             su4 = queries.su.view(queries.Q, gallery.C, gallery.H, queries.sw)
             d_true, _ = true_match_distances(ov4, su4, true_idx)
         counts = torch.zeros(max(queries.Q, 1), dtype=torch.int32, device=dev)
-        res = sweep_tc(gallery, queries, d_true=d_true, rank_count=counts, topk=topk)
+        if true_idx is None:
+            t32 = torch.arange(gallery.g_offset, gallery.g_offset + queries.Q, dtype=torch.int32, device=dev)
+        else:
+            t32 = (true_idx.to(dev, torch.int64) + gallery.g_offset).to(torch.int32).contiguous()
+        res = sweep_tc(gallery, queries, d_true=d_true, true_idx=t32, rank_count=counts, topk=topk, events=events)
         ranks = counts[: queries.Q].to(torch.int64)
     if topk:
         return ranks, res["topk_dist"], res["topk_idx"]

@@ -35,17 +35,17 @@ class CudaLocal(object):
         d, _ = ops.true_match_distances(ov_local, su_owned, local_idx)
         return d
 
-    def sweep(self, ov_local, su, d_true, g_offset, topk):
+    def sweep(self, ov_local, su, d_true, true_idx, g_offset, topk):
         g, q, ch, w, sw = ops._feature_dims("sweep", ov_local, su)
         dev = su.device
         if ops._pick_path(self.path, g, q, ch, w, sw) == "tc":
             gallery = ops.GalleryIndex(ov_local, sw, g_offset=g_offset, keep_fp32=False)
             queries = ops.QueryBatch(su, keep_fp32=False)
             counts = torch.zeros(max(q, 1), dtype=torch.int32, device=dev)
-            res = ops.sweep_tc(gallery, queries, d_true=d_true, rank_count=counts, topk=topk)
+            res = ops.sweep_tc(gallery, queries, d_true=d_true, true_idx=true_idx.to(torch.int32), rank_count=counts, topk=topk)
             return counts[:q].to(torch.int64), res.get("topk_dist"), res.get("topk_idx")
         _, dmat = ops.match(ov_local, su, path="fp32")
-        counts = (dmat <= d_true.unsqueeze(0)).sum(dim=0).to(torch.int64)
+        counts = (dmat <= d_true.unsqueeze(0)).sum(dim=0).to(torch.int64)  # fp32 path: the match compares equal to itself
         if topk:
             td, ti = ops.topk_from_distances(dmat, topk, g_offset=g_offset)
             return counts, td, ti
@@ -85,7 +85,7 @@ def evaluate_ranks_sharded(ov_local, surface_embed, g_offset, n_gallery_total, t
         dist.all_reduce(d_true, op=dist.ReduceOp.SUM, group=group)
 
     # (2) local sweep, then the count reduction
-    counts, td, ti = local.sweep(ov_local, surface_embed, d_true, g_offset, topk)
+    counts, td, ti = local.sweep(ov_local, surface_embed, d_true, t_idx, g_offset, topk)
     if world > 1:
         dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
     if not topk:

@@ -155,9 +155,13 @@ int witw_l2_rank_f32(const float* ov_dev, const float* su_dev, int64_t N, int64_
                      const int64_t* true_idx_dev, float* dist_dev, int64_t* ranks_dev,
                      witw_stream_t stream);
 
-/* Per query (column) the k smallest distances of dist [G,Q], ascending, ties by lower
- * gallery index; idx gets g + g_index_offset.  k <= 128.  out: [Q,k]. */
-int witw_topk_from_dist_f32(const float* dist_dev, int64_t G, int64_t Q, int k,
+/* Per query (column) the k smallest distances of dist [G,Q], ascending, ties by lower gallery index;
+ * idx gets g + g_index_offset; NaN / +inf never enter (unfilled slots are (+inf, -1)).  k <= 128.
+ * The gallery is cut into n_slices row slices (witw_topk_slices() suggests a count that fills the
+ * machine); slice s writes its candidate list to out[s][q][k].  n_slices == 1 gives the final [Q,k];
+ * otherwise merge with witw_topk_merge(). */
+int witw_topk_slices(int64_t G, int64_t Q);
+int witw_topk_from_dist_f32(const float* dist_dev, int64_t G, int64_t Q, int k, int n_slices,
                             float* topk_dist_dev, int32_t* topk_idx_dev, int32_t g_index_offset,
                             witw_stream_t stream);
 

@@ -61,11 +61,14 @@ def test_polar_plan_structure():
     assert hdr[12] == 2  # the two clip-quirk pixels are the only exceptions
     # fractions reproduce the float64 grid: fx = fp32(x - floor(x))
     x, y = O.polar_grid()
-    lut_off = int(buf[52:56].view(np.uint32)[0])
+    pw = int(hdr[13])
+    assert pw in (8, 16, 32)
+    lut_off = int(buf[56:60].view(np.uint32)[0])
     fx = buf[lut_off: lut_off + 4 * 65536].view(np.float32).reshape(4, 16, 1024)
     q, i, t = 2, 5, 777
-    lin = i * 1024 + t
-    row, col = lin // 128, q * 128 + lin % 128
+    patch, lane = i * 32 + t // 32, t % 32      # warps tile the quadrant with pw x 32/pw patches
+    npx = 128 // pw
+    row, col = (patch // npx) * (32 // pw) + lane // pw, q * 128 + (patch % npx) * pw + lane % pw
     assert fx[q, i, t] == np.float32(x[row, col] - np.floor(x[row, col]))
     # unsupported geometry is refused, not approximated
     assert lib.witw_polar_plan_bytes(100, 300, 256) == 0

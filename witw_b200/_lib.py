@@ -37,7 +37,8 @@ SIGNATURES = {
                               c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int32, c_void_p]),
     "witw_rank_from_dist_f32": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
     "witw_l2_rank_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "witw_topk_from_dist_f32": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_int32, c_void_p]),
+    "witw_topk_slices": (c_int, [c_int64, c_int64]),
+    "witw_topk_from_dist_f32": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p, c_int32, c_void_p]),
     "witw_topk_merge": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
 }
 

@@ -20,7 +20,7 @@
 //
 // cta_group::2 (default): a CTA pair computes a 256-query x 4-item tile per accumulator stage
 // (UMMA 256x256x16); each CTA stages its own 128 queries and 2 items.  Warp roles per CTA:
-// 0 TMA producer, 1 MMA issuer (leader) / full-barrier relay (peer), 2 TMEM allocator,
+// 0 TMA producer (cta_group::2 copies signal the leader's barrier), 1 MMA issuer (leader), 2 TMEM allocator,
 // 4-7 epilogue.  Two accumulator stages (2 x 256 TMEM columns) overlap epilogue and MMA.
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -157,7 +157,7 @@ __device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity) {
   for (uint32_t spin = 0; !done; ++spin) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
         : "r"(bar), "r"(parity)
@@ -179,16 +179,31 @@ __device__ __forceinline__ void bar_arrive_cluster(uint32_t local_bar, uint32_t 
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_bar), "r"(cta_rank));
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
+// Tile-mode TMA load.  CG == 2: both CTAs of the pair run this; the bytes land in the issuing CTA's shared
+// memory and complete_tx is signalled on the LEADER CTA's mbarrier (bar is a shared::cluster address).
+template <int CG>
 __device__ __forceinline__ void tma_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-      "l"(map), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
+  if constexpr (CG == 1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+  } else {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+  }
 }
-__device__ __forceinline__ void bulk_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
-               "r"(bytes), "r"(bar)
-               : "memory");
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t cta_rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(cta_rank));
+  return remote;
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -246,7 +261,6 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo_bytes,
 constexpr int kTopkMax = 16;
 
 struct TcParams {
-  const unsigned char* gal_op;   // [pairs][CH][bpc][8][8] bf16
   const float* crop_inv_norm;    // [G_pad4][64]
   const float* q_inv_norm;       // [Q]
   float* dist;                   // [G][Q] or null
@@ -262,13 +276,14 @@ struct TcParams {
   int n_qtiles, n_chunks, groups_per_chunk, n_groups;
   int kblocks, cpb, bpc, nkap;
   int sbo, lbo, kstep, b_bytes;
-  int64_t pair_bytes;            // CH * bpc * 128
+  int pair_rows;                 // CH * bpc: 128-byte blocks per item pair
+  int stage_rows;                // cpb * bpc: blocks per K block per CTA
   int n_stages;                  // depth of the operand ring (<= kTcMaxStages)
 };
 
 template <int CG>
 __global__ void __launch_bounds__(kTcThreads, 1)
-match_tc_kernel(const __grid_constant__ CUtensorMap q_map, const TcParams P) {
+match_tc_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant__ CUtensorMap g_map, const TcParams P) {
   constexpr int UM = 128 * CG;           // UMMA M
   constexpr int UN = 128 * CG;           // UMMA N  (= accumulator columns per stage)
   constexpr int IG = 2 * CG;             // gallery items per group
@@ -283,8 +298,7 @@ match_tc_kernel(const __grid_constant__ CUtensorMap q_map, const TcParams P) {
   uint64_t* bars = reinterpret_cast<uint64_t*>(b_base + kTcStages * b_stride);
   uint64_t* full = bars;                         // [n_stages]
   uint64_t* empty = bars + kTcMaxStages;         // [n_stages]
-  uint64_t* peer_full = bars + 2 * kTcMaxStages; // [n_stages]  (leader only)
-  uint64_t* tmem_full = bars + 3 * kTcMaxStages; // [2]
+  uint64_t* tmem_full = bars + 2 * kTcMaxStages; // [2]
   uint64_t* tmem_empty = tmem_full + 2;       // [2]          (leader only)
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
@@ -295,13 +309,15 @@ match_tc_kernel(const __grid_constant__ CUtensorMap q_map, const TcParams P) {
   const int unit = blockIdx.x / CG, n_units = gridDim.x / CG;
   const int n_items = P.n_chunks * P.n_qtiles;
 
-  if (warp == 0 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&q_map) : "memory");
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&q_map) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&g_map) : "memory");
+  }
   if (warp == 1 && lane == 0) {
     if (s2u(smem) & 1023u) __trap();  // SWIZZLE_128B operand tiles need a 1024-byte aligned base
     for (uint32_t s = 0; s < kTcStages; ++s) {
       bar_init(s2u(&full[s]), 1);
       bar_init(s2u(&empty[s]), 1);
-      bar_init(s2u(&peer_full[s]), 1);
     }
     for (int a = 0; a < 2; ++a) {
       bar_init(s2u(&tmem_full[a]), 1);
@@ -328,73 +344,70 @@ match_tc_kernel(const __grid_constant__ CUtensorMap q_map, const TcParams P) {
   const uint32_t tmem_base = *tmem_holder;
 
   if (warp == 0) {
-    // ===================== TMA producer (one lane) =====================
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int item = unit; item < n_items; item += n_units) {
-        const int chunk = item / P.n_qtiles, qt = item - chunk * P.n_qtiles;
-        const int q_row0 = qt * UM + (int)cta_rank * 128;
-        const int grp0 = chunk * P.groups_per_chunk;
-        const int grp1 = min(grp0 + P.groups_per_chunk, P.n_groups);
-        for (int grp = grp0; grp < grp1; ++grp) {
-          const unsigned char* pair_ptr = P.gal_op + ((int64_t)grp * CG + cta_rank) * P.pair_bytes;
-          for (int kb = 0; kb < P.kblocks; ++kb, ++it) {
-            const uint32_t s = it % kTcStages, ph = (it / kTcStages) & 1;
-            bar_wait(s2u(&empty[s]), ph ^ 1);
-            bar_expect_tx(s2u(&full[s]), (uint32_t)(kABytes + P.b_bytes));
-            tma_2d(s2u(a_base + s * kABytes), &q_map, s2u(&full[s]), kb * 64, q_row0);
-            bulk_1d(s2u(b_base + s * b_stride), pair_ptr + (int64_t)kb * P.b_bytes, (uint32_t)P.b_bytes, s2u(&full[s]));
+    // ===================== TMA producer (whole warp runs the loop, one elected lane issues) =====================
+    // Every stage's bytes -- this CTA's 128 queries and 2 items, and the peer's -- are accounted on the
+    // LEADER's full barrier: the leader arms it with the pair's total, the peer only issues its copies.
+    const uint32_t stage_tx = (uint32_t)CG * (uint32_t)(kABytes + P.b_bytes);
+    const uint32_t full0 = CG == 2 ? map_to_cta(s2u(&full[0]), 0) : s2u(&full[0]);
+    uint32_t s = 0, ph = 0;
+    for (int item = unit; item < n_items; item += n_units) {
+      const int qt = item / P.n_chunks, chunk = item - qt * P.n_chunks;
+      const int q_row0 = qt * UM + (int)cta_rank * 128;
+      const int grp0 = chunk * P.groups_per_chunk;
+      const int grp1 = min(grp0 + P.groups_per_chunk, P.n_groups);
+      for (int grp = grp0; grp < grp1; ++grp) {
+        int g_row = (grp * CG + (int)cta_rank) * P.pair_rows;
+        for (int kb = 0; kb < P.kblocks; ++kb, g_row += P.stage_rows) {
+          bar_wait(s2u(&empty[s]), ph ^ 1);
+          if (elect_one()) {
+            const uint32_t fb = full0 + s * 8;
+            if (leader) bar_expect_tx(s2u(&full[s]), stage_tx);
+            tma_2d<CG>(s2u(a_base) + s * kABytes, &q_map, fb, kb * 64, q_row0);
+            tma_2d<CG>(s2u(b_base) + s * b_stride, &g_map, fb, 0, g_row);
           }
+          __syncwarp();
+          if (++s == kTcStages) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     if (leader) {
-      // ===================== MMA issuer (one lane of the leader CTA) =====================
-      if (lane == 0) {
-        uint32_t it = 0, acc_it = 0;
-        for (int item = unit; item < n_items; item += n_units) {
-          const int chunk = item / P.n_qtiles;
-          const int grp0 = chunk * P.groups_per_chunk;
-          const int grp1 = min(grp0 + P.groups_per_chunk, P.n_groups);
-          for (int grp = grp0; grp < grp1; ++grp, ++acc_it) {
-            const uint32_t acc = acc_it & 1, acc_ph = (acc_it >> 1) & 1;
-            bar_wait(s2u(&tmem_empty[acc]), acc_ph ^ 1);
-            tc_fence_after();
-            const uint32_t tmem_d = tmem_base + acc * UN;
-            for (int kb = 0; kb < P.kblocks; ++kb, ++it) {
-              const uint32_t s = it % kTcStages, ph = (it / kTcStages) & 1;
-              bar_wait(s2u(&full[s]), ph);
-              if constexpr (CG == 2) bar_wait(s2u(&peer_full[s]), ph);
-              tc_fence_after();
-              const uint32_t a_addr = s2u(a_base + s * kABytes);
-              const uint32_t b_addr = s2u(b_base + s * b_stride);
+      // ===================== MMA issuer (leader CTA; warp-uniform loop, one elected lane issues) =====================
+      // Per K block: one barrier wait, four tcgen05.mma (K = 16 each) whose descriptors are the stage-0
+      // descriptors plus precomputed 16-byte-unit offsets, one commit.  Everything else is hoisted.
+      const uint64_t a_desc0 = make_desc(s2u(a_base), 16, 1024, 2 /*SWIZZLE_128B*/);
+      const uint64_t b_desc0 = make_desc(s2u(b_base), P.lbo, P.sbo, 0 /*no swizzle*/);
+      uint32_t b_off[4];
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {  // four K=16 steps of the 64-wide K block
-                const int c_in = j / P.nkap, kap = j - c_in * P.nkap;
-                const uint64_t da = make_desc(a_addr + j * 32, 16, 1024, 2 /*SWIZZLE_128B*/);
-                const uint64_t db = make_desc(b_addr + c_in * P.bpc * 128 + kap * P.kstep, P.lbo, P.sbo, 0 /*no swizzle*/);
-                umma_bf16<CG>(tmem_d, da, db, kIdesc, (kb | j) != 0 ? 1u : 0u);
-              }
-              umma_commit<CG>(s2u(&empty[s]));  // frees the stage in both CTAs when the MMAs retire
-            }
-            umma_commit<CG>(s2u(&tmem_full[acc]));
-          }
-        }
+      for (int j = 0; j < 4; ++j) {
+        const int c_in = j / P.nkap, kap = j - c_in * P.nkap;
+        b_off[j] = (uint32_t)(c_in * P.bpc * 128 + kap * P.kstep) >> 4;
       }
-    } else if constexpr (CG == 2) {
-      // ===================== peer CTA: relay "my operands have landed" to the leader =====================
-      if (lane == 0) {
-        uint32_t it = 0;
-        for (int item = unit; item < n_items; item += n_units) {
-          const int chunk = item / P.n_qtiles;
-          const int grp0 = chunk * P.groups_per_chunk;
-          const int grp1 = min(grp0 + P.groups_per_chunk, P.n_groups);
-          const uint32_t total = (uint32_t)(grp1 - grp0) * (uint32_t)P.kblocks;
-          for (uint32_t i = 0; i < total; ++i, ++it) {
-            const uint32_t s = it % kTcStages, ph = (it / kTcStages) & 1;
+      const uint32_t a_step = kABytes >> 4, b_step = b_stride >> 4;
+      uint32_t s = 0, ph = 0, acc_it = 0;
+      for (int item = unit; item < n_items; item += n_units) {
+        const int chunk = item % P.n_chunks;
+        const int grp0 = chunk * P.groups_per_chunk;
+        const int grp1 = min(grp0 + P.groups_per_chunk, P.n_groups);
+        for (int grp = grp0; grp < grp1; ++grp, ++acc_it) {
+          const uint32_t acc = acc_it & 1, acc_ph = (acc_it >> 1) & 1;
+          bar_wait(s2u(&tmem_empty[acc]), acc_ph ^ 1);
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + acc * UN;
+          for (int kb = 0; kb < P.kblocks; ++kb) {
             bar_wait(s2u(&full[s]), ph);
-            bar_arrive_cluster(s2u(&peer_full[s]), 0);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint64_t da = a_desc0 + (uint64_t)(s * a_step);
+              const uint64_t db = b_desc0 + (uint64_t)(s * b_step);
+#pragma unroll
+              for (int j = 0; j < 4; ++j)  // 32 bytes (2 units) along K per step inside the 128B-swizzled query rows
+                umma_bf16<CG>(tmem_d, da + (uint64_t)(2 * j), db + (uint64_t)b_off[j], kIdesc, (kb | j) != 0 ? 1u : 0u);
+              umma_commit<CG>(s2u(&empty[s]));  // frees the stage in both CTAs when these MMAs retire
+              if (kb == P.kblocks - 1) umma_commit<CG>(s2u(&tmem_full[acc]));
+            }
+            __syncwarp();
+            if (++s == kTcStages) { s = 0; ph ^= 1; }
           }
         }
       }
@@ -406,7 +419,7 @@ match_tc_kernel(const __grid_constant__ CUtensorMap q_map, const TcParams P) {
     const uint32_t lane_field = (uint32_t)(wq * 32) << 16;
     uint32_t acc_it = 0;
     for (int item = unit; item < n_items; item += n_units) {
-      const int chunk = item / P.n_qtiles, qt = item - chunk * P.n_qtiles;
+      const int qt = item / P.n_chunks, chunk = item - qt * P.n_chunks;
       const int64_t q = (int64_t)qt * UM + cta_rank * 128 + row;
       const bool q_ok = q < P.Q;
       const float qin = q_ok ? P.q_inv_norm[q] : 0.f;
@@ -606,19 +619,33 @@ extern "C" int witw_match_tc(const void* gal_op, const float* crop_inv_norm, con
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   WITW_REQUIRE(cr == CUDA_SUCCESS, WITW_ERR_CUDA, "cuTensorMapEncodeTiled(query operand) failed with CUresult %d", (int)cr);
 
+  // gallery operand as a [total_blocks][64] bf16 matrix of 128-byte blocks; one box = the blocks of one K block
+  const int64_t pairs = ceil_div<int64_t>(G, 4) * 2;
+  const int64_t total_rows = pairs * CH * geo.bpc;
+  WITW_REQUIRE(total_rows < (1ll << 31), WITW_ERR_UNSUPPORTED, "witw_match_tc: gallery of %lld items is too large for one sweep", (long long)G);
+  WITW_REQUIRE(geo.cpb * geo.bpc <= 256, WITW_ERR_UNSUPPORTED, "witw_match_tc: operand stage of %d blocks exceeds a TMA box", geo.cpb * geo.bpc);
+  CUtensorMap gmap;
+  const cuuint64_t gdims[2] = {64, (cuuint64_t)total_rows};
+  const cuuint64_t gstrides[1] = {128};
+  const cuuint32_t gbox[2] = {64, (cuuint32_t)(geo.cpb * geo.bpc)};
+  cr = encode(&gmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(gal_op), gdims, gstrides, gbox, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  WITW_REQUIRE(cr == CUDA_SUCCESS, WITW_ERR_CUDA, "cuTensorMapEncodeTiled(gallery operand) failed with CUresult %d", (int)cr);
+
   TcParams P;
   std::memset(&P, 0, sizeof(P));
-  P.gal_op = reinterpret_cast<const unsigned char*>(gal_op);
   P.crop_inv_norm = crop_inv_norm; P.q_inv_norm = q_inv_norm;
   P.dist = dist; P.ori = ori; P.d_true = d_true; P.true_idx = true_idx; P.rank_count = rank_count;
   P.topk_dist = topk_dist; P.topk_idx = topk_idx; P.G = G; P.Q = Q; P.topk = topk; P.g_offset = g_offset;
   P.n_qtiles = sch.n_qtiles; P.n_chunks = sch.n_chunks; P.groups_per_chunk = sch.groups_per_chunk; P.n_groups = sch.n_groups;
   P.kblocks = geo.kblocks; P.cpb = geo.cpb; P.bpc = geo.bpc; P.nkap = geo.nkap;
   P.sbo = geo.sbo; P.lbo = geo.lbo; P.kstep = geo.kstep; P.b_bytes = geo.b_bytes;
-  P.pair_bytes = (int64_t)CH * geo.bpc * 128;
+  P.pair_rows = CH * geo.bpc;
+  P.stage_rows = geo.cpb * geo.bpc;
 
   const uint32_t b_stride = (uint32_t)((geo.b_bytes + 127) & ~127);
-  const size_t fixed = (3 * kTcMaxStages + 4) * 8 + 16;
+  const size_t fixed = (2 * kTcMaxStages + 4) * 8 + 16;
   int n_stages = (int)std::min<size_t>(kTcMaxStages, (227 * 1024 - fixed) / (kABytes + b_stride));
   WITW_REQUIRE(n_stages >= 2, WITW_ERR_UNSUPPORTED, "witw_match_tc: operand stage of %u bytes does not fit shared memory twice", kABytes + b_stride);
   P.n_stages = n_stages;
@@ -640,10 +667,10 @@ extern "C" int witw_match_tc(const void* gal_op, const float* crop_inv_norm, con
   cfg.numAttrs = 1;
   if (sch.cg == 2) {
     WITW_CUDA(cudaFuncSetAttribute(match_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    WITW_CUDA(cudaLaunchKernelEx(&cfg, match_tc_kernel<2>, qmap, P));
+    WITW_CUDA(cudaLaunchKernelEx(&cfg, match_tc_kernel<2>, qmap, gmap, P));
   } else {
     WITW_CUDA(cudaFuncSetAttribute(match_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    WITW_CUDA(cudaLaunchKernelEx(&cfg, match_tc_kernel<1>, qmap, P));
+    WITW_CUDA(cudaLaunchKernelEx(&cfg, match_tc_kernel<1>, qmap, gmap, P));
   }
   WITW_LAUNCH_CHECK();
   return WITW_OK;

@@ -14,6 +14,7 @@
 //     margin), every output byte written once.
 #include <cuda.h>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -110,6 +111,7 @@ struct PolarPlanHeader {
   int32_t h_s, w_s, s_o;
   int32_t box_x0[4], box_y0[4];
   int32_t n_exc;
+  int32_t patch_w;   // a warp's 32 lanes cover patch_w columns x 32/patch_w rows of the output
   uint32_t lut_off;  // byte offset of the register table: float fx[4][PX][1024], float fy[..], uint32 off2[4][PX/2][1024]
                      // (off2 packs the 16-bit box offsets of pixels 2i and 2i+1)
   uint32_t exc_off;  // byte offset of PolarException[n_exc]
@@ -118,7 +120,28 @@ struct PolarPlanHeader {
 
 static bool polar_fast_supported(int h_s, int w_s, int s_o) {
   if (w_s % 128 != 0 || s_o < 8 || h_s < 1) return false;
+  if ((w_s / 4) % 32 != 0 || (kPolarThreads / 32) % ((w_s / 4) / 8) != 0) return false;
   return (int64_t)h_s * (w_s / 4) == (int64_t)kPolarThreads * kPolarPx;
+}
+
+static int polar_patch_w() {
+  // Lanes of a warp on a 2-D output patch touch a compact 2-D footprint of the staged source window, which
+  // spreads over the shared-memory banks better than 32 samples along one arc (measured: profiles/).
+  static int v = -1;
+  if (v < 0) {
+    const char* e = std::getenv("WITW_POLAR_PW");
+    v = e ? std::atoi(e) : 8;
+    if (v != 8 && v != 16 && v != 32) v = 8;
+  }
+  return v;
+}
+
+// pixel (row, col-in-quadrant) handled by thread t in iteration i: warps tile the quadrant with patch_w x 32/patch_w patches
+static inline void polar_thread_pixel(int i, int t, int qw, int pw, int* row, int* col) {
+  const int ph = 32 / pw, npx = qw / pw;
+  const int patch = i * (kPolarThreads / 32) + (t >> 5), lane = t & 31;
+  *col = (patch % npx) * pw + lane % pw;
+  *row = (patch / npx) * ph + lane / pw;
 }
 
 // Builds header + tables into `out` (may be null to only count).  Returns bytes, 0 if unsupported.
@@ -151,14 +174,19 @@ static size_t polar_plan_build_host(int h_s, int w_s, int s_o, void* out) {
     bx0[q] = std::min(bx0[q], fx0); bx1[q] = std::max(bx1[q], fx0 + 1);
     by0[q] = std::min(by0[q], fy0); by1[q] = std::max(by1[q], fy0 + 1);
   }
-  for (int q = 0; q < 4; ++q)
+  for (int q = 0; q < 4; ++q) {
+    // measured on B200 (tools/probe/tma_probe.cu): a tile-mode TMA whose innermost start coordinate is not a
+    // multiple of 16 bytes raises an illegal-instruction fault, so the box starts on a 4-float boundary
+    bx0[q] &= ~3;
     if (bx1[q] - bx0[q] + 1 > kBoxW || by1[q] - by0[q] + 1 > kBoxH) return 0;
+  }
   const size_t lut_elems = (size_t)4 * kPolarPx * kPolarThreads;
   PolarPlanHeader h;
   std::memset(&h, 0, sizeof(h));
   h.magic = kPlanMagic; h.h_s = h_s; h.w_s = w_s; h.s_o = s_o;
   for (int q = 0; q < 4; ++q) { h.box_x0[q] = bx0[q]; h.box_y0[q] = by0[q]; }
   h.n_exc = (int32_t)exc.size();
+  h.patch_w = polar_patch_w();
   h.lut_off = 256;
   h.exc_off = (uint32_t)(h.lut_off + 3 * lut_elems * 4);
   h.total_bytes = (uint32_t)(h.exc_off + std::max<size_t>(exc.size(), 1) * sizeof(PolarException));
@@ -172,8 +200,9 @@ static size_t polar_plan_build_host(int h_s, int w_s, int s_o, void* out) {
   for (int q = 0; q < 4; ++q)
     for (int i = 0; i < kPolarPx; ++i)
       for (int t = 0; t < kPolarThreads; ++t) {
-        const int lin = i * kPolarThreads + t;  // pixel index inside the quadrant, row-major [h_s][qw]
-        const int row = lin / qw, col = q * qw + lin % qw;
+        int row, qcol;
+        polar_thread_pixel(i, t, qw, h.patch_w, &row, &qcol);
+        const int col = q * qw + qcol;
         const int64_t p = (int64_t)row * w_s + col;
         const size_t o = ((size_t)q * kPolarPx + i) * kPolarThreads + t;
         const size_t o2 = ((size_t)q * (kPolarPx / 2) + i / 2) * kPolarThreads + t;
@@ -220,7 +249,7 @@ struct PolarQuadBoxes { int x0[4], y0[4]; };
 __global__ void __launch_bounds__(kPolarThreads, 1)
 polar_quadrant_kernel(const __grid_constant__ CUtensorMap src_map, float* __restrict__ dst, int n_img,
                       const float* __restrict__ lut_fx, const float* __restrict__ lut_fy,
-                      const uint32_t* __restrict__ lut_off, PolarQuadBoxes boxes, int h_s, int w_s) {
+                      const uint32_t* __restrict__ lut_off, PolarQuadBoxes boxes, int h_s, int w_s, int patch_w) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr uint32_t kStageBytes = kBoxW * kBoxH * 4;
   constexpr uint32_t kStageStride = (kStageBytes + 127) & ~127u;
@@ -242,10 +271,12 @@ polar_quadrant_kernel(const __grid_constant__ CUtensorMap src_map, float* __rest
   }
 #pragma unroll
   for (int i = 0; i < kPolarPx / 2; ++i) off2[i] = lut_off[((size_t)q * (kPolarPx / 2) + i) * kPolarThreads + tid];
-  // output offset of pixel i: rows advance by kPolarThreads/qw per i
-  const int rows_per_i = kPolarThreads / qw;
-  const size_t out_base = (size_t)(tid / qw) * w_s + (size_t)q * qw + (tid % qw);
-  const size_t out_step = (size_t)rows_per_i * w_s;
+  // output offset of this thread's pixel in iteration i (same tiling as polar_thread_pixel on the host):
+  // the 32 warps cover 32 patches per iteration, which is a whole number of patch rows, so the row advances
+  // by a constant kPolarThreads/qw per iteration
+  const int patch_h = 32 / patch_w, npx = qw / patch_w, lane = tid & 31, wrp = tid >> 5;
+  const size_t out_base = (size_t)((wrp / npx) * patch_h + lane / patch_w) * w_s + (size_t)q * qw + (wrp % npx) * patch_w + lane % patch_w;
+  const size_t out_step = (size_t)(kPolarThreads / qw) * w_s;
   const size_t plane_out = (size_t)h_s * w_s;
 
   if (tid == 0) {
@@ -426,7 +457,7 @@ extern "C" int witw_polar_resample_f32(const float* src, float* dst, int64_t n_i
   for (int q = 0; q < 4; ++q) { boxes.x0[q] = h.box_x0[q]; boxes.y0[q] = h.box_y0[q]; }
   int grid = (sm_count() / 4) * 4;
   if ((int64_t)grid > 4 * n_img) grid = (int)(4 * n_img);
-  polar_quadrant_kernel<<<grid, kPolarThreads, smem, as_stream(stream)>>>(map, dst, (int)n_img, fx, fy, off, boxes, h.h_s, h.w_s);
+  polar_quadrant_kernel<<<grid, kPolarThreads, smem, as_stream(stream)>>>(map, dst, (int)n_img, fx, fy, off, boxes, h.h_s, h.w_s, h.patch_w);
   WITW_LAUNCH_CHECK();
   if (h.n_exc > 0) {
     const int64_t n = n_img * h.n_exc;

@@ -109,7 +109,9 @@ constexpr int kTopkThreads = 64;
 
 __global__ void __launch_bounds__(kTopkThreads)
 topk_columns_kernel(const float* __restrict__ dist, int64_t G, int64_t Q, int k, float* __restrict__ out_d,
-                    int32_t* __restrict__ out_i, int32_t g_offset) {
+                    int32_t* __restrict__ out_i, int32_t g_offset, int64_t rows_per_slice) {
+  // blockIdx.x: 64 query columns (a warp reads 32 adjacent queries of one gallery row = one 128-byte line);
+  // blockIdx.y: gallery slice, whose candidate list goes to out[slice][q][k]
   extern __shared__ unsigned char raw[];
   float* ld = reinterpret_cast<float*>(raw);                       // [k][kTopkThreads]
   int32_t* li = reinterpret_cast<int32_t*>(ld + (size_t)k * kTopkThreads);
@@ -117,29 +119,42 @@ topk_columns_kernel(const float* __restrict__ dist, int64_t G, int64_t Q, int k,
   const int64_t q = (int64_t)blockIdx.x * kTopkThreads + t;
   const float inf = __int_as_float(0x7f800000);
   for (int j = 0; j < k; ++j) { ld[j * kTopkThreads + t] = inf; li[j * kTopkThreads + t] = -1; }
-  if (q < Q) {
-    float worst = inf;
-    int filled = 0;
-    for (int64_t g = 0; g < G; ++g) {
-      const float d = __ldcs(dist + g * Q + q);
-      // strict '<' keeps the earlier (lower) gallery index on ties; NaN never enters
-      if (d < worst || (filled < k && d <= inf && d == d)) {
-        int j = filled < k ? filled : k - 1;
-        while (j > 0 && ld[(j - 1) * kTopkThreads + t] > d) {
-          ld[j * kTopkThreads + t] = ld[(j - 1) * kTopkThreads + t];
-          li[j * kTopkThreads + t] = li[(j - 1) * kTopkThreads + t];
-          --j;
-        }
-        ld[j * kTopkThreads + t] = d;
-        li[j * kTopkThreads + t] = (int32_t)g + g_offset;
-        if (filled < k) ++filled;
-        if (filled == k) worst = ld[(k - 1) * kTopkThreads + t];
+  if (q >= Q) return;
+  const int64_t g0 = (int64_t)blockIdx.y * rows_per_slice;
+  const int64_t g1 = min(g0 + rows_per_slice, G);
+  float worst = inf;
+  int filled = 0;
+  auto consider = [&](float d, int64_t g) {
+    // strict '<' keeps the earlier (lower) gallery index on ties; NaN and +inf never enter
+    if (d < worst) {
+      int j = filled < k ? filled : k - 1;
+      while (j > 0 && ld[(j - 1) * kTopkThreads + t] > d) {
+        ld[j * kTopkThreads + t] = ld[(j - 1) * kTopkThreads + t];
+        li[j * kTopkThreads + t] = li[(j - 1) * kTopkThreads + t];
+        --j;
       }
+      ld[j * kTopkThreads + t] = d;
+      li[j * kTopkThreads + t] = (int32_t)g + g_offset;
+      if (filled < k) ++filled;
+      if (filled == k) worst = ld[(k - 1) * kTopkThreads + t];
     }
-    for (int j = 0; j < k; ++j) {
-      out_d[q * k + j] = ld[j * kTopkThreads + t];
-      out_i[q * k + j] = li[j * kTopkThreads + t];
-    }
+  };
+  constexpr int U = 8;  // independent loads in flight per thread
+  const float* p = dist + q;
+  int64_t g = g0;
+  for (; g + U <= g1; g += U) {
+    float v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) v[u] = __ldcs(p + (g + u) * Q);
+#pragma unroll
+    for (int u = 0; u < U; ++u) consider(v[u], g + u);
+  }
+  for (; g < g1; ++g) consider(__ldcs(p + g * Q), g);
+  float* od = out_d + ((int64_t)blockIdx.y * Q + q) * k;
+  int32_t* oi = out_i + ((int64_t)blockIdx.y * Q + q) * k;
+  for (int j = 0; j < k; ++j) {
+    od[j] = ld[j * kTopkThreads + t];
+    oi[j] = li[j * kTopkThreads + t];
   }
 }
 
@@ -221,15 +236,25 @@ extern "C" int witw_l2_rank_f32(const float* ov, const float* su, int64_t N, int
   return WITW_OK;
 }
 
-extern "C" int witw_topk_from_dist_f32(const float* dist, int64_t G, int64_t Q, int k, float* topk_dist, int32_t* topk_idx,
-                                       int32_t g_offset, witw_stream_t stream) {
+extern "C" int witw_topk_slices(int64_t G, int64_t Q) {
+  // enough (query block, gallery slice) CTAs for ~8 per SM, slices of at least 128 rows, at most 64 (merge limit)
+  const int64_t bx = ceil_div<int64_t>(std::max<int64_t>(Q, 1), kTopkThreads);
+  int64_t s = ceil_div<int64_t>((int64_t)sm_count() * 8, bx);
+  s = std::min<int64_t>(s, std::max<int64_t>(1, G / 128));
+  return (int)std::max<int64_t>(1, std::min<int64_t>(s, 64));
+}
+
+extern "C" int witw_topk_from_dist_f32(const float* dist, int64_t G, int64_t Q, int k, int n_slices, float* topk_dist,
+                                       int32_t* topk_idx, int32_t g_offset, witw_stream_t stream) {
   WITW_REQUIRE(G >= 0 && Q >= 0 && k > 0 && k <= 128, WITW_ERR_INVALID, "witw_topk_from_dist_f32: bad shape (k must be 1..128)");
+  WITW_REQUIRE(n_slices >= 1 && n_slices <= 64, WITW_ERR_INVALID, "witw_topk_from_dist_f32: n_slices must be 1..64");
   if (Q == 0) return WITW_OK;
   WITW_REQUIRE(topk_dist && topk_idx && (dist || G == 0), WITW_ERR_INVALID, "witw_topk_from_dist_f32: null pointer");
   const size_t smem = (size_t)k * kTopkThreads * 8;
   WITW_CUDA(cudaFuncSetAttribute(topk_columns_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  topk_columns_kernel<<<(unsigned)ceil_div<int64_t>(Q, kTopkThreads), kTopkThreads, smem, as_stream(stream)>>>(dist, G, Q, k, topk_dist,
-                                                                                                          topk_idx, g_offset);
+  const int64_t rows = ceil_div<int64_t>(std::max<int64_t>(G, 1), n_slices);
+  topk_columns_kernel<<<dim3((unsigned)ceil_div<int64_t>(Q, kTopkThreads), (unsigned)n_slices), kTopkThreads, smem, as_stream(stream)>>>(
+      dist, G, Q, k, topk_dist, topk_idx, g_offset, rows);
   WITW_LAUNCH_CHECK();
   return WITW_OK;
 }

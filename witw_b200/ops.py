@@ -410,7 +410,14 @@ def topk_from_distances(distances, k, g_offset=0):
     with torch.cuda.device(dev):
         td = torch.empty((q, k), dtype=torch.float32, device=dev)
         ti = torch.empty((q, k), dtype=torch.int32, device=dev)
-        _lib.call("witw_topk_from_dist_f32", d.data_ptr(), g, q, int(k), td.data_ptr(), ti.data_ptr(), int(g_offset), _stream())
+        slices = _lib.load().witw_topk_slices(g, q)
+        if slices <= 1:
+            _lib.call("witw_topk_from_dist_f32", d.data_ptr(), g, q, int(k), 1, td.data_ptr(), ti.data_ptr(), int(g_offset), _stream())
+        else:
+            cd = torch.empty((slices, q, k), dtype=torch.float32, device=dev)
+            ci = torch.empty((slices, q, k), dtype=torch.int32, device=dev)
+            _lib.call("witw_topk_from_dist_f32", d.data_ptr(), g, q, int(k), slices, cd.data_ptr(), ci.data_ptr(), int(g_offset), _stream())
+            _lib.call("witw_topk_merge", cd.data_ptr(), ci.data_ptr(), slices, q, int(k), td.data_ptr(), ti.data_ptr(), _stream())
     return td, ti
 
 

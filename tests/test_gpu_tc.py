@@ -97,3 +97,51 @@ def test_tc_properties_at_scale(W):
         W.sweep_tc(W.GalleryIndex(ovc[lo:hi], 16, g_offset=lo), W.QueryBatch(suc), d_true=d_true, true_idx=t32, rank_count=cnt)
         parts.append(cnt)
     assert torch.equal((parts[0] + parts[1]).long(), ranks)
+
+
+@pytest.mark.parametrize("fov", [360, 90])
+def test_tc_baseline_size_10k_x_10k(W, fov):
+    """BASELINE configs[1]/[2] at full size through size-independent properties:
+    every (gallery, query) pair is visited exactly once (count with an infinite threshold == G),
+    planted matches are rank 1 / top-1 with the planted orientation, distances are finite and in [0, 4]."""
+    G = Q = 10000
+    sw = int(fov / 360 * 512) // 8
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    ov = torch.randn(G, 16, 4, 64, device="cuda", generator=gen) * 0.06
+    shifts = torch.randint(0, 64, (Q,), device="cuda", generator=gen)
+    cols = (shifts.view(Q, 1) + torch.arange(sw, device="cuda").view(1, sw)) % 64
+    su = torch.gather(ov, 3, cols.view(Q, 1, 1, sw).expand(Q, 16, 4, sw)) + 0.03 * torch.randn(Q, 16, 4, sw, device="cuda", generator=gen)
+    gal, qry = W.GalleryIndex(ov, sw), W.QueryBatch(su)
+    inf = torch.full((Q,), float("inf"), device="cuda")
+    cnt = torch.zeros(Q, dtype=torch.int32, device="cuda")
+    W.sweep_tc(gal, qry, d_true=inf, rank_count=cnt)
+    assert int(cnt.min()) == G and int(cnt.max()) == G                    # coverage: each pair exactly once
+    cnt.zero_()
+    W.sweep_tc(gal, qry, d_true=-inf, rank_count=cnt)
+    assert int(cnt.abs().max()) == 0
+    ranks, td, ti = W.evaluate_ranks_prepared(gal, qry, topk=10)
+    assert int((ranks != 1).sum()) == 0
+    assert torch.equal(ti[:, 0].long(), torch.arange(Q, device="cuda"))
+    assert bool((td[:, 1:] >= td[:, :-1]).all()) and bool(torch.isfinite(td).all())
+    assert float(td.min()) >= 0.0 and float(td.max()) <= 4.0
+    d_true, o_true = W.true_match_distances(ov, su)
+    assert torch.equal(o_true, shifts)
+    assert (td[:, 0] - d_true).abs().max().item() <= 2e-3                 # bf16 sweep vs exact fp32 on the matches
+    rec = W.recall_from_ranks(ranks)
+    assert rec["top_one"] == 100.0 and rec["top_percent"] == 100.0 and rec["count"] == Q
+
+
+def test_tc_semantic_config_shapes(W):
+    """BASELINE configs[4] shapes at reduced count: 5-channel tiles through the polar transform, 90-degree
+    queries against a larger gallery than queries (Q != G), explicit true_idx."""
+    tiles = torch.randn(6, 5, 256, 256, device="cuda")
+    polar = W.polar_transform(tiles)
+    assert tuple(polar.shape) == (6, 5, 128, 512)
+    assert (polar - W.polar_transform(tiles, exact=True)).abs().max().item() <= 4e-6
+    ov, su, sh = O.synth_features(3000, 500, fov=90, noise=0.5, seed=8)
+    perm = torch.randperm(3000, generator=torch.Generator().manual_seed(1))
+    ovp = ov[perm]                                                        # query i now matches gallery item inv[i]
+    inv = torch.empty_like(perm)
+    inv[perm] = torch.arange(3000)
+    ranks = W.evaluate_ranks(ovp.cuda(), su.cuda(), true_idx=inv[:500].cuda(), path="tc")
+    assert int((ranks != 1).sum()) == 0

@@ -76,6 +76,17 @@ for fov in (360, 90):
     emit("gallery_prep fov=%d 10k items" % fov, ms, "GB/s", (gal.operand.numel() + ov.numel() * 4) / ms / 1e6, peaks["hbm_gbs"])
     del ov, su, gal, qry
 
+# BASELINE configs[4] sweep: 100k-tile gallery, 10k queries, 90 degrees (gallery operand 7.2 GB)
+ov = torch.randn(100000, 16, 4, 64, device=dev, generator=gen) * 0.06
+su = torch.randn(10000, 16, 4, 16, device=dev, generator=gen) * 0.06
+gal, qry = ops.GalleryIndex(ov, 16, keep_fp32=False), ops.QueryBatch(su, keep_fp32=False)
+d_true = torch.full((10000,), 1.0, device=dev)
+cnt = torch.zeros(10000, dtype=torch.int32, device=dev)
+ms = timeit(lambda: ops.sweep_tc(gal, qry, d_true=d_true, rank_count=cnt, topk=10), iters=3, warm=1)
+emit("match_tc_kernel fov=90 100k gallery x 10k queries (+rank count, top-10, merge)", ms, "TFLOP/s", 2.0 * 64 * 64 * 16 * 1e9 / ms / 1e9,
+     peaks["bf16_tflops_sustained"], {"queries_per_s": 1e4 / ms * 1e3})
+del ov, su, gal, qry
+
 # exact fp32 path, 2k x 2k at 360 degrees
 ov = torch.randn(2048, 16, 4, 64, device=dev, generator=gen) * 0.06
 su = torch.randn(2048, 16, 4, 64, device=dev, generator=gen) * 0.06

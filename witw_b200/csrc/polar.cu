@@ -130,8 +130,8 @@ static int polar_patch_w() {
   static int v = -1;
   if (v < 0) {
     const char* e = std::getenv("WITW_POLAR_PW");
-    v = e ? std::atoi(e) : 8;
-    if (v != 8 && v != 16 && v != 32) v = 8;
+    v = e ? std::atoi(e) : 16;  // measured on B200, 1024x3 planes: 32 -> 5053 GB/s, 16 -> 5515 GB/s, 8 -> 5332 GB/s
+    if (v != 8 && v != 16 && v != 32) v = 16;
   }
   return v;
 }

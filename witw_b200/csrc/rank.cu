@@ -107,54 +107,93 @@ l2_dist_kernel(const float* __restrict__ ov, const float* __restrict__ su, int64
 // ------------------------------------------------------------------------------------------
 constexpr int kTopkThreads = 64;
 
+template <int VEC>  // adjacent query columns per thread: 4 (float4 loads) or 1
 __global__ void __launch_bounds__(kTopkThreads)
 topk_columns_kernel(const float* __restrict__ dist, int64_t G, int64_t Q, int k, float* __restrict__ out_d,
                     int32_t* __restrict__ out_i, int32_t g_offset, int64_t rows_per_slice) {
-  // blockIdx.x: 64 query columns (a warp reads 32 adjacent queries of one gallery row = one 128-byte line);
+  // blockIdx.x: 64*VEC query columns (a warp reads 32*VEC adjacent queries of one gallery row);
   // blockIdx.y: gallery slice, whose candidate list goes to out[slice][q][k]
   extern __shared__ unsigned char raw[];
-  float* ld = reinterpret_cast<float*>(raw);                       // [k][kTopkThreads]
-  int32_t* li = reinterpret_cast<int32_t*>(ld + (size_t)k * kTopkThreads);
+  constexpr int LW = VEC * kTopkThreads;                            // lists per CTA
+  float* ld = reinterpret_cast<float*>(raw);                       // [k][VEC][kTopkThreads]
+  int32_t* li = reinterpret_cast<int32_t*>(ld + (size_t)k * LW);
   const int t = threadIdx.x;
-  const int64_t q = (int64_t)blockIdx.x * kTopkThreads + t;
+  const int64_t q0 = ((int64_t)blockIdx.x * kTopkThreads + t) * VEC;
   const float inf = __int_as_float(0x7f800000);
-  for (int j = 0; j < k; ++j) { ld[j * kTopkThreads + t] = inf; li[j * kTopkThreads + t] = -1; }
-  if (q >= Q) return;
+  for (int j = 0; j < k; ++j)
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) { ld[j * LW + c * kTopkThreads + t] = inf; li[j * LW + c * kTopkThreads + t] = -1; }
+  if (q0 >= Q) return;
   const int64_t g0 = (int64_t)blockIdx.y * rows_per_slice;
   const int64_t g1 = min(g0 + rows_per_slice, G);
-  float worst = inf;
-  int filled = 0;
-  auto consider = [&](float d, int64_t g) {
-    // strict '<' keeps the earlier (lower) gallery index on ties; NaN and +inf never enter
-    if (d < worst) {
-      int j = filled < k ? filled : k - 1;
-      while (j > 0 && ld[(j - 1) * kTopkThreads + t] > d) {
-        ld[j * kTopkThreads + t] = ld[(j - 1) * kTopkThreads + t];
-        li[j * kTopkThreads + t] = li[(j - 1) * kTopkThreads + t];
-        --j;
-      }
-      ld[j * kTopkThreads + t] = d;
-      li[j * kTopkThreads + t] = (int32_t)g + g_offset;
-      if (filled < k) ++filled;
-      if (filled == k) worst = ld[(k - 1) * kTopkThreads + t];
+  float worst[VEC];
+  int filled[VEC];
+#pragma unroll
+  for (int c = 0; c < VEC; ++c) { worst[c] = inf; filled[c] = 0; }
+  auto insert = [&](int c, float d, int64_t g) {
+    // the caller checked d < worst[c]: strict '<' keeps the earlier (lower) gallery index on ties; NaN, +inf never enter
+    float* cd = ld + c * kTopkThreads + t;
+    int32_t* ci = li + c * kTopkThreads + t;
+    int j = filled[c] < k ? filled[c] : k - 1;
+    while (j > 0 && cd[(j - 1) * LW] > d) {
+      cd[j * LW] = cd[(j - 1) * LW];
+      ci[j * LW] = ci[(j - 1) * LW];
+      --j;
     }
+    cd[j * LW] = d;
+    ci[j * LW] = (int32_t)g + g_offset;
+    if (filled[c] < k) ++filled[c];
+    if (filled[c] == k) worst[c] = cd[(k - 1) * LW];
   };
-  constexpr int U = 8;  // independent loads in flight per thread
-  const float* p = dist + q;
   int64_t g = g0;
-  for (; g + U <= g1; g += U) {
-    float v[U];
+  if constexpr (VEC == 4) {
+    constexpr int U = 4;  // 4 x 16 bytes in flight per thread
+    const float4* p = reinterpret_cast<const float4*>(dist + q0);
+    const int64_t stride4 = Q >> 2;
+    for (; g + U <= g1; g += U) {
+      float4 v[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) v[u] = __ldcs(p + (g + u) * Q);
+      for (int u = 0; u < U; ++u) v[u] = __ldcs(p + (g + u) * stride4);
 #pragma unroll
-    for (int u = 0; u < U; ++u) consider(v[u], g + u);
+      for (int u = 0; u < U; ++u) {
+        if (v[u].x < worst[0]) insert(0, v[u].x, g + u);
+        if (v[u].y < worst[1]) insert(1, v[u].y, g + u);
+        if (v[u].z < worst[2]) insert(2, v[u].z, g + u);
+        if (v[u].w < worst[3]) insert(3, v[u].w, g + u);
+      }
+    }
+    for (; g < g1; ++g) {
+      const float4 v = __ldcs(p + g * stride4);
+      if (v.x < worst[0]) insert(0, v.x, g);
+      if (v.y < worst[1]) insert(1, v.y, g);
+      if (v.z < worst[2]) insert(2, v.z, g);
+      if (v.w < worst[3]) insert(3, v.w, g);
+    }
+  } else {
+    constexpr int U = 8;
+    const float* p = dist + q0;
+    for (; g + U <= g1; g += U) {
+      float v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) v[u] = __ldcs(p + (g + u) * Q);
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (v[u] < worst[0]) insert(0, v[u], g + u);
+    }
+    for (; g < g1; ++g) {
+      const float v = __ldcs(p + g * Q);
+      if (v < worst[0]) insert(0, v, g);
+    }
   }
-  for (; g < g1; ++g) consider(__ldcs(p + g * Q), g);
-  float* od = out_d + ((int64_t)blockIdx.y * Q + q) * k;
-  int32_t* oi = out_i + ((int64_t)blockIdx.y * Q + q) * k;
-  for (int j = 0; j < k; ++j) {
-    od[j] = ld[j * kTopkThreads + t];
-    oi[j] = li[j * kTopkThreads + t];
+#pragma unroll
+  for (int c = 0; c < VEC; ++c) {
+    if (q0 + c >= Q) break;
+    float* od = out_d + ((int64_t)blockIdx.y * Q + q0 + c) * k;
+    int32_t* oi = out_i + ((int64_t)blockIdx.y * Q + q0 + c) * k;
+    for (int j = 0; j < k; ++j) {
+      od[j] = ld[j * LW + c * kTopkThreads + t];
+      oi[j] = li[j * LW + c * kTopkThreads + t];
+    }
   }
 }
 
@@ -237,10 +276,10 @@ extern "C" int witw_l2_rank_f32(const float* ov, const float* su, int64_t N, int
 }
 
 extern "C" int witw_topk_slices(int64_t G, int64_t Q) {
-  // enough (query block, gallery slice) CTAs for ~8 per SM, slices of at least 128 rows, at most 64 (merge limit)
-  const int64_t bx = ceil_div<int64_t>(std::max<int64_t>(Q, 1), kTopkThreads);
-  int64_t s = ceil_div<int64_t>((int64_t)sm_count() * 8, bx);
-  s = std::min<int64_t>(s, std::max<int64_t>(1, G / 128));
+  // enough (query block, gallery slice) CTAs for ~16 per SM, slices of at least 64 rows, at most 64 (merge limit)
+  const int64_t bx = ceil_div<int64_t>(std::max<int64_t>(Q, 1), kTopkThreads * 4);
+  int64_t s = ceil_div<int64_t>((int64_t)sm_count() * 16, bx);
+  s = std::min<int64_t>(s, std::max<int64_t>(1, G / 64));
   return (int)std::max<int64_t>(1, std::min<int64_t>(s, 64));
 }
 
@@ -250,11 +289,19 @@ extern "C" int witw_topk_from_dist_f32(const float* dist, int64_t G, int64_t Q, 
   WITW_REQUIRE(n_slices >= 1 && n_slices <= 64, WITW_ERR_INVALID, "witw_topk_from_dist_f32: n_slices must be 1..64");
   if (Q == 0) return WITW_OK;
   WITW_REQUIRE(topk_dist && topk_idx && (dist || G == 0), WITW_ERR_INVALID, "witw_topk_from_dist_f32: null pointer");
-  const size_t smem = (size_t)k * kTopkThreads * 8;
-  WITW_CUDA(cudaFuncSetAttribute(topk_columns_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t rows = ceil_div<int64_t>(std::max<int64_t>(G, 1), n_slices);
-  topk_columns_kernel<<<dim3((unsigned)ceil_div<int64_t>(Q, kTopkThreads), (unsigned)n_slices), kTopkThreads, smem, as_stream(stream)>>>(
-      dist, G, Q, k, topk_dist, topk_idx, g_offset, rows);
+  const bool vec = (Q % 4 == 0) && (((uintptr_t)dist & 15) == 0) && k <= 32;
+  if (vec) {
+    const size_t smem = (size_t)k * kTopkThreads * 4 * 8;
+    WITW_CUDA(cudaFuncSetAttribute(topk_columns_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    topk_columns_kernel<4><<<dim3((unsigned)ceil_div<int64_t>(Q, kTopkThreads * 4), (unsigned)n_slices), kTopkThreads, smem, as_stream(stream)>>>(
+        dist, G, Q, k, topk_dist, topk_idx, g_offset, rows);
+  } else {
+    const size_t smem = (size_t)k * kTopkThreads * 8;
+    WITW_CUDA(cudaFuncSetAttribute(topk_columns_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    topk_columns_kernel<1><<<dim3((unsigned)ceil_div<int64_t>(Q, kTopkThreads), (unsigned)n_slices), kTopkThreads, smem, as_stream(stream)>>>(
+        dist, G, Q, k, topk_dist, topk_idx, g_offset, rows);
+  }
   WITW_LAUNCH_CHECK();
   return WITW_OK;
 }

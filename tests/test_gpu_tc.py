@@ -145,3 +145,37 @@ def test_tc_semantic_config_shapes(W):
     inv[perm] = torch.arange(3000)
     ranks = W.evaluate_ranks(ovp.cuda(), su.cuda(), true_idx=inv[:500].cuda(), path="tc")
     assert int((ranks != 1).sum()) == 0
+
+
+def test_gallery_builder_matches_one_shot_prep(W):
+    """Encode-loop plumbing (cvig_fov.py:519-532): batches appended one by one give the same operand, crop norms
+    and ranks as preparing the concatenated gallery at once."""
+    ov, su, _ = O.synth_features(158, 158, fov=90, noise=6.0, seed=21)
+    ovc, suc = ov.cuda(), su.cuda()
+    whole = W.GalleryIndex(ovc, 16)
+    b = W.GalleryBuilder(200, 16)
+    for lo, hi in ((0, 64), (64, 128), (128, 158)):
+        b.append(ovc[lo:hi])
+    built = b.finish()
+    assert built.G == 158
+    assert torch.equal(built.operand[: whole.operand.numel()], whole.operand)
+    assert torch.equal(built.crop_inv_norm[: 160 * 64], whole.crop_inv_norm[: 160 * 64])
+    r1 = W.evaluate_ranks_prepared(whole, W.QueryBatch(suc))
+    r2 = W.evaluate_ranks_prepared(built, W.QueryBatch(suc))
+    assert torch.equal(r1, r2)
+    with pytest.raises(RuntimeError):
+        b.append(ovc[:4])          # the 30-item batch closed the builder
+
+
+def test_heatmap_sweep_one_query_many_tiles(W):
+    """tools/heatmap/heatmap.py:171-177 shape: one photo against a swept grid of tiles, both paths."""
+    ov, su, sh = O.synth_features(1200, 1, fov=70, noise=0.3, seed=3)
+    rdeg, rdis, rscore = O.heatmap_scores(ov, su)
+    for path in ("fp32", "tc"):
+        deg, dis, score = W.heatmap_scores(ov.cuda(), su.cuda(), path=path)
+        assert tuple(deg.shape) == (1200,) and tuple(dis.shape) == (1200,)
+        tol = 5e-6 if path == "fp32" else 2e-3
+        same = deg.cpu() == rdeg
+        assert same.float().mean().item() >= (1.0 if path == "fp32" else 0.98)
+        assert (dis.cpu() - rdis)[same].abs().max().item() <= tol
+        assert int(torch.argmin(dis)) == 0 and float(deg[0]) == float(sh[0]) * 360 / 64 - 180

@@ -7,6 +7,7 @@ hand-written CUDA in libwitw_b200.so (C ABI: include/witw_b200.h).  No CPU fallb
 from . import _lib
 from ._lib import WitwError
 from .ops import (
+    GalleryBuilder,
     GalleryIndex,
     PolarTransform,
     QueryBatch,
@@ -33,7 +34,7 @@ from .install import install, uninstall
 from .sharded import evaluate_ranks_sharded, shard_bounds
 
 __all__ = [
-    "GalleryIndex", "PolarTransform", "QueryBatch", "WitwError", "baseline_ranks", "bilinear_interpolate", "correlation",
+    "GalleryBuilder", "GalleryIndex", "PolarTransform", "QueryBatch", "WitwError", "baseline_ranks", "bilinear_interpolate", "correlation",
     "correlation_scores", "crop_overhead", "evaluate_ranks", "evaluate_ranks_prepared", "evaluate_ranks_sharded",
     "heatmap_scores", "install", "l2_distance", "match", "polar_grid", "polar_transform", "rank_from_distances",
     "recall_from_ranks", "shard_bounds", "sweep_tc", "tc_supported", "topk_from_distances", "true_match_distances",

@@ -197,31 +197,47 @@ topk_columns_kernel(const float* __restrict__ dist, int64_t G, int64_t Q, int k,
   }
 }
 
-__global__ void __launch_bounds__(128)
+constexpr int kMergeThreads = 64;
+
+__global__ void __launch_bounds__(kMergeThreads)
 topk_merge_kernel(const float* __restrict__ cd, const int32_t* __restrict__ ci, int n_lists, int64_t Q, int k,
                   float* __restrict__ out_d, int32_t* __restrict__ out_i) {
-  // thread per query; repeated selection of the smallest head among n_lists sorted lists.
-  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // Thread per query.  The running best-k (ascending, in shared memory [k][threads]) absorbs the sorted candidate
+  // lists one after the other; a list is abandoned at its first entry that cannot enter any more, so the cost is
+  // about n_lists + k*ln(n_lists) candidate reads per query rather than n_lists*k.  Lists are visited in order and
+  // insertion is strict, so among equal distances the earlier list (lower gallery indices) wins.
+  extern __shared__ unsigned char raw[];
+  float* ld = reinterpret_cast<float*>(raw);
+  int32_t* li = reinterpret_cast<int32_t*>(ld + (size_t)k * kMergeThreads);
+  const int t = threadIdx.x;
+  const int64_t q = (int64_t)blockIdx.x * kMergeThreads + t;
   if (q >= Q) return;
-  constexpr int kMaxLists = 64;
-  unsigned char head[kMaxLists];
-  for (int l = 0; l < n_lists; ++l) head[l] = 0;
   const float inf = __int_as_float(0x7f800000);
-  for (int j = 0; j < k; ++j) {
-    float best = inf;
-    int32_t best_i = -1;
-    int best_l = -1;
-    for (int l = 0; l < n_lists; ++l) {
-      if (head[l] >= k) continue;
-      const size_t o = ((size_t)l * Q + q) * k + head[l];
-      const float d = cd[o];
-      const int32_t i = ci[o];
-      if (i < 0) continue;  // exhausted list (padding)
-      if (best_l < 0 || d < best || (d == best && i < best_i)) { best = d; best_i = i; best_l = l; }
+  for (int j = 0; j < k; ++j) { ld[j * kMergeThreads + t] = inf; li[j * kMergeThreads + t] = -1; }
+  float worst = inf;
+  int filled = 0;
+  for (int l = 0; l < n_lists; ++l) {
+    const float* pd = cd + ((size_t)l * Q + q) * k;
+    const int32_t* pi = ci + ((size_t)l * Q + q) * k;
+    for (int e = 0; e < k; ++e) {
+      const float d = pd[e];
+      const int32_t i = pi[e];
+      if (i < 0 || !(d < worst)) break;  // padding, or nothing further in this sorted list can enter
+      int j = filled < k ? filled : k - 1;
+      while (j > 0 && ld[(j - 1) * kMergeThreads + t] > d) {
+        ld[j * kMergeThreads + t] = ld[(j - 1) * kMergeThreads + t];
+        li[j * kMergeThreads + t] = li[(j - 1) * kMergeThreads + t];
+        --j;
+      }
+      ld[j * kMergeThreads + t] = d;
+      li[j * kMergeThreads + t] = i;
+      if (filled < k) ++filled;
+      if (filled == k) worst = ld[(k - 1) * kMergeThreads + t];
     }
-    if (best_l >= 0) ++head[best_l];
-    out_d[q * k + j] = best_l >= 0 ? best : inf;
-    out_i[q * k + j] = best_i;
+  }
+  for (int j = 0; j < k; ++j) {
+    out_d[q * k + j] = ld[j * kMergeThreads + t];
+    out_i[q * k + j] = li[j * kMergeThreads + t];
   }
 }
 
@@ -311,7 +327,10 @@ extern "C" int witw_topk_merge(const float* cand_dist, const int32_t* cand_idx, 
   WITW_REQUIRE(n_lists > 0 && n_lists <= 64 && Q >= 0 && k > 0 && k <= 128, WITW_ERR_INVALID, "witw_topk_merge: bad shape (n_lists 1..64, k 1..128)");
   if (Q == 0) return WITW_OK;
   WITW_REQUIRE(cand_dist && cand_idx && topk_dist && topk_idx, WITW_ERR_INVALID, "witw_topk_merge: null pointer");
-  topk_merge_kernel<<<(unsigned)ceil_div<int64_t>(Q, 128), 128, 0, as_stream(stream)>>>(cand_dist, cand_idx, n_lists, Q, k, topk_dist, topk_idx);
+  const size_t smem = (size_t)k * kMergeThreads * 8;
+  WITW_CUDA(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  topk_merge_kernel<<<(unsigned)ceil_div<int64_t>(Q, kMergeThreads), kMergeThreads, smem, as_stream(stream)>>>(cand_dist, cand_idx, n_lists, Q, k,
+                                                                                                          topk_dist, topk_idx);
   WITW_LAUNCH_CHECK();
   return WITW_OK;
 }

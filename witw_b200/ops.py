@@ -232,6 +232,66 @@ class GalleryIndex(object):
                       self.crop_inv_norm.data_ptr(), _stream())
 
 
+class GalleryBuilder(object):
+    """Incremental GalleryIndex for the encode loop of test() (cvig_fov.py:519-532).
+
+    The reference grows ``overhead_embed`` with torch.cat per batch (O(n^2) copies).  Here each encoder
+    output batch is written once: fp32 features into a preallocated buffer (kept for the exact true-match
+    distances) and, through witw_gallery_prep, straight into its slot of the tensor-core operand.
+    Batches must hold a multiple of 4 items, except the last one.
+    """
+
+    def __init__(self, capacity, surface_width, channels=16, height=4, width=64, device=None, g_offset=0, keep_fp32=True):
+        if not torch.cuda.is_available():
+            raise RuntimeError("GalleryBuilder: no CUDA device; witw_b200 has no CPU fallback")
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.capacity, self.sw = int(capacity), int(surface_width)
+        self.C, self.H, self.W, self.CH = channels, height, width, channels * height
+        self.g_offset, self.count, self.closed = int(g_offset), 0, False
+        lib = _lib.load()
+        with torch.cuda.device(self.device):
+            nbytes = lib.witw_gallery_operand_bytes(self.capacity, self.CH, self.sw)
+            if nbytes == 0 or width != 64:
+                raise _lib.WitwError("GalleryBuilder: " + (_lib.last_error() if width == 64 else "tensor-core path needs W == 64"))
+            self.pair_bytes = lib.witw_gallery_operand_bytes(4, self.CH, self.sw) // 2
+            self.operand = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
+            cap4 = max((self.capacity + 3) // 4 * 4, 4)
+            self.crop_inv_norm = torch.zeros(cap4 * 64, dtype=torch.float32, device=self.device)
+            self.ov = torch.empty((self.capacity, channels, height, width), dtype=torch.float32, device=self.device) if keep_fp32 else None
+
+    def append(self, overhead_embed_part):
+        """Add one encoder output batch [n,C,H,W] (CUDA)."""
+        _need_cuda("GalleryBuilder.append", overhead_embed_part)
+        if self.closed:
+            raise RuntimeError("GalleryBuilder.append: a batch that is not a multiple of 4 items must be the last one")
+        n = overhead_embed_part.shape[0]
+        if tuple(overhead_embed_part.shape[1:]) != (self.C, self.H, self.W):
+            raise ValueError("GalleryBuilder.append: expected [n,%d,%d,%d]" % (self.C, self.H, self.W))
+        if self.count + n > self.capacity:
+            raise ValueError("GalleryBuilder.append: capacity %d exceeded" % self.capacity)
+        if n == 0:
+            return self
+        part = _f32c(overhead_embed_part)
+        with torch.cuda.device(self.device):
+            if self.ov is not None:
+                self.ov[self.count: self.count + n].copy_(part)
+            _lib.call("witw_gallery_prep", part.data_ptr(), n, self.CH, self.W, self.sw,
+                      self.operand.data_ptr() + (self.count // 2) * self.pair_bytes,
+                      self.crop_inv_norm.data_ptr() + self.count * 64 * 4, _stream())
+        self.count += n
+        self.closed = n % 4 != 0
+        return self
+
+    def finish(self):
+        """The GalleryIndex over everything appended so far."""
+        idx = GalleryIndex.__new__(GalleryIndex)
+        idx.device, idx.G, idx.CH, idx.W, idx.sw = self.device, self.count, self.CH, self.W, self.sw
+        idx.C, idx.H, idx.g_offset = self.C, self.H, self.g_offset
+        idx.ov = None if self.ov is None else self.ov[: self.count]
+        idx.operand, idx.crop_inv_norm = self.operand, self.crop_inv_norm
+        return idx
+
+
 class QueryBatch(object):
     """Query feature maps prepared for the tensor-core sweep (bf16 [Q, CH*sw_pad] + inverse norms)."""
 

@@ -201,13 +201,11 @@ def run_ours(args):
 
     class TimedLocal(W.sharded.CudaLocal):
         def sweep(self, ov_local, su_all, d_true, true_idx, g_off, topk):
-            gallery = ops.GalleryIndex(ov_local, 64, g_offset=g_off, keep_fp32=False)
-            queries = ops.QueryBatch(su_all, keep_fp32=False)
-            counts = torch.zeros(Q_TOTAL, dtype=torch.int32, device=device)
+            gallery = ops.GalleryIndex(ov_local, 64, g_offset=g_off)
+            queries = ops.QueryBatch(su_all)
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             sweep_events.append(ev)
-            res = ops.sweep_tc(gallery, queries, d_true=d_true, true_idx=true_idx.to(torch.int32), rank_count=counts, topk=topk, events=ev)
-            return counts.to(torch.int64), res["topk_dist"], res["topk_idx"]
+            return ops.evaluate_ranks_prepared(gallery, queries, true_idx=true_idx - g_off, topk=topk, d_true=d_true, events=ev)
 
     def barrier():
         if world > 1:
@@ -298,18 +296,20 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {
-            "workload": "cvig_fov 360deg eval: 10k queries x 10k-item gallery per GPU, orientation-searched distance + rank count + top-%d "
-                        "(BASELINE configs[1]%s)" % (TOPK, "" if world == 1 else "; gallery sharded, one 10k shard per GPU, NCCL count all-reduce + top-k all-gather"),
+            "workload": "cvig_fov 360deg eval: 10k queries x %d-item gallery per GPU, orientation-searched distance + rank count + top-%d "
+                        "(BASELINE %s%s)" % (G_PER_GPU, TOPK, "configs[1]" if G_PER_GPU == 10000 else "configs[3] when gallery_total = 1M",
+                                             "" if world == 1 else "; gallery sharded, one shard per GPU, NCCL count all-reduce + top-k all-gather"),
             "gallery_total": g_total, "gallery_per_gpu": G_PER_GPU, "queries": Q_TOTAL, "fov": FOV, "feature_shape": [16, 4, 64],
-            "unit_note": "one unit = one query swept over one 10k-item gallery shard; queries/s over the whole %d-item gallery = %.1f" % (g_total, value / world),
+            "unit_note": "one unit = one query swept over one %d-item gallery shard; queries/s over the whole %d-item gallery = %.1f" % (G_PER_GPU, g_total, value / world),
             "l2_policy": "inputs larger than L2 (fp32 features 328 MB + bf16 operands 1.3 GB per step vs 126 MB L2)",
-            "step": "fp32 features in HBM -> operand prep -> fp32 true-match distances -> tcgen05 sweep -> top-k merge",
+            "step": "fp32 features in HBM -> operand prep -> fp32 true-match distances -> tcgen05 sweep -> fp32 re-check of near-threshold rank decisions -> top-k merge -> fp32 re-rank of the top-k",
         },
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                      "kernel": "match_tc_kernel", "kernel_ms": kernel_ms, "flop_per_pair": FLOP_PER_PAIR, "peak_source": peak_src},
         "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / steps,
                 "note": "W.evaluate_ranks() on pinned-host inputs; H2D of step i+1 double-buffered on a copy stream behind step i"},
-        "gpu_launches": 6 * steps,  # gallery_blocks, crop_norm, query_prep, match_pairs, match_tc, topk_merge per step
+        "gpu_launches": 11 * steps,  # gallery_blocks, crop_norm, query_prep, match_pairs (true match), match_tc, match_pairs (re-check),
+                                     # recheck_apply, topk_merge, topk_refine_pairs, match_pairs (top-k), topk_refine_sort per step
         "clocks": clocks,
         "recall": {k: float(v) for k, v in recall.items()},
     }
@@ -323,12 +323,16 @@ def run_ours(args):
 
 
 def main():
+    global G_PER_GPU
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--gallery-per-gpu", type=int, default=G_PER_GPU,
+                    help="gallery items per GPU (default 10000 = BASELINE configs[1]; 125000 on 8 GPUs = configs[3], the 1M-tile gallery)")
     args = ap.parse_args()
+    G_PER_GPU = args.gallery_per_gpu
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)

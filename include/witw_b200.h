@@ -107,6 +107,16 @@ int witw_crop_gather_f32(const float* ov_dev, const int64_t* ori_dev, float* out
 int witw_l2_distance_f32(const float* crop_dev, const float* su_dev, float* dist_dev, int64_t G,
                          int64_t Q, int64_t K, witw_stream_t stream);
 
+/* Backward of a4 / a5 for the reference's train() (cvig_fov.py:450-460; correlation is an argmax and has no
+ * gradient).  crop_backward: grad_ov [G,CH,W] = scatter of grad_out [G,Q,CH,sw] back through the roll
+ * (deterministic, no atomics).  l2_distance_backward: grad_crop [G,Q,K] and/or grad_su [Q,K] (either may be
+ * NULL) from grad_dist [G,Q]; coef_scratch [G,Q,2] fp32 is required when grad_su is requested. */
+int witw_crop_backward_f32(const float* grad_out_dev, const int64_t* ori_dev, float* grad_ov_dev, int64_t G,
+                           int64_t Q, int CH, int W, int sw, witw_stream_t stream);
+int witw_l2_distance_backward_f32(const float* crop_dev, const float* su_dev, const float* grad_dist_dev,
+                                  float* grad_crop_dev, float* grad_su_dev, float* coef_scratch_dev,
+                                  int64_t G, int64_t Q, int64_t K, witw_stream_t stream);
+
 /* Tensor-core path (tcgen05, bf16 operands, fp32 accumulation in TMEM); W must be 64.
  * gallery_prep writes the gallery operand (pre-shifted 16-byte rows that a no-swizzle UMMA
  * descriptor reads as the Hankel matrix of all 64 azimuth shifts) and the table
@@ -134,8 +144,30 @@ int witw_match_tc_topk_slots(int64_t G, int64_t Q);
 int witw_match_tc(const void* gal_op_dev, const float* crop_inv_norm_dev, const void* qry_op_dev,
                   const float* q_inv_norm_dev, int64_t G, int64_t Q, int CH, int sw,
                   float* dist_dev, uint8_t* ori_dev, const float* d_true_dev,
-                  const int32_t* true_idx_dev, int32_t* rank_count_dev, int topk, float* topk_dist_dev, int32_t* topk_idx_dev,
-                  int32_t g_index_offset, witw_stream_t stream);
+                  const int32_t* true_idx_dev, int32_t* rank_count_dev, int topk,
+                  float* topk_dist_dev, int32_t* topk_idx_dev, int32_t g_index_offset,
+                  float recheck_band, int64_t* recheck_g_dev, int64_t* recheck_q_dev,
+                  int32_t* recheck_count_dev, int32_t recheck_capacity, witw_stream_t stream);
+
+/* Exact finish of the tensor-core rank count.  With recheck_capacity > 0 witw_match_tc does not
+ * count pairs whose bf16 distance is within recheck_band of d_true[q]; it appends them (local gallery
+ * index, query) to the lists and bumps recheck_count_dev[0] (recheck_count_dev[1] counts pairs that did
+ * not fit and were decided in bf16; the caller zeroes both).  witw_recheck_apply_f32 recomputes the
+ * listed pairs in exact fp32 and adds d_exact <= d_true[q] to rank_count -- so the ranks are those of
+ * the fp32 reference chain (cvig_fov.py:547-552) unless the list overflowed.  scratch: [capacity] fp32. */
+int witw_recheck_apply_f32(const float* ov_dev, const float* su_dev, const int64_t* recheck_g_dev,
+                           const int64_t* recheck_q_dev, const int32_t* recheck_count_dev,
+                           int32_t capacity, int CH, int W, int sw, const float* d_true_dev,
+                           int32_t* rank_count_dev, float* scratch_dev, witw_stream_t stream);
+
+/* Exact re-ranking of top-k candidates: cand_idx [Q,kc] (global indices, -1 = empty) of a gallery
+ * [G,...] whose first item has global index g_index_offset; distances are recomputed in fp32 and the
+ * k_out best kept, ascending, ties by lower index.  kc <= 32.  scratch: witw_topk_refine_scratch_bytes(). */
+size_t witw_topk_refine_scratch_bytes(int64_t Q, int kc);
+int witw_topk_refine_f32(const float* ov_dev, const float* su_dev, int64_t G, int64_t Q, int CH, int W,
+                         int sw, const int32_t* cand_idx_dev, int kc, int32_t g_index_offset, int k_out,
+                         float* topk_dist_dev, int32_t* topk_idx_dev, void* scratch_dev,
+                         witw_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * K4  rank / top-k               replaces model/cvig_fov.py:550-552 and

@@ -221,3 +221,32 @@ def test_install_on_namespace_runs_rank_loop(W, golden):
         distances = torch.squeeze(cvig.l2_distance(overhead_cropped_all, this_surface_embed))
         ranks[idx] = torch.sum(torch.le(distances, distances[idx])).item()
     assert np.array_equal(ranks, g["r90_ranks"])
+
+
+def test_train_step_gradients_match_reference_autograd(W):
+    """The forward/backward slice of train() (cvig_fov.py:450-460): correlation -> crop_overhead -> l2_distance ->
+    triplet loss -> backward, on the rebound names, against torch autograd through the oracle's functions."""
+    def triplet_loss(distances, alpha=10.0):                     # cvig_fov.py:366-382
+        n = distances.shape[0]
+        m = torch.diagonal(distances)
+        a = torch.sum(torch.log(1.0 + torch.exp(alpha * (m - distances))))
+        b = torch.sum(torch.log(1.0 + torch.exp(alpha * (m.unsqueeze(1) - distances))))
+        return (a + b) / (2.0 * n * (n - 1))
+
+    for fov in (360, 90):
+        ov, su, _ = O.synth_features(12, 12, fov=fov, noise=1.0, seed=fov + 1)
+        ov_r, su_r = ov.clone().requires_grad_(True), su.clone().requires_grad_(True)
+        ori_r = O.correlation(ov_r, su_r)
+        loss_r = triplet_loss(O.l2_distance(O.crop_overhead(ov_r, ori_r, su.shape[3]), su_r))
+        loss_r.backward()
+        ov_g, su_g = ov.cuda().requires_grad_(True), su.cuda().requires_grad_(True)
+        ori = W.correlation(ov_g, su_g, path="fp32")
+        assert torch.equal(ori.cpu(), ori_r)
+        loss = triplet_loss(W.l2_distance(W.crop_overhead(ov_g, ori, su.shape[3]), su_g))
+        loss.backward()
+        assert abs(loss.item() - loss_r.item()) <= 1e-5 * abs(loss_r.item())
+        for got, ref in ((ov_g.grad.cpu(), ov_r.grad), (su_g.grad.cpu(), su_r.grad)):
+            assert got.shape == ref.shape
+            assert (got - ref).abs().max().item() <= 2e-5 * ref.abs().max().item()
+    with pytest.raises(RuntimeError, match="forward-only"):
+        W.evaluate_ranks(ov_g, su_g)

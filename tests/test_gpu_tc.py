@@ -59,7 +59,7 @@ def test_tc_match_vs_oracle(W, fov, G, Q):
 @pytest.mark.parametrize("fov,n,noise", [(360, 300, 25.0), (90, 260, 10.0)])
 def test_tc_evaluate_ranks_vs_oracle(W, fov, n, noise):
     ov, su, _ = O.synth_features(n, n, fov=fov, noise=noise, seed=17)
-    ranks, td, ti = W.evaluate_ranks(ov.cuda(), su.cuda(), path="tc", topk=5)
+    ranks, td, ti = W.evaluate_ranks(ov.cuda(), su.cuda(), path="tc", topk=5, exact=False)
     ranks = ranks.cpu().numpy()
     ref_ori, ref = O.match(ov, su)
     want = (ref <= torch.diagonal(ref).unsqueeze(0)).sum(0).numpy()
@@ -179,3 +179,29 @@ def test_heatmap_sweep_one_query_many_tiles(W):
         assert same.float().mean().item() >= (1.0 if path == "fp32" else 0.98)
         assert (dis.cpu() - rdis)[same].abs().max().item() <= tol
         assert int(torch.argmin(dis)) == 0 and float(deg[0]) == float(sh[0]) * 360 / 64 - 180
+
+
+@pytest.mark.parametrize("fov,n,noise", [(360, 300, 25.0), (90, 260, 10.0), (70, 200, 8.0)])
+def test_tc_exact_finish_matches_fp32_reference(W, fov, n, noise):
+    """exact=True: near-threshold rank decisions are re-taken in fp32 and the top-k re-ranked in fp32, so ranks and top-k
+    are the fp32 reference's (cvig_fov.py:547-552) -- differences only where fp32 distances themselves tie to round-off."""
+    ov, su, _ = O.synth_features(n, n, fov=fov, noise=noise, seed=23)
+    ranks, td, ti = W.evaluate_ranks(ov.cuda(), su.cuda(), path="tc", topk=5)       # exact=True is the default
+    ranks = ranks.cpu().numpy()
+    ref_ori, ref = O.match(ov, su)
+    thr = torch.diagonal(ref).unsqueeze(0)
+    want = (ref <= thr).sum(0).numpy()
+    assert len(set(want.tolist())) > 5
+    tie = ((ref - thr).abs() <= 3e-6).sum(0).numpy() - 1                            # fp32 round-off ties only
+    assert np.all(np.abs(ranks - want) <= tie)
+    assert np.mean(ranks == want) >= 0.98
+    appended, dropped = W.ops.evaluate_ranks_prepared.last_recheck.cpu().tolist()
+    assert dropped == 0 and appended > 0
+    # top-k: the returned distances are the exact fp32 distances of the returned items, ascending; the match is first;
+    # the item set is the reference's wherever the bf16 candidate list (k + margin deep) reaches far enough
+    tdc, tic = td.cpu(), ti.cpu().long()
+    assert (tdc - torch.gather(ref.t(), 1, tic)).abs().max().item() <= 5e-6
+    assert bool((tdc[:, 1:] >= tdc[:, :-1]).all())
+    sd = torch.sort(ref.t(), dim=1, stable=True)
+    assert torch.equal(tic[:, 0], sd.indices[:, 0])
+    assert (tic == sd.indices[:, :5]).float().mean().item() >= (0.99 if fov == 360 else 0.9)

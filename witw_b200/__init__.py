@@ -4,7 +4,7 @@ Polar transform, orientation-searched correlation / crop / distance, rank and to
 evaluation, behind the reference's own function names (see ops.py), implemented as
 hand-written CUDA in libwitw_b200.so (C ABI: include/witw_b200.h).  No CPU fallback.
 """
-from . import _lib
+from . import _lib, ops
 from ._lib import WitwError
 from .ops import (
     GalleryBuilder,

@@ -28,13 +28,21 @@ SIGNATURES = {
     "witw_match_pairs_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "witw_crop_gather_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p]),
     "witw_l2_distance_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
+    "witw_crop_backward_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p]),
+    "witw_l2_distance_backward_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
     "witw_gallery_operand_bytes": (c_size_t, [c_int64, c_int, c_int]),
     "witw_query_operand_bytes": (c_size_t, [c_int64, c_int, c_int]),
     "witw_gallery_prep": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "witw_query_prep": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "witw_match_tc_topk_slots": (c_int, [c_int64, c_int64]),
     "witw_match_tc": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p,
-                              c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int32, c_void_p]),
+                              c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int32, c_float, c_void_p, c_void_p,
+                              c_void_p, c_int32, c_void_p]),
+    "witw_recheck_apply_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int, c_int, c_int, c_void_p,
+                                       c_void_p, c_void_p, c_void_p]),
+    "witw_topk_refine_scratch_bytes": (c_size_t, [c_int64, c_int]),
+    "witw_topk_refine_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p, c_int, c_int32, c_int,
+                                     c_void_p, c_void_p, c_void_p, c_void_p]),
     "witw_rank_from_dist_f32": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
     "witw_l2_rank_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "witw_topk_slices": (c_int, [c_int64, c_int64]),

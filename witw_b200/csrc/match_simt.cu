@@ -212,6 +212,98 @@ match_pairs_kernel(const float* __restrict__ ov, const float* __restrict__ su, c
   }
 }
 
+// Register-tiled variant for the reference geometry (W == 64, sw % 4 == 0, CH % 8 == 0): thread (slice, s4) owns the
+// four shifts 4*s4..4*s4+3 over one eighth of the feature rows; per 4 query columns it reads 12 gallery values
+// (two aligned 16-byte shared loads from the wrap-padded row) and 4 query values (one broadcast 16-byte load) for
+// 16 FMAs.  ~9x the throughput of match_pairs_kernel, which stays as the generic-shape path.
+__global__ void __launch_bounds__(128)
+match_pairs_w64_kernel(const float* __restrict__ ov, const float* __restrict__ su, const int64_t* __restrict__ pair_g,
+                       const int64_t* __restrict__ pair_q, int64_t n_pairs, const int32_t* __restrict__ n_pairs_dev, int group,
+                       int CH, int sw, float* __restrict__ dist, int64_t* __restrict__ ori) {
+  // one CTA per `group` consecutive pairs that share their query (group == 1: no such promise needed): the query is
+  // staged once, the gallery items stream through
+  extern __shared__ __align__(16) float smem[];
+  constexpr int W = 64, WP = 128;
+  float* o = smem;                 // CH * 128 : row followed by its own copy (circular wrap)
+  float* s = o + CH * WP;          // CH * sw
+  float* part = s + CH * sw;       // 8 * 64 partial correlations
+  float* col_part = part + 8 * W;  // 2 * 64 partial column energies
+  __shared__ float q_e_sh;
+  const int64_t p0 = (int64_t)blockIdx.x * group;
+  if (n_pairs_dev != nullptr && p0 >= (int64_t)*n_pairs_dev) return;
+  if (p0 >= n_pairs) return;
+  const int tid = threadIdx.x;
+  const int64_t q = pair_q[p0];
+  const float4* qsrc = reinterpret_cast<const float4*>(su + q * CH * sw);
+  for (int i = tid; i < CH * sw / 4; i += 128) reinterpret_cast<float4*>(s)[i] = qsrc[i];
+  const int s4 = tid & 15, slice = tid >> 4;
+  const int rows = CH >> 3;
+  for (int c = 0; c < group && p0 + c < n_pairs; ++c) {
+    const int64_t g = pair_g[p0 + c];
+    __syncthreads();  // previous item fully consumed (and, first time round, nothing yet)
+    const float4* gsrc = reinterpret_cast<const float4*>(ov + g * CH * W);
+    for (int i = tid; i < CH * 16; i += 128) {  // 16 float4 per row, written twice
+      const float4 v = gsrc[i];
+      const int ch = i >> 4, c4 = i & 15;
+      reinterpret_cast<float4*>(o + ch * WP)[c4] = v;
+      reinterpret_cast<float4*>(o + ch * WP + W)[c4] = v;
+    }
+    __syncthreads();
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int r = 0; r < rows; ++r) {
+      const int ch = slice * rows + r;
+      const float* orow = o + ch * WP + 4 * s4;
+      const float* srow = s + ch * sw;
+      for (int k = 0; k < sw; k += 4) {
+        const float4 a = *reinterpret_cast<const float4*>(orow + k);
+        const float4 b = *reinterpret_cast<const float4*>(orow + k + 4);
+        const float4 cq = *reinterpret_cast<const float4*>(srow + k);
+        const float w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        const float x[4] = {cq.x, cq.y, cq.z, cq.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int d = 0; d < 4; ++d) acc[d] = fmaf(w[d + j], x[j], acc[d]);
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < 4; ++d) part[slice * W + 4 * s4 + d] = acc[d];
+    {  // column energies (two halves of the rows)
+      const int j = tid & 63, half = tid >> 6;
+      float e = 0.f;
+      for (int ch = half * (CH >> 1); ch < (half + 1) * (CH >> 1); ++ch) e = fmaf(o[ch * WP + j], o[ch * WP + j], e);
+      col_part[half * W + j] = e;
+    }
+    if (c == 0 && tid >= 96) {  // query energy, once
+      float e = 0.f;
+      for (int i = tid - 96; i < CH * sw; i += 32) e = fmaf(s[i], s[i], e);
+      for (int m = 16; m > 0; m >>= 1) e += __shfl_xor_sync(0xffffffffu, e, m);
+      if (tid == 96) q_e_sh = e;
+    }
+    __syncthreads();
+    if (tid < 32) {  // warp 0: finish the 8-way sums, then a warp argmax with first-maximum tie-break
+      float c0 = 0.f, c1 = 0.f;
+#pragma unroll
+      for (int sl = 0; sl < 8; ++sl) { c0 += part[sl * W + tid]; c1 += part[sl * W + tid + 32]; }
+      float best = c0;
+      int arg = tid;
+      if (c1 > best || (c1 != c1 && best == best)) { best = c1; arg = tid + 32; }
+      for (int m = 16; m > 0; m >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, m);
+        const int oa = __shfl_xor_sync(0xffffffffu, arg, m);
+        const bool take = (ob > best) || (ob != ob && best == best) || (ob == best && oa < arg) || (ob != ob && best != best && oa < arg);
+        if (take) { best = ob; arg = oa; }
+      }
+      if (tid == 0) {
+        float cn2 = 0.f;
+        for (int k = 0; k < sw; ++k) { const int j = (arg + k) & 63; cn2 += col_part[j] + col_part[W + j]; }
+        if (dist != nullptr) dist[p0 + c] = 2.0f * (1.0f - best / (sqrtf(cn2) * sqrtf(q_e_sh)));
+        if (ori != nullptr) ori[p0 + c] = arg;
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256)
 crop_gather_kernel(const float* __restrict__ ov, const int64_t* __restrict__ ori, float* __restrict__ out, int64_t G,
                    int64_t Q, int CH, int W, int sw) {
@@ -287,16 +379,124 @@ extern "C" int witw_match_f32(const float* ov, const float* su, int64_t G, int64
   return WITW_OK;
 }
 
+static int launch_pairs(const float* ov, const float* su, const int64_t* pair_g, const int64_t* pair_q, int64_t n_pairs,
+                        const int32_t* n_pairs_dev, int CH, int W, int sw, float* dist, int64_t* ori, witw_stream_t stream,
+                        int group = 1) {
+  const bool fast = W == 64 && sw % 4 == 0 && CH % 8 == 0 && (((uintptr_t)ov | (uintptr_t)su) & 15) == 0;
+  if (fast) {
+    const size_t smem = sizeof(float) * ((size_t)CH * 128 + (size_t)CH * sw + 8 * 64 + 2 * 64);
+    if (smem <= 200 * 1024) {
+      WITW_CUDA(cudaFuncSetAttribute(match_pairs_w64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      match_pairs_w64_kernel<<<(unsigned)ceil_div<int64_t>(n_pairs, group), 128, smem, as_stream(stream)>>>(ov, su, pair_g, pair_q, n_pairs, n_pairs_dev,
+                                                                                                      group, CH, sw, dist, ori);
+      WITW_LAUNCH_CHECK();
+      return WITW_OK;
+    }
+  }
+  WITW_REQUIRE(n_pairs_dev == nullptr, WITW_ERR_UNSUPPORTED, "device-side pair count needs the W == 64 kernel");
+  const size_t smem = sizeof(float) * ((size_t)CH * W + (size_t)CH * sw + 2 * (size_t)W);
+  WITW_REQUIRE(smem <= 200 * 1024, WITW_ERR_UNSUPPORTED, "witw_match_pairs_f32: feature map of %d rows does not fit shared memory", CH);
+  WITW_CUDA(cudaFuncSetAttribute(match_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  match_pairs_kernel<<<(unsigned)n_pairs, 128, smem, as_stream(stream)>>>(ov, su, pair_g, pair_q, CH, W, sw, dist, ori);
+  WITW_LAUNCH_CHECK();
+  return WITW_OK;
+}
+
 extern "C" int witw_match_pairs_f32(const float* ov, const float* su, const int64_t* pair_g, const int64_t* pair_q,
                                     int64_t n_pairs, int CH, int W, int sw, float* dist, int64_t* ori, witw_stream_t stream) {
   int rc = check_match_shape("witw_match_pairs_f32", 1, 1, CH, W, sw);
   if (rc != WITW_OK) return rc;
   if (n_pairs == 0) return WITW_OK;
   WITW_REQUIRE(ov && su && pair_g && pair_q && n_pairs > 0 && n_pairs < (1ll << 31), WITW_ERR_INVALID, "witw_match_pairs_f32: bad arguments");
-  const size_t smem = sizeof(float) * ((size_t)CH * W + (size_t)CH * sw + 2 * (size_t)W);
-  WITW_REQUIRE(smem <= 200 * 1024, WITW_ERR_UNSUPPORTED, "witw_match_pairs_f32: feature map of %d rows does not fit shared memory", CH);
-  WITW_CUDA(cudaFuncSetAttribute(match_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  match_pairs_kernel<<<(unsigned)n_pairs, 128, smem, as_stream(stream)>>>(ov, su, pair_g, pair_q, CH, W, sw, dist, ori);
+  return launch_pairs(ov, su, pair_g, pair_q, n_pairs, nullptr, CH, W, sw, dist, ori, stream);
+}
+
+namespace witw {
+__global__ void __launch_bounds__(256)
+recheck_apply_kernel(const float* __restrict__ exact, const int64_t* __restrict__ list_q, const int32_t* __restrict__ count, int cap,
+                     const float* __restrict__ d_true, int32_t* __restrict__ rank_count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = min(*count, cap);
+  if (i >= n) return;
+  const int64_t q = list_q[i];
+  if (exact[i] <= d_true[q]) atomicAdd(rank_count + q, 1);
+}
+
+__global__ void __launch_bounds__(128)
+topk_refine_sort_kernel(const float* __restrict__ exact, const int32_t* __restrict__ cand_idx, int64_t Q, int kc, int k_out,
+                        float* __restrict__ out_d, int32_t* __restrict__ out_i) {
+  // thread per query: selection sort of its kc exact distances (ties by lower gallery index), first k_out kept
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= Q) return;
+  const float inf = __int_as_float(0x7f800000);
+  unsigned used = 0;  // kc <= 32
+  for (int j = 0; j < k_out; ++j) {
+    float best = inf;
+    int32_t best_i = -1;
+    int best_p = -1;
+    for (int p = 0; p < kc; ++p) {
+      if (used & (1u << p)) continue;
+      const int32_t i = cand_idx[q * kc + p];
+      if (i < 0) continue;
+      const float d = exact[q * kc + p];
+      if (!(d == d)) continue;
+      if (best_p < 0 || d < best || (d == best && i < best_i)) { best = d; best_i = i; best_p = p; }
+    }
+    if (best_p >= 0) used |= 1u << best_p;
+    out_d[q * k_out + j] = best_p >= 0 ? best : inf;
+    out_i[q * k_out + j] = best_i;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+topk_refine_pairs_kernel(const int32_t* __restrict__ cand_idx, int64_t n, int kc, int32_t g_offset, int64_t G, int64_t* __restrict__ pg,
+                         int64_t* __restrict__ pq) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int64_t g = (int64_t)cand_idx[i] - g_offset;
+  if (g < 0 || g >= G) g = 0;  // padding slot: any valid pair, its result is ignored (index stays -1)
+  pg[i] = g;
+  pq[i] = i / kc;
+}
+}  // namespace witw
+
+extern "C" int witw_recheck_apply_f32(const float* ov, const float* su, const int64_t* recheck_g, const int64_t* recheck_q,
+                                      const int32_t* recheck_count, int32_t capacity, int CH, int W, int sw, const float* d_true,
+                                      int32_t* rank_count, float* scratch, witw_stream_t stream) {
+  int rc = check_match_shape("witw_recheck_apply_f32", 1, 1, CH, W, sw);
+  if (rc != WITW_OK) return rc;
+  if (capacity == 0) return WITW_OK;
+  WITW_REQUIRE(capacity > 0 && ov && su && recheck_g && recheck_q && recheck_count && d_true && rank_count && scratch, WITW_ERR_INVALID,
+               "witw_recheck_apply_f32: bad arguments");
+  // one CTA per list slot; CTAs past the device-side count exit at once, so no host round trip is needed
+  rc = launch_pairs(ov, su, recheck_g, recheck_q, capacity, recheck_count, CH, W, sw, scratch, nullptr, stream);
+  if (rc != WITW_OK) return rc;
+  recheck_apply_kernel<<<(unsigned)ceil_div<int64_t>(capacity, 256), 256, 0, as_stream(stream)>>>(scratch, recheck_q, recheck_count, capacity, d_true,
+                                                                                           rank_count);
+  WITW_LAUNCH_CHECK();
+  return WITW_OK;
+}
+
+extern "C" size_t witw_topk_refine_scratch_bytes(int64_t Q, int kc) { return (size_t)std::max<int64_t>(Q, 1) * kc * (8 + 8 + 4); }
+
+extern "C" int witw_topk_refine_f32(const float* ov, const float* su, int64_t G, int64_t Q, int CH, int W, int sw, const int32_t* cand_idx,
+                                    int kc, int32_t g_offset, int k_out, float* out_dist, int32_t* out_idx, void* scratch,
+                                    witw_stream_t stream) {
+  int rc = check_match_shape("witw_topk_refine_f32", G, Q, CH, W, sw);
+  if (rc != WITW_OK) return rc;
+  WITW_REQUIRE(kc >= 1 && kc <= 32 && k_out >= 1 && k_out <= kc, WITW_ERR_INVALID, "witw_topk_refine_f32: need 1 <= k_out <= kc <= 32");
+  if (Q == 0) return WITW_OK;
+  WITW_REQUIRE(G > 0 && ov && su && cand_idx && out_dist && out_idx && scratch, WITW_ERR_INVALID, "witw_topk_refine_f32: bad arguments");
+  const int64_t n = Q * kc;
+  WITW_REQUIRE(n < (1ll << 31), WITW_ERR_UNSUPPORTED, "witw_topk_refine_f32: too many candidates");
+  int64_t* pg = reinterpret_cast<int64_t*>(scratch);
+  int64_t* pq = pg + n;
+  float* exact = reinterpret_cast<float*>(pq + n);
+  topk_refine_pairs_kernel<<<(unsigned)ceil_div<int64_t>(n, 256), 256, 0, as_stream(stream)>>>(cand_idx, n, kc, g_offset, G, pg, pq);
+  WITW_LAUNCH_CHECK();
+  rc = launch_pairs(ov, su, pg, pq, n, nullptr, CH, W, sw, exact, nullptr, stream, kc);  // the kc candidates of a query share one CTA
+  if (rc != WITW_OK) return rc;
+  topk_refine_sort_kernel<<<(unsigned)ceil_div<int64_t>(Q, 128), 128, 0, as_stream(stream)>>>(exact, cand_idx, Q, kc, k_out, out_dist, out_idx);
   WITW_LAUNCH_CHECK();
   return WITW_OK;
 }

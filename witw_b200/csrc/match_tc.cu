@@ -279,6 +279,13 @@ struct TcParams {
   int pair_rows;                 // CH * bpc: 128-byte blocks per item pair
   int stage_rows;                // cpb * bpc: blocks per K block per CTA
   int n_stages;                  // depth of the operand ring (<= kTcMaxStages)
+  // fp32 re-check of rank decisions the bf16 sweep cannot be trusted with: pairs whose distance is within
+  // `band` of the threshold are not counted here but appended to (recheck_g, recheck_q) for witw_recheck_apply_f32
+  float band;
+  int64_t* recheck_g;            // [recheck_cap] local gallery index
+  int64_t* recheck_q;            // [recheck_cap]
+  int32_t* recheck_count;        // [2]: pairs appended (may exceed the capacity), pairs dropped for lack of room
+  int32_t recheck_cap;
 };
 
 template <int CG>
@@ -474,7 +481,20 @@ match_tc_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant
             const float d = 2.0f * (1.0f - best[i] * cin * qin);
             if (P.dist) P.dist[g * P.Q + q] = d;
             if (P.ori) P.ori[g * P.Q + q] = (uint8_t)arg[i];
-            cnt += ((int32_t)g == self_g ? (dtrue == dtrue) : (d <= dtrue)) ? 1 : 0;
+            if ((int32_t)g == self_g) {
+              cnt += (dtrue == dtrue) ? 1 : 0;
+            } else if (P.recheck_cap > 0 && fabsf(d - dtrue) <= P.band) {
+              const int32_t pos = atomicAdd(P.recheck_count, 1);
+              if (pos < P.recheck_cap) {
+                P.recheck_g[pos] = g;
+                P.recheck_q[pos] = q;
+              } else {  // list full: fall back to the bf16 decision and say so
+                atomicAdd(P.recheck_count + 1, 1);
+                cnt += (d <= dtrue) ? 1 : 0;
+              }
+            } else {
+              cnt += (d <= dtrue) ? 1 : 0;
+            }
             if (P.topk > 0 && d < td[kTopkMax - 1]) {
               // insertion into the ascending register list (strict '<': earlier index wins ties)
               float cd = d;
@@ -589,7 +609,9 @@ extern "C" int witw_match_tc_topk_slots(int64_t G, int64_t Q) { return make_sche
 
 extern "C" int witw_match_tc(const void* gal_op, const float* crop_inv_norm, const void* qry_op, const float* q_inv_norm, int64_t G,
                              int64_t Q, int CH, int sw, float* dist, uint8_t* ori, const float* d_true, const int32_t* true_idx,
-                             int32_t* rank_count, int topk, float* topk_dist, int32_t* topk_idx, int32_t g_offset, witw_stream_t stream) {
+                             int32_t* rank_count, int topk, float* topk_dist, int32_t* topk_idx, int32_t g_offset, float recheck_band,
+                             int64_t* recheck_g, int64_t* recheck_q, int32_t* recheck_count, int32_t recheck_capacity,
+                             witw_stream_t stream) {
   TcGeom geo;
   WITW_REQUIRE(G >= 0 && Q >= 0 && make_geom(CH, sw, &geo), WITW_ERR_UNSUPPORTED, "witw_match_tc: unsupported CH=%d sw=%d", CH, sw);
   if (G == 0 || Q == 0) return WITW_OK;
@@ -597,6 +619,8 @@ extern "C" int witw_match_tc(const void* gal_op, const float* crop_inv_norm, con
   WITW_REQUIRE(topk >= 0 && topk <= kTopkMax, WITW_ERR_UNSUPPORTED, "witw_match_tc: fused top-k supports k <= %d (got %d)", kTopkMax, topk);
   WITW_REQUIRE(topk == 0 || (topk_dist && topk_idx), WITW_ERR_INVALID, "witw_match_tc: top-k buffers missing");
   WITW_REQUIRE(!rank_count || d_true, WITW_ERR_INVALID, "witw_match_tc: rank_count needs d_true");
+  WITW_REQUIRE(recheck_capacity >= 0 && (recheck_capacity == 0 || (rank_count && recheck_g && recheck_q && recheck_count && recheck_band >= 0.f)),
+               WITW_ERR_INVALID, "witw_match_tc: re-check list needs rank_count, both index buffers, the counter and a band >= 0");
   WITW_REQUIRE(G < (1ll << 31) && Q < (1ll << 31), WITW_ERR_INVALID, "witw_match_tc: sizes exceed 2^31");
   WITW_REQUIRE(((uintptr_t)qry_op & 15) == 0 && ((uintptr_t)gal_op & 15) == 0, WITW_ERR_INVALID, "witw_match_tc: operands must be 16-byte aligned");
   int rc = witw_device_check();
@@ -641,6 +665,7 @@ extern "C" int witw_match_tc(const void* gal_op, const float* crop_inv_norm, con
   P.n_qtiles = sch.n_qtiles; P.n_chunks = sch.n_chunks; P.groups_per_chunk = sch.groups_per_chunk; P.n_groups = sch.n_groups;
   P.kblocks = geo.kblocks; P.cpb = geo.cpb; P.bpc = geo.bpc; P.nkap = geo.nkap;
   P.sbo = geo.sbo; P.lbo = geo.lbo; P.kstep = geo.kstep; P.b_bytes = geo.b_bytes;
+  P.band = recheck_band; P.recheck_g = recheck_g; P.recheck_q = recheck_q; P.recheck_count = recheck_count; P.recheck_cap = recheck_capacity;
   P.pair_rows = CH * geo.bpc;
   P.stage_rows = geo.cpb * geo.bpc;
 

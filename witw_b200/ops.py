@@ -17,10 +17,11 @@ plus the fused forms the reference spells as a Python loop:
     baseline_ranks         cvig_baseline.py:453-460
     heatmap_scores         tools/heatmap/heatmap.py:171-177
 
-Everything runs on the CUDA device of its inputs; there is no CPU fallback.  These are
-forward-only kernels: tensors that require grad under an enabled grad mode are refused
-rather than silently detached (train() in the reference back-propagates through
-crop_overhead / l2_distance).
+Everything runs on the CUDA device of its inputs; there is no CPU fallback.  crop_overhead and
+l2_distance are differentiable (train() in the reference back-propagates through them,
+cvig_fov.py:450-460); correlation is an argmax and carries no gradient, as in the reference;
+the fused forms (match, evaluate_ranks, ...) are forward-only and refuse tensors that require
+grad under an enabled grad mode rather than silently detaching them.
 """
 import math
 
@@ -47,7 +48,7 @@ def _ptr(t):
     return 0 if t is None else t.data_ptr()
 
 
-def _need_cuda(name, *tensors):
+def _need_cuda(name, *tensors, allow_grad=False):
     for t in tensors:
         if not isinstance(t, torch.Tensor):
             raise TypeError("%s: expected torch tensors, got %r" % (name, type(t)))
@@ -55,7 +56,7 @@ def _need_cuda(name, *tensors):
             raise RuntimeError(
                 "%s: tensor is on %s; witw_b200 runs on a CUDA (sm_100a) device only and has no CPU fallback" % (name, t.device)
             )
-        if t.requires_grad and torch.is_grad_enabled():
+        if t.requires_grad and torch.is_grad_enabled() and not allow_grad:
             raise RuntimeError(
                 "%s: forward-only kernel got a tensor that requires grad; wrap the call in torch.no_grad() "
                 "(training through crop_overhead/l2_distance is not covered by witw_b200)" % name
@@ -328,10 +329,13 @@ def _pick_path(path, g, q, ch, w, sw):
     return path
 
 
-def sweep_tc(gallery, queries, want_dist=False, want_ori=False, d_true=None, true_idx=None, rank_count=None, topk=0, events=None):
+def sweep_tc(gallery, queries, want_dist=False, want_ori=False, d_true=None, true_idx=None, rank_count=None, topk=0, events=None,
+             recheck=None):
     """One tensor-core sweep of a QueryBatch over a GalleryIndex.  Returns a dict with the requested outputs.
 
-    events: optional (start, end) torch.cuda.Event pair recorded around the sweep kernel alone (bench.py's roofline timer)."""
+    events: optional (start, end) torch.cuda.Event pair recorded around the sweep kernel alone (bench.py's roofline timer).
+    recheck: optional RecheckList; rank decisions within its band of the threshold are deferred to it (see exact=True
+    of evaluate_ranks_prepared)."""
     if gallery.CH != queries.CH or gallery.sw != queries.sw or gallery.device != queries.device:
         raise ValueError("sweep_tc: gallery and queries disagree (CH %d/%d, sw %d/%d)" % (gallery.CH, queries.CH, gallery.sw, queries.sw))
     dev, g, q = gallery.device, gallery.G, queries.Q
@@ -350,7 +354,9 @@ def sweep_tc(gallery, queries, want_dist=False, want_ori=False, d_true=None, tru
                 events[0].record()
             _lib.call("witw_match_tc", gallery.operand.data_ptr(), gallery.crop_inv_norm.data_ptr(), queries.operand.data_ptr(),
                       queries.inv_norm.data_ptr(), g, q, gallery.CH, gallery.sw, _ptr(dist), _ptr(ori), _ptr(d_true),
-                      _ptr(true_idx), _ptr(rank_count), int(topk), _ptr(tk_d), _ptr(tk_i), gallery.g_offset, _stream())
+                      _ptr(true_idx), _ptr(rank_count), int(topk), _ptr(tk_d), _ptr(tk_i), gallery.g_offset,
+                      float(recheck.band) if recheck else 0.0, _ptr(recheck.g) if recheck else 0, _ptr(recheck.q) if recheck else 0,
+                      _ptr(recheck.count) if recheck else 0, int(recheck.capacity) if recheck else 0, _stream())
             if events is not None:
                 events[1].record()
         if topk:
@@ -395,41 +401,108 @@ def correlation_scores(overhead_embed, surface_embed):
 
 
 def correlation(overhead_embed, surface_embed, path="auto"):
-    """Drop-in for cvig_fov.py:297-315: orientation int64 [batch_overhead, batch_surface]."""
-    return match(overhead_embed, surface_embed, path=path)[0]
+    """Drop-in for cvig_fov.py:297-315: orientation int64 [batch_overhead, batch_surface].
+
+    An argmax: no gradient flows through it in the reference either, so tensors that require grad are accepted
+    (train() calls it on live encoder outputs, cvig_fov.py:450)."""
+    return match(overhead_embed.detach(), surface_embed.detach(), path=path)[0]
 
 
-def crop_overhead(overhead_embed, orientation, surface_width):
-    """Drop-in for cvig_fov.py:318-343: [G,Q,C,H,surface_width], rolled by the orientation and cropped.
-
-    The device is taken from the inputs (the reference reads a module-level ``device`` global).
-    """
-    dev = _need_cuda("crop_overhead", overhead_embed, orientation)
+def _crop_forward(overhead_embed, orientation, sw):
+    dev = overhead_embed.device
     g, c, h, w = overhead_embed.shape
-    if orientation.dim() != 2 or orientation.shape[0] != g:
-        raise ValueError("crop_overhead: orientation must be [G,Q]")
     q = orientation.shape[1]
-    sw = int(surface_width)
     ov = _f32c(overhead_embed)
     ori = orientation.detach().to(torch.int64).contiguous()
     with torch.cuda.device(dev):
         out = torch.empty((g, q, c, h, sw), dtype=torch.float32, device=dev)
         _lib.call("witw_crop_gather_f32", ov.data_ptr(), ori.data_ptr(), out.data_ptr(), g, q, c * h, w, sw, _stream())
-    return out
+    return out, ori
+
+
+class _CropOverheadFn(torch.autograd.Function):
+    """crop_overhead with the gradient train() needs (cvig_fov.py:451 feeds the loss through the crop)."""
+
+    @staticmethod
+    def forward(ctx, overhead_embed, orientation, sw):
+        out, ori = _crop_forward(overhead_embed, orientation, sw)
+        ctx.save_for_backward(ori)
+        ctx.shape, ctx.sw = tuple(overhead_embed.shape), sw
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (ori,) = ctx.saved_tensors
+        g, c, h, w = ctx.shape
+        go = _f32c(grad_out)
+        with torch.cuda.device(go.device):
+            grad_ov = torch.empty(ctx.shape, dtype=torch.float32, device=go.device)
+            _lib.call("witw_crop_backward_f32", go.data_ptr(), ori.data_ptr(), grad_ov.data_ptr(), g, ori.shape[1], c * h, w, ctx.sw, _stream())
+        return grad_ov, None, None
+
+
+def crop_overhead(overhead_embed, orientation, surface_width):
+    """Drop-in for cvig_fov.py:318-343: [G,Q,C,H,surface_width], rolled by the orientation and cropped.
+
+    The device is taken from the inputs (the reference reads a module-level ``device`` global).  Differentiable
+    with respect to ``overhead_embed`` (a scatter back through the roll), as train() requires.
+    """
+    _need_cuda("crop_overhead", overhead_embed, orientation, allow_grad=True)
+    g = overhead_embed.shape[0]
+    if overhead_embed.dim() != 4 or orientation.dim() != 2 or orientation.shape[0] != g:
+        raise ValueError("crop_overhead: expected [G,C,H,W] features and a [G,Q] orientation")
+    sw = int(surface_width)
+    if overhead_embed.requires_grad and torch.is_grad_enabled():
+        return _CropOverheadFn.apply(overhead_embed, orientation, sw)
+    return _crop_forward(overhead_embed, orientation, sw)[0]
+
+
+def _l2_forward(crop, su, g, q, k):
+    with torch.cuda.device(crop.device):
+        dist = torch.empty((g, q), dtype=torch.float32, device=crop.device)
+        _lib.call("witw_l2_distance_f32", crop.data_ptr(), su.data_ptr(), dist.data_ptr(), g, q, k, _stream())
+    return dist
+
+
+class _L2DistanceFn(torch.autograd.Function):
+    """l2_distance with gradients for both arguments (cvig_fov.py:453-460: the triplet loss back-propagates
+    into the overhead encoder through the crop and into the surface encoder directly)."""
+
+    @staticmethod
+    def forward(ctx, overhead_cropped, surface_embed):
+        g, q = overhead_cropped.shape[:2]
+        k = int(np.prod(overhead_cropped.shape[2:]))
+        crop, su = _f32c(overhead_cropped), _f32c(surface_embed)
+        ctx.save_for_backward(crop, su)
+        ctx.shapes = (tuple(overhead_cropped.shape), tuple(surface_embed.shape), g, q, k)
+        return _l2_forward(crop, su, g, q, k)
+
+    @staticmethod
+    def backward(ctx, grad_dist):
+        crop, su = ctx.saved_tensors
+        crop_shape, su_shape, g, q, k = ctx.shapes
+        gd = _f32c(grad_dist)
+        need_crop, need_su = ctx.needs_input_grad
+        with torch.cuda.device(gd.device):
+            grad_crop = torch.empty(crop_shape, dtype=torch.float32, device=gd.device) if need_crop else None
+            grad_su = torch.empty(su_shape, dtype=torch.float32, device=gd.device) if need_su else None
+            coef = torch.empty((g, q, 2), dtype=torch.float32, device=gd.device) if need_su else None
+            _lib.call("witw_l2_distance_backward_f32", crop.data_ptr(), su.data_ptr(), gd.data_ptr(), _ptr(grad_crop), _ptr(grad_su),
+                      _ptr(coef), g, q, k, _stream())
+        return grad_crop, grad_su
 
 
 def l2_distance(overhead_cropped, surface_embed):
-    """Drop-in for cvig_fov.py:346-363: chord distance fp32 [G,Q] of the L2-normalised maps (no epsilon)."""
-    dev = _need_cuda("l2_distance", overhead_cropped, surface_embed)
+    """Drop-in for cvig_fov.py:346-363: chord distance fp32 [G,Q] of the L2-normalised maps (no epsilon).
+    Differentiable in both arguments."""
+    _need_cuda("l2_distance", overhead_cropped, surface_embed, allow_grad=True)
     g, q = overhead_cropped.shape[:2]
     k = int(np.prod(overhead_cropped.shape[2:]))
     if surface_embed.shape[0] != q or int(np.prod(surface_embed.shape[1:])) != k:
         raise RuntimeError("l2_distance: shapes %s and %s do not broadcast" % (tuple(overhead_cropped.shape), tuple(surface_embed.shape)))
-    crop, su = _f32c(overhead_cropped), _f32c(surface_embed)
-    with torch.cuda.device(dev):
-        dist = torch.empty((g, q), dtype=torch.float32, device=dev)
-        _lib.call("witw_l2_distance_f32", crop.data_ptr(), su.data_ptr(), dist.data_ptr(), g, q, k, _stream())
-    return dist
+    if torch.is_grad_enabled() and (overhead_cropped.requires_grad or surface_embed.requires_grad):
+        return _L2DistanceFn.apply(overhead_cropped, surface_embed)
+    return _l2_forward(_f32c(overhead_cropped), _f32c(surface_embed), g, q, k)
 
 
 # ----------------------------------------------------------------------------- K4
@@ -481,13 +554,14 @@ def topk_from_distances(distances, k, g_offset=0):
     return td, ti
 
 
-def evaluate_ranks(overhead_embed, surface_embed, true_idx=None, path="auto", topk=0):
+def evaluate_ranks(overhead_embed, surface_embed, true_idx=None, path="auto", topk=0, exact=True):
     """The rank loop of test() (cvig_fov.py:543-552) as one call: ranks int64 [count] on the device.
 
     Query i matches gallery item i (or true_idx[i]).  The true-match distances are computed in
     exact fp32; on the tensor-core path the gallery sweep counts d[g,q] <= d_true[q] in the GEMM
-    epilogue without materialising the [G,Q] matrix.  With topk > 0 also returns
-    (topk_dist [Q,k], topk_idx [Q,k]).
+    epilogue without materialising the [G,Q] matrix; with exact=True (default) decisions within bf16 error of the
+    threshold are re-taken in fp32 and the top-k is re-ranked in fp32, so the results are the fp32 reference's.
+    With topk > 0 also returns (topk_dist [Q,k], topk_idx [Q,k]).
     """
     dev = _need_cuda("evaluate_ranks", overhead_embed, surface_embed)
     g, q, ch, w, sw = _feature_dims("evaluate_ranks", overhead_embed, surface_embed)
@@ -502,15 +576,42 @@ def evaluate_ranks(overhead_embed, surface_embed, true_idx=None, path="auto", to
         return ranks
     gallery = GalleryIndex(overhead_embed, sw)
     queries = QueryBatch(surface_embed)
-    return evaluate_ranks_prepared(gallery, queries, true_idx=true_idx, topk=topk)
+    return evaluate_ranks_prepared(gallery, queries, true_idx=true_idx, topk=topk, exact=exact)
 
 
-def evaluate_ranks_prepared(gallery, queries, true_idx=None, topk=0, d_true=None, events=None):
-    """evaluate_ranks on prepared operands (tensor-core path)."""
+class RecheckList(object):
+    """Device buffers for the (gallery, query) pairs whose rank decision the bf16 sweep defers to exact fp32."""
+
+    def __init__(self, capacity, band, device):
+        self.capacity, self.band = int(capacity), float(band)
+        self.g = torch.empty(self.capacity, dtype=torch.int64, device=device)
+        self.q = torch.empty(self.capacity, dtype=torch.int64, device=device)
+        self.count = torch.zeros(2, dtype=torch.int32, device=device)   # [appended, dropped for lack of room]
+        self.scratch = torch.empty(self.capacity, dtype=torch.float32, device=device)
+
+
+# How far the bf16 sweep can move a distance.  Full panoramas: only the rounding of the correlation, < 1e-3.  Limited
+# field of view: the crop norm depends on the chosen shift, so a bf16 argmax flip between two near-tied shifts moves
+# the distance of a weakly correlated pair by up to ~6e-3 (measured, SURVEY section 7.2) -- hence the wider band there.
+RECHECK_BAND_FULL = 4e-3
+RECHECK_BAND_CROPPED = 1.2e-2
+TOPK_MARGIN = 6
+
+
+def evaluate_ranks_prepared(gallery, queries, true_idx=None, topk=0, d_true=None, events=None, exact=True):
+    """evaluate_ranks on prepared operands (tensor-core path).
+
+    exact=True (needs the fp32 features kept in the operands): every rank decision whose bf16 distance falls within
+    the bf16 error band (RECHECK_BAND_*) of the fp32 threshold is re-taken in exact fp32, and the top-k is re-ranked in fp32 from the best
+    k + TOPK_MARGIN bf16 candidates -- so ranks and top-k are those of the fp32 reference chain, not bf16 approximations.
+    ``evaluate_ranks_prepared.last_recheck`` holds the [appended, dropped] counters of the last call (device tensor).
+    """
     dev = gallery.device
+    have_fp32 = gallery.ov is not None and queries.su is not None
+    exact = bool(exact) and have_fp32
     with torch.cuda.device(dev):
         if d_true is None:
-            if gallery.ov is None or queries.su is None:
+            if not have_fp32:
                 raise ValueError("evaluate_ranks_prepared: fp32 features were dropped; pass d_true")
             ov4 = gallery.ov.view(gallery.G, gallery.C, gallery.H, gallery.W)
             su4 = queries.su.view(queries.Q, gallery.C, gallery.H, queries.sw)
@@ -520,11 +621,37 @@ def evaluate_ranks_prepared(gallery, queries, true_idx=None, topk=0, d_true=None
             t32 = torch.arange(gallery.g_offset, gallery.g_offset + queries.Q, dtype=torch.int32, device=dev)
         else:
             t32 = (true_idx.to(dev, torch.int64) + gallery.g_offset).to(torch.int32).contiguous()
-        res = sweep_tc(gallery, queries, d_true=d_true, true_idx=t32, rank_count=counts, topk=topk, events=events)
+        recheck = RecheckList(max(4 * queries.Q, 1 << 16), RECHECK_BAND_FULL if gallery.sw >= gallery.W else RECHECK_BAND_CROPPED, dev) if exact else None
+        kc = min(16, topk + TOPK_MARGIN) if (topk and exact) else topk
+        res = sweep_tc(gallery, queries, d_true=d_true, true_idx=t32, rank_count=counts, topk=kc, events=events, recheck=recheck)
+        if exact and gallery.G > 0 and queries.Q > 0:
+            _lib.call("witw_recheck_apply_f32", gallery.ov.data_ptr(), queries.su.data_ptr(), recheck.g.data_ptr(), recheck.q.data_ptr(),
+                      recheck.count.data_ptr(), recheck.capacity, gallery.CH, gallery.W, gallery.sw, d_true.data_ptr(),
+                      counts.data_ptr(), recheck.scratch.data_ptr(), _stream())
+            evaluate_ranks_prepared.last_recheck = recheck.count
         ranks = counts[: queries.Q].to(torch.int64)
+        if topk and exact and queries.Q > 0:
+            td, ti = refine_topk(gallery, queries, res["topk_idx"], topk)
+            return ranks, td, ti
     if topk:
         return ranks, res["topk_dist"], res["topk_idx"]
     return ranks
+
+
+evaluate_ranks_prepared.last_recheck = None
+
+
+def refine_topk(gallery, queries, cand_idx, k):
+    """Exact fp32 re-ranking of bf16 top-k candidates [Q,kc] (global indices) -> (dist [Q,k], idx [Q,k])."""
+    dev = gallery.device
+    q, kc = cand_idx.shape
+    with torch.cuda.device(dev):
+        td = torch.empty((q, k), dtype=torch.float32, device=dev)
+        ti = torch.empty((q, k), dtype=torch.int32, device=dev)
+        scratch = torch.empty(_lib.load().witw_topk_refine_scratch_bytes(q, kc), dtype=torch.uint8, device=dev)
+        _lib.call("witw_topk_refine_f32", gallery.ov.data_ptr(), queries.su.data_ptr(), gallery.G, q, gallery.CH, gallery.W, gallery.sw,
+                  cand_idx.contiguous().data_ptr(), kc, gallery.g_offset, int(k), td.data_ptr(), ti.data_ptr(), scratch.data_ptr(), _stream())
+    return td, ti
 
 
 def baseline_ranks(overhead_embed, surface_embed, true_idx=None, return_distances=False):

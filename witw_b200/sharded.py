@@ -39,11 +39,14 @@ class CudaLocal(object):
         g, q, ch, w, sw = ops._feature_dims("sweep", ov_local, su)
         dev = su.device
         if ops._pick_path(self.path, g, q, ch, w, sw) == "tc":
-            gallery = ops.GalleryIndex(ov_local, sw, g_offset=g_offset, keep_fp32=False)
-            queries = ops.QueryBatch(su, keep_fp32=False)
-            counts = torch.zeros(max(q, 1), dtype=torch.int32, device=dev)
-            res = ops.sweep_tc(gallery, queries, d_true=d_true, true_idx=true_idx.to(torch.int32), rank_count=counts, topk=topk)
-            return counts[:q].to(torch.int64), res.get("topk_dist"), res.get("topk_idx")
+            # exact finish inside the shard: fp32 re-check of near-threshold rank decisions and fp32 re-ranking of the
+            # shard's top-k candidates, so what is exchanged are already the reference's counts and distances
+            gallery = ops.GalleryIndex(ov_local, sw, g_offset=g_offset)
+            queries = ops.QueryBatch(su)
+            res = ops.evaluate_ranks_prepared(gallery, queries, true_idx=true_idx - g_offset, topk=topk, d_true=d_true)
+            if topk:
+                return res
+            return res, None, None
         _, dmat = ops.match(ov_local, su, path="fp32")
         counts = (dmat <= d_true.unsqueeze(0)).sum(dim=0).to(torch.int64)  # fp32 path: the match compares equal to itself
         if topk:

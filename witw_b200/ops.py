@@ -513,9 +513,14 @@ def true_match_distances(overhead_embed, surface_embed, true_idx=None):
     ov, su = _f32c(overhead_embed), _f32c(surface_embed)
     with torch.cuda.device(dev):
         pq = torch.arange(q, dtype=torch.int64, device=dev)
-        pg = pq if true_idx is None else true_idx.to(dev, torch.int64).contiguous()
-        if q and (int(pg.max()) >= g or int(pg.min()) < 0):
-            raise IndexError("true_match_distances: true index outside the gallery")
+        if true_idx is None:
+            if q > g:
+                raise IndexError("true_match_distances: %d queries but only %d gallery items and no true_idx" % (q, g))
+            pg = pq                                   # identity: valid by construction, no device round trip
+        else:
+            pg = true_idx.to(dev, torch.int64).contiguous()
+            if q and (int(pg.max()) >= g or int(pg.min()) < 0):
+                raise IndexError("true_match_distances: true index outside the gallery")
         d = torch.empty(q, dtype=torch.float32, device=dev)
         o = torch.empty(q, dtype=torch.int64, device=dev)
         _lib.call("witw_match_pairs_f32", ov.data_ptr(), su.data_ptr(), pg.data_ptr(), pq.data_ptr(), q, ch, w, sw,

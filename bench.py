@@ -302,14 +302,15 @@ def run_ours(args):
             "gallery_total": g_total, "gallery_per_gpu": G_PER_GPU, "queries": Q_TOTAL, "fov": FOV, "feature_shape": [16, 4, 64],
             "unit_note": "one unit = one query swept over one %d-item gallery shard; queries/s over the whole %d-item gallery = %.1f" % (G_PER_GPU, g_total, value / world),
             "l2_policy": "inputs larger than L2 (fp32 features 328 MB + bf16 operands 1.3 GB per step vs 126 MB L2)",
-            "step": "fp32 features in HBM -> operand prep -> fp32 true-match distances -> tcgen05 sweep -> fp32 re-check of near-threshold rank decisions -> top-k merge -> fp32 re-rank of the top-k",
+            "step": "fp32 features in HBM -> operand prep (bf16 Hankel blocks, norms, fp32 azimuth spectra) -> fp32 true-match distances -> tcgen05 sweep -> fp32 re-check of near-threshold rank decisions -> top-k merge -> fp32 re-rank of the top-k",
         },
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                      "kernel": "match_tc_kernel", "kernel_ms": kernel_ms, "flop_per_pair": FLOP_PER_PAIR, "peak_source": peak_src},
         "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / steps,
                 "note": "W.evaluate_ranks() on pinned-host inputs; H2D of step i+1 double-buffered on a copy stream behind step i"},
-        "gpu_launches": 11 * steps,  # gallery_blocks, crop_norm, query_prep, match_pairs (true match), match_tc, match_pairs (re-check),
-                                     # recheck_apply, topk_merge, topk_refine_pairs, match_pairs (top-k), topk_refine_sort per step
+        "gpu_launches": 14 * steps,  # per step: gallery_blocks, crop_norm, query_prep, spectral_rows x2, spectral_pairs (true match),
+                                     # match_tc, topk_merge, spectral_pairs (re-check), recheck_apply, topk_refine_pairs,
+                                     # spectral_pairs (top-k), topk_refine_sort
         "clocks": clocks,
         "recall": {k: float(v) for k, v in recall.items()},
     }

@@ -169,6 +169,34 @@ int witw_topk_refine_f32(const float* ov_dev, const float* su_dev, int64_t G, in
                          float* topk_dist_dev, int32_t* topk_idx_dev, void* scratch_dev,
                          witw_stream_t stream);
 
+/* The same finishes in the azimuth-frequency domain (csrc/spectral.cu).  The circular correlation of
+ * cvig_fov.py:297-312 is evaluated through the correlation theorem on packed 64-point spectra of the
+ * feature rows: ~13k MACs per pair instead of 262k, and in fp32 closer to the float64 value than a
+ * 4096-term fp32 dot product.  W must be 64; narrower query rows are zero-padded.
+ *   witw_spectral_rows_f32: x [n_rows,row_len] fp32 -> spec [n_rows,64] fp32 (32 float2 slots per row:
+ *        slot f = (Re X_f, Im X_f) for f = 1..31, slot 0 = (X_0, X_32)).  Gallery: n_rows = G*CH,
+ *        row_len = 64; queries: n_rows = Q*CH, row_len = sw.
+ *   witw_match_pairs_spec_f32: exact (dist [n_pairs], ori [n_pairs] int64) of explicit pairs;
+ *        crop_inv_norm [G,64] and q_inv_norm [Q] are the fp32 tables of witw_gallery_prep / witw_query_prep.
+ *   witw_recheck_apply_spec_f32 / witw_topk_refine_spec_f32: as the _f32 forms above, on spectra. */
+int witw_spectral_rows_f32(const float* x_dev, int64_t n_rows, int row_len, float* spec_dev,
+                           witw_stream_t stream);
+int witw_match_pairs_spec_f32(const float* gal_spec_dev, const float* crop_inv_norm_dev,
+                              const float* qry_spec_dev, const float* q_inv_norm_dev,
+                              const int64_t* pair_g_dev, const int64_t* pair_q_dev, int64_t n_pairs, int CH,
+                              float* dist_dev, int64_t* ori_dev, witw_stream_t stream);
+int witw_recheck_apply_spec_f32(const float* gal_spec_dev, const float* crop_inv_norm_dev,
+                                const float* qry_spec_dev, const float* q_inv_norm_dev,
+                                const int64_t* recheck_g_dev, const int64_t* recheck_q_dev,
+                                const int32_t* recheck_count_dev, int32_t capacity, int CH,
+                                const float* d_true_dev, int32_t* rank_count_dev, float* scratch_dev,
+                                witw_stream_t stream);
+int witw_topk_refine_spec_f32(const float* gal_spec_dev, const float* crop_inv_norm_dev,
+                              const float* qry_spec_dev, const float* q_inv_norm_dev, int64_t G, int64_t Q,
+                              int CH, const int32_t* cand_idx_dev, int kc, int32_t g_index_offset, int k_out,
+                              float* topk_dist_dev, int32_t* topk_idx_dev, void* scratch_dev,
+                              witw_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * K4  rank / top-k               replaces model/cvig_fov.py:550-552 and
  *                                model/cvig_baseline.py:456-460

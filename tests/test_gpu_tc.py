@@ -181,6 +181,62 @@ def test_heatmap_sweep_one_query_many_tiles(W):
         assert int(torch.argmin(dis)) == 0 and float(deg[0]) == float(sh[0]) * 360 / 64 - 180
 
 
+@pytest.mark.parametrize("row_len", [64, 16, 13, 1])
+def test_spectral_rows_match_rfft(W, row_len):
+    """witw_spectral_rows_f32: packed 64-point spectra of (zero-padded) rows against numpy's float64 rfft."""
+    gen = torch.Generator().manual_seed(row_len)
+    x = torch.randn(517, row_len, generator=gen)
+    spec = W.ops.spectral_rows(x.cuda(), row_len).cpu().numpy().astype(np.float64)
+    pad = np.zeros((517, 64))
+    pad[:, :row_len] = x.numpy()
+    ref = np.fft.rfft(pad, axis=1)
+    want = np.empty((517, 64))
+    want[:, 0::2], want[:, 1::2] = ref.real[:, :32], ref.imag[:, :32]
+    want[:, 1] = ref.real[:, 32]
+    scale = np.abs(ref).max()
+    assert np.abs(spec - want).max() <= 4e-7 * scale
+
+
+@pytest.mark.parametrize("fov,G,Q", [(360, 96, 300), (90, 130, 70), (70, 64, 257), (6, 20, 9)])
+def test_spectral_pair_distances_vs_oracle(W, fov, G, Q):
+    """Exact fp32 pairs through the correlation theorem (csrc/spectral.cu) against the reference chain
+    (cvig_fov.py:547-549): every (gallery, query) pair of a small problem."""
+    ov, su, _ = O.synth_features(G, Q, fov=fov, noise=2.0, seed=31)
+    ov[3] = ov[2]                                             # exact ties between neighbouring items
+    ref_ori, ref = O.match(ov, su)
+    gallery, queries = W.GalleryIndex(ov.cuda(), su.shape[3]), W.QueryBatch(su.cuda())
+    pg = torch.arange(G).repeat_interleave(Q).cuda()
+    pq = torch.arange(Q).repeat(G).cuda()
+    d, o = W.ops.pair_distances_prepared(gallery, queries, pg, pq)
+    d, o = d.cpu().view(G, Q), o.cpu().view(G, Q)
+    diff = o != ref_ori
+    assert (d - ref)[~diff].abs().max().item() <= 5e-6
+    if bool(diff.any()):                                      # only between shifts whose float64 scores tie to fp32 round-off
+        corr = O.fused_fp64(ov, su)[0]
+        a = torch.gather(corr, 2, o.unsqueeze(-1)).squeeze(-1)
+        b = torch.gather(corr, 2, ref_ori.unsqueeze(-1)).squeeze(-1)
+        scale = corr.abs().amax(-1)
+        assert ((a - b).abs()[diff] <= 2e-6 * scale[diff]).all()
+    assert diff.float().mean().item() <= 1e-3
+
+
+def test_spectral_and_direct_finish_agree(W):
+    """The two implementations of the exact finish give the same ranks and the same top-k."""
+    ov, su, _ = O.synth_features(280, 280, fov=90, noise=10.0, seed=5)
+    out = {}
+    for impl in ("spectral", "direct"):
+        W.ops.EXACT_IMPL = impl
+        try:
+            out[impl] = W.evaluate_ranks(ov.cuda(), su.cuda(), path="tc", topk=5)
+        finally:
+            W.ops.EXACT_IMPL = "spectral"
+    ref = O.match(ov, su)[1]
+    tie = ((ref - torch.diagonal(ref).unsqueeze(0)).abs() <= 3e-6).sum(0) - 1
+    assert bool(((out["spectral"][0] - out["direct"][0]).abs().cpu() <= tie).all())
+    assert (out["spectral"][1] - out["direct"][1]).abs().max().item() <= 5e-6
+    assert (out["spectral"][2] == out["direct"][2]).float().mean().item() >= 0.995
+
+
 @pytest.mark.parametrize("fov,n,noise", [(360, 300, 25.0), (90, 260, 10.0), (70, 200, 8.0)])
 def test_tc_exact_finish_matches_fp32_reference(W, fov, n, noise):
     """exact=True: near-threshold rank decisions are re-taken in fp32 and the top-k re-ranked in fp32, so ranks and top-k

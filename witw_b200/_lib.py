@@ -43,6 +43,13 @@ SIGNATURES = {
     "witw_topk_refine_scratch_bytes": (c_size_t, [c_int64, c_int]),
     "witw_topk_refine_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p, c_int, c_int32, c_int,
                                      c_void_p, c_void_p, c_void_p, c_void_p]),
+    "witw_spectral_rows_f32": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),
+    "witw_match_pairs_spec_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p,
+                                          c_void_p]),
+    "witw_recheck_apply_spec_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int,
+                                            c_void_p, c_void_p, c_void_p, c_void_p]),
+    "witw_topk_refine_spec_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_int, c_int32,
+                                          c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "witw_rank_from_dist_f32": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
     "witw_l2_rank_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "witw_topk_slices": (c_int, [c_int64, c_int64]),

@@ -30,6 +30,12 @@ inline cudaStream_t as_stream(witw_stream_t s) { return reinterpret_cast<cudaStr
 
 int sm_count();  // SMs of the current device (cached per device)
 
+// spectral.cu: exact fp32 distances of explicit pairs from packed azimuth spectra (n_pairs_dev: optional device-side
+// count that caps n_pairs, so a list filled on the device needs no host round trip)
+int launch_pairs_spec(const float* gal_spec, const float* crop_inv_norm, const float* qry_spec, const float* q_inv_norm,
+                      const int64_t* pair_g, const int64_t* pair_q, int64_t n_pairs, const int32_t* n_pairs_dev, int CH,
+                      float* dist, int64_t* ori, witw_stream_t stream);
+
 template <typename T>
 __host__ __device__ constexpr T ceil_div(T a, T b) { return (a + b - 1) / b; }
 

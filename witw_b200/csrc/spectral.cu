@@ -1,0 +1,174 @@
+// Exact fp32 orientation-searched distance of explicit (gallery, query) pairs in the azimuth-frequency
+// domain.  Used for the "exact finish" of the tensor-core sweep (true-match thresholds, re-checks of
+// near-threshold rank decisions, re-ranking of top-k candidates): the same quantities as
+//   corr[s] = sum_{ch,k<sw} ov[ch,(s+k)%64] * su[ch,k]        model/cvig_fov.py:297-312
+//   ori     = first argmax_s corr[s]                           model/cvig_fov.py:313
+//   dist    = 2*(1 - corr[ori]/(||crop||*||su||))              model/cvig_fov.py:318-363
+// but with the circular correlation evaluated through the correlation theorem.  With O = rfft(ov row),
+// S = rfft(zero-padded su row) (64 columns -> 33 bins),
+//   corr = irfft( sum_ch O_ch * conj(S_ch) )
+// costs 64 rows x 32 complex MACs + one 64-point inverse per pair (~13k MACs) instead of 262k, and in
+// fp32 it is closer to the float64 value than a 4096-term fp32 dot product (measured: 1.5e-7 vs 3.4e-7
+// of the norm product).  The whole-gallery sweep stays a dense tensor-core contraction (match_tc.cu);
+// this file only serves the few pairs whose result must not carry bf16 rounding.
+//
+// Packed spectrum of one 64-column row: 32 float2 slots; slot f (1..31) = (Re X_f, Im X_f),
+// slot 0 = (X_0, X_32) (both real).
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace witw {
+
+__device__ __forceinline__ int brev5(int n) { return (int)(__brev((unsigned)n) >> 27); }
+
+// One warp per row: the 64 real samples are 32 complex points z[n] = x[2n] + i x[2n+1], one per lane;
+// a 5-stage decimation-in-frequency FFT over the lanes (shuffles), then the real-input split.
+__global__ void __launch_bounds__(256)
+spectral_rows_kernel(const float* __restrict__ x, int64_t n_rows, int row_len, float* __restrict__ spec) {
+  const int lane = threadIdx.x & 31;
+  const int64_t stride = (int64_t)gridDim.x * 8;
+  float2 tw[5];  // stage twiddles exp(-2 pi i (lane mod h) / 2h), h = 16, 8, 4, 2, 1
+#pragma unroll
+  for (int st = 0; st < 5; ++st) {
+    const int h = 16 >> st;
+    float s, c;
+    sincospif((float)(lane & (h - 1)) / (float)h, &s, &c);
+    tw[st] = make_float2(c, -s);
+  }
+  float ws, wc;  // exp(-2 pi i lane / 64) = (wc, -ws)
+  sincospif((float)lane / 32.0f, &ws, &wc);
+  const int src_k = brev5(lane), src_m = brev5((32 - lane) & 31);
+  const bool full = row_len == 64 && ((uintptr_t)x & 7) == 0;
+  for (int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); row < n_rows; row += stride) {
+    float2 z;
+    if (full) {
+      z = __ldg(reinterpret_cast<const float2*>(x + row * 64) + lane);
+    } else {  // query rows narrower than the gallery: zero-padded to 64 columns
+      const float* r = x + row * row_len;
+      const int j = 2 * lane;
+      z.x = j < row_len ? r[j] : 0.f;
+      z.y = j + 1 < row_len ? r[j + 1] : 0.f;
+    }
+#pragma unroll
+    for (int st = 0; st < 5; ++st) {
+      const int h = 16 >> st;
+      const float ox = __shfl_xor_sync(0xffffffffu, z.x, h), oy = __shfl_xor_sync(0xffffffffu, z.y, h);
+      if (lane & h) {
+        const float dx = ox - z.x, dy = oy - z.y;
+        z.x = dx * tw[st].x - dy * tw[st].y;
+        z.y = dx * tw[st].y + dy * tw[st].x;
+      } else {
+        z.x += ox;
+        z.y += oy;
+      }
+    }
+    // lane n now holds Z[bitrev(n)].  X_k = E_k + W^k O_k with E = (Z_k + conj Z_{32-k})/2, O = -i (Z_k - conj Z_{32-k})/2
+    const float ax = __shfl_sync(0xffffffffu, z.x, src_k), ay = __shfl_sync(0xffffffffu, z.y, src_k);
+    const float bx = __shfl_sync(0xffffffffu, z.x, src_m), by = -__shfl_sync(0xffffffffu, z.y, src_m);
+    const float ex = 0.5f * (ax + bx), ey = 0.5f * (ay + by);
+    const float ox = 0.5f * (ay - by), oy = -0.5f * (ax - bx);
+    float2 X;
+    X.x = ex + (wc * ox + ws * oy);
+    X.y = ey + (wc * oy - ws * ox);
+    if (lane == 0) { X.x = ax + ay; X.y = ax - ay; }  // X_0 and X_32
+    reinterpret_cast<float2*>(spec + row * 64)[lane] = X;
+  }
+}
+
+// One warp per pair, lane = frequency slot.  P_f = sum_ch O_f conj(S_f); then every lane evaluates the
+// inverse transform at shifts `lane` and `lane + 32` from the 32 broadcast P_f; warp argmax (first maximum,
+// NaN is the maximum -- torch.argmax); distance from the fp32 norm tables of the prep kernels.
+__global__ void __launch_bounds__(256)
+spectral_pairs_kernel(const float2* __restrict__ gal_spec, const float* __restrict__ crop_inv_norm,
+                      const float2* __restrict__ qry_spec, const float* __restrict__ q_inv_norm,
+                      const int64_t* __restrict__ pair_g, const int64_t* __restrict__ pair_q, int64_t n_pairs,
+                      const int32_t* __restrict__ n_pairs_dev, int CH, float* __restrict__ dist, int64_t* __restrict__ ori) {
+  __shared__ float2 tw[64];  // (cos, sin)(2 pi m / 64)
+  if (threadIdx.x < 64) {
+    float s, c;
+    sincospif((float)threadIdx.x / 32.0f, &s, &c);
+    tw[threadIdx.x] = make_float2(c, s);
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t p = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  int64_t n = n_pairs;
+  if (n_pairs_dev != nullptr) n = min(n, (int64_t)*n_pairs_dev);
+  if (p >= n) return;
+  const int64_t g = pair_g[p], q = pair_q[p];
+  const float2* go = gal_spec + g * CH * 32 + lane;
+  const float2* qo = qry_spec + q * CH * 32 + lane;
+  float a = 0.f, b = 0.f, c = 0.f;  // sum o.x s.x, sum o.y s.y, sum (o.y s.x - o.x s.y)
+#pragma unroll 8
+  for (int ch = 0; ch < CH; ++ch) {
+    const float2 o = __ldg(go + ch * 32), s = __ldg(qo + ch * 32);
+    a = fmaf(o.x, s.x, a);
+    b = fmaf(o.y, s.y, b);
+    c = fmaf(o.y, s.x, c);
+    c = fmaf(-o.x, s.y, c);
+  }
+  const float p0 = __shfl_sync(0xffffffffu, a, 0), p32 = __shfl_sync(0xffffffffu, b, 0);
+  const float re = a + b, im = c;
+  const float base = p0 + ((lane & 1) ? -p32 : p32);
+  float lo = 0.f, hi = 0.f;
+#pragma unroll
+  for (int f = 1; f < 32; ++f) {
+    const float fr = __shfl_sync(0xffffffffu, re, f), fi = __shfl_sync(0xffffffffu, im, f);
+    const float2 t = tw[(f * lane) & 63];
+    const float term = fr * t.x - fi * t.y;
+    lo += term;
+    hi += (f & 1) ? -term : term;
+  }
+  const float c_lo = (base + 2.0f * lo) * (1.0f / 64.0f), c_hi = (base + 2.0f * hi) * (1.0f / 64.0f);
+  float best = c_lo;
+  int arg = lane;
+  if (c_hi > best || (c_hi != c_hi && best == best)) { best = c_hi; arg = lane + 32; }
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, m);
+    const int oa = __shfl_xor_sync(0xffffffffu, arg, m);
+    const bool take = (ob > best) || (ob != ob && best == best) || (ob == best && oa < arg) || (ob != ob && best != best && oa < arg);
+    if (take) { best = ob; arg = oa; }
+  }
+  if (lane == 0) {
+    if (dist != nullptr) dist[p] = 2.0f * (1.0f - best * crop_inv_norm[g * 64 + arg] * q_inv_norm[q]);
+    if (ori != nullptr) ori[p] = arg;
+  }
+}
+
+int launch_pairs_spec(const float* gal_spec, const float* crop_inv_norm, const float* qry_spec, const float* q_inv_norm,
+                      const int64_t* pair_g, const int64_t* pair_q, int64_t n_pairs, const int32_t* n_pairs_dev, int CH,
+                      float* dist, int64_t* ori, witw_stream_t stream) {
+  WITW_REQUIRE(n_pairs > 0 && n_pairs < (1ll << 33), WITW_ERR_INVALID, "spectral pairs: bad pair count %lld", (long long)n_pairs);
+  WITW_REQUIRE((((uintptr_t)gal_spec | (uintptr_t)qry_spec) & 7) == 0, WITW_ERR_INVALID, "spectral pairs: spectra must be 8-byte aligned");
+  spectral_pairs_kernel<<<(unsigned)ceil_div<int64_t>(n_pairs, 8), 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const float2*>(gal_spec), crop_inv_norm, reinterpret_cast<const float2*>(qry_spec), q_inv_norm, pair_g, pair_q,
+      n_pairs, n_pairs_dev, CH, dist, ori);
+  WITW_LAUNCH_CHECK();
+  return WITW_OK;
+}
+
+}  // namespace witw
+
+using namespace witw;
+
+extern "C" int witw_spectral_rows_f32(const float* x, int64_t n_rows, int row_len, float* spec, witw_stream_t stream) {
+  WITW_REQUIRE(n_rows >= 0 && row_len >= 1 && row_len <= 64, WITW_ERR_INVALID, "witw_spectral_rows_f32: rows of 1..64 columns (got %d)", row_len);
+  if (n_rows == 0) return WITW_OK;
+  WITW_REQUIRE(x && spec, WITW_ERR_INVALID, "witw_spectral_rows_f32: null pointer");
+  WITW_REQUIRE(((uintptr_t)spec & 7) == 0, WITW_ERR_INVALID, "witw_spectral_rows_f32: output must be 8-byte aligned");
+  const int64_t blocks = std::min<int64_t>(ceil_div<int64_t>(n_rows, 8), (int64_t)sm_count() * 32);
+  spectral_rows_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(x, n_rows, row_len, spec);
+  WITW_LAUNCH_CHECK();
+  return WITW_OK;
+}
+
+extern "C" int witw_match_pairs_spec_f32(const float* gal_spec, const float* crop_inv_norm, const float* qry_spec,
+                                         const float* q_inv_norm, const int64_t* pair_g, const int64_t* pair_q, int64_t n_pairs,
+                                         int CH, float* dist, int64_t* ori, witw_stream_t stream) {
+  WITW_REQUIRE(CH > 0 && n_pairs >= 0, WITW_ERR_INVALID, "witw_match_pairs_spec_f32: bad shape");
+  if (n_pairs == 0) return WITW_OK;
+  WITW_REQUIRE(gal_spec && crop_inv_norm && qry_spec && q_inv_norm && pair_g && pair_q, WITW_ERR_INVALID, "witw_match_pairs_spec_f32: null pointer");
+  return launch_pairs_spec(gal_spec, crop_inv_norm, qry_spec, q_inv_norm, pair_g, pair_q, n_pairs, nullptr, CH, dist, ori, stream);
+}

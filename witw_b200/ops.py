@@ -39,6 +39,11 @@ OVERHEAD_SIZE = 256
 TC_MIN_PAIRS = 1 << 16
 
 
+# how the exact fp32 finish of the tensor-core sweep evaluates its pairs: "spectral" (correlation theorem on packed
+# azimuth spectra, csrc/spectral.cu) or "direct" (4096-term fp32 dot products per shift, csrc/match_simt.cu)
+EXACT_IMPL = "spectral"
+
+
 # ----------------------------------------------------------------------------- helpers
 def _stream():
     return torch.cuda.current_stream().cuda_stream
@@ -205,6 +210,16 @@ class PolarTransform(object):
 
 
 # ----------------------------------------------------------------------------- K2/K3
+def spectral_rows(rows, row_len):
+    """Packed 64-point azimuth spectra [n_rows,64] fp32 of contiguous fp32 feature rows (row_len <= 64 columns,
+    zero-padded): the operand of the exact fp32 finish (csrc/spectral.cu)."""
+    n_rows = rows.numel() // row_len
+    out = torch.empty((n_rows, 64), dtype=torch.float32, device=rows.device)
+    with torch.cuda.device(rows.device):
+        _lib.call("witw_spectral_rows_f32", rows.data_ptr(), n_rows, int(row_len), out.data_ptr(), _stream())
+    return out
+
+
 class GalleryIndex(object):
     """Gallery feature maps prepared for the tensor-core sweep (bf16 Hankel blocks + crop norms).
 
@@ -222,6 +237,7 @@ class GalleryIndex(object):
         self.g_offset = int(g_offset)
         ov = _f32c(overhead_embed)
         self.ov = ov if keep_fp32 else None
+        self.spec = None
         with torch.cuda.device(dev):
             nbytes = _lib.load().witw_gallery_operand_bytes(g, self.CH, self.sw)
             if nbytes == 0 or w != 64:
@@ -232,6 +248,14 @@ class GalleryIndex(object):
             _lib.call("witw_gallery_prep", ov.data_ptr(), g, self.CH, w, self.sw, self.operand.data_ptr(),
                       self.crop_inv_norm.data_ptr(), _stream())
 
+    def spectral(self):
+        """Packed azimuth spectra [G*CH,64] of the fp32 features (built on first use, then kept)."""
+        if self.spec is None:
+            if self.ov is None:
+                raise ValueError("GalleryIndex: the fp32 features were dropped (keep_fp32=False); no exact finish")
+            self.spec = spectral_rows(self.ov, self.W)
+        return self.spec
+
 
 class GalleryBuilder(object):
     """Incremental GalleryIndex for the encode loop of test() (cvig_fov.py:519-532).
@@ -239,10 +263,12 @@ class GalleryBuilder(object):
     The reference grows ``overhead_embed`` with torch.cat per batch (O(n^2) copies).  Here each encoder
     output batch is written once: fp32 features into a preallocated buffer (kept for the exact true-match
     distances) and, through witw_gallery_prep, straight into its slot of the tensor-core operand.
-    Batches must hold a multiple of 4 items, except the last one.
+    Batches must hold a multiple of 4 items, except the last one.  keep_fp32: keep what the exact fp32 finish needs
+    (the packed azimuth spectra of the features, 16 KB per item); keep_raw: also keep the raw fp32 features.
     """
 
-    def __init__(self, capacity, surface_width, channels=16, height=4, width=64, device=None, g_offset=0, keep_fp32=True):
+    def __init__(self, capacity, surface_width, channels=16, height=4, width=64, device=None, g_offset=0, keep_fp32=True,
+                 keep_raw=False):
         if not torch.cuda.is_available():
             raise RuntimeError("GalleryBuilder: no CUDA device; witw_b200 has no CPU fallback")
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
@@ -258,7 +284,8 @@ class GalleryBuilder(object):
             self.operand = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
             cap4 = max((self.capacity + 3) // 4 * 4, 4)
             self.crop_inv_norm = torch.zeros(cap4 * 64, dtype=torch.float32, device=self.device)
-            self.ov = torch.empty((self.capacity, channels, height, width), dtype=torch.float32, device=self.device) if keep_fp32 else None
+            self.ov = torch.empty((self.capacity, channels, height, width), dtype=torch.float32, device=self.device) if keep_raw else None
+            self.spec = torch.empty((self.capacity * self.CH, 64), dtype=torch.float32, device=self.device) if keep_fp32 else None
 
     def append(self, overhead_embed_part):
         """Add one encoder output batch [n,C,H,W] (CUDA)."""
@@ -276,6 +303,9 @@ class GalleryBuilder(object):
         with torch.cuda.device(self.device):
             if self.ov is not None:
                 self.ov[self.count: self.count + n].copy_(part)
+            if self.spec is not None:
+                _lib.call("witw_spectral_rows_f32", part.data_ptr(), n * self.CH, self.W,
+                          self.spec.data_ptr() + self.count * self.CH * 64 * 4, _stream())
             _lib.call("witw_gallery_prep", part.data_ptr(), n, self.CH, self.W, self.sw,
                       self.operand.data_ptr() + (self.count // 2) * self.pair_bytes,
                       self.crop_inv_norm.data_ptr() + self.count * 64 * 4, _stream())
@@ -289,6 +319,7 @@ class GalleryBuilder(object):
         idx.device, idx.G, idx.CH, idx.W, idx.sw = self.device, self.count, self.CH, self.W, self.sw
         idx.C, idx.H, idx.g_offset = self.C, self.H, self.g_offset
         idx.ov = None if self.ov is None else self.ov[: self.count]
+        idx.spec = None if self.spec is None else self.spec[: self.count * self.CH]
         idx.operand, idx.crop_inv_norm = self.operand, self.crop_inv_norm
         return idx
 
@@ -302,6 +333,7 @@ class QueryBatch(object):
         self.device, self.Q, self.CH, self.sw = dev, q, c * h, sw
         su = _f32c(surface_embed)
         self.su = su if keep_fp32 else None
+        self.spec = None
         with torch.cuda.device(dev):
             nbytes = _lib.load().witw_query_operand_bytes(q, self.CH, sw)
             if nbytes == 0:
@@ -309,6 +341,14 @@ class QueryBatch(object):
             self.operand = torch.empty(nbytes, dtype=torch.uint8, device=dev)
             self.inv_norm = torch.empty(max(q, 1), dtype=torch.float32, device=dev)
             _lib.call("witw_query_prep", su.data_ptr(), q, self.CH, sw, self.operand.data_ptr(), self.inv_norm.data_ptr(), _stream())
+
+    def spectral(self):
+        """Packed azimuth spectra [Q*CH,64] of the zero-padded fp32 query rows (built on first use, then kept)."""
+        if self.spec is None:
+            if self.su is None:
+                raise ValueError("QueryBatch: the fp32 features were dropped (keep_fp32=False); no exact finish")
+            self.spec = spectral_rows(self.su, self.sw)
+        return self.spec
 
 
 def tc_supported(ch, w, sw):
@@ -603,40 +643,87 @@ RECHECK_BAND_CROPPED = 1.2e-2
 TOPK_MARGIN = 6
 
 
+def _exact_mode(gallery, queries, exact):
+    """None (no exact finish), "spectral" or "direct" for this pair of operands."""
+    if not exact:
+        return None
+    g_spec = gallery.spec is not None or gallery.ov is not None
+    q_spec = queries.spec is not None or queries.su is not None
+    if EXACT_IMPL == "spectral" and gallery.W == 64 and g_spec and q_spec:
+        return "spectral"
+    if gallery.ov is not None and queries.su is not None:
+        return "direct"
+    return None
+
+
+def pair_distances_prepared(gallery, queries, pair_g, pair_q):
+    """Exact fp32 (distance, orientation) of explicit (local gallery index, query index) pairs on prepared operands,
+    through the packed azimuth spectra."""
+    dev = gallery.device
+    n = pair_g.numel()
+    with torch.cuda.device(dev):
+        d = torch.empty(n, dtype=torch.float32, device=dev)
+        o = torch.empty(n, dtype=torch.int64, device=dev)
+        _lib.call("witw_match_pairs_spec_f32", gallery.spectral().data_ptr(), gallery.crop_inv_norm.data_ptr(),
+                  queries.spectral().data_ptr(), queries.inv_norm.data_ptr(), pair_g.data_ptr(), pair_q.data_ptr(), n, gallery.CH,
+                  d.data_ptr(), o.data_ptr(), _stream())
+    return d, o
+
+
 def evaluate_ranks_prepared(gallery, queries, true_idx=None, topk=0, d_true=None, events=None, exact=True):
     """evaluate_ranks on prepared operands (tensor-core path).
 
-    exact=True (needs the fp32 features kept in the operands): every rank decision whose bf16 distance falls within
-    the bf16 error band (RECHECK_BAND_*) of the fp32 threshold is re-taken in exact fp32, and the top-k is re-ranked in fp32 from the best
-    k + TOPK_MARGIN bf16 candidates -- so ranks and top-k are those of the fp32 reference chain, not bf16 approximations.
+    exact=True (needs the fp32 features or their spectra kept in the operands): every rank decision whose bf16 distance
+    falls within the bf16 error band (RECHECK_BAND_*) of the fp32 threshold is re-taken in exact fp32, and the top-k is
+    re-ranked in fp32 from the best k + TOPK_MARGIN bf16 candidates -- so ranks and top-k are those of the fp32
+    reference chain, not bf16 approximations.  The fp32 pairs are evaluated per EXACT_IMPL.
     ``evaluate_ranks_prepared.last_recheck`` holds the [appended, dropped] counters of the last call (device tensor).
     """
     dev = gallery.device
-    have_fp32 = gallery.ov is not None and queries.su is not None
-    exact = bool(exact) and have_fp32
+    mode = _exact_mode(gallery, queries, True)
+    if d_true is None and mode is None:
+        raise ValueError("evaluate_ranks_prepared: fp32 features were dropped; pass d_true")
+    fin = mode if exact else None
     with torch.cuda.device(dev):
         if d_true is None:
-            if not have_fp32:
-                raise ValueError("evaluate_ranks_prepared: fp32 features were dropped; pass d_true")
-            ov4 = gallery.ov.view(gallery.G, gallery.C, gallery.H, gallery.W)
-            su4 = queries.su.view(queries.Q, gallery.C, gallery.H, queries.sw)
-            d_true, _ = true_match_distances(ov4, su4, true_idx)
+            if true_idx is None:
+                if queries.Q > gallery.G:
+                    raise IndexError("evaluate_ranks_prepared: %d queries but only %d gallery items and no true_idx" % (queries.Q, gallery.G))
+                pg = torch.arange(queries.Q, dtype=torch.int64, device=dev)
+                pq = pg
+            else:
+                pg = true_idx.to(dev, torch.int64).contiguous()
+                if queries.Q and (int(pg.max()) >= gallery.G or int(pg.min()) < 0):
+                    raise IndexError("evaluate_ranks_prepared: true index outside the gallery")
+                pq = torch.arange(queries.Q, dtype=torch.int64, device=dev)
+            if mode == "spectral":
+                d_true, _ = pair_distances_prepared(gallery, queries, pg, pq)
+            else:
+                ov4 = gallery.ov.view(gallery.G, gallery.C, gallery.H, gallery.W)
+                su4 = queries.su.view(queries.Q, gallery.C, gallery.H, queries.sw)
+                d_true, _ = true_match_distances(ov4, su4, true_idx)
         counts = torch.zeros(max(queries.Q, 1), dtype=torch.int32, device=dev)
         if true_idx is None:
             t32 = torch.arange(gallery.g_offset, gallery.g_offset + queries.Q, dtype=torch.int32, device=dev)
         else:
             t32 = (true_idx.to(dev, torch.int64) + gallery.g_offset).to(torch.int32).contiguous()
-        recheck = RecheckList(max(4 * queries.Q, 1 << 16), RECHECK_BAND_FULL if gallery.sw >= gallery.W else RECHECK_BAND_CROPPED, dev) if exact else None
-        kc = min(16, topk + TOPK_MARGIN) if (topk and exact) else topk
+        recheck = RecheckList(max(4 * queries.Q, 1 << 16), RECHECK_BAND_FULL if gallery.sw >= gallery.W else RECHECK_BAND_CROPPED, dev) if fin else None
+        kc = min(16, topk + TOPK_MARGIN) if (topk and fin) else topk
         res = sweep_tc(gallery, queries, d_true=d_true, true_idx=t32, rank_count=counts, topk=kc, events=events, recheck=recheck)
-        if exact and gallery.G > 0 and queries.Q > 0:
-            _lib.call("witw_recheck_apply_f32", gallery.ov.data_ptr(), queries.su.data_ptr(), recheck.g.data_ptr(), recheck.q.data_ptr(),
-                      recheck.count.data_ptr(), recheck.capacity, gallery.CH, gallery.W, gallery.sw, d_true.data_ptr(),
-                      counts.data_ptr(), recheck.scratch.data_ptr(), _stream())
+        if fin and gallery.G > 0 and queries.Q > 0:
+            if fin == "spectral":
+                _lib.call("witw_recheck_apply_spec_f32", gallery.spectral().data_ptr(), gallery.crop_inv_norm.data_ptr(),
+                          queries.spectral().data_ptr(), queries.inv_norm.data_ptr(), recheck.g.data_ptr(), recheck.q.data_ptr(),
+                          recheck.count.data_ptr(), recheck.capacity, gallery.CH, d_true.data_ptr(), counts.data_ptr(),
+                          recheck.scratch.data_ptr(), _stream())
+            else:
+                _lib.call("witw_recheck_apply_f32", gallery.ov.data_ptr(), queries.su.data_ptr(), recheck.g.data_ptr(), recheck.q.data_ptr(),
+                          recheck.count.data_ptr(), recheck.capacity, gallery.CH, gallery.W, gallery.sw, d_true.data_ptr(),
+                          counts.data_ptr(), recheck.scratch.data_ptr(), _stream())
             evaluate_ranks_prepared.last_recheck = recheck.count
         ranks = counts[: queries.Q].to(torch.int64)
-        if topk and exact and queries.Q > 0:
-            td, ti = refine_topk(gallery, queries, res["topk_idx"], topk)
+        if topk and fin and queries.Q > 0:
+            td, ti = refine_topk(gallery, queries, res["topk_idx"], topk, impl=fin)
             return ranks, td, ti
     if topk:
         return ranks, res["topk_dist"], res["topk_idx"]
@@ -646,16 +733,22 @@ def evaluate_ranks_prepared(gallery, queries, true_idx=None, topk=0, d_true=None
 evaluate_ranks_prepared.last_recheck = None
 
 
-def refine_topk(gallery, queries, cand_idx, k):
+def refine_topk(gallery, queries, cand_idx, k, impl=None):
     """Exact fp32 re-ranking of bf16 top-k candidates [Q,kc] (global indices) -> (dist [Q,k], idx [Q,k])."""
     dev = gallery.device
     q, kc = cand_idx.shape
+    impl = impl or _exact_mode(gallery, queries, True)
     with torch.cuda.device(dev):
         td = torch.empty((q, k), dtype=torch.float32, device=dev)
         ti = torch.empty((q, k), dtype=torch.int32, device=dev)
         scratch = torch.empty(_lib.load().witw_topk_refine_scratch_bytes(q, kc), dtype=torch.uint8, device=dev)
-        _lib.call("witw_topk_refine_f32", gallery.ov.data_ptr(), queries.su.data_ptr(), gallery.G, q, gallery.CH, gallery.W, gallery.sw,
-                  cand_idx.contiguous().data_ptr(), kc, gallery.g_offset, int(k), td.data_ptr(), ti.data_ptr(), scratch.data_ptr(), _stream())
+        if impl == "spectral":
+            _lib.call("witw_topk_refine_spec_f32", gallery.spectral().data_ptr(), gallery.crop_inv_norm.data_ptr(),
+                      queries.spectral().data_ptr(), queries.inv_norm.data_ptr(), gallery.G, q, gallery.CH,
+                      cand_idx.contiguous().data_ptr(), kc, gallery.g_offset, int(k), td.data_ptr(), ti.data_ptr(), scratch.data_ptr(), _stream())
+        else:
+            _lib.call("witw_topk_refine_f32", gallery.ov.data_ptr(), queries.su.data_ptr(), gallery.G, q, gallery.CH, gallery.W, gallery.sw,
+                      cand_idx.contiguous().data_ptr(), kc, gallery.g_offset, int(k), td.data_ptr(), ti.data_ptr(), scratch.data_ptr(), _stream())
     return td, ti
 
 

@@ -197,15 +197,9 @@ def run_ours(args):
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             sweep_events.append(ev)
             return ops.evaluate_ranks_prepared(gallery, queries, topk=TOPK, events=ev)
-        return evaluate_ranks_sharded(ov, su, g_offset, g_total, topk=TOPK, local=TimedLocal())
+        return evaluate_ranks_sharded(ov, su, g_offset, g_total, topk=TOPK, local=timed_local)
 
-    class TimedLocal(W.sharded.CudaLocal):
-        def sweep(self, ov_local, su_all, d_true, true_idx, g_off, topk):
-            gallery = ops.GalleryIndex(ov_local, 64, g_offset=g_off)
-            queries = ops.QueryBatch(su_all)
-            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-            sweep_events.append(ev)
-            return ops.evaluate_ranks_prepared(gallery, queries, true_idx=true_idx - g_off, topk=topk, d_true=d_true, events=ev)
+    timed_local = W.sharded.CudaLocal(event_sink=sweep_events)
 
     def barrier():
         if world > 1:

@@ -185,6 +185,34 @@ def test_rank_from_distances_and_topk(W):
         assert bool((ti.cpu()[~finite] == -1).all())
 
 
+@pytest.mark.parametrize("n_lists,Q,k", [(64, 300, 16), (40, 257, 10), (3, 33, 128), (1, 5, 4)])
+def test_topk_merge_kway(W, n_lists, Q, k):
+    """witw_topk_merge: k-way merge of sorted candidate lists with ties (lower list wins) and (+inf, -1) padding."""
+    from witw_b200 import _lib
+    gen = torch.Generator().manual_seed(n_lists)
+    d = (torch.randint(0, 50, (n_lists, Q, k), generator=gen).float() / 8)     # many exact ties
+    idx = torch.arange(n_lists * k, dtype=torch.int32).view(n_lists, 1, k).expand(n_lists, Q, k).clone()
+    d, order = torch.sort(d, dim=2, stable=True)
+    idx = torch.gather(idx, 2, order)
+    idx, _ = torch.sort(idx, dim=2)                                             # ascending index inside a list, as the kernels emit
+    fill = torch.randint(0, k + 1, (n_lists, Q), generator=gen)                 # lists filled to a random depth
+    pad = torch.arange(k).view(1, 1, k) >= fill.unsqueeze(-1)
+    d[pad], idx[pad] = float("inf"), -1
+    dc, ic = d.cuda().contiguous(), idx.cuda().contiguous()
+    out_d = torch.empty((Q, k), dtype=torch.float32, device="cuda")
+    out_i = torch.empty((Q, k), dtype=torch.int32, device="cuda")
+    _lib.call("witw_topk_merge", dc.data_ptr(), ic.data_ptr(), n_lists, Q, k, out_d.data_ptr(), out_i.data_ptr(),
+              torch.cuda.current_stream().cuda_stream)
+    flat_d = d.permute(1, 0, 2).reshape(Q, n_lists * k)                         # list-major: a stable sort prefers the lower list
+    flat_i = idx.permute(1, 0, 2).reshape(Q, n_lists * k)
+    ref = torch.sort(flat_d, dim=1, stable=True)
+    want_d = ref.values[:, :k]
+    want_i = torch.gather(flat_i, 1, ref.indices[:, :k])
+    assert torch.equal(out_d.cpu(), want_d)
+    assert torch.equal(out_i.cpu()[torch.isfinite(want_d)], want_i[torch.isfinite(want_d)])
+    assert bool((out_i.cpu()[~torch.isfinite(want_d)] == -1).all())
+
+
 def test_baseline_ranks_vs_golden(W, golden):
     g = golden("baseline")
     ranks, dist = W.baseline_ranks(cu(g["ov"].astype(np.float32)), cu(g["su"].astype(np.float32)), return_distances=True)

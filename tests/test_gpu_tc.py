@@ -261,3 +261,28 @@ def test_tc_exact_finish_matches_fp32_reference(W, fov, n, noise):
     sd = torch.sort(ref.t(), dim=1, stable=True)
     assert torch.equal(tic[:, 0], sd.indices[:, 0])
     assert (tic == sd.indices[:, :5]).float().mean().item() >= (0.99 if fov == 360 else 0.9)
+
+
+def test_sharded_cuda_local_single_process(W):
+    """witw_b200/sharded.py on the CUDA kernels without a process group: the whole gallery as one shard gives the ranks
+    and top-k of evaluate_ranks; a slice of it (true matches partly outside the slice) gives that slice's counts."""
+    from witw_b200.sharded import CudaLocal, evaluate_ranks_sharded
+    ov, su, _ = O.synth_features(600, 300, fov=90, noise=10.0, seed=12)
+    perm = torch.randperm(600, generator=torch.Generator().manual_seed(2))
+    inv = torch.empty_like(perm)
+    inv[perm] = torch.arange(600)
+    ovp, true_idx = ov[perm].cuda(), inv[:300].cuda()
+    want = W.evaluate_ranks(ovp, su.cuda(), true_idx=true_idx, path="tc", topk=5)
+    got = evaluate_ranks_sharded(ovp, su.cuda(), 0, 600, true_idx=true_idx, topk=5, local=CudaLocal(path="tc"))
+    for a, b in zip(want, got):
+        assert torch.equal(a, b)
+    # two shards evaluated one after the other with the exchanged thresholds: counts add up, candidates merge
+    ref = O.match(ov[perm], su)[1]
+    thr = ref[inv[:300], torch.arange(300)]
+    local = CudaLocal(path="tc")
+    parts = [local.sweep(ovp[lo:hi], su.cuda(), thr.cuda(), true_idx, lo, 5) for lo, hi in ((0, 288), (288, 600))]
+    counts = parts[0][0] + parts[1][0]
+    tie = ((ref - thr.unsqueeze(0)).abs() <= 3e-6).sum(0) - 1
+    assert bool(((counts.cpu() - want[0].cpu()).abs() <= tie).all())
+    td, ti = local.merge(torch.stack([parts[0][1], parts[1][1]]), torch.stack([parts[0][2], parts[1][2]]), 5)
+    assert torch.equal(ti, want[2]) and (td - want[1]).abs().max().item() <= 1e-6

@@ -79,32 +79,45 @@ static bool make_geom(int CH, int sw, TcGeom* g) {
 // ------------------------------------------------------------------------------------------
 // operand preparation
 // ------------------------------------------------------------------------------------------
+constexpr int kPrepRows = 16;  // feature rows of one item pair per CTA
+
 __global__ void __launch_bounds__(256)
-gallery_blocks_kernel(const float* __restrict__ ov, int64_t G, int CH, int bpc, int full, int nkap,
-                      uint4* __restrict__ out, int64_t n_chunks) {
-  // one thread per 16-byte row of a block: (pair, ch, b, r)
-  const int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (id >= n_chunks) return;
-  const int r = (int)(id & 7);
-  const int64_t blk = id >> 3;
-  const int b = (int)(blk % bpc);
-  const int64_t pc = blk / bpc;
-  const int ch = (int)(pc % CH);
-  const int64_t pair = pc / CH;
-  int vb = b;  // virtual Hankel block index t + 2u + 4kappa
-  if (full) { const int t = b & 15, u = (b >> 4) & 1, kap = b >> 5; vb = t + 2 * u + 4 * kap; }
-  const int64_t item = 2 * pair + (r & 1);
-  const int start = 4 * vb + (r >> 1);
-  uint32_t w[4] = {0, 0, 0, 0};
-  if (item < G) {
-    const float* row = ov + (item * CH + ch) * kW;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const __nv_bfloat162 p = __floats2bfloat162_rn(row[(start + 2 * j) & 63], row[(start + 2 * j + 1) & 63]);
-      w[j] = *reinterpret_cast<const uint32_t*>(&p);
-    }
+gallery_blocks_kernel(const float* __restrict__ ov, int64_t G, int CH, int bpc, int full, uint4* __restrict__ out) {
+  // CTA = (item pair, 16 feature rows).  Phase 1: the 2 x 16 rows are read once (coalesced float4), rounded to bf16
+  // once and laid out twice over in shared memory (circular wrap).  Phase 2: every 16-byte row of every block is
+  // eight consecutive bf16 of one of those rows; the stores are one contiguous run of the operand.
+  __shared__ __align__(16) unsigned short e[2][kPrepRows][136];  // [item][row][0..127 = row twice over]
+  const int64_t pair = blockIdx.y;
+  const int ch0 = blockIdx.x * kPrepRows;
+  const int n_rows = min(kPrepRows, CH - ch0);
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 2 * kPrepRows * 16; i += 256) {  // one float4 each
+    const int item_l = i / (kPrepRows * 16), rem = i - item_l * (kPrepRows * 16);
+    const int row = rem >> 4, c4 = rem & 15;
+    const int64_t item = 2 * pair + item_l;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (item < G && row < n_rows) v = __ldg(reinterpret_cast<const float4*>(ov + (item * CH + ch0 + row) * kW) + c4);
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    const uint2 w = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+    *reinterpret_cast<uint2*>(&e[item_l][row][4 * c4]) = w;
+    *reinterpret_cast<uint2*>(&e[item_l][row][64 + 4 * c4]) = w;
   }
-  out[id] = make_uint4(w[0], w[1], w[2], w[3]);
+  __syncthreads();
+  const int per_row = bpc * 8;
+  uint4* dst = out + ((pair * CH + ch0) * (int64_t)bpc) * 8;
+  for (int o = tid; o < n_rows * per_row; o += 256) {
+    const int row = o / per_row, rem = o - row * per_row;
+    const int b = rem >> 3, r = rem & 7;
+    int vb = b;  // virtual Hankel block index t + 2u + 4kappa
+    if (full) { const int t = b & 15, u = (b >> 4) & 1, kap = b >> 5; vb = t + 2 * u + 4 * kap; }
+    const unsigned short* src = &e[r & 1][row][4 * vb + (r >> 1)];
+    uint4 w;
+    w.x = (uint32_t)src[0] | ((uint32_t)src[1] << 16);
+    w.y = (uint32_t)src[2] | ((uint32_t)src[3] << 16);
+    w.z = (uint32_t)src[4] | ((uint32_t)src[5] << 16);
+    w.w = (uint32_t)src[6] | ((uint32_t)src[7] << 16);
+    dst[o] = w;
+  }
 }
 
 __global__ void __launch_bounds__(64)
@@ -585,10 +598,14 @@ extern "C" int witw_gallery_prep(const float* ov, int64_t G, int CH, int W, int 
   WITW_REQUIRE(ov && gal_op && crop_inv_norm, WITW_ERR_INVALID, "witw_gallery_prep: null pointer");
   WITW_REQUIRE(((uintptr_t)gal_op & 127) == 0, WITW_ERR_INVALID, "witw_gallery_prep: operand buffer must be 128-byte aligned");
   const int64_t g4 = ceil_div<int64_t>(G, 4) * 4;
-  const int64_t n_chunks = (g4 / 2) * CH * g.bpc * 8;
-  gallery_blocks_kernel<<<(unsigned)ceil_div<int64_t>(n_chunks, 256), 256, 0, as_stream(stream)>>>(
-      ov, G, CH, g.bpc, full_b_layout() ? 1 : 0, g.nkap, reinterpret_cast<uint4*>(gal_op), n_chunks);
-  WITW_LAUNCH_CHECK();
+  WITW_REQUIRE(((uintptr_t)ov & 15) == 0, WITW_ERR_INVALID, "witw_gallery_prep: features must be 16-byte aligned");
+  for (int64_t p0 = 0; p0 < g4 / 2; p0 += 65535) {  // gridDim.y limit
+    const int64_t np = std::min<int64_t>(65535, g4 / 2 - p0);
+    gallery_blocks_kernel<<<dim3((unsigned)ceil_div(CH, kPrepRows), (unsigned)np), 256, 0, as_stream(stream)>>>(
+        ov + p0 * 2 * CH * kW, G - 2 * p0, CH, g.bpc, full_b_layout() ? 1 : 0,
+        reinterpret_cast<uint4*>(gal_op) + p0 * CH * g.bpc * 8);
+    WITW_LAUNCH_CHECK();
+  }
   crop_norm_kernel<<<(unsigned)g4, 64, 0, as_stream(stream)>>>(ov, G, CH, sw, crop_inv_norm);
   WITW_LAUNCH_CHECK();
   return WITW_OK;

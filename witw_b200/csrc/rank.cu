@@ -197,47 +197,68 @@ topk_columns_kernel(const float* __restrict__ dist, int64_t G, int64_t Q, int k,
   }
 }
 
-constexpr int kMergeThreads = 64;
+// k-way merge of sorted candidate lists, one warp per query.  Lane l owns the heads of lists l and l + 32; k times the
+// warp takes the smallest head (ties: the lower list, i.e. the lower gallery indices, as a stable sort would) and its
+// owner advances.  Padding (index < 0) and NaN / +inf distances end a list.
+constexpr int kMergeWarps = 8;
 
-__global__ void __launch_bounds__(kMergeThreads)
+__global__ void __launch_bounds__(kMergeWarps * 32)
 topk_merge_kernel(const float* __restrict__ cd, const int32_t* __restrict__ ci, int n_lists, int64_t Q, int k,
                   float* __restrict__ out_d, int32_t* __restrict__ out_i) {
-  // Thread per query.  The running best-k (ascending, in shared memory [k][threads]) absorbs the sorted candidate
-  // lists one after the other; a list is abandoned at its first entry that cannot enter any more, so the cost is
-  // about n_lists + k*ln(n_lists) candidate reads per query rather than n_lists*k.  Lists are visited in order and
-  // insertion is strict, so among equal distances the earlier list (lower gallery indices) wins.
-  extern __shared__ unsigned char raw[];
-  float* ld = reinterpret_cast<float*>(raw);
-  int32_t* li = reinterpret_cast<int32_t*>(ld + (size_t)k * kMergeThreads);
-  const int t = threadIdx.x;
-  const int64_t q = (int64_t)blockIdx.x * kMergeThreads + t;
+  const int lane = threadIdx.x & 31;
+  const int64_t q = (int64_t)blockIdx.x * kMergeWarps + (threadIdx.x >> 5);
   if (q >= Q) return;
   const float inf = __int_as_float(0x7f800000);
-  for (int j = 0; j < k; ++j) { ld[j * kMergeThreads + t] = inf; li[j * kMergeThreads + t] = -1; }
-  float worst = inf;
-  int filled = 0;
-  for (int l = 0; l < n_lists; ++l) {
-    const float* pd = cd + ((size_t)l * Q + q) * k;
-    const int32_t* pi = ci + ((size_t)l * Q + q) * k;
-    for (int e = 0; e < k; ++e) {
-      const float d = pd[e];
-      const int32_t i = pi[e];
-      if (i < 0 || !(d < worst)) break;  // padding, or nothing further in this sorted list can enter
-      int j = filled < k ? filled : k - 1;
-      while (j > 0 && ld[(j - 1) * kMergeThreads + t] > d) {
-        ld[j * kMergeThreads + t] = ld[(j - 1) * kMergeThreads + t];
-        li[j * kMergeThreads + t] = li[(j - 1) * kMergeThreads + t];
-        --j;
-      }
-      ld[j * kMergeThreads + t] = d;
-      li[j * kMergeThreads + t] = i;
-      if (filled < k) ++filled;
-      if (filled == k) worst = ld[(k - 1) * kMergeThreads + t];
+  const float* pd[2];
+  const int32_t* pi[2];
+  float hd[2];
+  int32_t hi[2];
+  int pos[2] = {0, 0};
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int l = lane + 32 * h;
+    pd[h] = cd + ((size_t)min(l, n_lists - 1) * Q + q) * k;
+    pi[h] = ci + ((size_t)min(l, n_lists - 1) * Q + q) * k;
+    hd[h] = inf;
+    hi[h] = -1;
+    if (l < n_lists) {
+      const float d = pd[h][0];
+      const int32_t i = pi[h][0];
+      if (i >= 0 && d < inf) { hd[h] = d; hi[h] = i; }
     }
   }
   for (int j = 0; j < k; ++j) {
-    out_d[q * k + j] = ld[j * kMergeThreads + t];
-    out_i[q * k + j] = li[j * kMergeThreads + t];
+    // this lane's better head: list `lane` wins ties against list `lane + 32`
+    const int mine = (hd[1] < hd[0]) ? 1 : 0;
+    float bd = mine ? hd[1] : hd[0];
+    int bl = lane + 32 * mine;
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) {
+      const float od = __shfl_xor_sync(0xffffffffu, bd, m);
+      const int ol = __shfl_xor_sync(0xffffffffu, bl, m);
+      if (od < bd || (od == bd && ol < bl)) { bd = od; bl = ol; }
+    }
+    const bool any = bd < inf;
+    const int owner = bl & 31, which = bl >> 5;
+    int32_t widx = -1;
+    if (lane == owner && any) {
+      widx = which ? hi[1] : hi[0];
+      // advance the winning list
+      const int np = (which ? pos[1] : pos[0]) + 1;
+      float nd = inf;
+      int32_t ni = -1;
+      if (np < k) {
+        const float d = (which ? pd[1] : pd[0])[np];
+        const int32_t i = (which ? pi[1] : pi[0])[np];
+        if (i >= 0 && d < inf) { nd = d; ni = i; }
+      }
+      if (which) { pos[1] = np; hd[1] = nd; hi[1] = ni; } else { pos[0] = np; hd[0] = nd; hi[0] = ni; }
+    }
+    widx = __shfl_sync(0xffffffffu, widx, owner);
+    if (lane == 0) {
+      out_d[q * k + j] = any ? bd : inf;
+      out_i[q * k + j] = any ? widx : -1;
+    }
   }
 }
 
@@ -327,10 +348,9 @@ extern "C" int witw_topk_merge(const float* cand_dist, const int32_t* cand_idx, 
   WITW_REQUIRE(n_lists > 0 && n_lists <= 64 && Q >= 0 && k > 0 && k <= 128, WITW_ERR_INVALID, "witw_topk_merge: bad shape (n_lists 1..64, k 1..128)");
   if (Q == 0) return WITW_OK;
   WITW_REQUIRE(cand_dist && cand_idx && topk_dist && topk_idx, WITW_ERR_INVALID, "witw_topk_merge: null pointer");
-  const size_t smem = (size_t)k * kMergeThreads * 8;
-  WITW_CUDA(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  topk_merge_kernel<<<(unsigned)ceil_div<int64_t>(Q, kMergeThreads), kMergeThreads, smem, as_stream(stream)>>>(cand_dist, cand_idx, n_lists, Q, k,
-                                                                                                          topk_dist, topk_idx);
+  WITW_REQUIRE(ceil_div<int64_t>(Q, kMergeWarps) < (1ll << 31), WITW_ERR_INVALID, "witw_topk_merge: too many queries");
+  topk_merge_kernel<<<(unsigned)ceil_div<int64_t>(Q, kMergeWarps), kMergeWarps * 32, 0, as_stream(stream)>>>(cand_dist, cand_idx, n_lists, Q, k,
+                                                                                                       topk_dist, topk_idx);
   WITW_LAUNCH_CHECK();
   return WITW_OK;
 }

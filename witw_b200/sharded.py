@@ -4,7 +4,8 @@ Gallery items are independent, so rank p of P owns a contiguous slice of the gal
 every rank holds all queries.  One sweep needs three tiny exchanges over NCCL / NVLink:
 
   1. true-match distances: the owner of gallery item true_idx[q] computes d_true[q] in fp32;
-     all-reduce(sum) of a [Q] vector that is zero everywhere else
+     all-reduce(sum) of a [Q] vector that is zero everywhere else (a NaN distance -- zero-norm
+     features -- stays NaN through the sum, as it must)
   2. rank counts: all-reduce(sum) of the local #{g : d[g,q] <= d_true[q]}  -> the exact
      reference ranks (cvig_fov.py:552) for the whole gallery
   3. top-k: all-gather of each shard's [Q,k] (distance, global index) candidates, then a k-way merge
@@ -26,24 +27,54 @@ def shard_bounds(n_items, world_size, rank):
 
 
 class CudaLocal(object):
-    """Local shard compute on the B200 kernels."""
+    """Local shard compute on the B200 kernels.
 
-    def __init__(self, path="auto"):
+    event_sink: optional list; every tensor-core sweep appends the (start, end) torch.cuda.Event pair recorded around
+    the sweep kernel alone (bench.py's roofline timer)."""
+
+    def __init__(self, path="auto", event_sink=None):
         self.path = path
+        self.event_sink = event_sink
+        self._key = None
+        self._prepared = None
 
-    def true_distances(self, ov_local, su_owned, local_idx):
-        d, _ = ops.true_match_distances(ov_local, su_owned, local_idx)
+    def _operands(self, ov_local, su):
+        """Prepared (GalleryIndex, QueryBatch) of this shard, shared by true_distances() and sweep() of one evaluation."""
+        key = (ov_local.data_ptr(), tuple(ov_local.shape), su.data_ptr(), tuple(su.shape), ov_local._version, su._version)
+        if self._key != key:
+            self._prepared = (ops.GalleryIndex(ov_local, su.shape[3]), ops.QueryBatch(su))
+            self._key = key
+        return self._prepared
+
+    def _tc(self, ov_local, su):
+        g, q, ch, w, sw = ops._feature_dims("sweep", ov_local, su)
+        return ops._pick_path(self.path, g, q, ch, w, sw) == "tc"
+
+    def true_distances(self, ov_local, su, local_idx):
+        """Exact fp32 distance of query i to local gallery item local_idx[i]."""
+        if self._tc(ov_local, su) and ops.EXACT_IMPL == "spectral":
+            gallery, queries = self._operands(ov_local, su)
+            pq = torch.arange(su.shape[0], dtype=torch.int64, device=su.device)
+            return ops.pair_distances_prepared(gallery, queries, local_idx.to(torch.int64).contiguous(), pq)[0]
+        g = ov_local.shape[0]
+        if int(local_idx.numel()) and (int(local_idx.max()) >= g or int(local_idx.min()) < 0):
+            raise IndexError("true_distances: index outside the shard")
+        d, _ = ops.true_match_distances(ov_local, su, local_idx)
         return d
 
     def sweep(self, ov_local, su, d_true, true_idx, g_offset, topk):
-        g, q, ch, w, sw = ops._feature_dims("sweep", ov_local, su)
-        dev = su.device
-        if ops._pick_path(self.path, g, q, ch, w, sw) == "tc":
+        if self._tc(ov_local, su):
             # exact finish inside the shard: fp32 re-check of near-threshold rank decisions and fp32 re-ranking of the
             # shard's top-k candidates, so what is exchanged are already the reference's counts and distances
-            gallery = ops.GalleryIndex(ov_local, sw, g_offset=g_offset)
-            queries = ops.QueryBatch(su)
-            res = ops.evaluate_ranks_prepared(gallery, queries, true_idx=true_idx - g_offset, topk=topk, d_true=d_true)
+            gallery, queries = self._operands(ov_local, su)
+            gallery.g_offset = int(g_offset)
+            self._key = None   # one evaluation per preparation: the caller may overwrite the buffers in place
+            ev = None
+            if self.event_sink is not None:
+                ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                self.event_sink.append(ev)
+            # a true match outside this shard gets a local index outside [0, G): it is never counted by index here
+            res = ops.evaluate_ranks_prepared(gallery, queries, true_idx=true_idx - g_offset, topk=topk, d_true=d_true, events=ev)
             if topk:
                 return res
             return res, None, None
@@ -74,16 +105,22 @@ def evaluate_ranks_sharded(ov_local, surface_embed, g_offset, n_gallery_total, t
     dev = surface_embed.device
     q = surface_embed.shape[0]
     g_local = ov_local.shape[0]
-    t_idx = torch.arange(q, dtype=torch.int64, device=dev) if true_idx is None else true_idx.to(dev, torch.int64)
-    if q and (int(t_idx.max()) >= n_gallery_total or int(t_idx.min()) < 0):
-        raise IndexError("evaluate_ranks_sharded: true index outside the gallery")
+    if true_idx is None:
+        if q > n_gallery_total:
+            raise IndexError("evaluate_ranks_sharded: %d queries but only %d gallery items and no true_idx" % (q, n_gallery_total))
+        t_idx = torch.arange(q, dtype=torch.int64, device=dev)
+    else:
+        t_idx = true_idx.to(dev, torch.int64)
+        if q and (int(t_idx.max()) >= n_gallery_total or int(t_idx.min()) < 0):
+            raise IndexError("evaluate_ranks_sharded: true index outside the gallery")
 
-    # (1) true-match distances from their owners
+    # (1) true-match distances from their owners.  No host round trip: every rank evaluates all Q pairs with the index
+    # clamped into its slice and keeps the ones it owns; the others contribute zero to the sum
     d_true = torch.zeros(q, dtype=torch.float32, device=dev)
-    mine = (t_idx >= g_offset) & (t_idx < g_offset + g_local)
-    owned = torch.nonzero(mine).squeeze(1)
-    if owned.numel():
-        d_true[owned] = local.true_distances(ov_local, surface_embed[owned], t_idx[owned] - g_offset)
+    if g_local > 0 and q > 0:
+        mine = (t_idx >= g_offset) & (t_idx < g_offset + g_local)
+        d = local.true_distances(ov_local, surface_embed, (t_idx - g_offset).clamp(0, g_local - 1))
+        d_true = torch.where(mine, d.to(torch.float32), d_true)
     if world > 1:
         dist.all_reduce(d_true, op=dist.ReduceOp.SUM, group=group)
 

@@ -197,6 +197,35 @@ int witw_topk_refine_spec_f32(const float* gal_spec_dev, const float* crop_inv_n
                               float* topk_dist_dev, int32_t* topk_idx_dev, void* scratch_dev,
                               witw_stream_t stream);
 
+/* The whole-gallery sweep in the azimuth-frequency domain (csrc/match_spec.cu): the same contract as
+ * witw_match_tc -- correlation -> crop_overhead -> l2_distance of cvig_fov.py:297-363, the rank rule of :552 and a
+ * per-query top-k -- but the circular correlation is evaluated through the correlation theorem:
+ *     corr[g,q,:] = irfft( sum_r O[g,r,f] conj(S[q,r,f]) )
+ * The per-frequency products (33 bins x 64 feature rows of complex MACs, 16.9 kFLOP per pair instead of 524 kFLOP at
+ * 360 degrees) run on tcgen05 with bf16 spectra and fp32 accumulation in TMEM; the 64-point inverse real FFT, the
+ * argmax over the shift and everything after it run in the epilogue, register-local.  Needs C*H == 64 and W == 64.
+ *   witw_spec_gallery_prep: ov [G,64,64] fp32 -> bf16 spectra in the operand layout (16 KB per item, groups of 8
+ *        items) and crop_inv_norm [G rounded up to 8, 64].  g_first = index of ov[0] inside the operand (a multiple
+ *        of 8 unless it continues a partial group), so an encode loop can append batch by batch.
+ *   witw_spec_query_prep: su [Q,64,sw] fp32 -> bf16 spectra of the zero-padded rows, scaled by 1/64 (8 KB per
+ *        query), and q_inv_norm [Q].
+ *   witw_match_spec: arguments as witw_match_tc; top-k candidate lists: witw_match_spec_topk_slots(). */
+int witw_spec_supported(int CH, int W, int sw);
+size_t witw_spec_gallery_operand_bytes(int64_t G, int CH);
+size_t witw_spec_query_operand_bytes(int64_t Q, int CH);
+int witw_spec_gallery_prep(const float* ov_dev, int64_t G, int64_t g_first, int CH, int W, int sw,
+                           void* gal_op_dev, float* crop_inv_norm_dev, witw_stream_t stream);
+int witw_spec_query_prep(const float* su_dev, int64_t Q, int CH, int sw, void* qry_op_dev,
+                         float* q_inv_norm_dev, witw_stream_t stream);
+int witw_match_spec_topk_slots(int64_t G, int64_t Q);
+int witw_match_spec(const void* gal_op_dev, const float* crop_inv_norm_dev, const void* qry_op_dev,
+                    const float* q_inv_norm_dev, int64_t G, int64_t Q, int CH, int sw,
+                    float* dist_dev, uint8_t* ori_dev, const float* d_true_dev,
+                    const int32_t* true_idx_dev, int32_t* rank_count_dev, int topk,
+                    float* topk_dist_dev, int32_t* topk_idx_dev, int32_t g_index_offset,
+                    float recheck_band, int64_t* recheck_g_dev, int64_t* recheck_q_dev,
+                    int32_t* recheck_count_dev, int32_t recheck_capacity, witw_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * K4  rank / top-k               replaces model/cvig_fov.py:550-552 and
  *                                model/cvig_baseline.py:456-460

@@ -16,6 +16,14 @@ def W():
     return witw_b200
 
 
+@pytest.fixture(autouse=True)
+def _hankel_sweep(W):
+    """This module tests the dense-contraction sweep (csrc/match_tc.cu); tests/test_gpu_spec.py covers the spectral one."""
+    W.ops.TC_IMPL = "hankel"
+    yield
+    W.ops.TC_IMPL = "auto"
+
+
 def bf16_model(ov, su):
     """What the kernel computes, in float64: correlation of bf16-rounded operands, norms of the fp32 inputs."""
     corr = O.fused_fp64(ov.bfloat16().float(), su.bfloat16().float())[0]

@@ -17,28 +17,17 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "row_fft.cuh"
 
 namespace witw {
 
-__device__ __forceinline__ int brev5(int n) { return (int)(__brev((unsigned)n) >> 27); }
-
-// One warp per row: the 64 real samples are 32 complex points z[n] = x[2n] + i x[2n+1], one per lane;
-// a 5-stage decimation-in-frequency FFT over the lanes (shuffles), then the real-input split.
+// One warp per row (RowFft, row_fft.cuh).
 __global__ void __launch_bounds__(256)
 spectral_rows_kernel(const float* __restrict__ x, int64_t n_rows, int row_len, float* __restrict__ spec) {
   const int lane = threadIdx.x & 31;
   const int64_t stride = (int64_t)gridDim.x * 8;
-  float2 tw[5];  // stage twiddles exp(-2 pi i (lane mod h) / 2h), h = 16, 8, 4, 2, 1
-#pragma unroll
-  for (int st = 0; st < 5; ++st) {
-    const int h = 16 >> st;
-    float s, c;
-    sincospif((float)(lane & (h - 1)) / (float)h, &s, &c);
-    tw[st] = make_float2(c, -s);
-  }
-  float ws, wc;  // exp(-2 pi i lane / 64) = (wc, -ws)
-  sincospif((float)lane / 32.0f, &ws, &wc);
-  const int src_k = brev5(lane), src_m = brev5((32 - lane) & 31);
+  RowFft fft;
+  fft.init(lane);
   const bool full = row_len == 64 && ((uintptr_t)x & 7) == 0;
   for (int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); row < n_rows; row += stride) {
     float2 z;
@@ -50,29 +39,7 @@ spectral_rows_kernel(const float* __restrict__ x, int64_t n_rows, int row_len, f
       z.x = j < row_len ? r[j] : 0.f;
       z.y = j + 1 < row_len ? r[j + 1] : 0.f;
     }
-#pragma unroll
-    for (int st = 0; st < 5; ++st) {
-      const int h = 16 >> st;
-      const float ox = __shfl_xor_sync(0xffffffffu, z.x, h), oy = __shfl_xor_sync(0xffffffffu, z.y, h);
-      if (lane & h) {
-        const float dx = ox - z.x, dy = oy - z.y;
-        z.x = dx * tw[st].x - dy * tw[st].y;
-        z.y = dx * tw[st].y + dy * tw[st].x;
-      } else {
-        z.x += ox;
-        z.y += oy;
-      }
-    }
-    // lane n now holds Z[bitrev(n)].  X_k = E_k + W^k O_k with E = (Z_k + conj Z_{32-k})/2, O = -i (Z_k - conj Z_{32-k})/2
-    const float ax = __shfl_sync(0xffffffffu, z.x, src_k), ay = __shfl_sync(0xffffffffu, z.y, src_k);
-    const float bx = __shfl_sync(0xffffffffu, z.x, src_m), by = -__shfl_sync(0xffffffffu, z.y, src_m);
-    const float ex = 0.5f * (ax + bx), ey = 0.5f * (ay + by);
-    const float ox = 0.5f * (ay - by), oy = -0.5f * (ax - bx);
-    float2 X;
-    X.x = ex + (wc * ox + ws * oy);
-    X.y = ey + (wc * oy - ws * ox);
-    if (lane == 0) { X.x = ax + ay; X.y = ax - ay; }  // X_0 and X_32
-    reinterpret_cast<float2*>(spec + row * 64)[lane] = X;
+    reinterpret_cast<float2*>(spec + row * 64)[lane] = fft.run(z, lane);
   }
 }
 

@@ -39,6 +39,26 @@ OVERHEAD_SIZE = 256
 TC_MIN_PAIRS = 1 << 16
 
 
+# Which tensor-core sweep serves a (gallery, query width): "hankel" = the shift search as one dense contraction
+# (csrc/match_tc.cu, 8192*sw_pad FLOP per pair), "spectral" = per-frequency products + inverse FFT in the epilogue
+# (csrc/match_spec.cu, 16.9 kFLOP per pair whatever the width; needs C*H == 64).  "auto": spectral when it is
+# supported and the query is wider than SPEC_MIN_SW columns (below that the dense contraction is cheaper).
+TC_IMPL = "auto"
+SPEC_MIN_SW = 16
+
+
+def _pick_impl(impl, ch, w, sw):
+    impl = TC_IMPL if impl in (None, "auto") else impl
+    if impl == "auto":
+        ok = bool(_lib.load().witw_spec_supported(int(ch), int(w), int(sw)))
+        return "spectral" if (ok and sw > SPEC_MIN_SW) else "hankel"
+    if impl not in ("hankel", "spectral"):
+        raise ValueError("impl must be 'auto', 'hankel' or 'spectral'")
+    if impl == "spectral" and not _lib.load().witw_spec_supported(int(ch), int(w), int(sw)):
+        raise _lib.WitwError("spectral sweep does not cover CH=%d W=%d sw=%d" % (ch, w, sw))
+    return impl
+
+
 # how the exact fp32 finish of the tensor-core sweep evaluates its pairs: "spectral" (correlation theorem on packed
 # azimuth spectra, csrc/spectral.cu) or "direct" (4096-term fp32 dot products per shift, csrc/match_simt.cu)
 EXACT_IMPL = "spectral"
@@ -227,7 +247,7 @@ class GalleryIndex(object):
     global index of the first item when the gallery is one shard of a larger one.
     """
 
-    def __init__(self, overhead_embed, surface_width, g_offset=0, keep_fp32=True):
+    def __init__(self, overhead_embed, surface_width, g_offset=0, keep_fp32=True, impl=None):
         dev = _need_cuda("GalleryIndex", overhead_embed)
         if overhead_embed.dim() != 4:
             raise ValueError("GalleryIndex: expected [G,C,H,W]")
@@ -238,6 +258,16 @@ class GalleryIndex(object):
         ov = _f32c(overhead_embed)
         self.ov = ov if keep_fp32 else None
         self.spec = None
+        self.impl = _pick_impl(impl, self.CH, w, self.sw) if w == 64 else "hankel"
+        if self.impl == "spectral":
+            with torch.cuda.device(dev):
+                nbytes = _lib.load().witw_spec_gallery_operand_bytes(g, self.CH)
+                self.operand = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+                g8 = max((g + 7) // 8 * 8, 8)
+                self.crop_inv_norm = torch.empty(g8 * 64, dtype=torch.float32, device=dev)
+                _lib.call("witw_spec_gallery_prep", ov.data_ptr(), g, 0, self.CH, w, self.sw, self.operand.data_ptr(),
+                          self.crop_inv_norm.data_ptr(), _stream())
+            return
         with torch.cuda.device(dev):
             nbytes = _lib.load().witw_gallery_operand_bytes(g, self.CH, self.sw)
             if nbytes == 0 or w != 64:
@@ -263,12 +293,12 @@ class GalleryBuilder(object):
     The reference grows ``overhead_embed`` with torch.cat per batch (O(n^2) copies).  Here each encoder
     output batch is written once: fp32 features into a preallocated buffer (kept for the exact true-match
     distances) and, through witw_gallery_prep, straight into its slot of the tensor-core operand.
-    Batches must hold a multiple of 4 items, except the last one.  keep_fp32: keep what the exact fp32 finish needs
+    Batches must hold a multiple of 4 items (8 for the spectral sweep: ``batch_multiple``), except the last one.  keep_fp32: keep what the exact fp32 finish needs
     (the packed azimuth spectra of the features, 16 KB per item); keep_raw: also keep the raw fp32 features.
     """
 
     def __init__(self, capacity, surface_width, channels=16, height=4, width=64, device=None, g_offset=0, keep_fp32=True,
-                 keep_raw=False):
+                 keep_raw=False, impl=None):
         if not torch.cuda.is_available():
             raise RuntimeError("GalleryBuilder: no CUDA device; witw_b200 has no CPU fallback")
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
@@ -276,13 +306,19 @@ class GalleryBuilder(object):
         self.C, self.H, self.W, self.CH = channels, height, width, channels * height
         self.g_offset, self.count, self.closed = int(g_offset), 0, False
         lib = _lib.load()
+        self.impl = _pick_impl(impl, self.CH, width, self.sw) if width == 64 else "hankel"
+        self.batch_multiple = 8 if self.impl == "spectral" else 4
         with torch.cuda.device(self.device):
-            nbytes = lib.witw_gallery_operand_bytes(self.capacity, self.CH, self.sw)
-            if nbytes == 0 or width != 64:
-                raise _lib.WitwError("GalleryBuilder: " + (_lib.last_error() if width == 64 else "tensor-core path needs W == 64"))
-            self.pair_bytes = lib.witw_gallery_operand_bytes(4, self.CH, self.sw) // 2
+            if self.impl == "spectral":
+                nbytes = lib.witw_spec_gallery_operand_bytes(self.capacity, self.CH)
+                self.pair_bytes = 0
+            else:
+                nbytes = lib.witw_gallery_operand_bytes(self.capacity, self.CH, self.sw)
+                if nbytes == 0 or width != 64:
+                    raise _lib.WitwError("GalleryBuilder: " + (_lib.last_error() if width == 64 else "tensor-core path needs W == 64"))
+                self.pair_bytes = lib.witw_gallery_operand_bytes(4, self.CH, self.sw) // 2
             self.operand = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
-            cap4 = max((self.capacity + 3) // 4 * 4, 4)
+            cap4 = max((self.capacity + 7) // 8 * 8, 8)
             self.crop_inv_norm = torch.zeros(cap4 * 64, dtype=torch.float32, device=self.device)
             self.ov = torch.empty((self.capacity, channels, height, width), dtype=torch.float32, device=self.device) if keep_raw else None
             self.spec = torch.empty((self.capacity * self.CH, 64), dtype=torch.float32, device=self.device) if keep_fp32 else None
@@ -291,7 +327,7 @@ class GalleryBuilder(object):
         """Add one encoder output batch [n,C,H,W] (CUDA)."""
         _need_cuda("GalleryBuilder.append", overhead_embed_part)
         if self.closed:
-            raise RuntimeError("GalleryBuilder.append: a batch that is not a multiple of 4 items must be the last one")
+            raise RuntimeError("GalleryBuilder.append: a batch that is not a multiple of %d items must be the last one" % self.batch_multiple)
         n = overhead_embed_part.shape[0]
         if tuple(overhead_embed_part.shape[1:]) != (self.C, self.H, self.W):
             raise ValueError("GalleryBuilder.append: expected [n,%d,%d,%d]" % (self.C, self.H, self.W))
@@ -306,18 +342,22 @@ class GalleryBuilder(object):
             if self.spec is not None:
                 _lib.call("witw_spectral_rows_f32", part.data_ptr(), n * self.CH, self.W,
                           self.spec.data_ptr() + self.count * self.CH * 64 * 4, _stream())
-            _lib.call("witw_gallery_prep", part.data_ptr(), n, self.CH, self.W, self.sw,
-                      self.operand.data_ptr() + (self.count // 2) * self.pair_bytes,
-                      self.crop_inv_norm.data_ptr() + self.count * 64 * 4, _stream())
+            if self.impl == "spectral":
+                _lib.call("witw_spec_gallery_prep", part.data_ptr(), n, self.count, self.CH, self.W, self.sw, self.operand.data_ptr(),
+                          self.crop_inv_norm.data_ptr() + self.count * 64 * 4, _stream())
+            else:
+                _lib.call("witw_gallery_prep", part.data_ptr(), n, self.CH, self.W, self.sw,
+                          self.operand.data_ptr() + (self.count // 2) * self.pair_bytes,
+                          self.crop_inv_norm.data_ptr() + self.count * 64 * 4, _stream())
         self.count += n
-        self.closed = n % 4 != 0
+        self.closed = n % self.batch_multiple != 0
         return self
 
     def finish(self):
         """The GalleryIndex over everything appended so far."""
         idx = GalleryIndex.__new__(GalleryIndex)
         idx.device, idx.G, idx.CH, idx.W, idx.sw = self.device, self.count, self.CH, self.W, self.sw
-        idx.C, idx.H, idx.g_offset = self.C, self.H, self.g_offset
+        idx.C, idx.H, idx.g_offset, idx.impl = self.C, self.H, self.g_offset, self.impl
         idx.ov = None if self.ov is None else self.ov[: self.count]
         idx.spec = None if self.spec is None else self.spec[: self.count * self.CH]
         idx.operand, idx.crop_inv_norm = self.operand, self.crop_inv_norm
@@ -327,13 +367,20 @@ class GalleryBuilder(object):
 class QueryBatch(object):
     """Query feature maps prepared for the tensor-core sweep (bf16 [Q, CH*sw_pad] + inverse norms)."""
 
-    def __init__(self, surface_embed, keep_fp32=True):
+    def __init__(self, surface_embed, keep_fp32=True, impl=None):
         dev = _need_cuda("QueryBatch", surface_embed)
         q, c, h, sw = surface_embed.shape
         self.device, self.Q, self.CH, self.sw = dev, q, c * h, sw
         su = _f32c(surface_embed)
         self.su = su if keep_fp32 else None
         self.spec = None
+        self.impl = _pick_impl(impl, self.CH, 64, sw)
+        if self.impl == "spectral":
+            with torch.cuda.device(dev):
+                self.operand = torch.empty(_lib.load().witw_spec_query_operand_bytes(q, self.CH), dtype=torch.uint8, device=dev)
+                self.inv_norm = torch.empty(max(q, 1), dtype=torch.float32, device=dev)
+                _lib.call("witw_spec_query_prep", su.data_ptr(), q, self.CH, sw, self.operand.data_ptr(), self.inv_norm.data_ptr(), _stream())
+            return
         with torch.cuda.device(dev):
             nbytes = _lib.load().witw_query_operand_bytes(q, self.CH, sw)
             if nbytes == 0:
@@ -378,6 +425,9 @@ def sweep_tc(gallery, queries, want_dist=False, want_ori=False, d_true=None, tru
     of evaluate_ranks_prepared)."""
     if gallery.CH != queries.CH or gallery.sw != queries.sw or gallery.device != queries.device:
         raise ValueError("sweep_tc: gallery and queries disagree (CH %d/%d, sw %d/%d)" % (gallery.CH, queries.CH, gallery.sw, queries.sw))
+    if gallery.impl != queries.impl:
+        raise ValueError("sweep_tc: gallery operand is %r but the query operand is %r" % (gallery.impl, queries.impl))
+    fn_sweep, fn_slots = ("witw_match_spec", "witw_match_spec_topk_slots") if gallery.impl == "spectral" else ("witw_match_tc", "witw_match_tc_topk_slots")
     dev, g, q = gallery.device, gallery.G, queries.Q
     out = {}
     with torch.cuda.device(dev):
@@ -386,13 +436,13 @@ def sweep_tc(gallery, queries, want_dist=False, want_ori=False, d_true=None, tru
         tk_d = tk_i = None
         slots = 0
         if topk:
-            slots = _lib.load().witw_match_tc_topk_slots(g, q)
+            slots = getattr(_lib.load(), fn_slots)(g, q)
             tk_d = torch.empty((slots, q, topk), dtype=torch.float32, device=dev)
             tk_i = torch.empty((slots, q, topk), dtype=torch.int32, device=dev)
         if g > 0 and q > 0:
             if events is not None:
                 events[0].record()
-            _lib.call("witw_match_tc", gallery.operand.data_ptr(), gallery.crop_inv_norm.data_ptr(), queries.operand.data_ptr(),
+            _lib.call(fn_sweep, gallery.operand.data_ptr(), gallery.crop_inv_norm.data_ptr(), queries.operand.data_ptr(),
                       queries.inv_norm.data_ptr(), g, q, gallery.CH, gallery.sw, _ptr(dist), _ptr(ori), _ptr(d_true),
                       _ptr(true_idx), _ptr(rank_count), int(topk), _ptr(tk_d), _ptr(tk_i), gallery.g_offset,
                       float(recheck.band) if recheck else 0.0, _ptr(recheck.g) if recheck else 0, _ptr(recheck.q) if recheck else 0,
@@ -409,7 +459,7 @@ def sweep_tc(gallery, queries, want_dist=False, want_ori=False, d_true=None, tru
     return out
 
 
-def match(overhead_embed, surface_embed, path="auto"):
+def match(overhead_embed, surface_embed, path="auto", impl=None):
     """(orientation int64 [G,Q], distance fp32 [G,Q]) = a3 -> a4 -> a5 fused (cvig_fov.py:547-549).
 
     path 'fp32': exact fp32 kernel; 'tc': tcgen05 bf16 x bf16 -> fp32; 'auto': by problem size.
@@ -418,7 +468,8 @@ def match(overhead_embed, surface_embed, path="auto"):
     g, q, ch, w, sw = _feature_dims("match", overhead_embed, surface_embed)
     which = _pick_path(path, g, q, ch, w, sw)
     if which == "tc":
-        res = sweep_tc(GalleryIndex(overhead_embed, sw, keep_fp32=False), QueryBatch(surface_embed, keep_fp32=False),
+        impl = _pick_impl(impl, ch, w, sw)
+        res = sweep_tc(GalleryIndex(overhead_embed, sw, keep_fp32=False, impl=impl), QueryBatch(surface_embed, keep_fp32=False, impl=impl),
                        want_dist=True, want_ori=True)
         return res["ori"].to(torch.int64), res["dist"]
     ov, su = _f32c(overhead_embed), _f32c(surface_embed)
@@ -599,7 +650,7 @@ def topk_from_distances(distances, k, g_offset=0):
     return td, ti
 
 
-def evaluate_ranks(overhead_embed, surface_embed, true_idx=None, path="auto", topk=0, exact=True):
+def evaluate_ranks(overhead_embed, surface_embed, true_idx=None, path="auto", topk=0, exact=True, impl=None):
     """The rank loop of test() (cvig_fov.py:543-552) as one call: ranks int64 [count] on the device.
 
     Query i matches gallery item i (or true_idx[i]).  The true-match distances are computed in
@@ -619,8 +670,9 @@ def evaluate_ranks(overhead_embed, surface_embed, true_idx=None, path="auto", to
         if topk:
             return (ranks,) + topk_from_distances(dist, topk)
         return ranks
-    gallery = GalleryIndex(overhead_embed, sw)
-    queries = QueryBatch(surface_embed)
+    impl = _pick_impl(impl, ch, w, sw)
+    gallery = GalleryIndex(overhead_embed, sw, impl=impl)
+    queries = QueryBatch(surface_embed, impl=impl)
     return evaluate_ranks_prepared(gallery, queries, true_idx=true_idx, topk=topk, exact=exact)
 
 

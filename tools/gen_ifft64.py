@@ -56,9 +56,32 @@ class Emitter(object):
         v = np.float32(np.float64(self.vals[a]) * np.float64(np.float32(c)) + np.float64(self.vals[b]))
         return self._new("fmaf(%s, %s, %s)" % (a, self.lit(c), b), v)
 
-    def fmac_neg(self, a, c, b):  # a*c - b
-        v = np.float32(np.float64(self.vals[a]) * np.float64(np.float32(c)) - np.float64(self.vals[b]))
-        return self._new("fmaf(%s, %s, -%s)" % (a, self.lit(c), b), v)
+
+
+class PackedEmitter(Emitter):
+    """Same operation list on float2 operands: two independent transforms in the .x and .y halves, one packed
+    FADD2 / FMUL2 / FFMA2 (sm_100 f32x2) instruction per operation."""
+
+    def _new(self, expr, val):
+        name = "t%d" % self.n
+        self.n += 1
+        self.ops += 1
+        self.lines.append("  const float2 %s = %s;" % (name, expr))
+        self.vals[name] = np.float32(val)
+        return name
+
+    def add(self, a, b):
+        return self._new("__fadd2_rn(%s, %s)" % (a, b), self.vals[a] + self.vals[b])
+
+    def sub(self, a, b):
+        return self._new("__ffma2_rn(%s, neg1, %s)" % (b, a), self.vals[a] - self.vals[b])
+
+    def mulc(self, a, c):
+        return self._new("__fmul2_rn(%s, make_float2(%s, %s))" % (a, self.lit(c), self.lit(c)), self.vals[a] * np.float32(c))
+
+    def fmac(self, a, c, b):
+        v = np.float32(np.float64(self.vals[a]) * np.float64(np.float32(c)) + np.float64(self.vals[b]))
+        return self._new("__ffma2_rn(%s, make_float2(%s, %s), %s)" % (a, self.lit(c), self.lit(c), b), v)
 
 
 def brev5(i):
@@ -80,8 +103,8 @@ def build(e, re, im):
         di = e.add(im[k], im[kk])
         c, s = math.cos(2 * math.pi * k / 64), math.sin(2 * math.pi * k / 64)
         # T = D * w^k
-        p = e.mulc(di, s)
-        tr = e.fmac_neg(dr, c, p)        # dr*c - di*s
+        p = e.mulc(di, -s)
+        tr = e.fmac(dr, c, p)            # dr*c - di*s
         q = e.mulc(di, c)
         ti = e.fmac(dr, s, q)            # dr*s + di*c
         # Z_k = A + iT = (ar - ti, ai + tr);  Z_{32-k} = conj(A) + i conj(T) = (ar + ti, tr - ai)
@@ -110,8 +133,8 @@ def build(e, re, im):
                     o1 = (e.fmac(d, c, u[0]), e.fmac(f, c, u[1]))
                     o2 = (e.fmac(d, -c, u[0]), e.fmac(f, -c, u[1]))
                 else:
-                    p = e.mulc(v[1], s)
-                    tr = e.fmac_neg(v[0], c, p)
+                    p = e.mulc(v[1], -s)
+                    tr = e.fmac(v[0], c, p)
                     q = e.mulc(v[1], c)
                     ti = e.fmac(v[0], s, q)
                     o1 = (e.add(u[0], tr), e.add(u[1], ti))
@@ -127,28 +150,32 @@ def build(e, re, im):
 def main():
     rng = np.random.default_rng(7)
     worst = 0.0
-    e = None
-    for trial in range(4):
-        sig = rng.standard_normal(64)
-        spec = np.fft.rfft(sig) / 64.0
-        re_v = [spec[0].real] + [spec[f].real for f in range(1, 32)]
-        im_v = [spec[32].real] + [spec[f].imag for f in range(1, 32)]
-        e = Emitter()
-        re = [e.inp("re[%d]" % f, re_v[f]) for f in range(32)]
-        im = [e.inp("im[%d]" % f, im_v[f]) for f in range(32)]
-        out = build(e, re, im)
-        got = np.array([e.vals[o] for o in out], dtype=np.float64)
-        worst = max(worst, np.abs(got - sig).max() / np.abs(sig).max())
-    assert worst < 2e-6, worst
-    body = "\n".join(e.lines)
-    assign = "\n".join("  x[%d] = %s;" % (s, o) for s, o in enumerate(out))
+    bodies = {}
+    for cls in (Emitter, PackedEmitter):
+        for trial in range(4):
+            sig = rng.standard_normal(64)
+            spec = np.fft.rfft(sig) / 64.0
+            re_v = [spec[0].real] + [spec[f].real for f in range(1, 32)]
+            im_v = [spec[32].real] + [spec[f].imag for f in range(1, 32)]
+            e = cls()
+            re = [e.inp("re[%d]" % f, re_v[f]) for f in range(32)]
+            im = [e.inp("im[%d]" % f, im_v[f]) for f in range(32)]
+            out = build(e, re, im)
+            got = np.array([e.vals[o] for o in out], dtype=np.float64)
+            worst = max(worst, np.abs(got - sig).max() / np.abs(sig).max())
+        assert worst < 2e-6, worst
+        bodies[cls] = ("\n".join(e.lines), "\n".join("  x[%d] = %s;" % (s, o) for s, o in enumerate(out)))
     text = (
         "// GENERATED by tools/gen_ifft64.py -- do not edit.  %d fp32 operations, checked against numpy.fft.irfft\n"
         "// (worst relative error %.1e in float32).\n"
         "// x[s] = sum_f P_f e^{+2 pi i f s/64} for the packed Hermitian spectrum re[0]=P_0, im[0]=P_32, (re[f],im[f])=P_f.\n"
         "#pragma once\n\nnamespace witw {\n\n"
         "__device__ __forceinline__ void ifft64_hermitian(const float (&re)[32], const float (&im)[32], float (&x)[64]) {\n"
-        "%s\n%s\n}\n\n}  // namespace witw\n" % (e.ops, worst, body, assign)
+        "%s\n%s\n}\n\n"
+        "// Two transforms at once, one in each half of the float2 operands (FADD2 / FMUL2 / FFMA2).\n"
+        "__device__ __forceinline__ void ifft64_hermitian_x2(const float2 (&re)[32], const float2 (&im)[32], float2 (&x)[64]) {\n"
+        "  const float2 neg1 = make_float2(-1.0f, -1.0f);\n"
+        "%s\n%s\n}\n\n}  // namespace witw\n" % ((e.ops, worst) + bodies[Emitter] + bodies[PackedEmitter])
     )
     with open(OUT, "w") as f:
         f.write(text)

@@ -2,7 +2,8 @@
 # bring-up of the spectral sweep: parity tests first, then timing per cluster size
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv,noheader
-timeout 900 python -m pytest tests/test_gpu_spec.py -m gpu -q --no-header -p no:cacheprovider -x > gpurun_out/spec_tests.log 2>&1; echo "spec tests rc=$?"; tail -30 gpurun_out/spec_tests.log | cut -c1-400
+WITW_SPEC_CS=1 timeout 900 python -m pytest tests/test_gpu_spec.py -m gpu -q --no-header -p no:cacheprovider -k "not cluster_sizes" > gpurun_out/spec_tests_cs1.log 2>&1; echo "spec tests cs1 rc=$?"; tail -40 gpurun_out/spec_tests_cs1.log | cut -c1-300
+timeout 900 python -m pytest tests/test_gpu_spec.py -m gpu -q --no-header -p no:cacheprovider > gpurun_out/spec_tests.log 2>&1; echo "spec tests rc=$?"; tail -40 gpurun_out/spec_tests.log | cut -c1-300
 : > gpurun_out/spec_bench.jsonl
 for cs in 1 2 4 8; do
   WITW_SPEC_CS=$cs SPEC_BENCH_IMPLS=spectral timeout 300 python tools/spec_bench.py 360 >> gpurun_out/spec_bench.jsonl 2>> gpurun_out/spec_bench.err; echo "cs=$cs rc=$?"

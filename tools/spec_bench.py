@@ -46,7 +46,7 @@ for fov in fovs:
         ms_gp = timeit(lambda: ops.GalleryIndex(ov, sw, keep_fp32=False, impl=impl))
         ms_qp = timeit(lambda: ops.QueryBatch(su, keep_fp32=False, impl=impl))
         print(json.dumps({"impl": impl, "fov": fov, "G": G, "Q": Q, "cs": os.environ.get("WITW_SPEC_CS", "default"),
-                          "skip_ifft": os.environ.get("WITW_SPEC_SKIP_IFFT", "0"),
+                          "debug": os.environ.get("WITW_SPEC_DEBUG", "0"),
                           "sweep_topk16_merge_ms": ms_all, "sweep_kernel_ms": ms_k, "sweep_count_only_ms": ms_cnt,
                           "gallery_prep_ms": ms_gp, "query_prep_ms": ms_qp,
                           "eff_tflops": 2.0 * 64 * 64 * sw * G * Q / ms_k / 1e9, "queries_per_s": Q / ms_k * 1e3}), flush=True)

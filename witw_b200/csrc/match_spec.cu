@@ -15,13 +15,16 @@
 //   B_f[item,0]  = [ Re O_f(r) |  Im O_f(r) ]   -> Re P_f              (slot 0: [ O_0 | 0 ]   -> P_0)
 //   B_f[item,1]  = [ Im O_f(r) | -Re O_f(r) ]   -> Im P_f              (slot 0: [ 0 | O_32 ]  -> P_32)
 // M = 128 queries (TMEM lanes), N = 16 = 8 gallery items x (Re, Im), and the 32 slots fill the 512 TMEM columns:
-// column 16 f + 2 item + c.  The 64 accumulators of one (query, item) pair are 64 columns of one lane, so the
-// inverse real FFT (ifft64_gen.cuh, 612 fp32 operations) and the argmax over the shift are register-local.
+// column 16 f + 4 (item / 2) + 2 c + item % 2.  The 64 accumulators of one (query, item) pair are 64 columns of one
+// lane, so the inverse real FFT (ifft64_gen.cuh, 612 fp32 operations) and the argmax over the shift are
+// register-local; the epilogue transforms two items at once in the two halves of packed f32x2 operations.
 //
-// Per CTA (one per SM, persistent): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator,
-// warps 4-11 epilogue (two warps per TMEM lane quarter, four items each).  Operand ring of 12 stages
-// (16 KB of query spectra + 2 KB of gallery spectra per stage = one K half of one slot).  Clusters of CS CTAs
-// share a query tile: each CTA loads 1/CS of every query stage and multicasts it; gallery groups differ per CTA.
+// Per CTA (one per SM, persistent): warps 0-1 TMA producers, warps 2-3 MMA issuers (even / odd slots each: the
+// per-stage barrier round trip of a single issuing warp, ~430 cycles, would otherwise pace the 8 small MMAs of a
+// slot), warps 4-11 epilogue (two warps per TMEM lane quarter, four items each).  Operand ring of 6 stages; a stage
+// is one slot: 32 KB of query spectra (two 128-byte-swizzled K halves, one 3-D TMA box) + 4 KB of gallery spectra.
+// Measured and dropped: multicasting the query stage over a cluster (2/4/8 CTAs) -- L2 is not the limiter, the
+// lock-step costs 10-20 %.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <algorithm>
@@ -39,29 +42,21 @@ void* get_encode_tiled();                                                       
 int launch_crop_norm(const float* ov, int64_t G, int64_t G_pad, int CH, int sw, float* crop_inv_norm, witw_stream_t stream);  // match_tc.cu
 
 constexpr int kSpThreads = 384;
-constexpr int kSpMaxStages = 12;
-constexpr int kSpABytes = 128 * 128;   // 128 queries x 64 bf16 (one K half of one slot)
-constexpr int kSpBBytes = 16 * 128;    // 8 items x (Re, Im) x 64 bf16
+constexpr int kSpStages = 6;           // even: producer / issuer warp p owns the stages of parity p
+constexpr int kSpABytes = 2 * 128 * 128;  // 2 K halves x 128 queries x 64 bf16
+constexpr int kSpBBytes = 2 * 16 * 128;   // 2 K halves x 8 items x (Re, Im) x 64 bf16
 constexpr int kSpSlots = 32;
-constexpr int kSpStagesPerTile = 2 * kSpSlots;
 constexpr int kSpItems = 8;            // gallery items per tile (= per operand group)
 constexpr int kSpCH = 64;              // feature rows (C*H) the operand layout is built for
 constexpr int kSpTopkMax = 16;
 constexpr int kSpMaxChunks = 32;       // two candidate lists per chunk; witw_topk_merge takes up to 64
 
-static int spec_cluster_size() {
+// Timing experiments only (wrong results): WITW_SPEC_DEBUG bit 0 = no inverse FFT, bit 1 = no TMEM loads in the epilogue,
+// bit 2 = no tcgen05.mma (barriers only), bit 3 = no query-stage loads, bit 4 = chunk-major work order.
+static int spec_debug() {
   static int v = -1;
-  if (v < 0) {
-    const char* e = std::getenv("WITW_SPEC_CS");
-    const int c = e ? std::atoi(e) : 0;
-    v = (c == 1 || c == 2 || c == 4 || c == 8) ? c : 4;
-  }
+  if (v < 0) { const char* e = std::getenv("WITW_SPEC_DEBUG"); v = e ? std::atoi(e) : 0; }
   return v;
-}
-static bool spec_skip_ifft() {  // timing experiments only: argmax over the raw spectrum (wrong results)
-  static int v = -1;
-  if (v < 0) { const char* e = std::getenv("WITW_SPEC_SKIP_IFFT"); v = (e && e[0] == '1') ? 1 : 0; }
-  return v == 1;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -103,64 +98,61 @@ spec_gallery_prep_kernel(const float* __restrict__ ov, int64_t G, int64_t g_firs
       if (slot == 0) v[j] = (half == c) ? (half == 0 ? re : im) : 0.f;   // [O_0 | 0] and [0 | O_32]
       else v[j] = half == 0 ? (c == 0 ? re : im) : (c == 0 ? im : -re);  // [Re | Im] and [Im | -Re]
     }
-    const int64_t row = ((group * kSpSlots + slot) * 2 + half) * 16 + 2 * i + c;
+    const int64_t row = ((group * kSpSlots + slot) * 2 + half) * 16 + 4 * (i >> 1) + 2 * c + (i & 1);
     *reinterpret_cast<uint2*>(out + row * 64 + r0) = pack4_bf16(v[0], v[1], v[2], v[3]);
   }
 }
 
 // CTA = one query: spectra of the zero-padded rows scaled by 1/64 (the inverse transform's normalisation, exact in
-// bf16), laid out [slot][Re(r) | Im(r)]; and the fp32 inverse norm of the query.
+// bf16) and the fp32 inverse norm of the query.  Operand layout: [query tile of 128][slot][K half: Re(r) | Im(r)][query
+// row][64 bf16], so the two K-major tiles of one slot of one query tile are 32 contiguous KB (one TMA box).  Queries past Q
+// in the last tile are written as zeros.
 __global__ void __launch_bounds__(256)
-spec_query_prep_kernel(const float* __restrict__ su, int sw, __nv_bfloat16* __restrict__ out, float* __restrict__ q_inv_norm) {
+spec_query_prep_kernel(const float* __restrict__ su, int64_t Q, int sw, __nv_bfloat16* __restrict__ out, float* __restrict__ q_inv_norm) {
   __shared__ float sre[kSpSlots][kSpCH + 1], sim[kSpSlots][kSpCH + 1];
   __shared__ float red[8];
   const int64_t q = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  RowFft fft;
-  fft.init(lane);
-  float e = 0.f;
-  for (int row = warp; row < kSpCH; row += 8) {
-    const float* r = su + (q * kSpCH + row) * sw;
-    const int j = 2 * lane;
-    float2 z;
-    z.x = j < sw ? r[j] : 0.f;
-    z.y = j + 1 < sw ? r[j + 1] : 0.f;
-    e = fmaf(z.x, z.x, e);
-    e = fmaf(z.y, z.y, e);
-    const float2 X = fft.run(z, lane);
-    sre[lane][row] = X.x * (1.0f / 64.0f);
-    sim[lane][row] = X.y * (1.0f / 64.0f);
+  const bool live = q < Q;
+  if (live) {
+    RowFft fft;
+    fft.init(lane);
+    float e = 0.f;
+    for (int row = warp; row < kSpCH; row += 8) {
+      const float* r = su + (q * kSpCH + row) * sw;
+      const int j = 2 * lane;
+      float2 z;
+      z.x = j < sw ? r[j] : 0.f;
+      z.y = j + 1 < sw ? r[j + 1] : 0.f;
+      e = fmaf(z.x, z.x, e);
+      e = fmaf(z.y, z.y, e);
+      const float2 X = fft.run(z, lane);
+      sre[lane][row] = X.x * (1.0f / 64.0f);
+      sim[lane][row] = X.y * (1.0f / 64.0f);
+    }
+    for (int m = 16; m > 0; m >>= 1) e += __shfl_xor_sync(0xffffffffu, e, m);
+    if (lane == 0) red[warp] = e;
   }
-  for (int m = 16; m > 0; m >>= 1) e += __shfl_xor_sync(0xffffffffu, e, m);
-  if (lane == 0) red[warp] = e;
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (live && threadIdx.x == 0) {
     float t = 0.f;
     for (int w = 0; w < 8; ++w) t += red[w];
     q_inv_norm[q] = 1.0f / sqrtf(t);
   }
+  __nv_bfloat16* tile = out + (q >> 7) * (int64_t)(2 * kSpSlots * 128 * 64) + (q & 127) * 64;
   for (int idx = threadIdx.x; idx < kSpSlots * 2 * 16; idx += 256) {
     const int slot = idx >> 5, half = (idx >> 4) & 1, r0 = (idx & 15) * 4;
     const float* s = half == 0 ? &sre[slot][r0] : &sim[slot][r0];
-    *reinterpret_cast<uint2*>(out + q * (kSpSlots * 128) + slot * 128 + half * 64 + r0) = pack4_bf16(s[0], s[1], s[2], s[3]);
+    const uint2 v = live ? pack4_bf16(s[0], s[1], s[2], s[3]) : make_uint2(0u, 0u);
+    *reinterpret_cast<uint2*>(tile + (int64_t)(2 * slot + half) * (128 * 64) + r0) = v;
   }
 }
 
 // ------------------------------------------------------------------------------------------
 // PTX used only here
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void tma_2d_multicast(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
-      "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit_multicast1(uint32_t bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
-               : "memory");
-}
-__device__ __forceinline__ void tmem_ld2(uint32_t taddr, uint32_t& a, uint32_t& b) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "r"(taddr));
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(taddr));
 }
 
 struct SpParams {
@@ -177,8 +169,7 @@ struct SpParams {
   int topk;
   int32_t g_offset;
   int n_qtiles, n_chunks, groups_per_chunk, n_groups;
-  int n_stages;
-  int skip_ifft;
+  int debug;
   float band;
   int64_t* recheck_g;
   int64_t* recheck_q;
@@ -186,32 +177,26 @@ struct SpParams {
   int32_t recheck_cap;
 };
 
-template <int CS>
 __global__ void __launch_bounds__(kSpThreads, 1)
 match_spec_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant__ CUtensorMap g_map, const SpParams P) {
   constexpr uint32_t kTmemCols = 512;
   // kind::f16: D fp32, A/B bf16, both K-major, N = 16, M = 128
   constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-  constexpr uint16_t kMask = (uint16_t)((1u << CS) - 1u);
-  constexpr int kRowsPerCta = 128 / CS;               // query rows of a stage this CTA loads (and multicasts)
-  constexpr uint32_t kSliceBytes = kSpABytes / CS;
 
   extern __shared__ __align__(1024) unsigned char smem[];
-  const uint32_t n_stages = (uint32_t)P.n_stages;
-  unsigned char* a_base = smem;                                  // n_stages x 16 KB, 1024-aligned
-  unsigned char* b_base = smem + n_stages * kSpABytes;           // n_stages x 2 KB, 1024-aligned
-  uint64_t* bars = reinterpret_cast<uint64_t*>(b_base + n_stages * kSpBBytes);
-  uint64_t* full = bars;                      // [n_stages]
-  uint64_t* empty = bars + kSpMaxStages;      // [n_stages]
-  uint64_t* tmem_full = bars + 2 * kSpMaxStages;
+  unsigned char* a_base = smem;                                  // kSpStages x 32 KB, 1024-aligned
+  unsigned char* b_base = smem + kSpStages * kSpABytes;          // kSpStages x 4 KB, 1024-aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_base + kSpStages * kSpBBytes);
+  uint64_t* full = bars;                      // [kSpStages]
+  uint64_t* empty = bars + kSpStages;         // [kSpStages]
+  uint64_t* tmem_full = bars + 2 * kSpStages;
   uint64_t* tmem_empty = tmem_full + 1;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint32_t cta_rank = 0;
-  if constexpr (CS > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
-  const int unit = blockIdx.x / CS, n_units = gridDim.x / CS;
+  const int unit = blockIdx.x, n_units = gridDim.x;
   const int n_work = P.n_chunks * P.n_qtiles;
+  const bool chunk_major = (P.debug & 16) != 0;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&q_map) : "memory");
@@ -219,11 +204,11 @@ match_spec_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_consta
   }
   if (warp == 1 && lane == 0) {
     if (s2u(smem) & 1023u) __trap();  // SWIZZLE_128B operand tiles need a 1024-byte aligned base
-    for (uint32_t s = 0; s < n_stages; ++s) {
+    for (uint32_t s = 0; s < kSpStages; ++s) {
       bar_init(s2u(&full[s]), 1);
-      bar_init(s2u(&empty[s]), CS);   // one tcgen05.commit per CTA of the cluster
+      bar_init(s2u(&empty[s]), 1);
     }
-    bar_init(s2u(tmem_full), 1);
+    bar_init(s2u(tmem_full), 2);      // one tcgen05.commit per issuing warp
     bar_init(s2u(tmem_empty), 8);     // one arrive per epilogue warp
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -232,76 +217,82 @@ match_spec_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_consta
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
-  if constexpr (CS > 1) {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-  } else {
-    __syncthreads();
-  }
+  __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
 
-  if (warp == 0) {
-    // ===================== TMA producer =====================
-    // Stage = one K half of one slot: this CTA's slice of the 128-query tile (multicast to the cluster) and the
-    // 16 rows of its own gallery group.  Every CTA arms its own full barrier with the whole stage.
-    uint32_t s = 0, ph = 0;
+  // 384 threads start with 168 registers each; the four control warps give theirs up so that an epilogue thread can
+  // hold the 128 accumulators of two items plus the transform's temporaries (128 x 40 + 256 x 232 <= 64 K registers)
+  if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+  else asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+
+  if (warp < 2) {
+    // ===================== TMA producers: warp p loads the slots of parity p into the stages of parity p =====================
+    const int par = warp;
+    uint32_t k = 0, ph = 0;  // this warp's stage = 2k + par, k = 0..2
     for (int w = unit; w < n_work; w += n_units) {
-      const int qt = w / P.n_chunks, chunk = w - qt * P.n_chunks;
-      const int q_row = qt * 128 + (int)cta_rank * kRowsPerCta;
+      const int qt = chunk_major ? w % P.n_qtiles : w / P.n_chunks;
+      const int chunk = chunk_major ? w / P.n_qtiles : w - qt * P.n_chunks;
+      const int q_row = qt * (2 * kSpSlots * 128);   // first operand row of this query tile
       const int grp0 = chunk * P.groups_per_chunk;
       const int grp1 = min(grp0 + P.groups_per_chunk, P.n_groups);
-      for (int gb = grp0; gb < grp1; gb += CS) {
-        const int grp = min(gb + (int)cta_rank, P.n_groups - 1);  // tail of a chunk: reload a valid group, results unused
-        int g_row = grp * (kSpStagesPerTile * 16);
-        for (int st = 0; st < kSpStagesPerTile; ++st, g_row += 16) {
+      for (int grp = grp0; grp < grp1; ++grp) {
+        for (int slot = par; slot < kSpSlots; slot += 2) {
+          const uint32_t s = 2 * k + par;
           bar_wait(s2u(&empty[s]), ph ^ 1);
           if (elect_one()) {
             const uint32_t fb = s2u(&full[s]);
-            bar_expect_tx(fb, (uint32_t)(kSpABytes + kSpBBytes));
-            if constexpr (CS > 1)
-              tma_2d_multicast(s2u(a_base) + s * kSpABytes + cta_rank * kSliceBytes, &q_map, fb, st * 64, q_row, kMask);
-            else
-              tma_2d<1>(s2u(a_base) + s * kSpABytes, &q_map, fb, st * 64, q_row);
-            tma_2d<1>(s2u(b_base) + s * kSpBBytes, &g_map, fb, 0, g_row);
+            if (P.debug & 8) {
+              bar_expect_tx(fb, (uint32_t)kSpBBytes);
+            } else {
+              bar_expect_tx(fb, (uint32_t)(kSpABytes + kSpBBytes));
+              tma_2d<1>(s2u(a_base) + s * kSpABytes, &q_map, fb, 0, q_row + 256 * slot);
+            }
+            tma_2d<1>(s2u(b_base) + s * kSpBBytes, &g_map, fb, 0, (grp * kSpSlots + slot) * 32);
           }
           __syncwarp();
-          if (++s == n_stages) { s = 0; ph ^= 1; }
+          if (++k == kSpStages / 2) { k = 0; ph ^= 1; }
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+  } else if (warp < 4) {
+    // ===================== MMA issuers: warp 2 even slots, warp 3 odd slots =====================
+    const int par = warp - 2;
     const uint64_t a_desc0 = make_desc(s2u(a_base), 16, 1024, 2 /*SWIZZLE_128B*/);
     const uint64_t b_desc0 = make_desc(s2u(b_base), 16, 1024, 2 /*SWIZZLE_128B*/);
-    const uint32_t a_step = kSpABytes >> 4, b_step = kSpBBytes >> 4;
-    uint32_t s = 0, ph = 0, tile_it = 0;
+    uint32_t k = 0, ph = 0, tile_it = 0;
     for (int w = unit; w < n_work; w += n_units) {
-      const int chunk = w % P.n_chunks;
+      const int chunk = chunk_major ? w / P.n_qtiles : w % P.n_chunks;
       const int grp0 = chunk * P.groups_per_chunk;
       const int grp1 = min(grp0 + P.groups_per_chunk, P.n_groups);
-      for (int gb = grp0; gb < grp1; gb += CS, ++tile_it) {
+      for (int grp = grp0; grp < grp1; ++grp, ++tile_it) {
         bar_wait(s2u(tmem_empty), (tile_it & 1) ^ 1);
         tc_fence_after();
-        for (int st = 0; st < kSpStagesPerTile; ++st) {
+        for (int slot = par; slot < kSpSlots; slot += 2) {
+          const uint32_t s = 2 * k + par;
           bar_wait(s2u(&full[s]), ph);
           tc_fence_after();
           if (elect_one()) {
-            const uint64_t da = a_desc0 + (uint64_t)(s * a_step);
-            const uint64_t db = b_desc0 + (uint64_t)(s * b_step);
-            const uint32_t tmem_d = tmem_base + (uint32_t)(st >> 1) * 16u;
+            const uint64_t da = a_desc0 + (uint64_t)(s * (kSpABytes >> 4));
+            const uint64_t db = b_desc0 + (uint64_t)(s * (kSpBBytes >> 4));
+            const uint32_t tmem_d = tmem_base + (uint32_t)slot * 16u;
+            if (!(P.debug & 4)) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j)  // 32 bytes (2 descriptor units) along K per step inside the 128B-swizzled rows
-              umma_bf16<1>(tmem_d, da + (uint64_t)(2 * j), db + (uint64_t)(2 * j), kIdesc, ((st & 1) | j) != 0 ? 1u : 0u);
-            if constexpr (CS > 1) umma_commit_multicast1(s2u(&empty[s]), kMask);  // the stage is free once every CTA has read it
-            else umma_commit<1>(s2u(&empty[s]));
-            if (st == kSpStagesPerTile - 1) umma_commit<1>(s2u(tmem_full));
+              for (int h = 0; h < 2; ++h)    // K halves: tiles of 16 KB (queries) / 2 KB (items)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)  // 32 bytes (2 descriptor units) along K per step inside the 128B-swizzled rows
+                  umma_bf16<1>(tmem_d, da + (uint64_t)(h * (kSpABytes >> 5) + 2 * j), db + (uint64_t)(h * (kSpBBytes >> 5) + 2 * j), kIdesc,
+                               (h | j) != 0 ? 1u : 0u);
+            }
+            umma_commit<1>(s2u(&empty[s]));
+            if (slot >= kSpSlots - 2) umma_commit<1>(s2u(tmem_full));
           }
           __syncwarp();
-          if (++s == n_stages) { s = 0; ph ^= 1; }
+          if (++k == kSpStages / 2) { k = 0; ph ^= 1; }
         }
       }
     }
-  } else if (warp >= 4) {
+  } else {
     // ===================== epilogue: warps 4-7 items 0-3, warps 8-11 items 4-7 of each tile =====================
     const int wq = warp & 3;
     const int ihalf = (warp - 4) >> 2;
@@ -309,7 +300,8 @@ match_spec_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_consta
     const uint32_t lane_field = (uint32_t)(wq * 32) << 16;
     uint32_t tile_it = 0;
     for (int w = unit; w < n_work; w += n_units) {
-      const int qt = w / P.n_chunks, chunk = w - qt * P.n_chunks;
+      const int qt = chunk_major ? w % P.n_qtiles : w / P.n_chunks;
+      const int chunk = chunk_major ? w / P.n_qtiles : w - qt * P.n_chunks;
       const int64_t q = (int64_t)qt * 128 + row;
       const bool q_ok = q < P.Q;
       const float qin = q_ok ? P.q_inv_norm[q] : 0.f;
@@ -323,68 +315,76 @@ match_spec_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_consta
       for (int j = 0; j < kSpTopkMax; ++j) { td[j] = __int_as_float(0x7f800000); ti[j] = -1; }
       const int grp0 = chunk * P.groups_per_chunk;
       const int grp1 = min(grp0 + P.groups_per_chunk, P.n_groups);
-      for (int gb = grp0; gb < grp1; gb += CS, ++tile_it) {
-        const int grp = gb + (int)cta_rank;
-        const bool grp_ok = grp < grp1;
+      for (int grp = grp0; grp < grp1; ++grp, ++tile_it) {
         bar_wait(s2u(tmem_full), tile_it & 1);
         tc_fence_after();
 #pragma unroll 1
-        for (int ii = 0; ii < 4; ++ii) {
-          const int i = ihalf * 4 + ii;
-          float re[32], im[32], x[64];
-          const uint32_t t0 = tmem_base + lane_field + (uint32_t)(2 * i);
+        for (int pp = 0; pp < 2; ++pp) {
+          const int i0 = ihalf * 4 + pp * 2;      // items i0 and i0 + 1 in the .x / .y halves
+          float2 re[32], im[32], x[64];
+          const uint32_t t0 = tmem_base + lane_field + (uint32_t)(2 * i0);
+          if (P.debug & 2) {
 #pragma unroll
-          for (int f = 0; f < 32; ++f) {
-            uint32_t a, b;
-            tmem_ld2(t0 + 16u * f, a, b);
-            re[f] = __uint_as_float(a);
-            im[f] = __uint_as_float(b);
+            for (int f = 0; f < 32; ++f) { re[f] = make_float2((float)(f + lane), (float)f); im[f] = make_float2((float)(f - pp), 1.f); }
+          } else {
+#pragma unroll
+            for (int f = 0; f < 32; ++f) {
+              uint32_t a, b, c, d;
+              tmem_ld4(t0 + 16u * f, a, b, c, d);
+              re[f] = make_float2(__uint_as_float(a), __uint_as_float(b));
+              im[f] = make_float2(__uint_as_float(c), __uint_as_float(d));
+            }
+            tmem_ld_wait();
           }
-          tmem_ld_wait();
-          if (ii == 3) {  // this warp's share of the accumulators is in registers: hand TMEM back to the MMA issuer
+          if (pp == 1) {  // this warp's share of the accumulators is in registers: hand TMEM back to the MMA issuers
             tc_fence_before();
             __syncwarp();
             if (lane == 0) bar_arrive_local(s2u(tmem_empty));
           }
-          if (P.skip_ifft) {
+          if (P.debug & 1) {
 #pragma unroll
             for (int f = 0; f < 32; ++f) { x[2 * f] = re[f]; x[2 * f + 1] = im[f]; }
           } else {
-            ifft64_hermitian(re, im, x);
+            ifft64_hermitian_x2(re, im, x);
           }
-          float best = -__int_as_float(0x7f800000);
-          int arg = 0;
+          float best[2] = {-__int_as_float(0x7f800000), -__int_as_float(0x7f800000)};
+          int arg[2] = {0, 0};
 #pragma unroll
-          for (int sft = 0; sft < 64; ++sft)
-            if (x[sft] > best) { best = x[sft]; arg = sft; }  // strict '>' in ascending shift order: first maximum
-          const int64_t g = (int64_t)grp * kSpItems + i;
-          if (grp_ok && g < P.G && q_ok) {
-            const float cin = P.crop_inv_norm[g * 64 + arg];
-            const float d = 2.0f * (1.0f - best * cin * qin);
-            if (P.dist) P.dist[g * P.Q + q] = d;
-            if (P.ori) P.ori[g * P.Q + q] = (uint8_t)arg;
-            if ((int32_t)g == self_g) {
-              cnt += (dtrue == dtrue) ? 1 : 0;
-            } else if (P.recheck_cap > 0 && fabsf(d - dtrue) <= P.band) {
-              const int32_t pos = atomicAdd(P.recheck_count, 1);
-              if (pos < P.recheck_cap) {
-                P.recheck_g[pos] = g;
-                P.recheck_q[pos] = q;
-              } else {  // list full: fall back to the bf16 decision and say so
-                atomicAdd(P.recheck_count + 1, 1);
+          for (int sft = 0; sft < 64; ++sft) {  // strict '>' in ascending shift order: first maximum
+            if (x[sft].x > best[0]) { best[0] = x[sft].x; arg[0] = sft; }
+            if (x[sft].y > best[1]) { best[1] = x[sft].y; arg[1] = sft; }
+          }
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int64_t g = (int64_t)grp * kSpItems + i0 + e;
+            if (g < P.G && q_ok) {
+              const float cin = P.crop_inv_norm[g * 64 + arg[e]];
+              const float d = 2.0f * (1.0f - best[e] * cin * qin);
+              if (P.dist) P.dist[g * P.Q + q] = d;
+              if (P.ori) P.ori[g * P.Q + q] = (uint8_t)arg[e];
+              if ((int32_t)g == self_g) {
+                cnt += (dtrue == dtrue) ? 1 : 0;
+              } else if (P.recheck_cap > 0 && fabsf(d - dtrue) <= P.band) {
+                const int32_t pos = atomicAdd(P.recheck_count, 1);
+                if (pos < P.recheck_cap) {
+                  P.recheck_g[pos] = g;
+                  P.recheck_q[pos] = q;
+                } else {  // list full: fall back to the bf16 decision and say so
+                  atomicAdd(P.recheck_count + 1, 1);
+                  cnt += (d <= dtrue) ? 1 : 0;
+                }
+              } else {
                 cnt += (d <= dtrue) ? 1 : 0;
               }
-            } else {
-              cnt += (d <= dtrue) ? 1 : 0;
-            }
-            if (P.topk > 0 && d < td[kSpTopkMax - 1]) {
-              float cd = d;
-              int32_t ci = (int32_t)g + P.g_offset;
+              if (P.topk > 0 && d < td[kSpTopkMax - 1]) {
+                float cd = d;
+                int32_t ci = (int32_t)g + P.g_offset;
 #pragma unroll
-              for (int j = 0; j < kSpTopkMax; ++j) {
-                if (cd < td[j]) {
-                  const float t0f = td[j]; const int32_t t1 = ti[j];
-                  td[j] = cd; ti[j] = ci; cd = t0f; ci = t1;
+                for (int j = 0; j < kSpTopkMax; ++j) {
+                  if (cd < td[j]) {
+                    const float t0f = td[j]; const int32_t t1 = ti[j];
+                    td[j] = cd; ti[j] = ci; cd = t0f; ci = t1;
+                  }
                 }
               }
             }
@@ -394,7 +394,7 @@ match_spec_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_consta
       if (q_ok) {
         if (P.rank_count && cnt) atomicAdd(P.rank_count + q, cnt);
         if (P.topk > 0) {
-          const int64_t slot = (int64_t)(chunk * 2 + ihalf) * CS + cta_rank;
+          const int64_t slot = (int64_t)chunk * 2 + ihalf;
           float* od = P.topk_dist + (slot * P.Q + q) * P.topk;
           int32_t* oi = P.topk_idx + (slot * P.Q + q) * P.topk;
 #pragma unroll
@@ -407,66 +407,26 @@ match_spec_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_consta
 
   // ===================== teardown =====================
   tc_fence_before();
-  if constexpr (CS > 1) {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-  } else {
-    __syncthreads();
-  }
+  __syncthreads();
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
   }
 }
 
-struct SpSchedule { int cs, n_units, n_qtiles, n_groups, groups_per_chunk, n_chunks; };
+struct SpSchedule { int n_units, n_qtiles, n_groups, groups_per_chunk, n_chunks; };
 
 static SpSchedule make_spec_schedule(int64_t G, int64_t Q) {
   SpSchedule s;
-  s.cs = spec_cluster_size();
-  s.n_units = std::max(1, sm_count() / s.cs);
+  s.n_units = std::max(1, sm_count());
   s.n_qtiles = (int)ceil_div<int64_t>(std::max<int64_t>(Q, 1), 128);
   s.n_groups = (int)ceil_div<int64_t>(std::max<int64_t>(G, 1), kSpItems);
-  // about 16 work items per unit for balance; a chunk holds a multiple of CS groups; CS candidate lists per chunk half
-  const int max_chunks = std::max(1, kSpMaxChunks / s.cs);
+  // about 16 work items per CTA for balance; two candidate lists per chunk
   int64_t want = ceil_div<int64_t>((int64_t)s.n_units * 16, s.n_qtiles);
-  want = std::max<int64_t>(1, std::min<int64_t>(want, max_chunks));
-  int64_t gpc = ceil_div<int64_t>(s.n_groups, want);
-  gpc = ceil_div<int64_t>(gpc, s.cs) * s.cs;
-  s.groups_per_chunk = (int)gpc;
-  s.n_chunks = (int)ceil_div<int64_t>(s.n_groups, gpc);
+  want = std::max<int64_t>(1, std::min<int64_t>(want, kSpMaxChunks));
+  s.groups_per_chunk = (int)ceil_div<int64_t>(s.n_groups, want);
+  s.n_chunks = (int)ceil_div<int64_t>(s.n_groups, s.groups_per_chunk);
   return s;
-}
-
-template <int CS>
-static int launch_spec(const CUtensorMap& qmap, const CUtensorMap& gmap, const SpParams& P, const SpSchedule& sch, size_t smem,
-                       cudaStream_t stream) {
-  WITW_CUDA(cudaFuncSetAttribute(match_spec_kernel<CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  if (CS > 4) WITW_CUDA(cudaFuncSetAttribute(match_spec_kernel<CS>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-  cudaLaunchConfig_t cfg;
-  std::memset(&cfg, 0, sizeof(cfg));
-  cfg.blockDim = dim3(kSpThreads);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = (unsigned)CS;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  int units = sch.n_units;
-  if (CS > 1) {  // persistent clusters: as many as the GPCs can hold at once
-    cfg.gridDim = dim3((unsigned)(sch.n_units * CS));
-    int max_clusters = 0;
-    WITW_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, match_spec_kernel<CS>, &cfg));
-    WITW_REQUIRE(max_clusters >= 1, WITW_ERR_CUDA, "witw_match_spec: no cluster of %d CTAs fits this device", CS);
-    units = std::min(units, max_clusters);
-  }
-  units = std::min(units, P.n_chunks * P.n_qtiles);
-  cfg.gridDim = dim3((unsigned)(units * CS));
-  WITW_CUDA(cudaLaunchKernelEx(&cfg, match_spec_kernel<CS>, qmap, gmap, P));
-  WITW_LAUNCH_CHECK();
-  return WITW_OK;
 }
 
 }  // namespace witw
@@ -477,12 +437,12 @@ extern "C" int witw_spec_supported(int CH, int W, int sw) { return (CH == kSpCH 
 
 extern "C" size_t witw_spec_gallery_operand_bytes(int64_t G, int CH) {
   if (G < 0 || CH != kSpCH) { set_error(WITW_ERR_UNSUPPORTED, "witw_spec_gallery_operand_bytes: the spectral sweep needs C*H == %d (got %d)", kSpCH, CH); return 0; }
-  return (size_t)std::max<int64_t>(ceil_div<int64_t>(G, kSpItems), 1) * kSpStagesPerTile * kSpBBytes;
+  return (size_t)std::max<int64_t>(ceil_div<int64_t>(G, kSpItems), 1) * kSpSlots * kSpBBytes;
 }
 
 extern "C" size_t witw_spec_query_operand_bytes(int64_t Q, int CH) {
   if (Q < 0 || CH != kSpCH) { set_error(WITW_ERR_UNSUPPORTED, "witw_spec_query_operand_bytes: the spectral sweep needs C*H == %d (got %d)", kSpCH, CH); return 0; }
-  return (size_t)std::max<int64_t>(Q, 1) * kSpSlots * 128 * 2;
+  return (size_t)ceil_div<int64_t>(std::max<int64_t>(Q, 1), 128) * 128 * kSpSlots * 128 * 2;
 }
 
 extern "C" int witw_spec_gallery_prep(const float* ov, int64_t G, int64_t g_first, int CH, int W, int sw, void* gal_op,
@@ -507,15 +467,13 @@ extern "C" int witw_spec_query_prep(const float* su, int64_t Q, int CH, int sw, 
   if (Q == 0) return WITW_OK;
   WITW_REQUIRE(su && qry_op && q_inv_norm, WITW_ERR_INVALID, "witw_spec_query_prep: null pointer");
   WITW_REQUIRE(((uintptr_t)qry_op & 127) == 0, WITW_ERR_INVALID, "witw_spec_query_prep: operand must be 128-byte aligned");
-  spec_query_prep_kernel<<<(unsigned)Q, 256, 0, as_stream(stream)>>>(su, sw, reinterpret_cast<__nv_bfloat16*>(qry_op), q_inv_norm);
+  const int64_t q_pad = ceil_div<int64_t>(Q, 128) * 128;
+  spec_query_prep_kernel<<<(unsigned)q_pad, 256, 0, as_stream(stream)>>>(su, Q, sw, reinterpret_cast<__nv_bfloat16*>(qry_op), q_inv_norm);
   WITW_LAUNCH_CHECK();
   return WITW_OK;
 }
 
-extern "C" int witw_match_spec_topk_slots(int64_t G, int64_t Q) {
-  const SpSchedule s = make_spec_schedule(G, Q);
-  return s.n_chunks * 2 * s.cs;
-}
+extern "C" int witw_match_spec_topk_slots(int64_t G, int64_t Q) { return make_spec_schedule(G, Q).n_chunks * 2; }
 
 extern "C" int witw_match_spec(const void* gal_op, const float* crop_inv_norm, const void* qry_op, const float* q_inv_norm, int64_t G,
                                int64_t Q, int CH, int sw, float* dist, uint8_t* ori, const float* d_true, const int32_t* true_idx,
@@ -542,22 +500,24 @@ extern "C" int witw_match_spec(const void* gal_op, const float* crop_inv_norm, c
   auto encode = reinterpret_cast<EncodeTiledFn>(get_encode_tiled());
   WITW_REQUIRE(encode != nullptr, WITW_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   const cuuint32_t estr[2] = {1, 1};
-  // query spectra: [Q][32 slots x 128] bf16; one box = this CTA's rows of one K half of one slot
+  // query spectra: [query tiles x 32 slots x 2 K halves x 128 rows][64] bf16; one box = the 256 rows of one slot of one tile
   CUtensorMap qmap;
-  const cuuint64_t qdims[2] = {(cuuint64_t)(kSpSlots * 128), (cuuint64_t)Q};
-  const cuuint64_t qstrides[1] = {(cuuint64_t)(kSpSlots * 128 * 2)};
-  const cuuint32_t qbox[2] = {64, (cuuint32_t)(128 / sch.cs)};
+  const int64_t q_rows = ceil_div<int64_t>(Q, 128) * (2 * kSpSlots * 128);
+  WITW_REQUIRE(q_rows < (1ll << 31), WITW_ERR_UNSUPPORTED, "witw_match_spec: %lld queries are too many for one sweep", (long long)Q);
+  const cuuint64_t qdims[2] = {64, (cuuint64_t)q_rows};
+  const cuuint64_t qstrides[1] = {128};
+  const cuuint32_t qbox[2] = {64, 256};
   CUresult cr = encode(&qmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(qry_op), qdims, qstrides, qbox, estr,
                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   WITW_REQUIRE(cr == CUDA_SUCCESS, WITW_ERR_CUDA, "cuTensorMapEncodeTiled(query spectra) failed with CUresult %d", (int)cr);
-  // gallery spectra: [groups x 64 stages x 16 rows][64] bf16; one box = the 16 rows of one stage
+  // gallery spectra: [groups x 32 slots x 2 K halves x 16 rows][64] bf16; one box = the 32 rows of one slot
   CUtensorMap gmap;
-  const int64_t total_rows = (int64_t)sch.n_groups * kSpStagesPerTile * 16;
+  const int64_t total_rows = (int64_t)sch.n_groups * kSpSlots * 32;
   WITW_REQUIRE(total_rows < (1ll << 31), WITW_ERR_UNSUPPORTED, "witw_match_spec: gallery of %lld items is too large for one sweep", (long long)G);
   const cuuint64_t gdims[2] = {64, (cuuint64_t)total_rows};
   const cuuint64_t gstrides[1] = {128};
-  const cuuint32_t gbox[2] = {64, 16};
+  const cuuint32_t gbox[2] = {64, 32};
   cr = encode(&gmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(gal_op), gdims, gstrides, gbox, estr,
               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -570,14 +530,11 @@ extern "C" int witw_match_spec(const void* gal_op, const float* crop_inv_norm, c
   P.topk_dist = topk_dist; P.topk_idx = topk_idx; P.G = G; P.Q = Q; P.topk = topk; P.g_offset = g_offset;
   P.n_qtiles = sch.n_qtiles; P.n_chunks = sch.n_chunks; P.groups_per_chunk = sch.groups_per_chunk; P.n_groups = sch.n_groups;
   P.band = recheck_band; P.recheck_g = recheck_g; P.recheck_q = recheck_q; P.recheck_count = recheck_count; P.recheck_cap = recheck_capacity;
-  P.skip_ifft = spec_skip_ifft() ? 1 : 0;
-  const size_t fixed = (2 * kSpMaxStages + 2) * 8 + 16;
-  P.n_stages = kSpMaxStages;
-  const size_t smem = (size_t)P.n_stages * (kSpABytes + kSpBBytes) + fixed;
-  switch (sch.cs) {
-    case 1: return launch_spec<1>(qmap, gmap, P, sch, smem, as_stream(stream));
-    case 2: return launch_spec<2>(qmap, gmap, P, sch, smem, as_stream(stream));
-    case 4: return launch_spec<4>(qmap, gmap, P, sch, smem, as_stream(stream));
-    default: return launch_spec<8>(qmap, gmap, P, sch, smem, as_stream(stream));
-  }
+  P.debug = spec_debug();
+  const size_t smem = (size_t)kSpStages * (kSpABytes + kSpBBytes) + (2 * kSpStages + 2) * 8 + 16;
+  WITW_CUDA(cudaFuncSetAttribute(match_spec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = std::min(sch.n_units, sch.n_chunks * sch.n_qtiles);
+  match_spec_kernel<<<grid, kSpThreads, smem, as_stream(stream)>>>(qmap, gmap, P);
+  WITW_LAUNCH_CHECK();
+  return WITW_OK;
 }

@@ -8,7 +8,10 @@ Workload (BASELINE.json configs[1]): cvig_fov.py 360-degree eval, 10k queries x 
 orientation-searched distance + rank counting + top-10, synthetic feature maps [N,16,4,64].
 One step = one full pass from fp32 feature maps resident in HBM to per-query ranks and top-k:
 gallery/query operand prep -> exact fp32 true-match distances -> tcgen05 sweep (fused argmax,
-crop-normalise, distance, rank count, top-k) -> top-k merge.
+crop-normalise, distance, rank count, top-k) -> fp32 re-check -> top-k merge -> fp32 re-rank.
+--sweep spectral (default: what the library picks) evaluates the circular correlation through the
+correlation theorem (csrc/match_spec.cu: per-frequency tcgen05 products + in-register inverse FFT);
+--sweep hankel is the dense contraction over all 64 shifts (csrc/match_tc.cu).
 N > 1: the gallery is sharded, one 10k-item shard per GPU (weak scaling: gallery_total = N*10k),
 queries replicated; the exchange is an all-reduce of [Q] true distances and [Q] counts and an
 all-gather of [Q,10] top-k candidates over NCCL.  value = N*Q / t: queries swept per second, each
@@ -86,13 +89,13 @@ class ClockSampler(object):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def measured_traffic():
+def measured_traffic(kernel):
     """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/)."""
     path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.isfile(path):
         with open(path) as f:
             t = json.load(f)
-        return t.get("match_tc_kernel_10k_x_10k_fov360_dram_bytes"), t.get("source")
+        return t.get(kernel + "_10k_x_10k_fov360_dram_bytes"), t.get(kernel + "_source", t.get("source"))
     return None, None
 
 
@@ -173,6 +176,8 @@ def run_ours(args):
     from witw_b200 import ops
     from witw_b200.sharded import evaluate_ranks_sharded
 
+    if args.sweep != "auto":
+        ops.TC_IMPL = args.sweep
     world = env_int("WORLD_SIZE", 1)
     rank = env_int("RANK", 0)
     local_rank = env_int("LOCAL_RANK", 0)
@@ -285,7 +290,23 @@ def run_ours(args):
 
     peak, peak_src = measured_peaks()
     achieved = FLOP_PER_PAIR * float(G_PER_GPU) * float(Q_TOTAL) / (kernel_ms / 1000.0) / 1e12
-    traffic, traffic_src = measured_traffic()
+    sweep_impl = ops._pick_impl(None, 64, 64, 64)
+    kernel = "match_spec_kernel" if sweep_impl == "spectral" else "match_tc_kernel"
+    traffic, traffic_src = measured_traffic(kernel)
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+                "traffic_source": traffic_src, "kernel": kernel, "kernel_ms": kernel_ms, "flop_per_pair": FLOP_PER_PAIR, "peak_source": peak_src}
+    if sweep_impl == "spectral":
+        # the algorithmic count above is the direct form's; the spectral sweep executes 33 bins x 64 rows of
+        # complex MACs per pair on the tensor cores and a 64-point inverse FFT per pair on the CUDA cores
+        exec_tc = 2.0 * 128 * 16 * 16 * 256 / 1024.0          # FLOP per pair issued as tcgen05.mma (256 MMAs of 128x16x16 per 1024 pairs)
+        smem_bytes = 2.0 * (256 * 4608) / 1024.0              # per pair: operand bytes written by TMA + read by the MMAs
+        roofline.update({
+            "note": "frac > 1: achieved counts the direct form's 524 288 FLOP per pair; the kernel evaluates the same correlation "
+                    "through the correlation theorem with %d tensor FLOP + ~1 000 CUDA-core FLOP per pair" % int(exec_tc),
+            "executed_tensor_tflops": exec_tc * float(G_PER_GPU) * float(Q_TOTAL) / (kernel_ms / 1000.0) / 1e12,
+            "bound_detail": "shared-memory bandwidth feeding N=16 UMMAs (query stage written once by TMA, read once per 8 gallery items)",
+            "smem_gbs_per_sm": smem_bytes * float(G_PER_GPU) * float(Q_TOTAL) / 148.0 / (kernel_ms / 1000.0) / 1e9,
+        })
     line = {
         "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
@@ -295,16 +316,21 @@ def run_ours(args):
                                              "" if world == 1 else "; gallery sharded, one shard per GPU, NCCL count all-reduce + top-k all-gather"),
             "gallery_total": g_total, "gallery_per_gpu": G_PER_GPU, "queries": Q_TOTAL, "fov": FOV, "feature_shape": [16, 4, 64],
             "unit_note": "one unit = one query swept over one %d-item gallery shard; queries/s over the whole %d-item gallery = %.1f" % (G_PER_GPU, g_total, value / world),
-            "l2_policy": "inputs larger than L2 (fp32 features 328 MB + bf16 operands 1.3 GB per step vs 126 MB L2)",
-            "step": "fp32 features in HBM -> operand prep (bf16 Hankel blocks, norms, fp32 azimuth spectra) -> fp32 true-match distances -> tcgen05 sweep -> fp32 re-check of near-threshold rank decisions -> top-k merge -> fp32 re-rank of the top-k",
+            "l2_policy": "inputs larger than L2 (fp32 features 328 MB + fp32 spectra 328 MB + bf16 operands %s per step vs 126 MB L2)"
+                         % ("240 MB" if sweep_impl == "spectral" else "1.3 GB"),
+            "sweep": sweep_impl,
+            "step": ("fp32 features in HBM -> operand prep (bf16 azimuth spectra in UMMA layout, norms, fp32 spectra) -> fp32 true-match distances -> "
+                     "tcgen05 per-frequency products + in-register inverse FFT, argmax, distance, rank count, top-k -> fp32 re-check of near-threshold "
+                     "rank decisions -> top-k merge -> fp32 re-rank of the top-k") if sweep_impl == "spectral" else
+                    ("fp32 features in HBM -> operand prep (bf16 Hankel blocks, norms, fp32 azimuth spectra) -> fp32 true-match distances -> tcgen05 sweep -> "
+                     "fp32 re-check of near-threshold rank decisions -> top-k merge -> fp32 re-rank of the top-k"),
         },
-        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
-                     "kernel": "match_tc_kernel", "kernel_ms": kernel_ms, "flop_per_pair": FLOP_PER_PAIR, "peak_source": peak_src},
+        "roofline": roofline,
         "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / steps,
                 "note": "W.evaluate_ranks() on pinned-host inputs; H2D of step i+1 double-buffered on a copy stream behind step i"},
-        "gpu_launches": 14 * steps,  # per step: gallery_blocks, crop_norm, query_prep, spectral_rows x2, spectral_pairs (true match),
-                                     # match_tc, topk_merge, spectral_pairs (re-check), recheck_apply, topk_refine_pairs,
-                                     # spectral_pairs (top-k), topk_refine_sort
+        # per step: gallery prep, crop_norm, query prep, (hankel: spectral_rows x2,) spectral_pairs (true match), the sweep,
+        # topk_merge, spectral_pairs (re-check), recheck_apply, topk_refine_pairs, spectral_pairs (top-k), topk_refine_sort
+        "gpu_launches": (11 if sweep_impl == "spectral" else 14) * steps,
         "clocks": clocks,
         "recall": {k: float(v) for k, v in recall.items()},
     }
@@ -324,6 +350,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--sweep", choices=["auto", "spectral", "hankel"], default="auto",
+                    help="tensor-core sweep: spectral (correlation theorem, default where supported) or hankel (dense contraction over the shifts)")
     ap.add_argument("--gallery-per-gpu", type=int, default=G_PER_GPU,
                     help="gallery items per GPU (default 10000 = BASELINE configs[1]; 125000 on 8 GPUs = configs[3], the 1M-tile gallery)")
     args = ap.parse_args()

@@ -208,15 +208,18 @@ int witw_topk_refine_spec_f32(const float* gal_spec_dev, const float* crop_inv_n
  *        items) and crop_inv_norm [G rounded up to 8, 64].  g_first = index of ov[0] inside the operand (a multiple
  *        of 8 unless it continues a partial group), so an encode loop can append batch by batch.
  *   witw_spec_query_prep: su [Q,64,sw] fp32 -> bf16 spectra of the zero-padded rows, scaled by 1/64 (8 KB per
- *        query), and q_inv_norm [Q].
+ *        query, laid out per tile of 128 queries), and q_inv_norm [Q].
+ *   spec_out (both, optional): the fp32 spectra of the same rows in the layout of witw_spectral_rows_f32
+ *        ([G*64,64] / [Q*64,64]) -- the operands of the exact finish, produced in the same pass.
  *   witw_match_spec: arguments as witw_match_tc; top-k candidate lists: witw_match_spec_topk_slots(). */
 int witw_spec_supported(int CH, int W, int sw);
 size_t witw_spec_gallery_operand_bytes(int64_t G, int CH);
 size_t witw_spec_query_operand_bytes(int64_t Q, int CH);
 int witw_spec_gallery_prep(const float* ov_dev, int64_t G, int64_t g_first, int CH, int W, int sw,
-                           void* gal_op_dev, float* crop_inv_norm_dev, witw_stream_t stream);
+                           void* gal_op_dev, float* crop_inv_norm_dev, float* spec_out_dev /* optional */,
+                           witw_stream_t stream);
 int witw_spec_query_prep(const float* su_dev, int64_t Q, int CH, int sw, void* qry_op_dev,
-                         float* q_inv_norm_dev, witw_stream_t stream);
+                         float* q_inv_norm_dev, float* spec_out_dev /* optional */, witw_stream_t stream);
 int witw_match_spec_topk_slots(int64_t G, int64_t Q);
 int witw_match_spec(const void* gal_op_dev, const float* crop_inv_norm_dev, const void* qry_op_dev,
                     const float* q_inv_norm_dev, int64_t G, int64_t Q, int CH, int sw,

@@ -53,8 +53,8 @@ SIGNATURES = {
     "witw_spec_supported": (c_int, [c_int, c_int, c_int]),
     "witw_spec_gallery_operand_bytes": (c_size_t, [c_int64, c_int]),
     "witw_spec_query_operand_bytes": (c_size_t, [c_int64, c_int]),
-    "witw_spec_gallery_prep": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
-    "witw_spec_query_prep": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "witw_spec_gallery_prep": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "witw_spec_query_prep": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "witw_match_spec_topk_slots": (c_int, [c_int64, c_int64]),
     "witw_match_spec": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p,
                                 c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int32, c_float, c_void_p, c_void_p,

@@ -70,7 +70,8 @@ __device__ __forceinline__ uint2 pack4_bf16(float a, float b, float c, float d) 
 // CTA = one gallery item: 64 warp-level row FFTs, then the item's 128 operand rows of 128 bytes
 // (slot, K half, Re/Im) are written into its group's tiles.
 __global__ void __launch_bounds__(256)
-spec_gallery_prep_kernel(const float* __restrict__ ov, int64_t G, int64_t g_first, __nv_bfloat16* __restrict__ out) {
+spec_gallery_prep_kernel(const float* __restrict__ ov, int64_t G, int64_t g_first, __nv_bfloat16* __restrict__ out,
+                         float* __restrict__ spec_out) {
   __shared__ float sre[kSpSlots][kSpCH + 1], sim[kSpSlots][kSpCH + 1];  // [slot][feature row]
   const int64_t g_local = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -84,6 +85,10 @@ spec_gallery_prep_kernel(const float* __restrict__ ov, int64_t G, int64_t g_firs
     sim[lane][row] = X.y;
   }
   __syncthreads();
+  if (spec_out != nullptr && g_local < G) {  // the fp32 spectra the exact finish works on (layout of witw_spectral_rows_f32)
+    float2* dst = reinterpret_cast<float2*>(spec_out + g_local * (kSpCH * 64));
+    for (int idx = threadIdx.x; idx < kSpCH * 32; idx += 256) dst[idx] = make_float2(sre[idx & 31][idx >> 5], sim[idx & 31][idx >> 5]);
+  }
   const int64_t g = g_first + g_local;
   const int64_t group = g >> 3;
   const int i = (int)(g & 7);
@@ -108,7 +113,8 @@ spec_gallery_prep_kernel(const float* __restrict__ ov, int64_t G, int64_t g_firs
 // row][64 bf16], so the two K-major tiles of one slot of one query tile are 32 contiguous KB (one TMA box).  Queries past Q
 // in the last tile are written as zeros.
 __global__ void __launch_bounds__(256)
-spec_query_prep_kernel(const float* __restrict__ su, int64_t Q, int sw, __nv_bfloat16* __restrict__ out, float* __restrict__ q_inv_norm) {
+spec_query_prep_kernel(const float* __restrict__ su, int64_t Q, int sw, __nv_bfloat16* __restrict__ out, float* __restrict__ q_inv_norm,
+                       float* __restrict__ spec_out) {
   __shared__ float sre[kSpSlots][kSpCH + 1], sim[kSpSlots][kSpCH + 1];
   __shared__ float red[8];
   const int64_t q = blockIdx.x;
@@ -127,8 +133,8 @@ spec_query_prep_kernel(const float* __restrict__ su, int64_t Q, int sw, __nv_bfl
       e = fmaf(z.x, z.x, e);
       e = fmaf(z.y, z.y, e);
       const float2 X = fft.run(z, lane);
-      sre[lane][row] = X.x * (1.0f / 64.0f);
-      sim[lane][row] = X.y * (1.0f / 64.0f);
+      sre[lane][row] = X.x;
+      sim[lane][row] = X.y;
     }
     for (int m = 16; m > 0; m >>= 1) e += __shfl_xor_sync(0xffffffffu, e, m);
     if (lane == 0) red[warp] = e;
@@ -139,11 +145,16 @@ spec_query_prep_kernel(const float* __restrict__ su, int64_t Q, int sw, __nv_bfl
     for (int w = 0; w < 8; ++w) t += red[w];
     q_inv_norm[q] = 1.0f / sqrtf(t);
   }
+  if (spec_out != nullptr && live) {
+    float2* dst = reinterpret_cast<float2*>(spec_out + q * (kSpCH * 64));
+    for (int idx = threadIdx.x; idx < kSpCH * 32; idx += 256) dst[idx] = make_float2(sre[idx & 31][idx >> 5], sim[idx & 31][idx >> 5]);
+  }
   __nv_bfloat16* tile = out + (q >> 7) * (int64_t)(2 * kSpSlots * 128 * 64) + (q & 127) * 64;
   for (int idx = threadIdx.x; idx < kSpSlots * 2 * 16; idx += 256) {
     const int slot = idx >> 5, half = (idx >> 4) & 1, r0 = (idx & 15) * 4;
     const float* s = half == 0 ? &sre[slot][r0] : &sim[slot][r0];
-    const uint2 v = live ? pack4_bf16(s[0], s[1], s[2], s[3]) : make_uint2(0u, 0u);
+    const float k = 1.0f / 64.0f;
+    const uint2 v = live ? pack4_bf16(s[0] * k, s[1] * k, s[2] * k, s[3] * k) : make_uint2(0u, 0u);
     *reinterpret_cast<uint2*>(tile + (int64_t)(2 * slot + half) * (128 * 64) + r0) = v;
   }
 }
@@ -446,7 +457,7 @@ extern "C" size_t witw_spec_query_operand_bytes(int64_t Q, int CH) {
 }
 
 extern "C" int witw_spec_gallery_prep(const float* ov, int64_t G, int64_t g_first, int CH, int W, int sw, void* gal_op,
-                                      float* crop_inv_norm, witw_stream_t stream) {
+                                      float* crop_inv_norm, float* spec_out, witw_stream_t stream) {
   WITW_REQUIRE(witw_spec_supported(CH, W, sw), WITW_ERR_UNSUPPORTED, "witw_spec_gallery_prep: needs C*H == 64, W == 64, 1 <= sw <= 64 (got %d, %d, %d)", CH, W, sw);
   WITW_REQUIRE(G >= 0 && g_first >= 0, WITW_ERR_INVALID, "witw_spec_gallery_prep: negative size");
   if (G == 0) return WITW_OK;
@@ -456,19 +467,22 @@ extern "C" int witw_spec_gallery_prep(const float* ov, int64_t G, int64_t g_firs
   const int64_t g_end = ceil_div<int64_t>(g_first + G, kSpItems) * kSpItems;
   const int64_t n = g_end - g_first;
   WITW_REQUIRE(n < (1ll << 31), WITW_ERR_INVALID, "witw_spec_gallery_prep: too many items in one call");
-  spec_gallery_prep_kernel<<<(unsigned)n, 256, 0, as_stream(stream)>>>(ov, G, g_first, reinterpret_cast<__nv_bfloat16*>(gal_op));
+  WITW_REQUIRE(((uintptr_t)spec_out & 7) == 0, WITW_ERR_INVALID, "witw_spec_gallery_prep: spectra must be 8-byte aligned");
+  spec_gallery_prep_kernel<<<(unsigned)n, 256, 0, as_stream(stream)>>>(ov, G, g_first, reinterpret_cast<__nv_bfloat16*>(gal_op), spec_out);
   WITW_LAUNCH_CHECK();
   return launch_crop_norm(ov, G, n, CH, sw, crop_inv_norm, stream);
 }
 
-extern "C" int witw_spec_query_prep(const float* su, int64_t Q, int CH, int sw, void* qry_op, float* q_inv_norm, witw_stream_t stream) {
+extern "C" int witw_spec_query_prep(const float* su, int64_t Q, int CH, int sw, void* qry_op, float* q_inv_norm, float* spec_out,
+                                    witw_stream_t stream) {
   WITW_REQUIRE(witw_spec_supported(CH, 64, sw), WITW_ERR_UNSUPPORTED, "witw_spec_query_prep: needs C*H == 64 and 1 <= sw <= 64 (got %d, %d)", CH, sw);
   WITW_REQUIRE(Q >= 0 && Q < (1ll << 31), WITW_ERR_INVALID, "witw_spec_query_prep: bad query count");
   if (Q == 0) return WITW_OK;
   WITW_REQUIRE(su && qry_op && q_inv_norm, WITW_ERR_INVALID, "witw_spec_query_prep: null pointer");
   WITW_REQUIRE(((uintptr_t)qry_op & 127) == 0, WITW_ERR_INVALID, "witw_spec_query_prep: operand must be 128-byte aligned");
   const int64_t q_pad = ceil_div<int64_t>(Q, 128) * 128;
-  spec_query_prep_kernel<<<(unsigned)q_pad, 256, 0, as_stream(stream)>>>(su, Q, sw, reinterpret_cast<__nv_bfloat16*>(qry_op), q_inv_norm);
+  WITW_REQUIRE(((uintptr_t)spec_out & 7) == 0, WITW_ERR_INVALID, "witw_spec_query_prep: spectra must be 8-byte aligned");
+  spec_query_prep_kernel<<<(unsigned)q_pad, 256, 0, as_stream(stream)>>>(su, Q, sw, reinterpret_cast<__nv_bfloat16*>(qry_op), q_inv_norm, spec_out);
   WITW_LAUNCH_CHECK();
   return WITW_OK;
 }

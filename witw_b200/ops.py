@@ -42,16 +42,18 @@ TC_MIN_PAIRS = 1 << 16
 # Which tensor-core sweep serves a (gallery, query width): "hankel" = the shift search as one dense contraction
 # (csrc/match_tc.cu, 8192*sw_pad FLOP per pair), "spectral" = per-frequency products + inverse FFT in the epilogue
 # (csrc/match_spec.cu, 16.9 kFLOP per pair whatever the width; needs C*H == 64).  "auto": spectral when it is
-# supported and the query is wider than SPEC_MIN_SW columns (below that the dense contraction is cheaper).
+# supported and the query has at least SPEC_MIN_SW columns (the spectral sweep costs the same at every width -- 8.0 ms
+# for 10k x 10k against 36.6 ms (360 deg) / 8.9 ms (90 deg) of the dense contraction; narrower queries than that have
+# flat spectra whose bf16 rounding costs more accuracy than the dense form's).
 TC_IMPL = "auto"
-SPEC_MIN_SW = 16
+SPEC_MIN_SW = 8
 
 
 def _pick_impl(impl, ch, w, sw):
     impl = TC_IMPL if impl in (None, "auto") else impl
     if impl == "auto":
         ok = bool(_lib.load().witw_spec_supported(int(ch), int(w), int(sw)))
-        return "spectral" if (ok and sw > SPEC_MIN_SW) else "hankel"
+        return "spectral" if (ok and sw >= SPEC_MIN_SW) else "hankel"
     if impl not in ("hankel", "spectral"):
         raise ValueError("impl must be 'auto', 'hankel' or 'spectral'")
     if impl == "spectral" and not _lib.load().witw_spec_supported(int(ch), int(w), int(sw)):
@@ -265,8 +267,10 @@ class GalleryIndex(object):
                 self.operand = torch.empty(nbytes, dtype=torch.uint8, device=dev)
                 g8 = max((g + 7) // 8 * 8, 8)
                 self.crop_inv_norm = torch.empty(g8 * 64, dtype=torch.float32, device=dev)
+                if keep_fp32:       # the exact finish's fp32 spectra come out of the same pass over the features
+                    self.spec = torch.empty((g * self.CH, 64), dtype=torch.float32, device=dev)
                 _lib.call("witw_spec_gallery_prep", ov.data_ptr(), g, 0, self.CH, w, self.sw, self.operand.data_ptr(),
-                          self.crop_inv_norm.data_ptr(), _stream())
+                          self.crop_inv_norm.data_ptr(), _ptr(self.spec), _stream())
             return
         with torch.cuda.device(dev):
             nbytes = _lib.load().witw_gallery_operand_bytes(g, self.CH, self.sw)
@@ -339,13 +343,13 @@ class GalleryBuilder(object):
         with torch.cuda.device(self.device):
             if self.ov is not None:
                 self.ov[self.count: self.count + n].copy_(part)
-            if self.spec is not None:
-                _lib.call("witw_spectral_rows_f32", part.data_ptr(), n * self.CH, self.W,
-                          self.spec.data_ptr() + self.count * self.CH * 64 * 4, _stream())
+            spec_ptr = 0 if self.spec is None else self.spec.data_ptr() + self.count * self.CH * 64 * 4
             if self.impl == "spectral":
                 _lib.call("witw_spec_gallery_prep", part.data_ptr(), n, self.count, self.CH, self.W, self.sw, self.operand.data_ptr(),
-                          self.crop_inv_norm.data_ptr() + self.count * 64 * 4, _stream())
+                          self.crop_inv_norm.data_ptr() + self.count * 64 * 4, spec_ptr, _stream())
             else:
+                if spec_ptr:
+                    _lib.call("witw_spectral_rows_f32", part.data_ptr(), n * self.CH, self.W, spec_ptr, _stream())
                 _lib.call("witw_gallery_prep", part.data_ptr(), n, self.CH, self.W, self.sw,
                           self.operand.data_ptr() + (self.count // 2) * self.pair_bytes,
                           self.crop_inv_norm.data_ptr() + self.count * 64 * 4, _stream())
@@ -379,7 +383,10 @@ class QueryBatch(object):
             with torch.cuda.device(dev):
                 self.operand = torch.empty(_lib.load().witw_spec_query_operand_bytes(q, self.CH), dtype=torch.uint8, device=dev)
                 self.inv_norm = torch.empty(max(q, 1), dtype=torch.float32, device=dev)
-                _lib.call("witw_spec_query_prep", su.data_ptr(), q, self.CH, sw, self.operand.data_ptr(), self.inv_norm.data_ptr(), _stream())
+                if keep_fp32:
+                    self.spec = torch.empty((q * self.CH, 64), dtype=torch.float32, device=dev)
+                _lib.call("witw_spec_query_prep", su.data_ptr(), q, self.CH, sw, self.operand.data_ptr(), self.inv_norm.data_ptr(),
+                          _ptr(self.spec), _stream())
             return
         with torch.cuda.device(dev):
             nbytes = _lib.load().witw_query_operand_bytes(q, self.CH, sw)

@@ -19,10 +19,12 @@
 // lane, so the inverse real FFT (ifft64_gen.cuh, 612 fp32 operations) and the argmax over the shift are
 // register-local; the epilogue transforms two items at once in the two halves of packed f32x2 operations.
 //
-// Per CTA (one per SM, persistent): warps 0-1 TMA producers, warps 2-3 MMA issuers (even / odd slots each: the
-// per-stage barrier round trip of a single issuing warp, ~430 cycles, would otherwise pace the 8 small MMAs of a
-// slot), warps 4-11 epilogue (two warps per TMEM lane quarter, four items each).  Operand ring of 6 stages; a stage
-// is one slot: 32 KB of query spectra (two 128-byte-swizzled K halves, one 3-D TMA box) + 4 KB of gallery spectra.
+// Per CTA (one per SM, persistent, 16 warps): warps 0-1 TMA producers (even / odd stages), warps 2-7 MMA issuers,
+// one per stage of the operand ring -- the 8 MMAs of a slot accumulate into the same 16 TMEM columns, a dependent
+// chain of small (N = 16) operations, so six issuers keep six independent chains in flight and split the per-stage
+// barrier round trip (~430 cycles for a single warp) -- warps 8-15 epilogue (two warps per TMEM lane quarter, four
+// items each).  Operand ring of 6 stages; a stage is one slot: 32 KB of query spectra (two 128-byte-swizzled K
+// halves, contiguous in the tile-major operand: one TMA box) + 4 KB of gallery spectra.
 // Measured and dropped: multicasting the query stage over a cluster (2/4/8 CTAs) -- L2 is not the limiter, the
 // lock-step costs 10-20 %.
 #include <cuda.h>
@@ -41,7 +43,7 @@ namespace witw {
 void* get_encode_tiled();                                                                         // polar.cu
 int launch_crop_norm(const float* ov, int64_t G, int64_t G_pad, int CH, int sw, float* crop_inv_norm, witw_stream_t stream);  // match_tc.cu
 
-constexpr int kSpThreads = 384;
+constexpr int kSpThreads = 512;
 constexpr int kSpStages = 6;           // even: producer / issuer warp p owns the stages of parity p
 constexpr int kSpABytes = 2 * 128 * 128;  // 2 K halves x 128 queries x 64 bf16
 constexpr int kSpBBytes = 2 * 16 * 128;   // 2 K halves x 8 items x (Re, Im) x 64 bf16
@@ -219,7 +221,7 @@ match_spec_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_consta
       bar_init(s2u(&full[s]), 1);
       bar_init(s2u(&empty[s]), 1);
     }
-    bar_init(s2u(tmem_full), 2);      // one tcgen05.commit per issuing warp
+    bar_init(s2u(tmem_full), kSpStages);   // one tcgen05.commit per issuing warp
     bar_init(s2u(tmem_empty), 8);     // one arrive per epilogue warp
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -232,10 +234,10 @@ match_spec_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
 
-  // 384 threads start with 168 registers each; the four control warps give theirs up so that an epilogue thread can
-  // hold the 128 accumulators of two items plus the transform's temporaries (128 x 40 + 256 x 232 <= 64 K registers)
-  if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-  else asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+  // 512 threads start with 128 registers each; the eight control warps give theirs up so that an epilogue thread can
+  // hold the 128 accumulators of two items plus the transform's temporaries (256 x 40 + 256 x 216 = 64 K registers)
+  if (warp < 8) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+  else asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
 
   if (warp < 2) {
     // ===================== TMA producers: warp p loads the slots of parity p into the stages of parity p =====================
@@ -266,47 +268,46 @@ match_spec_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_consta
         }
       }
     }
-  } else if (warp < 4) {
-    // ===================== MMA issuers: warp 2 even slots, warp 3 odd slots =====================
-    const int par = warp - 2;
-    const uint64_t a_desc0 = make_desc(s2u(a_base), 16, 1024, 2 /*SWIZZLE_128B*/);
-    const uint64_t b_desc0 = make_desc(s2u(b_base), 16, 1024, 2 /*SWIZZLE_128B*/);
-    uint32_t k = 0, ph = 0, tile_it = 0;
+  } else if (warp < 8) {
+    // ===================== MMA issuers: warp 2 + k owns stage k, i.e. every sixth slot of this CTA's slot sequence =====================
+    const uint32_t k = (uint32_t)(warp - 2);
+    uint32_t n_tiles = 0;
     for (int w = unit; w < n_work; w += n_units) {
       const int chunk = chunk_major ? w / P.n_qtiles : w % P.n_chunks;
       const int grp0 = chunk * P.groups_per_chunk;
-      const int grp1 = min(grp0 + P.groups_per_chunk, P.n_groups);
-      for (int grp = grp0; grp < grp1; ++grp, ++tile_it) {
+      n_tiles += (uint32_t)(min(grp0 + P.groups_per_chunk, P.n_groups) - grp0);
+    }
+    const uint64_t da = make_desc(s2u(a_base) + k * kSpABytes, 16, 1024, 2 /*SWIZZLE_128B*/);
+    const uint64_t db = make_desc(s2u(b_base) + k * kSpBBytes, 16, 1024, 2 /*SWIZZLE_128B*/);
+    const uint32_t full_k = s2u(&full[k]), empty_k = s2u(&empty[k]);
+    uint32_t ph = 0, seen_tile = 0xffffffffu;
+    for (uint32_t c = k; c < n_tiles * kSpSlots; c += kSpStages, ph ^= 1) {
+      const uint32_t tile_it = c / kSpSlots, slot = c % kSpSlots;
+      if (tile_it != seen_tile) {  // first slot of a new tile: the epilogue must have drained the previous one
+        seen_tile = tile_it;
         bar_wait(s2u(tmem_empty), (tile_it & 1) ^ 1);
-        tc_fence_after();
-        for (int slot = par; slot < kSpSlots; slot += 2) {
-          const uint32_t s = 2 * k + par;
-          bar_wait(s2u(&full[s]), ph);
-          tc_fence_after();
-          if (elect_one()) {
-            const uint64_t da = a_desc0 + (uint64_t)(s * (kSpABytes >> 4));
-            const uint64_t db = b_desc0 + (uint64_t)(s * (kSpBBytes >> 4));
-            const uint32_t tmem_d = tmem_base + (uint32_t)slot * 16u;
-            if (!(P.debug & 4)) {
-#pragma unroll
-              for (int h = 0; h < 2; ++h)    // K halves: tiles of 16 KB (queries) / 2 KB (items)
-#pragma unroll
-                for (int j = 0; j < 4; ++j)  // 32 bytes (2 descriptor units) along K per step inside the 128B-swizzled rows
-                  umma_bf16<1>(tmem_d, da + (uint64_t)(h * (kSpABytes >> 5) + 2 * j), db + (uint64_t)(h * (kSpBBytes >> 5) + 2 * j), kIdesc,
-                               (h | j) != 0 ? 1u : 0u);
-            }
-            umma_commit<1>(s2u(&empty[s]));
-            if (slot >= kSpSlots - 2) umma_commit<1>(s2u(tmem_full));
-          }
-          __syncwarp();
-          if (++k == kSpStages / 2) { k = 0; ph ^= 1; }
-        }
       }
+      bar_wait(full_k, ph);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t tmem_d = tmem_base + slot * 16u;
+        if (!(P.debug & 4)) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h)    // K halves: tiles of 16 KB (queries) / 2 KB (items)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)  // 32 bytes (2 descriptor units) along K per step inside the 128B-swizzled rows
+              umma_bf16<1>(tmem_d, da + (uint64_t)(h * (kSpABytes >> 5) + 2 * j), db + (uint64_t)(h * (kSpBBytes >> 5) + 2 * j), kIdesc,
+                           (h | j) != 0 ? 1u : 0u);
+        }
+        umma_commit<1>(empty_k);
+        if ((c + kSpStages) / kSpSlots != tile_it) umma_commit<1>(s2u(tmem_full));  // this warp's last slot of the tile
+      }
+      __syncwarp();
     }
   } else {
-    // ===================== epilogue: warps 4-7 items 0-3, warps 8-11 items 4-7 of each tile =====================
+    // ===================== epilogue: warps 8-11 items 0-3, warps 12-15 items 4-7 of each tile =====================
     const int wq = warp & 3;
-    const int ihalf = (warp - 4) >> 2;
+    const int ihalf = (warp - 8) >> 2;
     const int row = wq * 32 + lane;
     const uint32_t lane_field = (uint32_t)(wq * 32) << 16;
     uint32_t tile_it = 0;

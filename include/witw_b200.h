@@ -75,6 +75,26 @@ int witw_polar_plan_build(int h_s, int w_s, int s_o, void* plan_host);
 int witw_polar_resample_f32(const float* src_dev, float* dst_dev, int64_t n_img,
                             const void* plan_host, const void* plan_dev, witw_stream_t stream);
 
+/* uint8 tiles in, normalised polar images out: ImageNormalization (cvig_fov.py:137-149, norm(data / 255.)) fused
+ * into the polar transform (cvig_fov.py:186-209) for tiles that already have the model's size, where Resize
+ * (cvig_fov.py:133) is the identity.  The source is read at one byte per pixel instead of four.
+ *   witw_norm_lut (host): lut[c][v] = ((v / divisor[c]) - mean[c]) / std[c] for v = 0..255, each step rounded to
+ *        fp32 as torch does (divisor 255 for image channels).
+ *   witw_bilinear_gather_u8: the bit-exact path -- every tap is looked up in the table, then blended in the
+ *        reference's order; plane p uses channel p % n_ch.  lut_dev: [n_ch][256] fp32 on the device.
+ *   witw_polar_resample_u8: the staged throughput path on a plan built by witw_polar_plan_build_u8 (box rows of
+ *        160 bytes starting on a 16-pixel boundary); the raw pixels are blended and the channel's affine map
+ *        a*v + b applied once per output pixel (within 1e-6 of the table form), clipped pixels patched exactly. */
+int witw_norm_lut(const float* divisor, const float* mean, const float* std, int n_ch, float* lut_host);
+int witw_bilinear_gather_u8(const uint8_t* src_dev, float* dst_dev, const int32_t* idx4_dev,
+                            const float* w4_dev, int64_t n_planes, int src_h, int src_w, int64_t n_out,
+                            const float* lut_dev, int n_ch, witw_stream_t stream);
+size_t witw_polar_plan_bytes_u8(int h_s, int w_s, int s_o);
+int witw_polar_plan_build_u8(int h_s, int w_s, int s_o, void* plan_host);
+int witw_polar_resample_u8(const uint8_t* src_dev, float* dst_dev, int64_t n_planes, int n_ch,
+                           const float* lut_host, const float* lut_dev, const void* plan_host,
+                           const void* plan_dev, witw_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * K2/K3  orientation-searched distance       replaces model/cvig_fov.py:297-363
  *        (correlation -> crop_overhead -> l2_distance)

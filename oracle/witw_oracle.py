@@ -90,6 +90,26 @@ def polar_transform(overhead, h_s=SURFACE_H, w_s=SURFACE_W, s_o=OVERHEAD):
     return bilinear_interpolate(overhead, x_src, y_src)
 
 
+# --------------------------------------------------------------------------- f4 (upstream of a2)
+IMG_MEAN = (0.485, 0.456, 0.406)   # model/cvig_fov.py:24-25
+IMG_STD = (0.229, 0.224, 0.225)
+
+
+def image_normalization(img_u8, mean=IMG_MEAN, std=IMG_STD):
+    """model/cvig_fov.py:137-149 on one image [C,H,W] uint8 -> fp32: ``norm(data / 255.)`` with torchvision's
+    Normalize, i.e. ((x / 255) - mean) / std, every step rounded to fp32."""
+    x = img_u8 / 255.
+    m = torch.as_tensor(mean, dtype=x.dtype).view(-1, 1, 1)
+    sd = torch.as_tensor(std, dtype=x.dtype).view(-1, 1, 1)
+    return (x - m) / sd
+
+
+def normalized_polar(overhead_u8, mean=IMG_MEAN, std=IMG_STD):
+    """ImageNormalization then PolarTransform on a uint8 tile that is already 256 x 256 (Resize is the identity there:
+    cvig_fov.py:133, 147, 208)."""
+    return polar_transform(image_normalization(overhead_u8, mean, std))
+
+
 # --------------------------------------------------------------------------- a3
 def correlation_scores(overhead_embed, surface_embed):
     """Un-normalised circular cross-correlation, fp32 [G,Q,W].

@@ -80,6 +80,16 @@ def main():
     np.savez_compressed(os.path.join(HERE, "bilinear.npz"), im=im.numpy(), x=bx, y=by,
                         out=cvig.bilinear_interpolate(im, bx, by).numpy())
 
+    # ---- uint8 tile -> ImageNormalization -> PolarTransform (the transform chain upstream of a2) ----
+    gen = torch.Generator().manual_seed(9)
+    tile8 = torch.randint(0, 256, (3, 256, 256), generator=gen, dtype=torch.uint8)
+    tile8[0, 255, 128], tile8[1, 128, 255] = 255, 0            # the taps of the two zero-weight pixels
+    d = cvig.ImageNormalization()({"surface": tile8[:, :128, :].clone(), "overhead": tile8.clone()})
+    d = cvig.PolarTransform()(d)
+    assert d["overhead"].dtype == torch.float32
+    np.savez_compressed(os.path.join(HERE, "prep.npz"), tile_u8=tile8.numpy(), norm_rows=d["overhead"][:, ::37, :].numpy(),
+                        polar=d["polar"].numpy())
+
     # ---- correlation / crop / distance (a3-a5) -----------------------------------
     cases = {}
     for name, (g, q, fov, seed) in {

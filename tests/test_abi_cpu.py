@@ -48,6 +48,33 @@ def test_host_grid_and_lut_match_oracle():
         assert np.array_equal(w[:, col].reshape(x.shape), ref)
 
 
+def test_norm_table_matches_oracle():
+    """witw_norm_lut (host): the 256 possible values of every channel after cvig_fov.py:147, bit for bit."""
+    from witw_b200 import _lib
+
+    mean = np.asarray(O.IMG_MEAN, np.float32)
+    std = np.asarray(O.IMG_STD, np.float32)
+    div = np.full(3, 255.0, np.float32)
+    lut = np.empty((3, 256), np.float32)
+    _lib.call("witw_norm_lut", div.ctypes.data, mean.ctypes.data, std.ctypes.data, 3, lut.ctypes.data)
+    ramp = torch.arange(256, dtype=torch.uint8).view(1, 1, 256).expand(3, 1, 256)
+    want = O.image_normalization(ramp).numpy().reshape(3, 256)
+    assert np.array_equal(lut, want)
+
+
+def test_polar_plan_u8_structure():
+    from witw_b200 import _lib
+
+    lib = _lib.load()
+    nbytes = lib.witw_polar_plan_bytes_u8(128, 512, 256)
+    assert nbytes == lib.witw_polar_plan_bytes(128, 512, 256)      # same tables, different box geometry
+    buf = np.zeros(nbytes, np.uint8)
+    _lib.call("witw_polar_plan_build_u8", 128, 512, 256, buf.ctypes.data)
+    hdr = buf[:80].view(np.int32)
+    assert hdr[1:4].tolist() == [128, 512, 256]
+    assert all(x % 16 == 0 for x in hdr[4:8].tolist())               # box starts on 16-byte boundaries of the uint8 rows
+
+
 def test_polar_plan_structure():
     from witw_b200 import _lib
 

@@ -295,3 +295,41 @@ def test_train_step_gradients_match_reference_autograd(W):
     ov_g, su_g = ov.cuda().requires_grad_(True), su.cuda().requires_grad_(True)
     with pytest.raises(RuntimeError, match="forward-only"):
         W.evaluate_ranks(ov_g, su_g)
+
+
+# ----------------------------------------------------------------------------- f4: uint8 -> normalised polar
+def test_normalized_polar_exact_matches_reference_chain(W, golden):
+    """exact=True: bit-identical to ImageNormalization -> PolarTransform of the unmodified reference (golden prep.npz)."""
+    g = golden("prep")
+    tile = torch.from_numpy(g["tile_u8"]).cuda()
+    out = W.normalized_polar(tile, exact=True)
+    assert out.dtype == torch.float32 and tuple(out.shape) == (3, 128, 512)
+    assert torch.equal(out.cpu(), torch.from_numpy(g["polar"]))
+
+
+def test_normalized_polar_fast_path(W, golden):
+    """The staged uint8 kernel: within 4e-6 of the reference chain, exactly 0 at the two zero-weight pixels, batched and
+    equal to polar_transform(normalised fp32 tile) to the same tolerance."""
+    g = golden("prep")
+    tile = torch.from_numpy(g["tile_u8"]).cuda()
+    out = W.normalized_polar(tile)
+    ref = torch.from_numpy(g["polar"])
+    assert (out.cpu() - ref).abs().max().item() <= 4e-6
+    assert float(out[:, 0, 0].abs().max()) == 0.0 and float(out[:, 0, 384].abs().max()) == 0.0
+    gen = torch.Generator().manual_seed(3)
+    batch = torch.randint(0, 256, (37, 3, 256, 256), generator=gen, dtype=torch.uint8)
+    got = W.normalized_polar(batch.cuda()).cpu()
+    want = torch.stack([O.normalized_polar(b) for b in batch[:5]])
+    assert (got[:5] - want).abs().max().item() <= 4e-6
+    exact = W.normalized_polar(batch.cuda(), exact=True).cpu()
+    assert torch.equal(exact[:5], want)
+    assert (got - exact).abs().max().item() <= 4e-6
+
+
+def test_normalized_polar_rejects_other_inputs(W):
+    with pytest.raises(TypeError):
+        W.normalized_polar(torch.zeros(3, 256, 256).cuda())
+    with pytest.raises(ValueError):
+        W.normalized_polar(torch.zeros(3, 750, 750, dtype=torch.uint8).cuda())     # needs the reference's Resize first
+    with pytest.raises(RuntimeError):
+        W.normalized_polar(torch.zeros(3, 256, 256, dtype=torch.uint8))            # CPU tensor: no fallback

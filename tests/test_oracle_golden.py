@@ -32,6 +32,18 @@ def test_polar_transform_bit_exact(golden):
     assert float(out[:, 0, 0].abs().max()) == 0.0 and float(out[:, 0, 384].abs().max()) == 0.0
 
 
+def test_image_normalization_and_polar_chain_bit_exact(golden):
+    """uint8 tile -> ImageNormalization -> PolarTransform of the unmodified reference (cvig_fov.py:137-149, 186-209)."""
+    g = golden("prep")
+    tile = t(g["tile_u8"])
+    assert tile.dtype == torch.uint8
+    norm = O.image_normalization(tile)
+    assert norm.dtype == torch.float32 and torch.equal(norm[:, ::37, :], t(g["norm_rows"]))
+    out = O.normalized_polar(tile)
+    assert torch.equal(out, t(g["polar"]))
+    assert float(out[:, 0, 0].abs().max()) == 0.0 and float(out[:, 0, 384].abs().max()) == 0.0
+
+
 def test_bilinear_generic_bit_exact(golden):
     g = golden("bilinear")
     out = O.bilinear_interpolate(t(g["im"]), g["x"], g["y"])

@@ -49,6 +49,15 @@ for c, n in ((3, 1024), (5, 600)):
     emit("bilinear_gather_kernel (exact) C=%d" % c, ms, "GB/s", byts / ms / 1e6, peaks["hbm_gbs"], {"tiles": n, "tiles_per_s": n / ms * 1e3})
     del tiles
 
+# K1 fused with ImageNormalization: uint8 tiles in, normalised fp32 polar out
+tiles8 = torch.randint(0, 256, (2048, 3, 256, 256), device=dev, dtype=torch.uint8, generator=gen)
+ms = timeit(lambda: W.normalized_polar(tiles8))
+byts = 2048 * 3 * (256 * 256 * 1.0 + 128 * 512 * 4.0)
+emit("polar_quadrant_kernel<uint8> C=3 (normalise + polar)", ms, "GB/s", byts / ms / 1e6, peaks["hbm_gbs"], {"tiles": 2048, "tiles_per_s": 2048 / ms * 1e3})
+ms = timeit(lambda: W.normalized_polar(tiles8, exact=True), iters=5)
+emit("bilinear_gather_kernel<uint8> (exact) C=3", ms, "GB/s", byts / ms / 1e6, peaks["hbm_gbs"], {"tiles": 2048, "tiles_per_s": 2048 / ms * 1e3})
+del tiles8
+
 # K4 rank / top-k on a materialised 10k x 10k matrix (400 MB)
 d = torch.rand(10000, 10000, device=dev, generator=gen)
 ms = timeit(lambda: W.rank_from_distances(d))
@@ -62,30 +71,35 @@ for fov in (360, 90):
     sw = int(fov / 360 * 512) // 8
     ov = torch.randn(10000, 16, 4, 64, device=dev, generator=gen) * 0.06
     su = torch.randn(10000, 16, 4, sw, device=dev, generator=gen) * 0.06
-    gal, qry = ops.GalleryIndex(ov, sw), ops.QueryBatch(su)
     d_true, _ = ops.true_match_distances(ov, su)
     t32 = torch.arange(10000, dtype=torch.int32, device=dev)
     cnt = torch.zeros(10000, dtype=torch.int32, device=dev)
-    ms = timeit(lambda: ops.sweep_tc(gal, qry, d_true=d_true, true_idx=t32, rank_count=cnt, topk=10), iters=5)
     flop = 2.0 * 64 * 64 * sw * 1e8
-    emit("match_tc_kernel fov=%d 10k x 10k (+rank count, top-10, merge)" % fov, ms, "TFLOP/s", flop / ms / 1e9, peaks["bf16_tflops_sustained"],
-         {"queries_per_s": 1e4 / ms * 1e3})
-    ms = timeit(lambda: ops.sweep_tc(gal, qry, want_dist=True, want_ori=True), iters=5)
-    emit("match_tc_kernel fov=%d 10k x 10k (full dist+ori matrices)" % fov, ms, "TFLOP/s", flop / ms / 1e9, peaks["bf16_tflops_sustained"])
-    ms = timeit(lambda: ops.GalleryIndex(ov, sw), iters=5)
-    emit("gallery_prep fov=%d 10k items" % fov, ms, "GB/s", (gal.operand.numel() + ov.numel() * 4) / ms / 1e6, peaks["hbm_gbs"])
-    del ov, su, gal, qry
+    for impl, kname in (("spectral", "match_spec_kernel"), ("hankel", "match_tc_kernel")):
+        gal, qry = ops.GalleryIndex(ov, sw, impl=impl), ops.QueryBatch(su, impl=impl)
+        ms = timeit(lambda: ops.sweep_tc(gal, qry, d_true=d_true, true_idx=t32, rank_count=cnt, topk=10), iters=5)
+        emit("%s fov=%d 10k x 10k (+rank count, top-10, merge)" % (kname, fov), ms, "TFLOP/s", flop / ms / 1e9, peaks["bf16_tflops_sustained"],
+             {"queries_per_s": 1e4 / ms * 1e3, "flop_count": "direct form, 8192*sw per pair"})
+        ms = timeit(lambda: ops.sweep_tc(gal, qry, want_dist=True, want_ori=True), iters=5)
+        emit("%s fov=%d 10k x 10k (full dist+ori matrices)" % (kname, fov), ms, "TFLOP/s", flop / ms / 1e9, peaks["bf16_tflops_sustained"])
+        ms = timeit(lambda: ops.GalleryIndex(ov, sw, impl=impl), iters=5)
+        emit("gallery prep (%s, incl. fp32 spectra for spectral) fov=%d 10k items" % (impl, fov), ms, "GB/s",
+             (gal.operand.numel() + ov.numel() * 4 * (2 if impl == "spectral" else 1)) / ms / 1e6, peaks["hbm_gbs"])
+        del gal, qry
+    del ov, su
 
 # BASELINE configs[4] sweep: 100k-tile gallery, 10k queries, 90 degrees (gallery operand 7.2 GB)
 ov = torch.randn(100000, 16, 4, 64, device=dev, generator=gen) * 0.06
 su = torch.randn(10000, 16, 4, 16, device=dev, generator=gen) * 0.06
-gal, qry = ops.GalleryIndex(ov, 16, keep_fp32=False), ops.QueryBatch(su, keep_fp32=False)
 d_true = torch.full((10000,), 1.0, device=dev)
 cnt = torch.zeros(10000, dtype=torch.int32, device=dev)
-ms = timeit(lambda: ops.sweep_tc(gal, qry, d_true=d_true, rank_count=cnt, topk=10), iters=3, warm=1)
-emit("match_tc_kernel fov=90 100k gallery x 10k queries (+rank count, top-10, merge)", ms, "TFLOP/s", 2.0 * 64 * 64 * 16 * 1e9 / ms / 1e9,
-     peaks["bf16_tflops_sustained"], {"queries_per_s": 1e4 / ms * 1e3})
-del ov, su, gal, qry
+for impl, kname in (("spectral", "match_spec_kernel"), ("hankel", "match_tc_kernel")):
+    gal, qry = ops.GalleryIndex(ov, 16, keep_fp32=False, impl=impl), ops.QueryBatch(su, keep_fp32=False, impl=impl)
+    ms = timeit(lambda: ops.sweep_tc(gal, qry, d_true=d_true, rank_count=cnt, topk=10), iters=3, warm=1)
+    emit("%s fov=90 100k gallery x 10k queries (+rank count, top-10, merge)" % kname, ms, "TFLOP/s", 2.0 * 64 * 64 * 16 * 1e9 / ms / 1e9,
+         peaks["bf16_tflops_sustained"], {"queries_per_s": 1e4 / ms * 1e3})
+    del gal, qry
+del ov, su
 
 # exact fp32 path, 2k x 2k at 360 degrees
 ov = torch.randn(2048, 16, 4, 64, device=dev, generator=gen) * 0.06

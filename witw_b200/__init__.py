@@ -21,6 +21,7 @@ from .ops import (
     heatmap_scores,
     l2_distance,
     match,
+    normalized_polar,
     polar_grid,
     polar_transform,
     rank_from_distances,
@@ -36,7 +37,7 @@ from .sharded import evaluate_ranks_sharded, shard_bounds
 __all__ = [
     "GalleryBuilder", "GalleryIndex", "PolarTransform", "QueryBatch", "WitwError", "baseline_ranks", "bilinear_interpolate", "correlation",
     "correlation_scores", "crop_overhead", "evaluate_ranks", "evaluate_ranks_prepared", "evaluate_ranks_sharded",
-    "heatmap_scores", "install", "l2_distance", "match", "polar_grid", "polar_transform", "rank_from_distances",
+    "heatmap_scores", "install", "l2_distance", "match", "normalized_polar", "polar_grid", "polar_transform", "rank_from_distances",
     "recall_from_ranks", "shard_bounds", "sweep_tc", "tc_supported", "topk_from_distances", "true_match_distances",
     "uninstall",
 ]

@@ -65,12 +65,17 @@ static void bilinear_lut_host(const double* x, const double* y, int64_t n, int s
 // ------------------------------------------------------------------------------------------
 // generic gather kernel (bit-exact path)
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) bilinear_gather_kernel(const float* __restrict__ src,
+__device__ __forceinline__ float gather_value(const float* s, int o, const float*, int) { return __ldg(s + o); }
+__device__ __forceinline__ float gather_value(const uint8_t* s, int o, const float* lut, int c) { return __ldg(lut + c * 256 + __ldg(s + o)); }
+
+template <typename T>
+__global__ void __launch_bounds__(256) bilinear_gather_kernel(const T* __restrict__ src,
                                                               float* __restrict__ dst,
                                                               const int4* __restrict__ idx4,
                                                               const float4* __restrict__ w4,
                                                               int64_t n_img, int src_h, int src_w,
-                                                              int64_t n_out, int img_per_block) {
+                                                              int64_t n_out, int img_per_block,
+                                                              const float* __restrict__ lut, int n_ch) {
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n_out) return;
   const int4 t = idx4[p];  // x0, x1, y0, y1
@@ -80,8 +85,10 @@ __global__ void __launch_bounds__(256) bilinear_gather_kernel(const float* __res
   const int64_t i0 = (int64_t)blockIdx.y * img_per_block;
   const int64_t i1 = min(i0 + img_per_block, n_img);
   for (int64_t i = i0; i < i1; ++i) {
-    const float* s = src + i * plane;
-    const float a = __ldg(s + oa), b = __ldg(s + ob), c = __ldg(s + oc), d = __ldg(s + od);
+    const T* s = src + i * plane;
+    const int ch = n_ch > 0 ? (int)(i % n_ch) : 0;
+    const float a = gather_value(s, oa, lut, ch), b = gather_value(s, ob, lut, ch), c = gather_value(s, oc, lut, ch),
+                d = gather_value(s, od, lut, ch);
     // ((wa*Ia + wb*Ib) + wc*Ic) + wd*Id, no contraction (cvig_fov.py:183)
     float r = __fadd_rn(__fmul_rn(w.x, a), __fmul_rn(w.y, b));
     r = __fadd_rn(r, __fmul_rn(w.z, c));
@@ -96,6 +103,7 @@ __global__ void __launch_bounds__(256) bilinear_gather_kernel(const float* __res
 constexpr int kPolarThreads = 1024;
 constexpr int kPolarPx = 16;  // output pixels per thread per quadrant
 constexpr int kBoxW = 132;    // floats per staged source row (multiple of 4: TMA inner box is 16-byte granular)
+constexpr int kBoxWU8 = 160;  // bytes per staged row of a uint8 source (box start on a 16-pixel boundary: up to 15 + 130 columns)
 constexpr int kBoxH = 129;
 constexpr int kPolarStages = 3;
 constexpr uint32_t kPlanMagic = 0x57495031u;  // "WIP1"
@@ -116,6 +124,8 @@ struct PolarPlanHeader {
                      // (off2 packs the 16-bit box offsets of pixels 2i and 2i+1)
   uint32_t exc_off;  // byte offset of PolarException[n_exc]
   uint32_t total_bytes;
+  int32_t box_w;      // elements per staged source row (kBoxW for fp32 sources, kBoxWU8 for uint8 sources)
+  int32_t elem_bytes; // 4 or 1
 };
 
 static bool polar_fast_supported(int h_s, int w_s, int s_o) {
@@ -145,8 +155,10 @@ static inline void polar_thread_pixel(int i, int t, int qw, int pw, int* row, in
 }
 
 // Builds header + tables into `out` (may be null to only count).  Returns bytes, 0 if unsupported.
-static size_t polar_plan_build_host(int h_s, int w_s, int s_o, void* out) {
+static size_t polar_plan_build_host(int h_s, int w_s, int s_o, void* out, int elem_bytes = 4) {
   if (!polar_fast_supported(h_s, w_s, s_o)) return 0;
+  const int box_w = elem_bytes == 4 ? kBoxW : kBoxWU8;
+  const int align = 16 / elem_bytes;  // elements per 16 bytes
   const int64_t n = (int64_t)h_s * w_s;
   std::vector<double> x(n), y(n);
   polar_grid_host(h_s, w_s, s_o, x.data(), y.data());
@@ -177,8 +189,8 @@ static size_t polar_plan_build_host(int h_s, int w_s, int s_o, void* out) {
   for (int q = 0; q < 4; ++q) {
     // measured on B200 (tools/probe/tma_probe.cu): a tile-mode TMA whose innermost start coordinate is not a
     // multiple of 16 bytes raises an illegal-instruction fault, so the box starts on a 4-float boundary
-    bx0[q] &= ~3;
-    if (bx1[q] - bx0[q] + 1 > kBoxW || by1[q] - by0[q] + 1 > kBoxH) return 0;
+    bx0[q] &= ~(align - 1);
+    if (bx1[q] - bx0[q] + 1 > box_w || by1[q] - by0[q] + 1 > kBoxH) return 0;
   }
   const size_t lut_elems = (size_t)4 * kPolarPx * kPolarThreads;
   PolarPlanHeader h;
@@ -187,6 +199,7 @@ static size_t polar_plan_build_host(int h_s, int w_s, int s_o, void* out) {
   for (int q = 0; q < 4; ++q) { h.box_x0[q] = bx0[q]; h.box_y0[q] = by0[q]; }
   h.n_exc = (int32_t)exc.size();
   h.patch_w = polar_patch_w();
+  h.box_w = box_w; h.elem_bytes = elem_bytes;
   h.lut_off = 256;
   h.exc_off = (uint32_t)(h.lut_off + 3 * lut_elems * 4);
   h.total_bytes = (uint32_t)(h.exc_off + std::max<size_t>(exc.size(), 1) * sizeof(PolarException));
@@ -211,7 +224,7 @@ static size_t polar_plan_build_host(int h_s, int w_s, int s_o, void* out) {
         const int fx0 = (int)std::floor(x[p]), fy0 = (int)std::floor(y[p]);
         fx[o] = (float)(x[p] - (double)fx0);
         fy[o] = (float)(y[p] - (double)fy0);
-        off[o2] |= (uint32_t)((fy0 - by0[q]) * kBoxW + (fx0 - bx0[q])) << sh;
+        off[o2] |= (uint32_t)((fy0 - by0[q]) * box_w + (fx0 - bx0[q])) << sh;
       }
   if (!exc.empty()) std::memcpy(base + h.exc_off, exc.data(), exc.size() * sizeof(PolarException));
   return h.total_bytes;
@@ -246,12 +259,19 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
 
 struct PolarQuadBoxes { int x0[4], y0[4]; };
 
+// uint8 sources: per-channel affine form of the reference's ImageNormalization (cvig_fov.py:137-149),
+// value = a[c] * pixel + b[c]; plane p of the batch is channel p % n_ch.  fp32 sources: unused.
+constexpr int kMaxNormCh = 8;
+struct PolarNorm { float a[kMaxNormCh], b[kMaxNormCh]; int n_ch; };
+
+template <typename T, int BOXW>
 __global__ void __launch_bounds__(kPolarThreads, 1)
 polar_quadrant_kernel(const __grid_constant__ CUtensorMap src_map, float* __restrict__ dst, int n_img,
                       const float* __restrict__ lut_fx, const float* __restrict__ lut_fy,
-                      const uint32_t* __restrict__ lut_off, PolarQuadBoxes boxes, int h_s, int w_s, int patch_w) {
+                      const uint32_t* __restrict__ lut_off, PolarQuadBoxes boxes, int h_s, int w_s, int patch_w,
+                      const __grid_constant__ PolarNorm norm) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  constexpr uint32_t kStageBytes = kBoxW * kBoxH * 4;
+  constexpr uint32_t kStageBytes = BOXW * kBoxH * sizeof(T);
   constexpr uint32_t kStageStride = (kStageBytes + 127) & ~127u;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + kPolarStages * kStageStride);
 
@@ -301,16 +321,22 @@ polar_quadrant_kernel(const __grid_constant__ CUtensorMap src_map, float* __rest
   for (int it = worker; it < n_img; it += n_workers, ++j) {
     const int s = j % kPolarStages;
     mbar_wait(&full[s], (uint32_t)((j / kPolarStages) & 1));
-    const float* tile = reinterpret_cast<const float*>(smem_raw + s * kStageStride);
+    const T* tile = reinterpret_cast<const T*>(smem_raw + s * kStageStride);
     float* o = dst + (size_t)it * plane_out + out_base;
+    float na = 1.f, nb = 0.f;
+    if constexpr (sizeof(T) == 1) {
+      const int c = it % norm.n_ch;
+      na = norm.a[c];
+      nb = norm.b[c];
+    }
 #pragma unroll
     for (int b = 0; b < kPolarPx; b += 4) {  // batches of 4 pixels bound the live registers (1024 threads -> 64 regs each)
       float r[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int i = b + u;
-        const float* p = tile + ((off2[i >> 1] >> ((i & 1) * 16)) & 0xffffu);
-        const float ia = p[0], ic = p[1], ib = p[kBoxW], id = p[kBoxW + 1];
+        const T* p = tile + ((off2[i >> 1] >> ((i & 1) * 16)) & 0xffffu);
+        const float ia = (float)p[0], ic = (float)p[1], ib = (float)p[BOXW], id = (float)p[BOXW + 1];
         // the four weights are recomputed per plane on purpose: hoisting them out of the plane loop
         // would cost 64 more registers per thread (the empty asm makes fxi/fyi opaque to LICM)
         float fxi = fx[i], fyi = fy[i];
@@ -319,7 +345,9 @@ polar_quadrant_kernel(const __grid_constant__ CUtensorMap src_map, float* __rest
         // reference order (cvig_fov.py:178-183): wa=(x1-x)(y1-y) wb=(x1-x)(y-y0) wc=(x-x0)(y1-y) wd=(x-x0)(y-y0)
         float t = __fadd_rn(__fmul_rn(__fmul_rn(ax, ay), ia), __fmul_rn(__fmul_rn(ax, fyi), ib));
         t = __fadd_rn(t, __fmul_rn(__fmul_rn(fxi, ay), ic));
-        r[u] = __fadd_rn(t, __fmul_rn(__fmul_rn(fxi, fyi), id));
+        t = __fadd_rn(t, __fmul_rn(__fmul_rn(fxi, fyi), id));
+        // uint8 source: the blend of the raw pixels, then the channel's normalisation (the four weights sum to one)
+        r[u] = sizeof(T) == 1 ? fmaf(na, t, nb) : t;
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) __stcs(o + (b + u) * out_step, r[u]);
@@ -336,14 +364,23 @@ polar_quadrant_kernel(const __grid_constant__ CUtensorMap src_map, float* __rest
   }
 }
 
-__global__ void polar_exception_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t n_img,
-                                       const PolarException* __restrict__ exc, int n_exc, int s_o, int64_t plane_out) {
+// value of a source pixel as the reference's blend sees it: the fp32 pixel, or the exact normalised value of a uint8
+// pixel from the per-channel table lut[c][256] (built on the host with the reference's fp32 operations)
+__device__ __forceinline__ float polar_src_value(const float* s, int o, const float*, int) { return s[o]; }
+__device__ __forceinline__ float polar_src_value(const uint8_t* s, int o, const float* lut, int c) { return __ldg(lut + c * 256 + s[o]); }
+
+template <typename T>
+__global__ void polar_exception_kernel(const T* __restrict__ src, float* __restrict__ dst, int64_t n_img,
+                                       const PolarException* __restrict__ exc, int n_exc, int s_o, int64_t plane_out,
+                                       const float* __restrict__ lut, int n_ch) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_img * n_exc) return;
   const int64_t img = i / n_exc;
   const PolarException e = exc[i % n_exc];
-  const float* s = src + img * (int64_t)s_o * s_o;
-  const float a = s[e.y0 * s_o + e.x0], b = s[e.y1 * s_o + e.x0], c = s[e.y0 * s_o + e.x1], d = s[e.y1 * s_o + e.x1];
+  const T* s = src + img * (int64_t)s_o * s_o;
+  const int ch = n_ch > 0 ? (int)(img % n_ch) : 0;
+  const float a = polar_src_value(s, e.y0 * s_o + e.x0, lut, ch), b = polar_src_value(s, e.y1 * s_o + e.x0, lut, ch),
+              c = polar_src_value(s, e.y0 * s_o + e.x1, lut, ch), d = polar_src_value(s, e.y1 * s_o + e.x1, lut, ch);
   float r = __fadd_rn(__fmul_rn(e.w[0], a), __fmul_rn(e.w[1], b));
   r = __fadd_rn(r, __fmul_rn(e.w[2], c));
   r = __fadd_rn(r, __fmul_rn(e.w[3], d));
@@ -384,11 +421,12 @@ extern "C" int witw_bilinear_lut(const double* x, const double* y, int64_t n, in
   return WITW_OK;
 }
 
-extern "C" int witw_bilinear_gather_f32(const float* src, float* dst, const int32_t* idx4, const float* w4, int64_t n_img,
-                                        int src_h, int src_w, int64_t n_out, witw_stream_t stream) {
-  WITW_REQUIRE(src && dst && idx4 && w4, WITW_ERR_INVALID, "witw_bilinear_gather_f32: null pointer");
+template <typename T>
+static int launch_gather(const T* src, float* dst, const int32_t* idx4, const float* w4, int64_t n_img, int src_h, int src_w,
+                         int64_t n_out, const float* lut, int n_ch, witw_stream_t stream, const char* who) {
+  WITW_REQUIRE(src && dst && idx4 && w4, WITW_ERR_INVALID, "%s: null pointer", who);
   WITW_REQUIRE(n_img >= 0 && n_out >= 0 && src_h > 0 && src_w > 0 && (int64_t)src_h * src_w < (1ll << 31), WITW_ERR_INVALID,
-               "witw_bilinear_gather_f32: bad shape");
+               "%s: bad shape", who);
   if (n_img == 0 || n_out == 0) return WITW_OK;
   const int64_t bx = ceil_div<int64_t>(n_out, 256);
   // enough blocks in y to fill the machine a few times over, each looping over a run of planes
@@ -396,10 +434,33 @@ extern "C" int witw_bilinear_gather_f32(const float* src, float* dst, const int3
   by = std::min<int64_t>(by, 65535);
   const int per = (int)ceil_div<int64_t>(n_img, by);
   by = ceil_div<int64_t>(n_img, per);
-  WITW_REQUIRE(bx < (1ll << 31), WITW_ERR_INVALID, "witw_bilinear_gather_f32: too many sample points");
-  bilinear_gather_kernel<<<dim3((unsigned)bx, (unsigned)by), 256, 0, as_stream(stream)>>>(
-      src, dst, reinterpret_cast<const int4*>(idx4), reinterpret_cast<const float4*>(w4), n_img, src_h, src_w, n_out, per);
+  WITW_REQUIRE(bx < (1ll << 31), WITW_ERR_INVALID, "%s: too many sample points", who);
+  bilinear_gather_kernel<T><<<dim3((unsigned)bx, (unsigned)by), 256, 0, as_stream(stream)>>>(
+      src, dst, reinterpret_cast<const int4*>(idx4), reinterpret_cast<const float4*>(w4), n_img, src_h, src_w, n_out, per, lut, n_ch);
   WITW_LAUNCH_CHECK();
+  return WITW_OK;
+}
+
+extern "C" int witw_bilinear_gather_f32(const float* src, float* dst, const int32_t* idx4, const float* w4, int64_t n_img,
+                                        int src_h, int src_w, int64_t n_out, witw_stream_t stream) {
+  return launch_gather<float>(src, dst, idx4, w4, n_img, src_h, src_w, n_out, nullptr, 0, stream, "witw_bilinear_gather_f32");
+}
+
+extern "C" int witw_bilinear_gather_u8(const uint8_t* src, float* dst, const int32_t* idx4, const float* w4, int64_t n_planes,
+                                       int src_h, int src_w, int64_t n_out, const float* norm_lut, int n_ch, witw_stream_t stream) {
+  WITW_REQUIRE(norm_lut && n_ch >= 1, WITW_ERR_INVALID, "witw_bilinear_gather_u8: the normalisation table [n_ch][256] is required");
+  return launch_gather<uint8_t>(src, dst, idx4, w4, n_planes, src_h, src_w, n_out, norm_lut, n_ch, stream, "witw_bilinear_gather_u8");
+}
+
+extern "C" int witw_norm_lut(const float* divisor, const float* mean, const float* std, int n_ch, float* lut_host) {
+  WITW_REQUIRE(divisor && mean && std && lut_host && n_ch >= 1, WITW_ERR_INVALID, "witw_norm_lut: bad arguments");
+  for (int c = 0; c < n_ch; ++c)
+    for (int v = 0; v < 256; ++v) {
+      // cvig_fov.py:147: norm(data / 255.) = ((v / 255) - mean) / std, every step rounded to fp32 as torch does
+      volatile float x = (float)v / divisor[c];
+      volatile float y = x - mean[c];
+      lut_host[c * 256 + v] = y / std[c];
+    }
   return WITW_OK;
 }
 
@@ -416,14 +477,29 @@ extern "C" int witw_polar_plan_build(int h_s, int w_s, int s_o, void* plan_host)
   return WITW_OK;
 }
 
-extern "C" int witw_polar_resample_f32(const float* src, float* dst, int64_t n_img, const void* plan_host,
-                                       const void* plan_dev, witw_stream_t stream) {
-  WITW_REQUIRE(src && dst && plan_host && plan_dev, WITW_ERR_INVALID, "witw_polar_resample_f32: null pointer");
+extern "C" size_t witw_polar_plan_bytes_u8(int h_s, int w_s, int s_o) {
+  const size_t b = polar_plan_build_host(h_s, w_s, s_o, nullptr, 1);
+  if (b == 0) set_error(WITW_ERR_UNSUPPORTED, "witw_polar_plan_u8: geometry %dx%d from %d is outside the staged fast path", h_s, w_s, s_o);
+  return b;
+}
+
+extern "C" int witw_polar_plan_build_u8(int h_s, int w_s, int s_o, void* plan_host) {
+  WITW_REQUIRE(plan_host, WITW_ERR_INVALID, "witw_polar_plan_build_u8: null plan");
+  const size_t b = polar_plan_build_host(h_s, w_s, s_o, plan_host, 1);
+  WITW_REQUIRE(b != 0, WITW_ERR_UNSUPPORTED, "witw_polar_plan_build_u8: geometry %dx%d from %d is outside the staged fast path", h_s, w_s, s_o);
+  return WITW_OK;
+}
+
+template <typename T, int BOXW>
+static int launch_polar(const T* src, float* dst, int64_t n_img, const void* plan_host, const void* plan_dev, const PolarNorm& norm,
+                        const float* lut_dev, witw_stream_t stream, const char* who) {
+  WITW_REQUIRE(src && dst && plan_host && plan_dev, WITW_ERR_INVALID, "%s: null pointer", who);
   PolarPlanHeader h;
   std::memcpy(&h, plan_host, sizeof(h));
-  WITW_REQUIRE(h.magic == kPlanMagic, WITW_ERR_INVALID, "witw_polar_resample_f32: plan_host is not a polar plan");
-  WITW_REQUIRE(n_img >= 0 && n_img < (1ll << 31), WITW_ERR_INVALID, "witw_polar_resample_f32: bad n_img");
-  WITW_REQUIRE(((uintptr_t)src & 15) == 0, WITW_ERR_INVALID, "witw_polar_resample_f32: src must be 16-byte aligned");
+  WITW_REQUIRE(h.magic == kPlanMagic, WITW_ERR_INVALID, "%s: plan_host is not a polar plan", who);
+  WITW_REQUIRE(h.elem_bytes == (int)sizeof(T) && h.box_w == BOXW, WITW_ERR_INVALID, "%s: the plan was built for %d-byte source pixels", who, h.elem_bytes);
+  WITW_REQUIRE(n_img >= 0 && n_img < (1ll << 31), WITW_ERR_INVALID, "%s: bad plane count", who);
+  WITW_REQUIRE(((uintptr_t)src & 15) == 0, WITW_ERR_INVALID, "%s: src must be 16-byte aligned", who);
   if (n_img == 0) return WITW_OK;
   int rc = witw_device_check();
   if (rc != WITW_OK) return rc;
@@ -432,22 +508,18 @@ extern "C" int witw_polar_resample_f32(const float* src, float* dst, int64_t n_i
   WITW_REQUIRE(encode != nullptr, WITW_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   CUtensorMap map;
   const cuuint64_t dims[3] = {(cuuint64_t)h.s_o, (cuuint64_t)h.s_o, (cuuint64_t)n_img};
-  const cuuint64_t strides[2] = {(cuuint64_t)h.s_o * 4, (cuuint64_t)h.s_o * h.s_o * 4};
-  const cuuint32_t box[3] = {kBoxW, kBoxH, 1};
+  const cuuint64_t strides[2] = {(cuuint64_t)h.s_o * sizeof(T), (cuuint64_t)h.s_o * h.s_o * sizeof(T)};
+  const cuuint32_t box[3] = {BOXW, kBoxH, 1};
   const cuuint32_t estr[3] = {1, 1, 1};
-  CUresult cr = encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(src), dims, strides, box, estr,
-                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+  CUresult cr = encode(&map, sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<T*>(src), dims,
+                       strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   WITW_REQUIRE(cr == CUDA_SUCCESS, WITW_ERR_CUDA, "cuTensorMapEncodeTiled(polar source) failed with CUresult %d", (int)cr);
 
-  constexpr uint32_t kStageBytes = kBoxW * kBoxH * 4;
+  constexpr uint32_t kStageBytes = BOXW * kBoxH * sizeof(T);
   constexpr uint32_t kStageStride = (kStageBytes + 127) & ~127u;
   const size_t smem = (size_t)kPolarStages * kStageStride + kPolarStages * sizeof(uint64_t);
-  static bool attr_set = false;
-  if (!attr_set) {
-    WITW_CUDA(cudaFuncSetAttribute(polar_quadrant_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  WITW_CUDA(cudaFuncSetAttribute(polar_quadrant_kernel<T, BOXW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const char* pd = (const char*)plan_dev;
   const size_t lut_elems = (size_t)4 * kPolarPx * kPolarThreads;
   const float* fx = (const float*)(pd + h.lut_off);
@@ -457,13 +529,35 @@ extern "C" int witw_polar_resample_f32(const float* src, float* dst, int64_t n_i
   for (int q = 0; q < 4; ++q) { boxes.x0[q] = h.box_x0[q]; boxes.y0[q] = h.box_y0[q]; }
   int grid = (sm_count() / 4) * 4;
   if ((int64_t)grid > 4 * n_img) grid = (int)(4 * n_img);
-  polar_quadrant_kernel<<<grid, kPolarThreads, smem, as_stream(stream)>>>(map, dst, (int)n_img, fx, fy, off, boxes, h.h_s, h.w_s, h.patch_w);
+  polar_quadrant_kernel<T, BOXW><<<grid, kPolarThreads, smem, as_stream(stream)>>>(map, dst, (int)n_img, fx, fy, off, boxes, h.h_s, h.w_s,
+                                                                                  h.patch_w, norm);
   WITW_LAUNCH_CHECK();
   if (h.n_exc > 0) {
     const int64_t n = n_img * h.n_exc;
-    polar_exception_kernel<<<(unsigned)ceil_div<int64_t>(n, 256), 256, 0, as_stream(stream)>>>(
-        src, dst, n_img, (const PolarException*)(pd + h.exc_off), h.n_exc, h.s_o, (int64_t)h.h_s * h.w_s);
+    polar_exception_kernel<T><<<(unsigned)ceil_div<int64_t>(n, 256), 256, 0, as_stream(stream)>>>(
+        src, dst, n_img, (const PolarException*)(pd + h.exc_off), h.n_exc, h.s_o, (int64_t)h.h_s * h.w_s, lut_dev, norm.n_ch);
     WITW_LAUNCH_CHECK();
   }
   return WITW_OK;
+}
+
+extern "C" int witw_polar_resample_f32(const float* src, float* dst, int64_t n_img, const void* plan_host,
+                                       const void* plan_dev, witw_stream_t stream) {
+  PolarNorm norm;
+  std::memset(&norm, 0, sizeof(norm));
+  return launch_polar<float, kBoxW>(src, dst, n_img, plan_host, plan_dev, norm, nullptr, stream, "witw_polar_resample_f32");
+}
+
+extern "C" int witw_polar_resample_u8(const uint8_t* src, float* dst, int64_t n_planes, int n_ch, const float* norm_lut_host,
+                                      const float* norm_lut_dev, const void* plan_host, const void* plan_dev, witw_stream_t stream) {
+  WITW_REQUIRE(norm_lut_host && norm_lut_dev, WITW_ERR_INVALID, "witw_polar_resample_u8: the normalisation table is required on host and device");
+  WITW_REQUIRE(n_ch >= 1 && n_ch <= kMaxNormCh, WITW_ERR_UNSUPPORTED, "witw_polar_resample_u8: 1..%d channels (got %d)", kMaxNormCh, n_ch);
+  PolarNorm norm;
+  std::memset(&norm, 0, sizeof(norm));
+  norm.n_ch = n_ch;
+  for (int c = 0; c < n_ch; ++c) {  // the table is affine in the pixel value up to fp32 rounding: value = a * v + b
+    norm.b[c] = norm_lut_host[c * 256];
+    norm.a[c] = (float)(((double)norm_lut_host[c * 256 + 255] - (double)norm_lut_host[c * 256]) / 255.0);
+  }
+  return launch_polar<uint8_t, kBoxWU8>(src, dst, n_planes, plan_host, plan_dev, norm, norm_lut_dev, stream, "witw_polar_resample_u8");
 }

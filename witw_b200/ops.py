@@ -204,6 +204,80 @@ def polar_transform(overhead, h_s=SURFACE_HEIGHT_MAX, w_s=SURFACE_WIDTH_MAX, s_o
     return out
 
 
+IMG_MEAN = (0.485, 0.456, 0.406)   # model/cvig_fov.py:24-25
+IMG_STD = (0.229, 0.224, 0.225)
+_norm_cache = {}
+
+
+def _norm_table(mean, std, divisor, device):
+    """(host, device) copies of the per-channel normalisation table [C,256] fp32 of cvig_fov.py:147."""
+    mean = tuple(float(m) for m in mean)
+    std = tuple(float(v) for v in std)
+    divisor = tuple(float(d) for d in (divisor if hasattr(divisor, "__len__") else [divisor] * len(mean)))
+    if not (len(mean) == len(std) == len(divisor)) or not mean:
+        raise ValueError("normalized_polar: mean, std and divisor must have one entry per channel")
+    key = (mean, std, divisor, str(device))
+    if key not in _norm_cache:
+        c = len(mean)
+        host = np.empty((c, 256), dtype=np.float32)
+        m, sd, dv = (np.asarray(v, dtype=np.float32) for v in (mean, std, divisor))
+        _lib.call("witw_norm_lut", dv.ctypes.data, m.ctypes.data, sd.ctypes.data, c, host.ctypes.data)
+        _norm_cache[key] = (host, torch.from_numpy(host).to(device))
+    return _norm_cache[key]
+
+
+def normalized_polar(overhead_u8, mean=IMG_MEAN, std=IMG_STD, divisor=255.0, exact=False,
+                     h_s=SURFACE_HEIGHT_MAX, w_s=SURFACE_WIDTH_MAX, s_o=OVERHEAD_SIZE):
+    """ImageNormalization + PolarTransform in one kernel (cvig_fov.py:137-149 then 186-209) for uint8 tiles
+    [..., C, s_o, s_o] on CUDA that already have the model's size (Resize, cvig_fov.py:133, is the identity for those;
+    other sizes are refused: torchvision's resize is not restated here).  Returns [..., C, h_s, w_s] fp32 =
+    ``polar(norm(tile / 255.))``.  One byte per source pixel is read instead of four.
+
+    exact=False: the staged kernel (within 4e-6 absolute of the reference chain); exact=True: every tap through the
+    reference's fp32 normalisation table and the reference's blend order, bit-identical to the chain.
+    """
+    dev = _need_cuda("normalized_polar", overhead_u8)
+    if overhead_u8.dtype != torch.uint8:
+        raise TypeError("normalized_polar: expected uint8 tiles, got %s" % overhead_u8.dtype)
+    if overhead_u8.dim() < 3 or overhead_u8.shape[-1] != s_o or overhead_u8.shape[-2] != s_o:
+        raise ValueError("normalized_polar: expected [...,C,%d,%d] tiles (the Resize of the reference is not part of this kernel), got %s"
+                         % (s_o, s_o, tuple(overhead_u8.shape)))
+    src = overhead_u8.contiguous()
+    c = src.shape[-3]
+    if c != len(mean):
+        raise ValueError("normalized_polar: %d channels but %d means" % (c, len(mean)))
+    lead = tuple(src.shape[:-2])
+    n_planes = int(np.prod(lead))
+    out = torch.empty(lead + (h_s, w_s), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        lut_host, lut_dev = _norm_table(mean, std, divisor, dev)
+        plan = None
+        if not exact:
+            key = ("u8", h_s, w_s, s_o, str(dev))
+            if key not in _plan_cache:
+                nbytes = _lib.load().witw_polar_plan_bytes_u8(h_s, w_s, s_o)
+                if nbytes == 0:
+                    _plan_cache[key] = None
+                else:
+                    host = np.zeros(nbytes, dtype=np.uint8)
+                    _lib.call("witw_polar_plan_build_u8", h_s, w_s, s_o, host.ctypes.data)
+                    _plan_cache[key] = (host, torch.from_numpy(host).to(dev))
+            plan = _plan_cache[key]
+        if plan is None:
+            key = ("grid", h_s, w_s, s_o, str(dev))
+            if key not in _lut_cache:
+                gx, gy = polar_grid(h_s, w_s, s_o)
+                _lut_cache[key] = _gather_lut(gx, gy, s_o, s_o, dev)
+            idx, w = _lut_cache[key]
+            _lib.call("witw_bilinear_gather_u8", src.data_ptr(), out.data_ptr(), idx.data_ptr(), w.data_ptr(), n_planes, s_o, s_o,
+                      h_s * w_s, lut_dev.data_ptr(), c, _stream())
+        else:
+            host, devplan = plan
+            _lib.call("witw_polar_resample_u8", src.data_ptr(), out.data_ptr(), n_planes, c, lut_host.ctypes.data, lut_dev.data_ptr(),
+                      host.ctypes.data, devplan.data_ptr(), _stream())
+    return out
+
+
 class PolarTransform(object):
     """Drop-in for cvig_fov.py:186-209: ``data['polar'] = polar(data['overhead'])``, other keys kept.
 

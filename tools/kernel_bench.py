@@ -58,6 +58,9 @@ ms = timeit(lambda: W.normalized_polar(tiles8, exact=True), iters=5)
 emit("bilinear_gather_kernel<uint8> (exact) C=3", ms, "GB/s", byts / ms / 1e6, peaks["hbm_gbs"], {"tiles": 2048, "tiles_per_s": 2048 / ms * 1e3})
 del tiles8
 
+if os.environ.get("KB_ONLY") == "polar":
+    sys.exit(0)
+
 # K4 rank / top-k on a materialised 10k x 10k matrix (400 MB)
 d = torch.rand(10000, 10000, device=dev, generator=gen)
 ms = timeit(lambda: W.rank_from_distances(d))

@@ -337,15 +337,13 @@ polar_quadrant_kernel(const __grid_constant__ CUtensorMap src_map, float* __rest
         const int i = b + u;
         const T* p = tile + ((off2[i >> 1] >> ((i & 1) * 16)) & 0xffffu);
         const float ia = (float)p[0], ic = (float)p[1], ib = (float)p[BOXW], id = (float)p[BOXW + 1];
-        // the four weights are recomputed per plane on purpose: hoisting them out of the plane loop
-        // would cost 64 more registers per thread (the empty asm makes fxi/fyi opaque to LICM)
-        float fxi = fx[i], fyi = fy[i];
-        asm volatile("" : "+f"(fxi), "+f"(fyi));
-        const float ax = 1.0f - fxi, ay = 1.0f - fyi;
-        // reference order (cvig_fov.py:178-183): wa=(x1-x)(y1-y) wb=(x1-x)(y-y0) wc=(x-x0)(y1-y) wd=(x-x0)(y-y0)
-        float t = __fadd_rn(__fmul_rn(__fmul_rn(ax, ay), ia), __fmul_rn(__fmul_rn(ax, fyi), ib));
-        t = __fadd_rn(t, __fmul_rn(__fmul_rn(fxi, ay), ic));
-        t = __fadd_rn(t, __fmul_rn(__fmul_rn(fxi, fyi), id));
+        // separable form of the reference's four-weight blend (cvig_fov.py:178-183): lerp along x on both rows, then
+        // along y -- 3 subtractions + 3 FMAs and no weight registers; within a few fp32 roundings of the reference's
+        // sum (the bit-exact form is witw_bilinear_gather_*)
+        const float fxi = fx[i], fyi = fy[i];
+        const float top = fmaf(fxi, ic - ia, ia);
+        const float bot = fmaf(fxi, id - ib, ib);
+        float t = fmaf(fyi, bot - top, top);
         // uint8 source: the blend of the raw pixels, then the channel's normalisation (the four weights sum to one)
         r[u] = sizeof(T) == 1 ? fmaf(na, t, nb) : t;
       }

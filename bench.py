@@ -45,7 +45,7 @@ def env_int(name, default):
 
 
 class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms during the timed regions."""
 
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -58,7 +58,7 @@ class ClockSampler(object):
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
-                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
             self.proc = None
@@ -235,7 +235,6 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     ms_total, out = timed(step_device, steps)
-    clocks = sampler.stop() if rank == 0 else None
     ms_step = ms_total / steps
     value = world * Q_TOTAL / (ms_step / 1000.0)
     kernel_ms = statistics.mean(a.elapsed_time(b) for a, b in sweep_events[:steps])
@@ -279,6 +278,7 @@ def run_ours(args):
 
     run_e2e(2)
     e2e_ms, e2e_out = timed(lambda: run_e2e(steps), 1)
+    clocks = sampler.stop() if rank == 0 else None      # sampled over both timed regions (device-resident and end-to-end)
     e2e_value = world * Q_TOTAL / (e2e_ms / steps / 1000.0)
     h2d = ov_host.numel() * 4 + su_host.numel() * 4
     d2h = sum(t.numel() * t.element_size() for t in e2e_out)

@@ -62,6 +62,18 @@ def test_norm_table_matches_oracle():
     assert np.array_equal(lut, want)
 
 
+def test_sweep_schedules_stay_within_the_merge_width():
+    """Candidate-list counts of both sweeps (host-side schedules, no GPU): 1..64 lists for any problem size."""
+    from witw_b200 import _lib
+
+    lib = _lib.load()
+    for g, q in ((1, 1), (8, 128), (10000, 10000), (125000, 10000), (1000000, 1), (4096, 2048), (333, 100000)):
+        for fn in (lib.witw_match_spec_topk_slots, lib.witw_match_tc_topk_slots):
+            n = fn(g, q)
+            assert 1 <= n <= 64, (g, q, n)
+    assert lib.witw_match_spec_topk_slots(10000, 10000) == 56       # 28 chunks x 2 lists: the best-balanced split (DESIGN 4.2s)
+
+
 def test_polar_plan_u8_structure():
     from witw_b200 import _lib
 

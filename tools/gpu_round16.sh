@@ -13,5 +13,5 @@ b=json.load(open('gpurun_out/bench_hankel.log')); print('hankel value',b['value'
 PY
 bash tools/gpu_launches.sh > /dev/null
 python tools/launch_table.py gpurun_out/launches.csv 20 | tail -45
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:match_spec_kernel -s 3 -c 1 -o gpurun_out/match_spec_r1e -f python bench.py --steps 1 --warmup 3 > gpurun_out/ncu_full.log 2>&1; echo "ncu full rc=$?"
-python tools/summarize_ncu.py gpurun_out/match_spec_r1e.ncu-rep > gpurun_out/match_spec_r1e.txt 2>&1; head -40 gpurun_out/match_spec_r1e.txt
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:match_spec_kernel -s 3 -c 1 -o gpurun_out/match_spec_r1g -f python bench.py --steps 1 --warmup 3 > gpurun_out/ncu_full.log 2>&1; echo "ncu full rc=$?"
+python tools/summarize_ncu.py gpurun_out/match_spec_r1g.ncu-rep > gpurun_out/match_spec_r1g.txt 2>&1; head -40 gpurun_out/match_spec_r1g.txt

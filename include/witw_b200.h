@@ -277,6 +277,14 @@ int witw_topk_from_dist_f32(const float* dist_dev, int64_t G, int64_t Q, int k, 
                             float* topk_dist_dev, int32_t* topk_idx_dev, int32_t g_index_offset,
                             witw_stream_t stream);
 
+/* The same result for large galleries (G >= 1024, k <= 32, Q a multiple of 4) without candidate lists: thresholds from
+ * a strided row sample, one streaming pass that appends the elements at or below the threshold to per-column survivor
+ * buffers, and a warp-per-column selection.  scratch: witw_topk_select_scratch_bytes(). */
+size_t witw_topk_select_scratch_bytes(int64_t Q, int k);
+int witw_topk_select_f32(const float* dist_dev, int64_t G, int64_t Q, int k, float* topk_dist_dev,
+                         int32_t* topk_idx_dev, int32_t g_index_offset, void* scratch_dev,
+                         witw_stream_t stream);
+
 /* Merge n_lists sorted candidate lists per query ([n_lists,Q,k] each) into one [Q,k]. */
 int witw_topk_merge(const float* cand_dist_dev, const int32_t* cand_idx_dev, int n_lists,
                     int64_t Q, int k, float* topk_dist_dev, int32_t* topk_idx_dev,

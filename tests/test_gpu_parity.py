@@ -333,3 +333,22 @@ def test_normalized_polar_rejects_other_inputs(W):
         W.normalized_polar(torch.zeros(3, 750, 750, dtype=torch.uint8).cuda())     # needs the reference's Resize first
     with pytest.raises(RuntimeError):
         W.normalized_polar(torch.zeros(3, 256, 256, dtype=torch.uint8))            # CPU tensor: no fallback
+
+
+@pytest.mark.parametrize("G,Q,k,levels", [(10000, 512, 10, 0), (16384, 260, 7, 50), (9000, 64, 32, 3), (8192, 1000, 1, 0)])
+def test_topk_from_distances_large_gallery_thresholded(W, G, Q, k, levels):
+    """Galleries of >= 8192 rows take the two-pass form (strided sample pass -> admission thresholds -> full pass): same
+    result as a stable sort, including ties (quantised distances) broken by the lower gallery index, NaN / +inf never entering."""
+    gen = torch.Generator().manual_seed(G + k)
+    d = torch.rand(G, Q, generator=gen)
+    if levels:
+        d = torch.floor(d * levels) / levels                       # many exact ties, also at the k-th value
+    d[5, :] = float("nan")
+    d[7, ::3] = float("inf")
+    d[11, 1] = -0.0
+    d[13, 2] = -1e-7
+    td, ti = W.topk_from_distances(d.cuda(), k, g_offset=3)
+    clean = torch.where(torch.isnan(d), torch.full_like(d, float("inf")), d)
+    sd = torch.sort(clean.t(), dim=1, stable=True)
+    assert torch.equal(td.cpu(), sd.values[:, :k])
+    assert torch.equal(ti.cpu().long(), sd.indices[:, :k] + 3)

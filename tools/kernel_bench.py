@@ -66,7 +66,7 @@ d = torch.rand(10000, 10000, device=dev, generator=gen)
 ms = timeit(lambda: W.rank_from_distances(d))
 emit("rank_count_vec4_kernel 10k x 10k", ms, "GB/s", 4e8 / ms / 1e6, peaks["hbm_gbs"])
 ms = timeit(lambda: W.topk_from_distances(d, 10), iters=3, warm=1)
-emit("topk_columns_kernel k=10 10k x 10k", ms, "GB/s", 4e8 / ms / 1e6, peaks["hbm_gbs"])
+emit("topk_from_distances k=10 10k x 10k (threshold + filter + select)", ms, "GB/s", 4e8 / ms / 1e6, peaks["hbm_gbs"])
 del d
 
 # K2/K3 tensor-core sweeps with the gallery prepared once: 360 / 90 degrees, 10k x 10k

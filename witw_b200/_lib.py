@@ -68,6 +68,8 @@ SIGNATURES = {
     "witw_l2_rank_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "witw_topk_slices": (c_int, [c_int64, c_int64]),
     "witw_topk_from_dist_f32": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p, c_int32, c_void_p]),
+    "witw_topk_select_scratch_bytes": (c_size_t, [c_int64, c_int]),
+    "witw_topk_select_f32": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_int32, c_void_p, c_void_p]),
     "witw_topk_merge": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
 }
 

@@ -104,13 +104,18 @@ l2_dist_kernel(const float* __restrict__ ov, const float* __restrict__ su, int64
 // ------------------------------------------------------------------------------------------
 // top-k: one thread per query column keeps an ascending list of k (distance, index) in shared
 // memory, laid out [k][threads] so a warp's accesses to one list slot hit 32 different banks.
+// The gallery is cut into row slices for parallelism; short slices never warm their lists up (a slice of 167 rows
+// inserts 23 % of its elements), so a first pass over a strided sample of the rows (row_stride > 1) leaves candidate
+// lists whose k-th entries bound every column's k-th smallest distance from above, and the full pass (tau_lists set)
+// starts each list with that bound as its admission threshold: ~1 % of the elements are inserted instead of 23 %.
 // ------------------------------------------------------------------------------------------
 constexpr int kTopkThreads = 64;
 
 template <int VEC>  // adjacent query columns per thread: 4 (float4 loads) or 1
 __global__ void __launch_bounds__(kTopkThreads)
 topk_columns_kernel(const float* __restrict__ dist, int64_t G, int64_t Q, int k, float* __restrict__ out_d,
-                    int32_t* __restrict__ out_i, int32_t g_offset, int64_t rows_per_slice) {
+                    int32_t* __restrict__ out_i, int32_t g_offset, int64_t rows_per_slice, int64_t row_stride,
+                    const float* tau_lists, int tau_slices) {
   // blockIdx.x: 64*VEC query columns (a warp reads 32*VEC adjacent queries of one gallery row);
   // blockIdx.y: gallery slice, whose candidate list goes to out[slice][q][k]
   extern __shared__ unsigned char raw[];
@@ -126,10 +131,21 @@ topk_columns_kernel(const float* __restrict__ dist, int64_t G, int64_t Q, int k,
   if (q0 >= Q) return;
   const int64_t g0 = (int64_t)blockIdx.y * rows_per_slice;
   const int64_t g1 = min(g0 + rows_per_slice, G);
-  float worst[VEC];
+  float worst[VEC], bound[VEC];
   int filled[VEC];
 #pragma unroll
-  for (int c = 0; c < VEC; ++c) { worst[c] = inf; filled[c] = 0; }
+  for (int c = 0; c < VEC; ++c) {
+    // admission threshold: d < worst.  Any full list's k-th entry is >= the column's k-th smallest distance, so the
+    // smallest such entry of the sample pass (or of a slice that already finished: the slots are reused, every value
+    // ever stored there is a valid bound) admits exactly the elements <= it; an unfilled list gives +inf.
+    float tau = inf;
+    if (tau_lists != nullptr && q0 + c < Q)
+      for (int sl = 0; sl < tau_slices; ++sl) tau = fminf(tau, __ldcg(tau_lists + ((int64_t)sl * Q + q0 + c) * k + (k - 1)));
+    bound[c] = tau < inf ? __uint_as_float(__float_as_uint(tau) + (tau >= 0.f ? 1u : 0xffffffffu)) : inf;  // next float above tau
+    if (tau == 0.f) bound[c] = __uint_as_float(1u);
+    worst[c] = bound[c];
+    filled[c] = 0;
+  }
   auto insert = [&](int c, float d, int64_t g) {
     // the caller checked d < worst[c]: strict '<' keeps the earlier (lower) gallery index on ties; NaN, +inf never enter
     float* cd = ld + c * kTopkThreads + t;
@@ -141,15 +157,15 @@ topk_columns_kernel(const float* __restrict__ dist, int64_t G, int64_t Q, int k,
       --j;
     }
     cd[j * LW] = d;
-    ci[j * LW] = (int32_t)g + g_offset;
+    ci[j * LW] = (int32_t)(g * row_stride) + g_offset;
     if (filled[c] < k) ++filled[c];
-    if (filled[c] == k) worst[c] = cd[(k - 1) * LW];
+    if (filled[c] == k) worst[c] = fminf(bound[c], cd[(k - 1) * LW]);
   };
   int64_t g = g0;
   if constexpr (VEC == 4) {
     constexpr int U = 4;  // 4 x 16 bytes in flight per thread
     const float4* p = reinterpret_cast<const float4*>(dist + q0);
-    const int64_t stride4 = Q >> 2;
+    const int64_t stride4 = (Q >> 2) * row_stride;
     for (; g + U <= g1; g += U) {
       float4 v[U];
 #pragma unroll
@@ -172,16 +188,17 @@ topk_columns_kernel(const float* __restrict__ dist, int64_t G, int64_t Q, int k,
   } else {
     constexpr int U = 8;
     const float* p = dist + q0;
+    const int64_t stride1 = Q * row_stride;
     for (; g + U <= g1; g += U) {
       float v[U];
 #pragma unroll
-      for (int u = 0; u < U; ++u) v[u] = __ldcs(p + (g + u) * Q);
+      for (int u = 0; u < U; ++u) v[u] = __ldcs(p + (g + u) * stride1);
 #pragma unroll
       for (int u = 0; u < U; ++u)
         if (v[u] < worst[0]) insert(0, v[u], g + u);
     }
     for (; g < g1; ++g) {
-      const float v = __ldcs(p + g * Q);
+      const float v = __ldcs(p + g * stride1);
       if (v < worst[0]) insert(0, v, g);
     }
   }
@@ -313,9 +330,11 @@ extern "C" int witw_l2_rank_f32(const float* ov, const float* su, int64_t N, int
 }
 
 extern "C" int witw_topk_slices(int64_t G, int64_t Q) {
-  // enough (query block, gallery slice) CTAs for ~16 per SM, slices of at least 64 rows, at most 64 (merge limit)
+  // enough (query block, gallery slice) CTAs for ~16 per SM (~8 for the thresholded two-pass form of large galleries, whose
+  // per-slice cost is the list set-up and write-back rather than insertions), slices of at least 64 rows, at most 64
+  // (merge limit)
   const int64_t bx = ceil_div<int64_t>(std::max<int64_t>(Q, 1), kTopkThreads * 4);
-  int64_t s = ceil_div<int64_t>((int64_t)sm_count() * 16, bx);
+  int64_t s = ceil_div<int64_t>((int64_t)sm_count() * (G >= 8192 ? 8 : 16), bx);
   s = std::min<int64_t>(s, std::max<int64_t>(1, G / 64));
   return (int)std::max<int64_t>(1, std::min<int64_t>(s, 64));
 }
@@ -328,19 +347,237 @@ extern "C" int witw_topk_from_dist_f32(const float* dist, int64_t G, int64_t Q, 
   WITW_REQUIRE(topk_dist && topk_idx && (dist || G == 0), WITW_ERR_INVALID, "witw_topk_from_dist_f32: null pointer");
   const int64_t rows = ceil_div<int64_t>(std::max<int64_t>(G, 1), n_slices);
   const bool vec = (Q % 4 == 0) && (((uintptr_t)dist & 15) == 0) && k <= 32;
-  if (vec) {
-    const size_t smem = (size_t)k * kTopkThreads * 4 * 8;
-    WITW_CUDA(cudaFuncSetAttribute(topk_columns_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    topk_columns_kernel<4><<<dim3((unsigned)ceil_div<int64_t>(Q, kTopkThreads * 4), (unsigned)n_slices), kTopkThreads, smem, as_stream(stream)>>>(
-        dist, G, Q, k, topk_dist, topk_idx, g_offset, rows);
-  } else {
-    const size_t smem = (size_t)k * kTopkThreads * 8;
-    WITW_CUDA(cudaFuncSetAttribute(topk_columns_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    topk_columns_kernel<1><<<dim3((unsigned)ceil_div<int64_t>(Q, kTopkThreads), (unsigned)n_slices), kTopkThreads, smem, as_stream(stream)>>>(
-        dist, G, Q, k, topk_dist, topk_idx, g_offset, rows);
+  const size_t smem = vec ? (size_t)k * kTopkThreads * 4 * 8 : (size_t)k * kTopkThreads * 8;
+  const unsigned bx = (unsigned)ceil_div<int64_t>(Q, kTopkThreads * (vec ? 4 : 1));
+  auto launch = [&](int64_t g_rows, int slices, int64_t rows_per, int64_t stride, const float* tau, int tau_slices) -> int {
+    if (vec) {
+      WITW_CUDA(cudaFuncSetAttribute(topk_columns_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      topk_columns_kernel<4><<<dim3(bx, (unsigned)slices), kTopkThreads, smem, as_stream(stream)>>>(
+          dist, g_rows, Q, k, topk_dist, topk_idx, g_offset, rows_per, stride, tau, tau_slices);
+    } else {
+      WITW_CUDA(cudaFuncSetAttribute(topk_columns_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      topk_columns_kernel<1><<<dim3(bx, (unsigned)slices), kTopkThreads, smem, as_stream(stream)>>>(
+          dist, g_rows, Q, k, topk_dist, topk_idx, g_offset, rows_per, stride, tau, tau_slices);
+    }
+    WITW_LAUNCH_CHECK();
+    return WITW_OK;
+  };
+  // sample pass: 8 slices over a strided sample of the rows (about G/16 of them, at least 1024) written to candidate slots
+  // 0..7, merged into slot 8: its k-th entry is the k-th smallest of the whole sample, which admits ~k/n_samples of the
+  // elements in the full pass.  The full pass overwrites these slots with its own lists afterwards; whatever a reader finds
+  // at a k-th entry is the k-th entry of some full list (or +inf), i.e. a valid bound.
+  const int tau_slices = 8;
+  if (n_slices > tau_slices && G >= 8192 && rows >= 4 * (int64_t)k) {
+    const int64_t n_samples = std::max<int64_t>(1024, G / 16);
+    const int64_t stride = std::max<int64_t>(1, G / n_samples);
+    const int64_t n_rows = G / stride;
+    int rc = launch(n_rows, tau_slices, ceil_div<int64_t>(n_rows, tau_slices), stride, nullptr, 0);
+    if (rc != WITW_OK) return rc;
+    float* slot8_d = topk_dist + (int64_t)tau_slices * Q * k;
+    int32_t* slot8_i = topk_idx + (int64_t)tau_slices * Q * k;
+    rc = witw_topk_merge(topk_dist, topk_idx, tau_slices, Q, k, slot8_d, slot8_i, stream);
+    if (rc != WITW_OK) return rc;
+    return launch(G, n_slices, rows, 1, slot8_d, 1);
   }
-  WITW_LAUNCH_CHECK();
-  return WITW_OK;
+  return launch(G, n_slices, rows, 1, nullptr, 0);
+}
+
+// ------------------------------------------------------------------------------------------
+// top-k of large galleries by threshold + filter + select (witw_topk_select_f32).  The thread-per-column lists above
+// diverge on every insertion, and a warp row of 128 columns almost always holds one; so for G >= 8192 the full pass only
+// FILTERS: an element at or below the column's threshold tau (an upper bound of its k-th smallest distance, see
+// topk_groupmin_kernel) is appended to the column's survivor buffer with one atomic, and a warp per column then selects
+// the k smallest survivors in (distance, index) order.  About 4 k (ln k + 0.6) survivors per column are expected from a
+// quarter-of-the-rows sample; a column whose buffer overflows (massive ties at tau) is selected from the whole column
+// instead -- slow, exact.
+// ------------------------------------------------------------------------------------------
+constexpr int kFilterThreads = 128;
+
+// Threshold of a column = max over k disjoint row groups of the group's minimum: k distinct elements lie at or below
+// it, so it bounds the k-th smallest distance from above -- from min / max reductions alone, no lists.  Sampled row
+// i * row_stride belongs to group i % k; CTA (x, j, s) reduces group j over slice s of the sample.
+__global__ void __launch_bounds__(kFilterThreads)
+topk_groupmin_kernel(const float* __restrict__ dist, int64_t n_rows, int64_t row_stride, int64_t Q, int k, int64_t rows_per_slice,
+                     float* __restrict__ partial /* [slices][k][Q] */) {
+  const int64_t q0 = ((int64_t)blockIdx.x * kFilterThreads + threadIdx.x) * 4;
+  if (q0 >= Q) return;
+  const int j = blockIdx.y;
+  const int64_t i0 = (int64_t)blockIdx.z * rows_per_slice, i1 = min(i0 + rows_per_slice, n_rows);
+  const float inf = __int_as_float(0x7f800000);
+  float4 m = make_float4(inf, inf, inf, inf);
+  const float4* p = reinterpret_cast<const float4*>(dist + q0);
+  const int64_t stride4 = (Q >> 2) * row_stride;
+  int64_t i = i0 + ((j - i0 % k) % k + k) % k;   // first sampled row of group j in this slice
+  constexpr int U = 4;
+  for (; i + (U - 1) * k < i1; i += U * k) {
+    float4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) v[u] = __ldcs(p + (i + (int64_t)u * k) * stride4);
+#pragma unroll
+    for (int u = 0; u < U; ++u) { m.x = fminf(m.x, v[u].x); m.y = fminf(m.y, v[u].y); m.z = fminf(m.z, v[u].z); m.w = fminf(m.w, v[u].w); }
+  }
+  for (; i < i1; i += k) {
+    const float4 v = __ldcs(p + i * stride4);
+    m.x = fminf(m.x, v.x); m.y = fminf(m.y, v.y); m.z = fminf(m.z, v.z); m.w = fminf(m.w, v.w);
+  }
+  *reinterpret_cast<float4*>(partial + ((int64_t)blockIdx.z * k + j) * Q + q0) = m;
+}
+
+__global__ void __launch_bounds__(256)
+topk_tau_kernel(const float* __restrict__ partial, int n_slices, int k, int64_t Q, float* __restrict__ tau) {
+  const int64_t q = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (q >= Q) return;
+  const float inf = __int_as_float(0x7f800000);
+  float t = -inf;
+  for (int j = 0; j < k; ++j) {
+    float m = inf;
+    for (int s = 0; s < n_slices; ++s) m = fminf(m, partial[((int64_t)s * k + j) * Q + q]);
+    t = fmaxf(t, m);
+  }
+  tau[q] = t;
+}
+
+__global__ void __launch_bounds__(kFilterThreads)
+topk_filter_kernel(const float* __restrict__ dist, int64_t G, int64_t Q, const float* __restrict__ tau,
+                   int64_t rows_per_slice, int cap, int32_t* __restrict__ cnt, float* __restrict__ buf_d,
+                   int32_t* __restrict__ buf_i) {
+  const int64_t q0 = ((int64_t)blockIdx.x * kFilterThreads + threadIdx.x) * 4;
+  if (q0 >= Q) return;
+  const float inf = __int_as_float(0x7f800000);
+  float bound[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {  // admit d <= tau, written as d < (next float above tau); a NaN or missing tau admits every finite value
+    const bool live = q0 + c < Q;
+    const float t = live ? tau[q0 + c] : 0.f;
+    bound[c] = t < inf ? __uint_as_float(__float_as_uint(t) + (t >= 0.f ? 1u : 0xffffffffu)) : inf;
+    if (t == 0.f) bound[c] = __uint_as_float(1u);
+    if (!live) bound[c] = -inf;
+  }
+  const int64_t g0 = (int64_t)blockIdx.y * rows_per_slice;
+  const int64_t g1 = min(g0 + rows_per_slice, G);
+  auto keep = [&](int c, float d, int64_t g) {
+    const int32_t pos = atomicAdd(cnt + q0 + c, 1);
+    if (pos < cap) {
+      buf_d[(q0 + c) * cap + pos] = d;
+      buf_i[(q0 + c) * cap + pos] = (int32_t)g;
+    }
+  };
+  constexpr int U = 4;
+  const float4* p = reinterpret_cast<const float4*>(dist + q0);
+  const int64_t stride4 = Q >> 2;
+  int64_t g = g0;
+  for (; g + U <= g1; g += U) {
+    float4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) v[u] = __ldcs(p + (g + u) * stride4);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (v[u].x < bound[0]) keep(0, v[u].x, g + u);
+      if (v[u].y < bound[1]) keep(1, v[u].y, g + u);
+      if (v[u].z < bound[2]) keep(2, v[u].z, g + u);
+      if (v[u].w < bound[3]) keep(3, v[u].w, g + u);
+    }
+  }
+  for (; g < g1; ++g) {
+    const float4 v = __ldcs(p + g * stride4);
+    if (v.x < bound[0]) keep(0, v.x, g);
+    if (v.y < bound[1]) keep(1, v.y, g);
+    if (v.z < bound[2]) keep(2, v.z, g);
+    if (v.w < bound[3]) keep(3, v.w, g);
+  }
+}
+
+// (d, i) < (e, j) in the order of a stable ascending sort
+__device__ __forceinline__ bool pair_less(float d, int32_t i, float e, int32_t j) { return d < e || (d == e && i < j); }
+
+// Smallest (d, i) pair strictly after (last_d, last_i) among m entries of a column -- survivors from the buffer, or the
+// column itself (whole == true) -- reduced over the warp.  NaN and +inf never qualify.
+__device__ __forceinline__ void select_next(bool whole, const float* __restrict__ col, int64_t Q, const float* __restrict__ bd_buf,
+                                            const int32_t* __restrict__ bi_buf, int64_t m, int lane, bool first, float last_d,
+                                            int32_t last_i, float* out_d, int32_t* out_i) {
+  const float inf = __int_as_float(0x7f800000);
+  float bd = inf;
+  int32_t bi = 0x7fffffff;
+  for (int64_t e = lane; e < m; e += 32) {
+    const float d = whole ? __ldg(col + e * Q) : bd_buf[e];
+    const int32_t i = whole ? (int32_t)e : bi_buf[e];
+    if (d < inf && (first || pair_less(last_d, last_i, d, i)) && pair_less(d, i, bd, bi)) { bd = d; bi = i; }
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) {
+    const float od = __shfl_xor_sync(0xffffffffu, bd, s);
+    const int32_t oi = __shfl_xor_sync(0xffffffffu, bi, s);
+    if (pair_less(od, oi, bd, bi)) { bd = od; bi = oi; }
+  }
+  *out_d = bd;
+  *out_i = bi;
+}
+
+__global__ void __launch_bounds__(256)
+topk_select_kernel(const float* __restrict__ dist, int64_t G, int64_t Q, int k, int cap, const int32_t* __restrict__ cnt,
+                   float* __restrict__ buf_d, int32_t* __restrict__ buf_i, int32_t g_offset,
+                   float* __restrict__ out_d, int32_t* __restrict__ out_i) {
+  const int lane = threadIdx.x & 31;
+  const int64_t q = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (q >= Q) return;
+  const float inf = __int_as_float(0x7f800000);
+  float* bd_buf = buf_d + q * cap;
+  int32_t* bi_buf = buf_i + q * cap;
+  const float* col = dist + q;
+  int64_t m = cnt[q];
+  bool whole = false;
+  if (m > cap) {
+    // The buffer holds only the first `cap` survivors.  Their k-th smallest is still an upper bound of the column's
+    // k-th smallest (a subset's order statistics are no smaller), and a much tighter one: rescan the column once with
+    // it, refilling the buffer.  Only if that overflows too (> cap ties) is every pick taken from the whole column.
+    float td = -inf;
+    int32_t ti = -1;
+    bool first = true;
+    for (int j = 0; j < k; ++j) {
+      select_next(false, col, Q, bd_buf, bi_buf, cap, lane, first, td, ti, &td, &ti);
+      first = false;
+      if (!(td < inf)) break;
+    }
+    __syncwarp();
+    int64_t n2 = 0;
+    constexpr int RU = 8;  // column loads in flight per lane (the column is strided by Q: one sector per element)
+    for (int64_t e0 = 0; e0 < G; e0 += 32 * RU) {
+      float v[RU];
+#pragma unroll
+      for (int u = 0; u < RU; ++u) {
+        const int64_t e = e0 + 32 * u + lane;
+        v[u] = e < G ? __ldg(col + e * Q) : inf;
+      }
+#pragma unroll
+      for (int u = 0; u < RU; ++u) {
+        const bool keep = v[u] <= td && v[u] < inf;
+        const unsigned mask = __ballot_sync(0xffffffffu, keep);
+        const int64_t pos = n2 + __popc(mask & ((1u << lane) - 1u));
+        if (keep && pos < cap) { bd_buf[pos] = v[u]; bi_buf[pos] = (int32_t)(e0 + 32 * u + lane); }
+        n2 += __popc(mask);
+      }
+    }
+    __syncwarp();
+    m = n2;
+    if (n2 > cap) { whole = true; m = G; }
+  }
+  float last_d = -inf;
+  int32_t last_i = -1;
+  bool first = true;
+  for (int j = 0; j < k; ++j) {
+    float bd;
+    int32_t bi;
+    select_next(whole, col, Q, bd_buf, bi_buf, m, lane, first, last_d, last_i, &bd, &bi);
+    if (lane == 0) {
+      out_d[q * k + j] = bd;
+      out_i[q * k + j] = bd < inf ? bi + g_offset : -1;
+    }
+    if (!(bd < inf)) {  // exhausted: pad the rest
+      for (int r = j + 1 + lane; r < k; r += 32) { out_d[q * k + r] = inf; out_i[q * k + r] = -1; }
+      break;
+    }
+    last_d = bd; last_i = bi; first = false;
+  }
 }
 
 extern "C" int witw_topk_merge(const float* cand_dist, const int32_t* cand_idx, int n_lists, int64_t Q, int k, float* topk_dist,
@@ -351,6 +588,54 @@ extern "C" int witw_topk_merge(const float* cand_dist, const int32_t* cand_idx, 
   WITW_REQUIRE(ceil_div<int64_t>(Q, kMergeWarps) < (1ll << 31), WITW_ERR_INVALID, "witw_topk_merge: too many queries");
   topk_merge_kernel<<<(unsigned)ceil_div<int64_t>(Q, kMergeWarps), kMergeWarps * 32, 0, as_stream(stream)>>>(cand_dist, cand_idx, n_lists, Q, k,
                                                                                                        topk_dist, topk_idx);
+  WITW_LAUNCH_CHECK();
+  return WITW_OK;
+}
+
+static int select_cap(int k) { return std::max(128, 48 * k); }
+
+constexpr int kTauSlices = 4;
+
+extern "C" size_t witw_topk_select_scratch_bytes(int64_t Q, int k) {
+  const int64_t q = std::max<int64_t>(Q, 1);
+  // counters, survivor buffers (distance + index), group minima [slices][k][Q], thresholds [Q]
+  return (size_t)(q * 4 + q * select_cap(k) * 8 + (int64_t)kTauSlices * k * q * 4 + q * 4 + 1024);
+}
+
+extern "C" int witw_topk_select_f32(const float* dist, int64_t G, int64_t Q, int k, float* topk_dist, int32_t* topk_idx,
+                                    int32_t g_offset, void* scratch, witw_stream_t stream) {
+  WITW_REQUIRE(G >= 1024 && Q >= 0 && k > 0 && k <= 32, WITW_ERR_UNSUPPORTED, "witw_topk_select_f32: needs G >= 1024 and 1 <= k <= 32");
+  WITW_REQUIRE(Q % 4 == 0 && (((uintptr_t)dist & 15) == 0), WITW_ERR_UNSUPPORTED, "witw_topk_select_f32: Q must be a multiple of 4 and dist 16-byte aligned");
+  if (Q == 0) return WITW_OK;
+  WITW_REQUIRE(dist && topk_dist && topk_idx && scratch && (((uintptr_t)scratch & 15) == 0), WITW_ERR_INVALID, "witw_topk_select_f32: null or misaligned pointer");
+  const int cap = select_cap(k);
+  char* base = reinterpret_cast<char*>(scratch);
+  auto take = [&](size_t bytes) { char* p = base; base += (bytes + 255) & ~(size_t)255; return p; };
+  int32_t* cnt = reinterpret_cast<int32_t*>(take((size_t)Q * 4));
+  float* buf_d = reinterpret_cast<float*>(take((size_t)Q * cap * 4));
+  int32_t* buf_i = reinterpret_cast<int32_t*>(take((size_t)Q * cap * 4));
+  float* partial = reinterpret_cast<float*>(take((size_t)kTauSlices * k * Q * 4));
+  float* tau = reinterpret_cast<float*>(take((size_t)Q * 4));
+  // 1. thresholds from every fourth row: k group minima per column, their maximum
+  const int64_t stride = 4;
+  const int64_t n_rows = G / stride;
+  const int64_t bx = ceil_div<int64_t>(Q, kFilterThreads * 4);
+  const int64_t rows_tau = ceil_div<int64_t>(n_rows, kTauSlices);
+  topk_groupmin_kernel<<<dim3((unsigned)bx, (unsigned)k, kTauSlices), kFilterThreads, 0, as_stream(stream)>>>(dist, n_rows, stride, Q, k, rows_tau, partial);
+  WITW_LAUNCH_CHECK();
+  topk_tau_kernel<<<(unsigned)ceil_div<int64_t>(Q, 256), 256, 0, as_stream(stream)>>>(partial, kTauSlices, k, Q, tau);
+  WITW_LAUNCH_CHECK();
+  // 2. filter the whole matrix into the survivor buffers
+  WITW_CUDA(cudaMemsetAsync(cnt, 0, (size_t)Q * 4, as_stream(stream)));
+  int64_t slices = std::max<int64_t>(1, std::min<int64_t>(ceil_div<int64_t>((int64_t)sm_count() * 12, bx), G / 64));
+  slices = std::min<int64_t>(slices, 65535);
+  const int64_t rows = ceil_div<int64_t>(G, slices);
+  topk_filter_kernel<<<dim3((unsigned)bx, (unsigned)ceil_div<int64_t>(G, rows)), kFilterThreads, 0, as_stream(stream)>>>(
+      dist, G, Q, tau, rows, cap, cnt, buf_d, buf_i);
+  WITW_LAUNCH_CHECK();
+  // 3. k smallest survivors per column
+  topk_select_kernel<<<(unsigned)ceil_div<int64_t>(Q, 8), 256, 0, as_stream(stream)>>>(dist, G, Q, k, cap, cnt, buf_d, buf_i, g_offset,
+                                                                                      topk_dist, topk_idx);
   WITW_LAUNCH_CHECK();
   return WITW_OK;
 }

@@ -37,6 +37,8 @@ OVERHEAD_SIZE = 256
 
 # problems with at least this many (gallery, query) pairs go to the tensor-core kernel
 TC_MIN_PAIRS = 1 << 16
+# standalone top-k over a materialised matrix: galleries of at least this many rows use threshold + filter + select
+SELECT_MIN_ROWS = 8192
 
 
 # Which tensor-core sweep serves a (gallery, query width): "hankel" = the shift search as one dense contraction
@@ -720,6 +722,11 @@ def topk_from_distances(distances, k, g_offset=0):
     with torch.cuda.device(dev):
         td = torch.empty((q, k), dtype=torch.float32, device=dev)
         ti = torch.empty((q, k), dtype=torch.int32, device=dev)
+        if g >= SELECT_MIN_ROWS and k <= 32 and q % 4 == 0 and q > 0 and d.data_ptr() % 16 == 0:
+            # large galleries: sample thresholds -> streaming filter -> per-column selection (csrc/rank.cu)
+            scratch = torch.empty(_lib.load().witw_topk_select_scratch_bytes(q, int(k)), dtype=torch.uint8, device=dev)
+            _lib.call("witw_topk_select_f32", d.data_ptr(), g, q, int(k), td.data_ptr(), ti.data_ptr(), int(g_offset), scratch.data_ptr(), _stream())
+            return td, ti
         slices = _lib.load().witw_topk_slices(g, q)
         if slices <= 1:
             _lib.call("witw_topk_from_dist_f32", d.data_ptr(), g, q, int(k), 1, td.data_ptr(), ti.data_ptr(), int(g_offset), _stream())

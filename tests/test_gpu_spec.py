@@ -205,3 +205,38 @@ def test_spec_nan_and_zero_inputs(W):
     keep = torch.ones(40, dtype=torch.bool)
     keep[7] = False
     assert (dist.cpu()[:, keep] - ref[:, keep]).abs().max().item() <= 2e-3
+
+
+def test_spec_heatmap_sweep_one_query_many_tiles(W):
+    """tools/heatmap/heatmap.py:171-177 shape on the spectral sweep: one photo against a swept grid of tiles."""
+    ov, su, sh = O.synth_features(1200, 1, fov=70, noise=0.3, seed=3)
+    rdeg, rdis, rscore = O.heatmap_scores(ov, su)
+    deg, dis, score = W.heatmap_scores(ov.cuda(), su.cuda(), path="tc")
+    assert tuple(deg.shape) == (1200,) and tuple(dis.shape) == (1200,)
+    same = deg.cpu() == rdeg
+    assert same.float().mean().item() >= 0.98
+    assert (dis.cpu() - rdis)[same].abs().max().item() <= 2e-3
+    assert (score.cpu() - rscore)[same].abs().max().item() <= 2e-2 * float(rscore.max())
+    assert int(torch.argmin(dis)) == 0 and float(deg[0]) == float(sh[0]) * 360 / 64 - 180
+
+
+def test_spec_sharded_single_process_matches_unsharded(W):
+    """witw_b200/sharded.py on the spectral sweep without a process group: whole gallery as one shard == evaluate_ranks;
+    a true match outside the shard is never counted by index."""
+    from witw_b200.sharded import CudaLocal, evaluate_ranks_sharded
+    ov, su, _ = O.synth_features(600, 300, fov=180, noise=10.0, seed=12)
+    perm = torch.randperm(600, generator=torch.Generator().manual_seed(2))
+    inv = torch.empty_like(perm)
+    inv[perm] = torch.arange(600)
+    ovp, true_idx = ov[perm].cuda(), inv[:300].cuda()
+    want = W.evaluate_ranks(ovp, su.cuda(), true_idx=true_idx, path="tc", topk=5)
+    got = evaluate_ranks_sharded(ovp, su.cuda(), 0, 600, true_idx=true_idx, topk=5, local=CudaLocal(path="tc"))
+    for a, b in zip(want, got):
+        assert torch.equal(a, b)
+    ref = O.match(ov[perm], su)[1]
+    thr = ref[inv[:300], torch.arange(300)]
+    local = CudaLocal(path="tc")
+    parts = [local.sweep(ovp[lo:hi], su.cuda(), thr.cuda(), true_idx, lo, 5) for lo, hi in ((0, 288), (288, 600))]
+    counts = parts[0][0] + parts[1][0]
+    tie = ((ref - thr.unsqueeze(0)).abs() <= 3e-6).sum(0) - 1
+    assert bool(((counts.cpu() - want[0].cpu()).abs() <= tie).all())

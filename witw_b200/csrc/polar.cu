@@ -336,7 +336,17 @@ polar_quadrant_kernel(const __grid_constant__ CUtensorMap src_map, float* __rest
       for (int u = 0; u < 4; ++u) {
         const int i = b + u;
         const T* p = tile + ((off2[i >> 1] >> ((i & 1) * 16)) & 0xffffu);
-        const float ia = (float)p[0], ic = (float)p[1], ib = (float)p[BOXW], id = (float)p[BOXW + 1];
+        float ia, ib, ic, id;
+        if constexpr (sizeof(T) == 1) {
+          // uint8 -> fp32 without I2F (a quarter-rate conversion): 0x4B000000 | v is the float 2^23 + v, and subtracting
+          // 2^23 is exact
+          ia = __uint_as_float(0x4B000000u | p[0]) - 8388608.0f;
+          ic = __uint_as_float(0x4B000000u | p[1]) - 8388608.0f;
+          ib = __uint_as_float(0x4B000000u | p[BOXW]) - 8388608.0f;
+          id = __uint_as_float(0x4B000000u | p[BOXW + 1]) - 8388608.0f;
+        } else {
+          ia = p[0]; ic = p[1]; ib = p[BOXW]; id = p[BOXW + 1];
+        }
         // separable form of the reference's four-weight blend (cvig_fov.py:178-183): lerp along x on both rows, then
         // along y -- 3 subtractions + 3 FMAs and no weight registers; within a few fp32 roundings of the reference's
         // sum (the bit-exact form is witw_bilinear_gather_*)

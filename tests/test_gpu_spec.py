@@ -240,3 +240,31 @@ def test_spec_sharded_single_process_matches_unsharded(W):
     counts = parts[0][0] + parts[1][0]
     tie = ((ref - thr.unsqueeze(0)).abs() <= 3e-6).sum(0) - 1
     assert bool(((counts.cpu() - want[0].cpu()).abs() <= tie).all())
+
+
+def test_spec_random_shapes_against_oracle(W):
+    """Seeded random problem shapes (gallery not a multiple of 8, queries not a multiple of 128, several work chunks, query
+    widths 8..64): distances / orientations of the sweep and exact-finish ranks against the fp32 reference chain."""
+    rng = np.random.default_rng(2024)
+    for trial in range(10):
+        G = int(rng.integers(9, 1200))
+        Q = int(rng.integers(1, 300))
+        sw = int(rng.integers(8, 65))
+        gen = torch.Generator().manual_seed(trial)
+        ov = torch.randn(G, 16, 4, 64, generator=gen) * 0.06
+        su = torch.randn(Q, 16, 4, sw, generator=gen) * 0.06
+        n = min(G, Q)
+        sh = torch.randint(0, 64, (n,), generator=gen)
+        cols = (sh.view(n, 1) + torch.arange(sw).view(1, sw)) % 64
+        su[:n] = torch.gather(ov[:n], 3, cols.view(n, 1, 1, sw).expand(n, 16, 4, sw)) + 6.0 * su[:n]
+        ref_ori, ref = O.match(ov, su)
+        ori, dist = W.match(ov.cuda(), su.cuda(), path="tc")
+        same = ori.cpu() == ref_ori
+        assert same.float().mean().item() >= 0.97, (G, Q, sw)
+        assert (dist.cpu() - ref)[same].abs().max().item() <= 3e-3, (G, Q, sw)
+        if Q <= G:
+            ranks = W.evaluate_ranks(ov.cuda(), su.cuda(), path="tc").cpu().numpy()
+            thr = torch.diagonal(ref[:Q]).unsqueeze(0)
+            want = (ref <= thr).sum(0).numpy()
+            tie = ((ref - thr).abs() <= 3e-6).sum(0).numpy() - 1
+            assert np.all(np.abs(ranks - want) <= tie), (G, Q, sw)

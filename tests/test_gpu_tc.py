@@ -294,3 +294,27 @@ def test_sharded_cuda_local_single_process(W):
     assert bool(((counts.cpu() - want[0].cpu()).abs() <= tie).all())
     td, ti = local.merge(torch.stack([parts[0][1], parts[1][1]]), torch.stack([parts[0][2], parts[1][2]]), 5)
     assert torch.equal(ti, want[2]) and (td - want[1]).abs().max().item() <= 1e-6
+
+
+def test_tc_random_shapes_exact_finish_against_oracle(W):
+    """Seeded random problem shapes on the dense sweep, narrow to full query widths: exact-finish ranks equal the fp32
+    reference chain's up to fp32 round-off ties (the re-check band widens as 0.4 / sw for cropped queries)."""
+    rng = np.random.default_rng(77)
+    for trial in range(8):
+        G = int(rng.integers(40, 900))
+        Q = int(rng.integers(1, min(G, 260) + 1))
+        sw = int(rng.integers(4, 65))
+        gen = torch.Generator().manual_seed(100 + trial)
+        ov = torch.randn(G, 16, 4, 64, generator=gen) * 0.06
+        su = torch.randn(Q, 16, 4, sw, generator=gen) * 0.06
+        sh = torch.randint(0, 64, (Q,), generator=gen)
+        cols = (sh.view(Q, 1) + torch.arange(sw).view(1, sw)) % 64
+        su = torch.gather(ov[:Q], 3, cols.view(Q, 1, 1, sw).expand(Q, 16, 4, sw)) + 6.0 * su
+        ref = O.match(ov, su)[1]
+        ranks = W.evaluate_ranks(ov.cuda(), su.cuda(), path="tc").cpu().numpy()
+        appended, dropped = W.ops.evaluate_ranks_prepared.last_recheck.cpu().tolist()
+        assert dropped == 0, (G, Q, sw, appended)
+        thr = torch.diagonal(ref[:Q]).unsqueeze(0)
+        want = (ref <= thr).sum(0).numpy()
+        tie = ((ref - thr).abs() <= 3e-6).sum(0).numpy() - 1
+        assert np.all(np.abs(ranks - want) <= tie), (G, Q, sw)

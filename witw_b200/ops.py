@@ -783,6 +783,16 @@ RECHECK_BAND_CROPPED = 1.2e-2
 TOPK_MARGIN = 6
 
 
+def recheck_band(sw, w=64):
+    """Half-width of the distance band around the fp32 threshold inside which a bf16 rank decision is re-taken in fp32.
+    Measured worst |d_bf16 - d_fp32| over all pairs (float64 models of both sweeps, tests/test_gpu_spec.py: spec_model,
+    tests/test_gpu_tc.py: bf16_model): 3e-4 at sw = 64; with a cropped query an argmax flip between near-tied shifts swaps
+    the crop norm, and the error grows as ~0.2 / sw (5e-3 at 32, 1.3e-2 at 16, 1.8e-2 at 12, 3.3e-2 at 8)."""
+    if sw >= w:
+        return RECHECK_BAND_FULL
+    return max(RECHECK_BAND_CROPPED, 0.4 / max(int(sw), 1))
+
+
 def _exact_mode(gallery, queries, exact):
     """None (no exact finish), "spectral" or "direct" for this pair of operands."""
     if not exact:
@@ -847,7 +857,7 @@ def evaluate_ranks_prepared(gallery, queries, true_idx=None, topk=0, d_true=None
             t32 = torch.arange(gallery.g_offset, gallery.g_offset + queries.Q, dtype=torch.int32, device=dev)
         else:
             t32 = (true_idx.to(dev, torch.int64) + gallery.g_offset).to(torch.int32).contiguous()
-        recheck = RecheckList(max(4 * queries.Q, 1 << 16), RECHECK_BAND_FULL if gallery.sw >= gallery.W else RECHECK_BAND_CROPPED, dev) if fin else None
+        recheck = RecheckList(max(4 * queries.Q, 1 << 16), recheck_band(gallery.sw, gallery.W), dev) if fin else None
         kc = min(16, topk + TOPK_MARGIN) if (topk and fin) else topk
         res = sweep_tc(gallery, queries, d_true=d_true, true_idx=t32, rank_count=counts, topk=kc, events=events, recheck=recheck)
         if fin and gallery.G > 0 and queries.Q > 0:

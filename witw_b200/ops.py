@@ -44,8 +44,8 @@ SELECT_MIN_ROWS = 8192
 # Which tensor-core sweep serves a (gallery, query width): "hankel" = the shift search as one dense contraction
 # (csrc/match_tc.cu, 8192*sw_pad FLOP per pair), "spectral" = per-frequency products + inverse FFT in the epilogue
 # (csrc/match_spec.cu, 16.9 kFLOP per pair whatever the width; needs C*H == 64).  "auto": spectral when it is
-# supported and the query has at least SPEC_MIN_SW columns (the spectral sweep costs the same at every width -- 8.0 ms
-# for 10k x 10k against 36.6 ms (360 deg) / 8.9 ms (90 deg) of the dense contraction; narrower queries than that have
+# supported and the query has at least SPEC_MIN_SW columns (the spectral sweep costs the same at every width -- 6.8 ms
+# for 10k x 10k against 36.3 ms (360 deg) / 9.6 ms (90 deg) of the dense contraction; narrower queries than that have
 # flat spectra whose bf16 rounding costs more accuracy than the dense form's).
 TC_IMPL = "auto"
 SPEC_MIN_SW = 8

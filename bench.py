@@ -168,6 +168,62 @@ def make_data(torch, device, n_gallery, n_query, seed, planted):
     return ov, su
 
 
+def dense_sweep_roofline(torch, ops, ov, su, peak, iters=5):
+    """The north star's kernel (2): the shift search as one dense bf16 contraction on tcgen05 (csrc/match_tc.cu), timed alone
+    on the bench workload with CUDA events -- the tensor-pipe roofline figure that the spectral default cannot show, because
+    the spectral sweep does 31x fewer tensor FLOPs per pair.  Outside the timed step; N=1 only."""
+    gallery = ops.GalleryIndex(ov, 64, impl="hankel")
+    queries = ops.QueryBatch(su, impl="hankel")
+    evs = []
+    for i in range(2 + iters):
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ops.evaluate_ranks_prepared(gallery, queries, topk=TOPK, events=ev)
+        if i >= 2:
+            evs.append(ev)
+    torch.cuda.synchronize()
+    ms = statistics.mean(a.elapsed_time(b) for a, b in evs)
+    achieved = FLOP_PER_PAIR * float(ov.shape[0]) * float(su.shape[0]) / (ms / 1000.0) / 1e12
+    del gallery, queries
+    return {"kernel": "match_tc_kernel", "bound": "tensor", "kernel_ms": ms, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+            "frac": achieved / peak, "launches": iters,
+            "note": "dense contraction over all 64 shifts, 524 288 tensor FLOP per pair as executed; same operands and epilogue outputs "
+                    "(rank count + top-k candidates) as the step's spectral sweep; ncu: profiles/match_tc_r1c.txt"}
+
+
+def gallery_size_sweep(torch, ops, device, value_10k, sizes=(1000, 100000), iters=5):
+    """The metric's other axis: queries/s of the same device-resident step (10k queries, 360 deg) at other gallery sizes."""
+    rows = []
+    for g in sizes:
+        try:
+            ov, su = make_data(torch, device, g, Q_TOTAL, seed=7, planted=False)
+            true_idx = torch.arange(Q_TOTAL, device=device) % g
+            gen = torch.Generator(device=device).manual_seed(11)      # every query is a rolled, noised copy of its gallery item
+            cols = (torch.randint(0, 64, (Q_TOTAL, 1), generator=gen, device=device) + torch.arange(64, device=device).view(1, 64)) % 64
+            su = torch.gather(ov[true_idx], 3, cols.view(Q_TOTAL, 1, 1, 64).expand(Q_TOTAL, 16, 4, 64)) + 0.5 * su
+
+            def step():
+                return ops.evaluate_ranks_prepared(ops.GalleryIndex(ov, 64), ops.QueryBatch(su), true_idx=true_idx, topk=TOPK)
+
+            for _ in range(3):
+                step()
+            torch.cuda.synchronize()
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+            for _ in range(iters):
+                step()
+            t1.record()
+            torch.cuda.synchronize()
+            ms = t0.elapsed_time(t1) / iters
+            rows.append({"gallery": g, "queries": Q_TOTAL, "ms_per_step": ms, "queries_per_s": Q_TOTAL / (ms / 1000.0),
+                         "pairs_per_s": float(g) * Q_TOTAL / (ms / 1000.0)})
+            del ov, su
+        except Exception as exc:      # a side measurement must not take the bench line down with it
+            rows.append({"gallery": g, "error": "%s: %s" % (type(exc).__name__, exc)})
+        torch.cuda.empty_cache()
+    rows.append({"gallery": G_PER_GPU, "queries": Q_TOTAL, "queries_per_s": value_10k, "note": "the timed step above"})
+    return sorted(rows, key=lambda r: r["gallery"])
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -339,6 +395,8 @@ def run_ours(args):
         "recall": {k: float(v) for k, v in recall.items()},
     }
     if world == 1:
+        line["dense_sweep"] = dense_sweep_roofline(torch, ops, ov, su, peak)
+        line["gallery_sweep"] = gallery_size_sweep(torch, ops, device, value)
         v, cores, sample = cpu_reference_queries_per_s(15.0)
         line["cpu_baseline"] = {"value": v, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample}
     print(json.dumps(line))

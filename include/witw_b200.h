@@ -95,6 +95,23 @@ int witw_polar_resample_u8(const uint8_t* src_dev, float* dst_dev, int64_t n_pla
                            const float* lut_host, const float* lut_dev, const void* plan_host,
                            const void* plan_dev, witw_stream_t stream);
 
+/* Raw images in, model-sized normalised images out: Resize (cvig_fov.py:117-134 -- torchvision's bilinear
+ * resize of a float image, align_corners=False; the surface panorama's wrap-around column window of
+ * cvig_fov.py:120-129) fused with ImageNormalization (cvig_fov.py:137-149; cvig_semantic.py:163-176 divides only the
+ * first three channels by 255, hence a per-channel divisor).  The overhead output feeds witw_polar_resample_f32.
+ *   plan (host-built, then copied to the device; pass both copies): separable tap tables with ATen's arithmetic,
+ *        antialias = 0: upsample_bilinear2d (the reference's pinned torchvision 0.9.1 / torch 1.8.1),
+ *        antialias = 1: _upsample_bilinear2d_aa (torchvision >= 0.17's default: the reference as it runs today).
+ *   witw_resize_norm: n_planes planes [in_h, in_w] (uint8 when src_is_u8, else fp32) -> [out_h, col_count] fp32;
+ *        output column x shows column (col_start + x) % out_w of the resized image; plane p is channel p % n_ch;
+ *        mean == NULL: resize only; else dst = ((v / divisor[c]) - mean[c]) / std[c], each step rounded to fp32
+ *        (n_ch <= 8).  Resampling: width first with an fp32 intermediate, then height (ATen's order). */
+size_t witw_resize_plan_bytes(int in_h, int in_w, int out_h, int out_w, int antialias);
+int witw_resize_plan_build(int in_h, int in_w, int out_h, int out_w, int antialias, void* plan_host);
+int witw_resize_norm(const void* src_dev, int src_is_u8, float* dst_dev, int64_t n_planes, int n_ch,
+                     const void* plan_host, const void* plan_dev, int col_start, int col_count,
+                     const float* divisor, const float* mean, const float* std, witw_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * K2/K3  orientation-searched distance       replaces model/cvig_fov.py:297-363
  *        (correlation -> crop_overhead -> l2_distance)

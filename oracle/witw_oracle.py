@@ -110,6 +110,115 @@ def normalized_polar(overhead_u8, mean=IMG_MEAN, std=IMG_STD):
     return polar_transform(image_normalization(overhead_u8, mean, std))
 
 
+# --------------------------------------------------------------------------- f4: Resize (upstream of ImageNormalization)
+def resize_taps(in_size, out_size, antialias):
+    """Per-output-index taps of the bilinear resize the reference's ``Resize`` performs along one axis
+    (model/cvig_fov.py:119, 131, 133: torchvision.transforms.functional.resize on a float tensor, bilinear,
+    align_corners=False).  The arithmetic lives in torch (third party, not under /root/reference):
+
+    * antialias=False -- what the reference's pinned torchvision 0.9.1 / torch 1.8.1 (model/requirements.txt) computes:
+      ``src = max(scale*(i+0.5)-0.5, 0)``, ``i0 = int(src)``, ``i1 = i0 + (i0 < in-1)``, ``l1 = src - i0``, ``l0 = 1 - l1``
+      (ATen upsample_bilinear2d, area_pixel_compute_source_index), all in fp32, ``scale = float(in)/out``.
+    * antialias=True -- what torchvision >= 0.17 does by default, i.e. the reference as it runs in the build container:
+      triangle filter of half-width ``support = max(scale, 1)`` around ``center = scale*(i+0.5)``; taps
+      ``[int(center-support+0.5), int(center+support+0.5))`` clipped to the axis, weights ``1-|(j-center+0.5)/max(scale,1)|``
+      normalised by their sum (ATen _upsample_bilinear2d_aa, _compute_indices_min_size_weights_aa), fp32.
+
+    Returns (start int64 [out], count int64 [out], weights fp32 [out, kmax]) -- unused weight slots are 0."""
+    f32 = np.float32
+    scale = f32(in_size) / f32(out_size)
+    if not antialias:
+        start = np.zeros(out_size, dtype=np.int64)
+        count = np.full(out_size, 2, dtype=np.int64)
+        wts = np.zeros((out_size, 2), dtype=np.float32)
+        for i in range(out_size):
+            if in_size == out_size:     # ATen: a scale of exactly 1 is a plain copy
+                start[i], count[i], wts[i, 0] = i, 1, 1.0
+                continue
+            src = max(f32(scale * f32(i + 0.5)) - f32(0.5), f32(0.0))
+            i0 = int(src)
+            l1 = min(max(f32(src - f32(i0)), f32(0.0)), f32(1.0))
+            start[i] = i0
+            if i0 < in_size - 1:
+                wts[i] = (f32(1.0) - l1, l1)
+            else:                       # i1 == i0: both lambdas land on the last sample
+                count[i] = 1
+                wts[i] = ((f32(1.0) - l1) + l1, 0.0)
+        return start, count, wts
+    # ATen keeps scale / support / center / the weights in float but writes its 0.5 and 1.0 literals as doubles, so some
+    # sub-expressions are evaluated in double before they are rounded back; the float64 casts below mirror that
+    f64 = np.float64
+    support = f32(scale) if scale >= 1.0 else f32(1.0)
+    invscale = f32(1.0 / f64(scale)) if scale >= 1.0 else f32(1.0)
+    kmax = int(math.ceil(support)) * 2 + 1
+    start = np.zeros(out_size, dtype=np.int64)
+    count = np.zeros(out_size, dtype=np.int64)
+    wts = np.zeros((out_size, kmax), dtype=np.float32)
+    for i in range(out_size):
+        center = f32(f64(scale) * (i + 0.5))
+        lo = max(int(f64(f32(center - support)) + 0.5), 0)
+        n = min(int(f64(f32(center + support)) + 0.5), in_size) - lo
+        w = np.zeros(n, dtype=np.float32)
+        total = f32(0.0)
+        for j in range(n):
+            x = abs(f32((f64(f32(f32(j + lo) - center)) + 0.5) * f64(invscale)))
+            w[j] = f32(1.0) - x if x < 1.0 else f32(0.0)
+            total = f32(total + w[j])
+        if total != 0.0:
+            w = (w / total).astype(np.float32)
+        start[i], count[i] = lo, n
+        wts[i, :n] = w
+    return start, count, wts
+
+
+def _resample_axis(x, start, count, wts, axis):
+    """One separable pass in fp32: out[i] = sum_j w[i,j] * x[start[i]+j], accumulated left to right."""
+    x = np.moveaxis(np.asarray(x, dtype=np.float32), axis, -1)
+    out = np.zeros(x.shape[:-1] + (len(start),), dtype=np.float32)
+    for i in range(len(start)):
+        acc = x[..., start[i]] * wts[i, 0]
+        for j in range(1, count[i]):
+            acc = (acc + x[..., start[i] + j] * wts[i, j]).astype(np.float32)
+        out[..., i] = acc
+    return np.moveaxis(out, -1, axis)
+
+
+def resize_bilinear(img, out_h, out_w, antialias=True):
+    """``torchvision.transforms.functional.resize(img, (out_h, out_w))`` on a float image [..., H, W] as the reference calls it
+    (model/cvig_fov.py:119, 131, 133).  antialias=True: separable, width first then height with an fp32 intermediate
+    (ATen separable_upsample_generic_Nd_kernel_impl).  antialias=False: ``hl0*(wl0*a + wl1*b) + hl1*(wl0*c + wl1*d)``
+    (ATen upsample_bilinear2d) -- the same two passes with the rows blended last."""
+    x = np.asarray(img, dtype=np.float32)
+    in_h, in_w = x.shape[-2:]
+    sx, cx, wx = resize_taps(in_w, out_w, antialias)
+    sy, cy, wy = resize_taps(in_h, out_h, antialias)
+    if antialias and in_w == out_w:
+        tmp = x             # ATen skips a pass whose size does not change
+    else:
+        tmp = _resample_axis(x, sx, cx, wx, -1)
+    if antialias and in_h == out_h:
+        return torch.from_numpy(np.ascontiguousarray(tmp))
+    return torch.from_numpy(np.ascontiguousarray(_resample_axis(tmp, sy, cy, wy, -2)))
+
+
+def resize_pair(surface, overhead, fov=360, panorama=True, start=0, antialias=True):
+    """``Resize.__call__`` (model/cvig_fov.py:117-134) on float images [C,H,W]: the surface image to 128 x 512 and a
+    ``surface_width = int(fov/360*512)`` wide window starting at column ``start`` with wrap-around (panorama, 119-129), or
+    directly to 128 x surface_width (131); the overhead image to 256 x 256 (133).  ``start`` is the value the reference
+    draws with torch.randint (121-124).  Returns (surface, overhead)."""
+    sw = int(fov / 360 * SURFACE_W)
+    if panorama:
+        su = resize_bilinear(surface, SURFACE_H, SURFACE_W, antialias)
+        end = start + sw
+        if end < SURFACE_W:
+            su = su[:, :, start:end]
+        else:
+            su = torch.cat((su[:, :, start:], su[:, :, : end - SURFACE_W]), dim=2)
+    else:
+        su = resize_bilinear(surface, SURFACE_H, sw, antialias)
+    return su, resize_bilinear(overhead, OVERHEAD, OVERHEAD, antialias)
+
+
 # --------------------------------------------------------------------------- a3
 def correlation_scores(overhead_embed, surface_embed):
     """Un-normalised circular cross-correlation, fp32 [G,Q,W].

@@ -53,7 +53,44 @@ def planted(g, q, fov, seed, noise=0.5, c=16, h=4, w=64):
     return ov, su, sh
 
 
+def make_resize():
+    """Resize -> ImageNormalization -> PolarTransform of the reference's dataset transform chain (cvig_fov.py:389-392) on
+    raw-sized float images, exactly as ImagePairDataset.__getitem__ feeds them (uint8 pixels cast to float32,
+    cvig_fov.py:88-91).  With the torchvision of the build container Resize antialiases (its pinned 0.9.1 did not); the
+    non-antialiased variant is frozen from the call torchvision 0.9.1 made: F.interpolate(bilinear, align_corners=False)."""
+    import torch.nn.functional as F
+    gen = torch.Generator().manual_seed(41)
+    ov8 = torch.randint(0, 256, (3, 301, 283), generator=gen, dtype=torch.uint8)     # downsample by ~1.1-1.2
+    su8 = torch.randint(0, 256, (3, 97, 411), generator=gen, dtype=torch.uint8)      # upsample
+    big8 = torch.randint(0, 256, (3, 750, 750), generator=gen, dtype=torch.uint8)    # CVUSA's aerial size, ~2.9x down
+    # the 750 x 750 image is not stored (1.7 MB of noise): the tests redraw it from the seed and check this checksum
+    blob = {"ov_u8": ov8.numpy(), "su_u8": su8.numpy(), "big_seed": 41, "big_sum": int(big8.long().sum()),
+            "big_corner": big8[:, :4, :4].numpy()}
+    torch.manual_seed(5)                                                              # the generator Resize draws its start from
+    state = torch.get_rng_state()
+    start = int(torch.randint(0, 512, ()))
+    torch.set_rng_state(state)
+    d = cvig.Resize("cvusa", fov=90, random_orientation=True)({"surface": su8.float(), "overhead": ov8.float()})
+    blob["pano_start"] = start
+    blob["pano_surface"] = d["surface"].numpy()                 # [3,128,128]
+    blob["pano_overhead_sub"] = d["overhead"][:, ::3, ::5].numpy()
+    d = cvig.PolarTransform()(cvig.ImageNormalization()(d))
+    blob["pano_surface_norm_sub"] = d["surface"][:, ::3, ::3].numpy()
+    blob["pano_polar_sub"] = d["polar"][:, ::3, ::7].numpy()
+    d = cvig.Resize("witw", fov=70)({"surface": su8.float(), "overhead": big8.float()})
+    blob["witw_surface_sub"] = d["surface"][:, ::2, ::3].numpy()   # [3,128,99] -> sub
+    blob["witw_overhead_sub"] = d["overhead"][:, ::5, ::3].numpy()
+    # the pinned torchvision 0.9.1's resize of a float tensor
+    blob["noaa_overhead_sub"] = F.interpolate(big8.float()[None], size=(256, 256), mode="bilinear", align_corners=False)[0][:, ::5, ::3].numpy()
+    blob["noaa_surface_sub"] = F.interpolate(su8.float()[None], size=(128, 512), mode="bilinear", align_corners=False)[0][:, ::3, ::5].numpy()
+    np.savez_compressed(os.path.join(HERE, "resize.npz"), **blob)
+    print("resize.npz", os.path.getsize(os.path.join(HERE, "resize.npz")))
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "resize":
+        return make_resize()
+    make_resize()
     # ---- polar transform (a1, a2) ------------------------------------------------
     gen = torch.Generator().manual_seed(7)
     tile = torch.randn(2, 256, 256, generator=gen)

@@ -58,7 +58,26 @@ ms = timeit(lambda: W.normalized_polar(tiles8, exact=True), iters=5)
 emit("bilinear_gather_kernel<uint8> (exact) C=3", ms, "GB/s", byts / ms / 1e6, peaks["hbm_gbs"], {"tiles": 2048, "tiles_per_s": 2048 / ms * 1e3})
 del tiles8
 
-if os.environ.get("KB_ONLY") == "polar":
+# Resize + ImageNormalization front end (csrc/resize.cu): CVUSA-sized raw images in, model-sized normalised images out
+# algorithmic bytes: every source byte once + every output byte once
+for name, shape, out_hw, aa in (("aerial 750x750 u8 -> 256x256, antialias", (512, 3, 750, 750), (256, 256), True),
+                                ("aerial 750x750 u8 -> 256x256, no antialias", (512, 3, 750, 750), (256, 256), False),
+                                ("panorama 224x1232 u8 -> 128x512, antialias", (1024, 3, 224, 1232), (128, 512), True),
+                                ("tile 256x256 u8 -> 256x256 (normalise only)", (2048, 3, 256, 256), (256, 256), False)):
+    raw = torch.randint(0, 256, shape, device=dev, dtype=torch.uint8, generator=gen)
+    ms = timeit(lambda: W.resize_normalize(raw, out_hw[0], out_hw[1], aa, mean=ops.IMG_MEAN, std=ops.IMG_STD))
+    byts = shape[0] * shape[1] * (shape[2] * shape[3] * 1.0 + out_hw[0] * out_hw[1] * 4.0)
+    emit("resize_norm_kernel " + name, ms, "GB/s", byts / ms / 1e6, peaks["hbm_gbs"], {"images": shape[0], "images_per_s": shape[0] / ms * 1e3})
+    del raw
+raw_ov = torch.randint(0, 256, (512, 3, 750, 750), device=dev, dtype=torch.uint8, generator=gen)
+raw_su = torch.randint(0, 256, (512, 3, 224, 1232), device=dev, dtype=torch.uint8, generator=gen)
+ms = timeit(lambda: W.prepare_pair(raw_su, raw_ov, fov=360, panorama=True, start=77))
+emit("prepare_pair (resize+norm surface, resize+norm aerial, polar) 512 CVUSA-sized pairs", ms, "GB/s",
+     512 * 3 * (750 * 750 + 224 * 1232 + 4.0 * (128 * 512 * 2 + 256 * 256 * 2 + 128 * 512)) / ms / 1e6, peaks["hbm_gbs"],
+     {"pairs": 512, "pairs_per_s": 512 / ms * 1e3})
+del raw_ov, raw_su
+
+if os.environ.get("KB_ONLY") in ("polar", "resize"):
     sys.exit(0)
 
 # K4 rank / top-k on a materialised 10k x 10k matrix (400 MB)

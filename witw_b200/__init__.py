@@ -9,8 +9,10 @@ from ._lib import WitwError
 from .ops import (
     GalleryBuilder,
     GalleryIndex,
+    ImageNormalization,
     PolarTransform,
     QueryBatch,
+    Resize,
     baseline_ranks,
     bilinear_interpolate,
     correlation,
@@ -24,8 +26,10 @@ from .ops import (
     normalized_polar,
     polar_grid,
     polar_transform,
+    prepare_pair,
     rank_from_distances,
     recall_from_ranks,
+    resize_normalize,
     sweep_tc,
     tc_supported,
     topk_from_distances,
@@ -35,9 +39,9 @@ from .install import install, uninstall
 from .sharded import evaluate_ranks_sharded, shard_bounds
 
 __all__ = [
-    "GalleryBuilder", "GalleryIndex", "PolarTransform", "QueryBatch", "WitwError", "baseline_ranks", "bilinear_interpolate", "correlation",
+    "GalleryBuilder", "GalleryIndex", "ImageNormalization", "PolarTransform", "QueryBatch", "Resize", "WitwError", "baseline_ranks", "bilinear_interpolate", "correlation",
     "correlation_scores", "crop_overhead", "evaluate_ranks", "evaluate_ranks_prepared", "evaluate_ranks_sharded",
-    "heatmap_scores", "install", "l2_distance", "match", "normalized_polar", "polar_grid", "polar_transform", "rank_from_distances",
-    "recall_from_ranks", "shard_bounds", "sweep_tc", "tc_supported", "topk_from_distances", "true_match_distances",
+    "heatmap_scores", "install", "l2_distance", "match", "normalized_polar", "polar_grid", "polar_transform", "prepare_pair", "rank_from_distances",
+    "recall_from_ranks", "resize_normalize", "shard_bounds", "sweep_tc", "tc_supported", "topk_from_distances", "true_match_distances",
     "uninstall",
 ]

@@ -29,6 +29,10 @@ SIGNATURES = {
     "witw_polar_plan_bytes_u8": (c_size_t, [c_int, c_int, c_int]),
     "witw_polar_plan_build_u8": (c_int, [c_int, c_int, c_int, c_void_p]),
     "witw_polar_resample_u8": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "witw_resize_plan_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    "witw_resize_plan_build": (c_int, [c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "witw_resize_norm": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                 c_void_p]),
     "witw_match_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "witw_match_pairs_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "witw_crop_gather_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p]),

@@ -15,13 +15,19 @@ _REBOUND = ("bilinear_interpolate", "PolarTransform", "correlation", "crop_overh
 _ADDED = ("match", "evaluate_ranks", "recall_from_ranks", "heatmap_scores", "polar_transform")
 
 
-def install(module):
+# the dataset transforms upstream of PolarTransform (cvig_fov.py:100-149); rebound only on request because the reference runs
+# them inside forked DataLoader workers, where CUDA is not available (use num_workers=0 or a spawn context)
+_TRANSFORMS = ("Resize", "ImageNormalization")
+
+
+def install(module, transforms=False):
     """Rebind the hot-path names of a reference module (cvig_fov / cvig_semantic) to witw_b200.
 
+    transforms=True also rebinds ``Resize`` and ``ImageNormalization``.
     Returns the dict of replaced originals (also kept on the module as ``_witw_b200_originals``).
     """
     originals = {}
-    for name in _REBOUND:
+    for name in _REBOUND + (_TRANSFORMS if transforms else ()):
         if not hasattr(module, name):
             raise AttributeError("install: %s has no attribute %r -- not a WITW cvig module?" % (getattr(module, "__name__", module), name))
         originals[name] = getattr(module, name)
@@ -39,9 +45,9 @@ def uninstall(module):
     originals = getattr(module, "_witw_b200_originals", None)
     if originals is None:
         return
-    for name in _REBOUND + _ADDED:
+    for name in _REBOUND + _TRANSFORMS + _ADDED:
         if name in originals:
             setattr(module, name, originals[name])
-        elif hasattr(module, name):
+        elif name in _ADDED and hasattr(module, name):
             delattr(module, name)
     del module._witw_b200_originals

@@ -280,6 +280,130 @@ def normalized_polar(overhead_u8, mean=IMG_MEAN, std=IMG_STD, divisor=255.0, exa
     return out
 
 
+# ----------------------------------------------------------------------------- Resize + ImageNormalization (8f item 4)
+PANORAMA = {"cvusa": True, "witw": False}     # Globals.path_formats[...]['panorama'], model/cvig_fov.py:36-51
+_resize_cache = {}
+
+
+def resize_plan_host(in_h, in_w, out_h, out_w, antialias):
+    """Host copy (uint8 array) of the separable tap tables of one resize geometry; layout: csrc/resize.cu."""
+    nbytes = _lib.load().witw_resize_plan_bytes(int(in_h), int(in_w), int(out_h), int(out_w), int(bool(antialias)))
+    if nbytes == 0:
+        raise ValueError("resize: sizes must be positive, got %dx%d -> %dx%d" % (in_h, in_w, out_h, out_w))
+    host = np.zeros(nbytes, dtype=np.uint8)
+    _lib.call("witw_resize_plan_build", int(in_h), int(in_w), int(out_h), int(out_w), int(bool(antialias)), host.ctypes.data)
+    return host
+
+
+def _resize_plan(in_h, in_w, out_h, out_w, antialias, device):
+    key = (int(in_h), int(in_w), int(out_h), int(out_w), bool(antialias), str(device))
+    if key not in _resize_cache:
+        host = resize_plan_host(in_h, in_w, out_h, out_w, antialias)
+        _resize_cache[key] = (host, torch.from_numpy(host).to(device))
+    return _resize_cache[key]
+
+
+def resize_normalize(images, out_h, out_w, antialias=True, mean=None, std=None, divisor=255.0, col_start=0, col_count=None):
+    """Bilinear resize (+ optional normalisation) of raw images [..., C, H, W] (uint8 or fp32, CUDA) in one kernel:
+    ``torchvision.transforms.functional.resize(img, (out_h, out_w))`` as Resize calls it (cvig_fov.py:119, 131, 133), then
+    -- when ``mean`` is given -- ImageNormalization, ``((x / divisor) - mean) / std`` per channel (cvig_fov.py:147;
+    cvig_semantic.py:174-175 uses divisor (255, 255, 255, 1, 1)).  antialias=True is what the reference computes with today's
+    torchvision (>= 0.17 antialiases tensors by default), antialias=False what its pinned torchvision 0.9.1 computed.
+    col_start / col_count: the wrap-around column window of a panorama (cvig_fov.py:120-129).  Returns fp32
+    [..., C, out_h, col_count]."""
+    dev = _need_cuda("resize_normalize", images)
+    if images.dtype not in (torch.uint8, torch.float32):
+        raise TypeError("resize_normalize: expected uint8 or float32 images, got %s" % images.dtype)
+    if images.dim() < 3:
+        raise ValueError("resize_normalize: expected [..., C, H, W] images")
+    src = images.detach().contiguous()
+    c, in_h, in_w = src.shape[-3:]
+    lead = tuple(src.shape[:-2])
+    n_planes = int(np.prod(lead))
+    col_count = int(out_w if col_count is None else col_count)
+    norm = [0, 0, 0]
+    if mean is not None:
+        mean = [float(m) for m in mean]
+        std = [float(v) for v in std]
+        divisor = [float(d) for d in (divisor if hasattr(divisor, "__len__") else [divisor] * len(mean))]
+        if not (len(mean) == len(std) == len(divisor) == c):
+            raise ValueError("resize_normalize: %d channels but %d means / %d stds / %d divisors" % (c, len(mean), len(std), len(divisor)))
+        norm = [np.asarray(v, dtype=np.float32) for v in (divisor, mean, std)]
+    out = torch.empty(lead + (int(out_h), col_count), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        host, devplan = _resize_plan(in_h, in_w, out_h, out_w, antialias, dev)
+        _lib.call("witw_resize_norm", src.data_ptr(), int(src.dtype == torch.uint8), out.data_ptr(), n_planes, c, host.ctypes.data,
+                  devplan.data_ptr(), int(col_start), col_count, *[v.ctypes.data if mean is not None else 0 for v in norm], _stream())
+    return out
+
+
+def _via_device(t, device, fn, *args, **kwargs):
+    """fn(t, ...) on the GPU: a CUDA tensor is used where it is; a CPU tensor (the reference's transforms run on CPU samples)
+    is copied to ``device`` (default: the current CUDA device), processed there and returned on the CPU.  No CPU arithmetic."""
+    if t.is_cuda:
+        return fn(t, *args, **kwargs)
+    if not torch.cuda.is_available():
+        raise RuntimeError("%s: no CUDA device; witw_b200 has no CPU fallback" % fn.__name__)
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    return fn(t.to(dev, non_blocking=True), *args, **kwargs).to(t.device)
+
+
+class Resize(object):
+    """Drop-in for cvig_fov.py:100-134 on CUDA tensors ([C,H,W] samples or [N,C,H,W] batches, uint8 or fp32):
+    the surface image to 128 x 512 and a window of ``int(fov/360*512)`` columns from a random start with wrap-around
+    (panoramas, 'cvusa'), or straight to 128 x that width ('witw'); the overhead image to 256 x 256.  The start column is
+    drawn exactly as the reference draws it (``torch.randint(0, 512, ())`` on the CPU generator)."""
+
+    def __init__(self, dataset, fov=360, random_orientation=True, antialias=True, device=None):
+        self.fov = fov
+        self.surface_width = int(self.fov / 360 * SURFACE_WIDTH_MAX)
+        self.panorama = PANORAMA[dataset]
+        self.random_orientation = random_orientation
+        self.antialias = antialias
+        self.device = device
+
+    def __call__(self, data):
+        if self.panorama:
+            start = int(torch.randint(0, SURFACE_WIDTH_MAX, ())) if self.random_orientation else 0
+            data["surface"] = _via_device(data["surface"], self.device, resize_normalize, SURFACE_HEIGHT_MAX, SURFACE_WIDTH_MAX,
+                                          self.antialias, col_start=start, col_count=self.surface_width)
+        else:
+            data["surface"] = _via_device(data["surface"], self.device, resize_normalize, SURFACE_HEIGHT_MAX, self.surface_width,
+                                          self.antialias)
+        data["overhead"] = _via_device(data["overhead"], self.device, resize_normalize, OVERHEAD_SIZE, OVERHEAD_SIZE, self.antialias)
+        return data
+
+
+class ImageNormalization(object):
+    """Drop-in for cvig_fov.py:137-149 (divisor 255) / cvig_semantic.py:163-176 (pass divisor=(255, 255, 255, 1, 1) and the
+    five-channel mean / std) on CUDA tensors: ``data[key] = ((data[key] / divisor) - mean) / std`` for both images."""
+
+    def __init__(self, mean=IMG_MEAN, std=IMG_STD, divisor=255.0, device=None):
+        self.keys = ["surface", "overhead"]
+        self.mean, self.std, self.divisor, self.device = mean, std, divisor, device
+
+    def __call__(self, data):
+        for key in self.keys:
+            h, w = data[key].shape[-2:]
+            data[key] = _via_device(data[key], self.device, resize_normalize, h, w, antialias=False, mean=self.mean, std=self.std,
+                                    divisor=self.divisor)
+        return data
+
+
+def prepare_pair(surface, overhead, fov=360, panorama=True, start=0, antialias=True, mean=IMG_MEAN, std=IMG_STD, divisor=255.0):
+    """The whole transform chain of the reference's datasets (cvig_fov.py:389-392: Resize -> ImageNormalization ->
+    PolarTransform) on raw CUDA images, three kernels: resize + normalise the surface image(s), resize + normalise the
+    overhead image(s), polar-transform the latter.  Returns {'surface', 'overhead', 'polar'} like the reference's sample
+    dict; ``start`` is the panorama's first column (the reference draws it at random, cvig_fov.py:121-124)."""
+    sw = int(fov / 360 * SURFACE_WIDTH_MAX)
+    if panorama:
+        su = resize_normalize(surface, SURFACE_HEIGHT_MAX, SURFACE_WIDTH_MAX, antialias, mean, std, divisor, col_start=start, col_count=sw)
+    else:
+        su = resize_normalize(surface, SURFACE_HEIGHT_MAX, sw, antialias, mean, std, divisor)
+    ov = resize_normalize(overhead, OVERHEAD_SIZE, OVERHEAD_SIZE, antialias, mean, std, divisor)
+    return {"surface": su, "overhead": ov, "polar": polar_transform(ov)}
+
+
 class PolarTransform(object):
     """Drop-in for cvig_fov.py:186-209: ``data['polar'] = polar(data['overhead'])``, other keys kept.
 

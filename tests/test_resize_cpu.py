@@ -70,14 +70,17 @@ def test_resize_oracle_tracks_torch_interpolate():
 
 
 def parse_plan(host):
-    h = np.frombuffer(host[:68].tobytes(), dtype=np.int32)
-    in_h, in_w, out_h, out_w, aa, kx, ky, tile_rows, span = (int(v) for v in h[1:10])
-    off = [int(v) for v in h[10:16]]
+    """Header of csrc/resize.cu's plan blob: magic, geometry, taps per column / row, widest tile, rows per CTA and source-row
+    span for uint8 / fp32 sources, table offsets."""
+    h = np.frombuffer(host[:80].tobytes(), dtype=np.int32)
+    in_h, in_w, out_h, out_w, aa, kx, ky, cols_max = (int(v) for v in h[1:9])
+    off = [int(v) for v in h[13:19]]
 
     def arr(o, n, dt):
         return np.frombuffer(host[o:o + 4 * n].tobytes(), dtype=dt)
 
-    return {"geom": (in_h, in_w, out_h, out_w, aa), "kx": kx, "ky": ky, "tile_rows": tile_rows, "span": span,
+    return {"geom": (in_h, in_w, out_h, out_w, aa), "kx": kx, "ky": ky, "cols_max": cols_max,
+            "tile_rows": (int(h[9]), int(h[10])), "span": (int(h[11]), int(h[12])),
             "sx": arr(off[0], out_w, np.int32), "cx": arr(off[1], out_w, np.int32), "wx": arr(off[2], out_w * kx, np.float32).reshape(out_w, kx),
             "sy": arr(off[3], out_h, np.int32), "cy": arr(off[4], out_h, np.int32), "wy": arr(off[5], out_h * ky, np.float32).reshape(out_h, ky)}
 
@@ -95,11 +98,23 @@ def test_resize_plan_tables_equal_the_oracles(geom, antialias):
     sy, cy, wy = O.resize_taps(ih, oh, antialias)
     for name, ref in (("sx", sx), ("cx", cx), ("wx", wx), ("sy", sy), ("cy", cy), ("wy", wy)):
         assert np.array_equal(p[name], ref), name
-    # every row tile's source rows fit the kernel's shared-memory tile, and the taps stay inside the image
-    assert 1 <= p["tile_rows"] <= 32 and p["span"] <= 176
-    for y0 in range(0, oh, p["tile_rows"]):
-        y1 = min(y0 + p["tile_rows"], oh) - 1
-        assert p["sy"][y1] + p["cy"][y1] - p["sy"][y0] <= p["span"]
+    # every tile's source rectangle fits the shared memory the launch asks for, and the taps stay inside the image
+    for t, esz in ((0, 1), (1, 4)):
+        rows = p["tile_rows"][t]
+        if rows == 0:
+            continue
+        assert rows in (1, 2, 4, 8, 16, 32)
+        pitch = (p["cols_max"] * esz + 15) // 16 * 16 + 16          # a landing row: one chunk more than the widest rectangle
+        assert 2 * p["span"][t] * pitch + rows * ((p["cols_max"] + 3) // 4 * 4) * 4 <= 200 * 1024
+        for y0 in range(0, oh, rows):
+            y1 = min(y0 + rows, oh) - 1
+            assert p["sy"][y1] + p["cy"][y1] - p["sy"][y0] <= p["span"][t]
+    assert p["tile_rows"][0] > 0
+    for x0 in range(0, ow, 64):
+        x1 = min(x0 + 64, ow) - 1
+        assert p["sx"][x1] + p["cx"][x1] - p["sx"][x0] <= p["cols_max"]
+    assert (np.diff(p["sx"]) >= 0).all() and (np.diff(p["sx"] + p["cx"]) >= 0).all()
+    assert (np.diff(p["sy"]) >= 0).all() and (np.diff(p["sy"] + p["cy"]) >= 0).all()
     assert (p["sx"] >= 0).all() and (p["sx"] + p["cx"] <= iw).all() and (p["cx"] >= 1).all()
     assert (p["sy"] >= 0).all() and (p["sy"] + p["cy"] <= ih).all() and (p["cy"] >= 1).all()
 
@@ -113,28 +128,39 @@ def test_resize_plan_rejects_what_the_kernel_cannot_do():
         ops.resize_plan_host(0, 10, 256, 256, True)
 
 
-def test_plan_driven_resample_equals_oracle():
-    """The kernel's data flow (x pass over the rows a tile needs into an fp32 tile, then the y pass) replayed in numpy from
-    the plan tables reproduces the oracle's resize exactly -- the tile / span bookkeeping is what is being checked."""
+def test_plan_driven_resample_tracks_oracle():
+    """The kernel's data flow replayed in numpy from the plan tables: per (64-column, tile_rows) tile, stage the source
+    rectangle, y pass over four-column groups into an fp32 tile, x pass from that tile.  Checks the tile / rectangle
+    bookkeeping; the y-first order moves results by an ulp or two of the pixel scale against the oracle's x-first order."""
     from witw_b200 import ops
 
     gen = torch.Generator().manual_seed(9)
-    ih, iw, oh, ow = 131, 277, 64, 100
+    ih, iw, oh, ow = 131, 277, 70, 150
     x = torch.randint(0, 256, (ih, iw), generator=gen).float().numpy()
     p = parse_plan(ops.resize_plan_host(ih, iw, oh, ow, True))
-    out = np.zeros((oh, ow), np.float32)
-    for y0 in range(0, oh, p["tile_rows"]):
-        y1 = min(y0 + p["tile_rows"], oh)
-        r_lo, r_hi = p["sy"][y0], p["sy"][y1 - 1] + p["cy"][y1 - 1]
-        tile = np.zeros((r_hi - r_lo, ow), np.float32)
-        for c in range(ow):
-            acc = x[r_lo:r_hi, p["sx"][c]] * p["wx"][c, 0]
-            for j in range(1, p["cx"][c]):
-                acc = (acc + x[r_lo:r_hi, p["sx"][c] + j] * p["wx"][c, j]).astype(np.float32)
-            tile[:, c] = acc
-        for y in range(y0, y1):
-            acc = tile[p["sy"][y] - r_lo] * p["wy"][y, 0]
-            for j in range(1, p["cy"][y]):
-                acc = (acc + tile[p["sy"][y] - r_lo + j] * p["wy"][y, j]).astype(np.float32)
-            out[y] = acc
-    assert np.array_equal(out, O.resize_bilinear(x, oh, ow, True).numpy())
+    rows = p["tile_rows"][0]
+    pitch = (p["cols_max"] + 15) // 16 * 16
+    out = np.full((oh, ow), np.nan, np.float32)
+    for x0 in range(0, ow, 64):
+        x1 = min(x0 + 64, ow)
+        c_lo, c_hi = p["sx"][x0], p["sx"][x1 - 1] + p["cx"][x1 - 1]
+        n_groups = (c_hi - c_lo + 3) // 4
+        assert 4 * n_groups <= pitch
+        for y0 in range(0, oh, rows):
+            y1 = min(y0 + rows, oh)
+            r_lo, r_hi = p["sy"][y0], p["sy"][y1 - 1] + p["cy"][y1 - 1]
+            raw = np.zeros((r_hi - r_lo, pitch), np.float32)
+            raw[:, : c_hi - c_lo] = x[r_lo:r_hi, c_lo:c_hi]
+            mid = np.zeros((y1 - y0, pitch), np.float32)
+            for y in range(y0, y1):
+                acc = np.zeros(4 * n_groups, np.float32)
+                for j in range(p["cy"][y]):
+                    acc = (acc + raw[p["sy"][y] - r_lo + j, : 4 * n_groups] * p["wy"][y, j]).astype(np.float32)
+                mid[y - y0, : 4 * n_groups] = acc
+            for c in range(x0, x1):
+                t = mid[:, p["sx"][c] - c_lo:]
+                acc = t[:, 0] * p["wx"][c, 0]
+                for j in range(1, p["cx"][c]):
+                    acc = (acc + t[:, j] * p["wx"][c, j]).astype(np.float32)
+                out[y0:y1, c] = acc
+    assert np.abs(out - O.resize_bilinear(x, oh, ow, True).numpy()).max() <= RESIZE_TOL

@@ -8,9 +8,18 @@
 // lives in torch, not under /root/reference):
 //   antialias = 0  ATen upsample_bilinear2d -- the reference's pinned torch 1.8.1 / torchvision 0.9.1
 //   antialias = 1  ATen _upsample_bilinear2d_aa -- torchvision >= 0.17's default, the reference as it runs today
-// Kernel: one CTA per (64-column x tile_rows) output tile of one plane.  Pass 1 resamples the source rows the tile needs
-// along x into shared memory (fp32, rounded once, as ATen's intermediate tensor is); pass 2 blends those rows along y,
-// normalises and stores 256-byte row segments.  Each thread owns one output column, so its x taps live in registers.
+//
+// Kernel: one CTA per (64 resized columns x tile_rows) output tile, looping over planes with a two-deep pipeline:
+//   A  the source rectangle the tile needs in the NEXT plane is copied into one of two shared-memory landing buffers with
+//      16-byte cp.async copies of aligned global chunks, while the current plane is computed.  Rows of an image whose row
+//      pitch is not a multiple of 16 bytes start at any byte offset inside their first chunk; the offset is a per-row
+//      constant that phase B applies (a funnel shift of two adjacent words on the rows that are not word aligned).
+//   B  y pass first (it shrinks the rows by the scale factor before the irregular x pass): a warp owns an output row, a
+//      lane four adjacent source columns -- one 32-bit shared load brings four uint8 pixels (a float4 for aligned fp32
+//      rows) per tap row, blended with packed f32x2 operations -- and writes the fp32 intermediate tile
+//   C  x pass: a thread owns one output column (its taps live in registers), blends, normalises, stores 128-byte rows.
+// ATen runs the x pass first and rounds its intermediate to fp32; running y first moves results by an ulp or two of the
+// pixel scale (measured against the oracle in tests/test_gpu_resize.py), well inside the parity tolerance.
 #include <cmath>
 #include <cstring>
 #include <vector>
@@ -23,14 +32,16 @@ struct ResizePlanHeader {
   uint32_t magic;
   int32_t in_h, in_w, out_h, out_w, antialias;
   int32_t kx, ky;            // taps per output column / row (table stride)
-  int32_t tile_rows;         // output rows per CTA
-  int32_t span_max;          // most source rows any row tile touches
+  int32_t cols_max;          // most source columns any 64-column tile touches
+  int32_t tile_rows[2];      // output rows per CTA for uint8 / fp32 sources (0: that source type does not fit)
+  int32_t span[2];           // most source rows any row tile of that height touches
   int32_t off_sx, off_cx, off_wx, off_sy, off_cy, off_wy;   // byte offsets from the start of the blob
   int32_t total_bytes;
 };
-static constexpr uint32_t kResizeMagic = 0x575a5352u;  // "RSZW"
+static constexpr uint32_t kResizeMagic = 0x325a5352u;  // "RSZ2"
 static constexpr int kTileCols = 64;
-static constexpr int kMaxSpanRows = 176;                // 176 x 64 floats = 44 KB of static-limit shared memory
+static constexpr size_t kSmemPreferred = 72 * 1024;     // three CTAs per SM (the register file allows no more)
+static constexpr size_t kSmemLimit = 200 * 1024;
 
 // taps of one axis, mirroring the C++ types of ATen (float scalar_t; the 0.5 literals are doubles)
 static int axis_kmax(int in_size, int out_size, int antialias) {
@@ -91,6 +102,16 @@ static void axis_taps(int in_size, int out_size, int antialias, int k, int32_t* 
 
 static size_t align16(size_t v) { return (v + 15) / 16 * 16; }
 
+// shared memory of one CTA: two landing buffers (span rows x pitch bytes, raw source type; two chunks more than the widest
+// rectangle: a row starts anywhere inside its first 16-byte chunk, and the y pass reads one word past a lane's last group)
+// + the fp32 intermediate tile
+static size_t land_pitch_bytes(int cols_max, int esz) { return align16((size_t)cols_max * esz) + 32; }
+static size_t mid_pitch_cols(int cols_max) { return (size_t)(cols_max + 3) / 4 * 4; }
+static constexpr int kMidPad = 32;   // floats after the intermediate tile: the x pass may read up to its tap bound past a row's end
+static size_t tile_smem_bytes(int span, int tile_rows, int cols_max, int esz) {
+  return 2 * (size_t)span * land_pitch_bytes(cols_max, esz) + ((size_t)tile_rows * mid_pitch_cols(cols_max) + kMidPad) * sizeof(float);
+}
+
 static bool plan_layout(int in_h, int in_w, int out_h, int out_w, int antialias, ResizePlanHeader* h) {
   if (in_h < 1 || in_w < 1 || out_h < 1 || out_w < 1) return false;
   std::memset(h, 0, sizeof(*h));
@@ -113,7 +134,8 @@ static bool plan_layout(int in_h, int in_w, int out_h, int out_w, int antialias,
 // device
 // ------------------------------------------------------------------------------------------
 struct ResizeArgs {
-  const void* src;
+  const unsigned char* src;       // 16-byte aligned
+  const unsigned char* src_end16; // end of the source tensor rounded up to 16 bytes
   float* dst;
   long long n_planes;
   int n_ch;
@@ -121,25 +143,83 @@ struct ResizeArgs {
   const int32_t* sx; const int32_t* cx; const float* wx; int kx;
   const int32_t* sy; const int32_t* cy; const float* wy; int ky;
   int tile_rows;
-  int normalize;
-  float divisor[8], mean[8], stdv[8];
+  int pitch_bytes;                // row pitch of a landing buffer (multiple of 16)
+  int land_bytes;                 // span x pitch_bytes: size of one landing buffer
+  int pitch_cols;                 // row pitch of the intermediate tile, in floats (multiple of 4)
+  int lpr_shift;                  // phase B: log2 of the lanes that share an output row (5, 4 or 3)
+  int normalize;                  // 0: resize only, 1: (v / divisor - mean) / std with IEEE divisions, 2: v * scale + bias
+  float divisor[8], mean[8], stdv[8], scale[8], bias[8];
 };
 
-__device__ __forceinline__ float px(const float* p) { return __ldg(p); }
-__device__ __forceinline__ float px(const uint8_t* p) { return (float)__ldg(p); }
+// uint8 -> fp32 without the conversion pipe: byte i of w becomes the mantissa of 2^23 + v
+__device__ __forceinline__ float byte_to_float(uint32_t w, int i) {
+  return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540u + i)) - 8388608.0f;
+}
 
-template <typename T, int KX>
+// phase B: one tap row of GPL adjacent four-column groups, accumulated with packed f32x2 operations (two columns per
+// instruction).  `row` points at the 4-byte word holding the row's first needed byte and `bs` is that byte's bit offset
+// in the word (uint8); for fp32 rows `row` is the first needed float and `bs` its byte offset from 16-byte alignment.
+struct Acc4 { float2 lo, hi; };
+
+template <int GPL>
+__device__ __forceinline__ void tap_run(Acc4 (&acc)[GPL], const uint8_t*, const unsigned char* row, uint32_t bs, int g0, float2 w2) {
+  const uint32_t* wp = reinterpret_cast<const uint32_t*>(row) + g0;
+  uint32_t w[GPL + 1];
+#pragma unroll
+  for (int i = 0; i <= GPL; ++i) w[i] = wp[i];
+  const float2 bias = make_float2(-8388608.0f, -8388608.0f);
+#pragma unroll
+  for (int i = 0; i < GPL; ++i) {
+    const uint32_t v = __funnelshift_r(w[i], w[i + 1], bs);      // bs == 0: the word itself
+    // byte k of v becomes the mantissa of 2^23 + pixel (PRMT, no conversion pipe); the packed add removes the 2^23
+    const float2 p01 = __fadd2_rn(make_float2(__uint_as_float(__byte_perm(v, 0x4B000000u, 0x7540u)),
+                                              __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7541u))), bias);
+    const float2 p23 = __fadd2_rn(make_float2(__uint_as_float(__byte_perm(v, 0x4B000000u, 0x7542u)),
+                                              __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7543u))), bias);
+    acc[i].lo = __ffma2_rn(p01, w2, acc[i].lo);
+    acc[i].hi = __ffma2_rn(p23, w2, acc[i].hi);
+  }
+}
+
+template <int GPL>
+__device__ __forceinline__ void tap_run(Acc4 (&acc)[GPL], const float*, const unsigned char* row, uint32_t bs, int g0, float2 w2) {
+  const float* fp = reinterpret_cast<const float*>(row) + 4 * g0;
+#pragma unroll
+  for (int i = 0; i < GPL; ++i) {
+    float4 v;
+    if (bs == 0) v = *reinterpret_cast<const float4*>(fp + 4 * i);
+    else v = make_float4(fp[4 * i], fp[4 * i + 1], fp[4 * i + 2], fp[4 * i + 3]);
+    acc[i].lo = __ffma2_rn(make_float2(v.x, v.y), w2, acc[i].lo);
+    acc[i].hi = __ffma2_rn(make_float2(v.z, v.w), w2, acc[i].hi);
+  }
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <typename T, int KX, int GPL>
 __global__ void __launch_bounds__(256) resize_norm_kernel(const ResizeArgs a) {
-  extern __shared__ float tmp[];                     // [span][kTileCols]
-  const int col = threadIdx.x & (kTileCols - 1);
-  const int lane_row = threadIdx.x >> 6;             // 0..3
-  const int xo = blockIdx.x * kTileCols + col;       // output column
-  const bool col_ok = xo < a.out_cols;
-  // the column of the full resized image this output column shows (panorama window with wrap-around)
-  int xg = xo + a.col_start;
-  if (xg >= a.full_w) xg -= a.full_w;
+  extern __shared__ __align__(16) unsigned char smem[];
+  float* mid = reinterpret_cast<float*>(smem + 2 * (size_t)a.land_bytes);   // [tile_rows][pitch_cols] fp32 + kMidPad
+  constexpr int ESZ = (int)sizeof(T);
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int col = tid & (kTileCols - 1);
+  const int lane_row = tid >> 6;                     // 0..3
+  // tiles are cut in the resized image's own columns xg; the panorama window maps xg to output column xo
+  const int xg = blockIdx.x * kTileCols + col;
+  const bool col_ok = xg < a.full_w;
+  int xo = xg - a.col_start;
+  if (xo < 0) xo += a.full_w;
+  const bool mine = col_ok && xo < a.out_cols;
+  if (!__syncthreads_or(mine)) return;               // no column of this tile is inside the window
   int sx = 0, cx = 0;
-  float wx[KX];
+  float wx[KX];                                      // this column's taps; the table holds zeros past its count
 #pragma unroll
   for (int j = 0; j < KX; ++j) wx[j] = 0.0f;
   if (col_ok) {
@@ -149,52 +229,135 @@ __global__ void __launch_bounds__(256) resize_norm_kernel(const ResizeArgs a) {
     for (int j = 0; j < KX; ++j)
       if (j < a.kx) wx[j] = __ldg(a.wx + (size_t)xg * a.kx + j);
   }
+  const int x_first = blockIdx.x * kTileCols;
+  const int x_last = min(x_first + kTileCols, a.full_w) - 1;
+  const int c_lo = __ldg(a.sx + x_first);
+  const int c_hi = __ldg(a.sx + x_last) + __ldg(a.cx + x_last);
+  const int n_chunks = (((c_hi - c_lo) * ESZ + 15) >> 4) + 1;      // aligned 16-byte chunks that can hold a row of the rectangle
+  const int n_groups = (c_hi - c_lo + 3) >> 2;                     // four-column groups per row
   const int y0 = blockIdx.y * a.tile_rows;
   const int y1 = min(y0 + a.tile_rows, a.out_h);
+  const int rows = y1 - y0;
   const int r_lo = __ldg(a.sy + y0);
   const int r_hi = __ldg(a.sy + (y1 - 1)) + __ldg(a.cy + (y1 - 1));
-  const size_t plane_in = (size_t)a.in_h * a.in_w;
+  const int span = r_hi - r_lo;
+  const size_t plane_bytes = (size_t)a.in_h * a.in_w * ESZ;
+  const uint32_t row_bytes = (uint32_t)a.in_w * ESZ;
   const size_t plane_out = (size_t)a.out_h * a.out_cols;
+  const int step_rr = 256 / n_chunks, step_ch = 256 - step_rr * n_chunks;
+  const int rr_first = tid / n_chunks, ch_first = tid - rr_first * n_chunks;
+  // phase B: 2^lpr_shift lanes share an output row, so a warp works on 32 >> lpr_shift rows at a time
+  const int lpr = 1 << a.lpr_shift;
+  const int sub = lane >> a.lpr_shift, l = lane & (lpr - 1);
+  const int rows_per_warp = 32 >> a.lpr_shift;
+  const int pitch_bytes = a.pitch_bytes, pitch_cols = a.pitch_cols;
 
-  for (long long p = blockIdx.z; p < a.n_planes; p += gridDim.z) {
-    const T* src = reinterpret_cast<const T*>(a.src) + (size_t)p * plane_in;
-    // pass 1: along x, one fp32 rounding per intermediate sample
-    if (col_ok) {
-      for (int r = r_lo + lane_row; r < r_hi; r += 4) {
-        const T* row = src + (size_t)r * a.in_w + sx;
-        float acc = px(row) * wx[0];
+  // the x pass reads KX taps per column with zero weights past the column's own count: what it reads there must be finite
+  for (int i = tid; i < a.tile_rows * pitch_cols + kMidPad; i += 256) mid[i] = 0.0f;
+
+  // A: asynchronous copy of plane p's source rectangle [r_lo, r_hi) x [c_lo, c_hi) into landing buffer `buf`.
+  // Row rr lands from the aligned chunk that holds its first byte; chunks past the tensor's last chunk are skipped.
+  auto prefetch = [&](long long p, int buf) {
+    const unsigned char* rect = a.src + (size_t)p * plane_bytes + ((size_t)r_lo * a.in_w + c_lo) * ESZ;
+    unsigned char* land = smem + (size_t)buf * a.land_bytes;
+    int rr = rr_first, ch = ch_first;                 // item tid, then steps of 256 without further divisions
+    for (; rr < span; ch += step_ch, rr += step_rr) {
+      if (ch >= n_chunks) { ch -= n_chunks; ++rr; if (rr >= span) break; }
+      const unsigned char* g = rect + (size_t)rr * row_bytes;
+      const unsigned char* chunk = g - (reinterpret_cast<uintptr_t>(g) & 15) + 16 * ch;
+      if (chunk < a.src_end16) cp_async16(land + rr * pitch_bytes + 16 * ch, chunk);
+    }
+    cp_async_commit();
+  };
+
+  int buf = 0;
+  prefetch(blockIdx.z, 0);                            // gridDim.z <= n_planes
+  for (long long p = blockIdx.z; p < a.n_planes; p += gridDim.z, buf ^= 1) {
+    const long long p_next = p + gridDim.z;
+    if (p_next < a.n_planes) {
+      prefetch(p_next, buf ^ 1);                      // that buffer was last read before the previous iteration's second barrier
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();                                  // everybody's copies of plane p have landed; phase C of the previous plane is over
+    const unsigned char* land = smem + (size_t)buf * a.land_bytes;
+    // low bits of the address of the rectangle's first byte: they give every row's offset inside its first chunk
+    const uint32_t rect_lo = (uint32_t)reinterpret_cast<uintptr_t>(a.src + (size_t)p * plane_bytes + ((size_t)r_lo * a.in_w + c_lo) * ESZ);
+    // B: y pass.  lpr lanes share an output row; a lane takes GPL adjacent four-column groups per pass
+    for (int yy = warp * rows_per_warp + sub; yy < rows; yy += 8 * rows_per_warp) {
+      const int y = y0 + yy;
+      const int sy = __ldg(a.sy + y), cy = __ldg(a.cy + y);
+      const float* wy = a.wy + (size_t)y * a.ky;
+      float* mrow = mid + yy * pitch_cols;
+      const int rr0 = sy - r_lo;
+      for (int g0 = GPL * l; g0 < n_groups; g0 += GPL * lpr) {
+        Acc4 acc[GPL];
 #pragma unroll
-        for (int j = 1; j < KX; ++j)
-          if (j < cx) acc = __fmaf_rn(px(row + j), wx[j], acc);
-        tmp[(r - r_lo) * kTileCols + col] = acc;
+        for (int i = 0; i < GPL; ++i) acc[i].lo = acc[i].hi = make_float2(0.f, 0.f);
+        uint32_t g_lo = rect_lo + (uint32_t)rr0 * row_bytes;
+        const unsigned char* lrow = land + rr0 * pitch_bytes;
+        for (int j = 0; j < cy; ++j, g_lo += row_bytes, lrow += pitch_bytes) {
+          const float wj = __ldg(wy + j);
+          const uint32_t off = g_lo & 15u;            // where the row starts in its chunk
+          tap_run<GPL>(acc, static_cast<const T*>(nullptr), lrow + (off & 12u), ESZ == 1 ? (off & 3u) * 8u : off, g0, make_float2(wj, wj));
+        }
+#pragma unroll
+        for (int i = 0; i < GPL; ++i)
+          if (g0 + i < n_groups)
+            *reinterpret_cast<float4*>(mrow + 4 * (g0 + i)) = make_float4(acc[i].lo.x, acc[i].lo.y, acc[i].hi.x, acc[i].hi.y);
       }
     }
     __syncthreads();
-    // pass 2: along y, then ImageNormalization: (v / 255 - mean) / std, each step rounded to fp32 as torch does
-    if (col_ok) {
+    // C: x pass, then ImageNormalization
+    if (mine) {
       const int c = (int)(p % a.n_ch);
-      for (int y = y0 + lane_row; y < y1; y += 4) {
-        const int sy = __ldg(a.sy + y), cy = __ldg(a.cy + y);
-        const float* wy = a.wy + (size_t)y * a.ky;
-        const float* t = tmp + (sy - r_lo) * kTileCols + col;
-        float acc = t[0] * __ldg(wy);
-        for (int j = 1; j < cy; ++j) acc = __fmaf_rn(t[j * kTileCols], __ldg(wy + j), acc);
-        if (a.normalize) acc = __fdiv_rn(__fsub_rn(__fdiv_rn(acc, a.divisor[c]), a.mean[c]), a.stdv[c]);
-        __stcs(a.dst + (size_t)p * plane_out + (size_t)y * a.out_cols + xo, acc);
+      const float dv = a.divisor[c], mn = a.mean[c], sd = a.stdv[c], sc = a.scale[c], bi = a.bias[c];
+      const float* t = mid + (sx - c_lo) + lane_row * pitch_cols;
+      float* o = a.dst + (size_t)p * plane_out + (size_t)(y0 + lane_row) * a.out_cols + xo;
+      for (int yy = lane_row; yy < rows; yy += 4, t += 4 * pitch_cols, o += 4 * (size_t)a.out_cols) {
+        float acc = t[0] * wx[0];
+#pragma unroll
+        for (int j = 1; j < KX; ++j) {
+          if (ESZ == 1) acc = __fmaf_rn(t[j], wx[j], acc);           // zero weight past the column's count, finite operand
+          else if (j < cx) acc = __fmaf_rn(t[j], wx[j], acc);        // fp32 sources: what lies past the rectangle may be NaN
+        }
+        // 1: (v / divisor - mean) / std, each step rounded to fp32 as torch does (the drop-in for ImageNormalization itself);
+        // 2: one multiply-add with the same constants folded (behind a resize, whose result is an ulp or two from ATen's anyway)
+        if (a.normalize == 1) acc = __fdiv_rn(__fsub_rn(__fdiv_rn(acc, dv), mn), sd);
+        else if (a.normalize == 2) acc = __fmaf_rn(acc, sc, bi);
+        __stcs(o, acc);
       }
     }
-    __syncthreads();
   }
 }
 
-template <typename T>
-static int launch_resize(const ResizeArgs& a, dim3 grid, size_t smem, cudaStream_t st) {
-  if (a.kx <= 2) resize_norm_kernel<T, 2><<<grid, 256, smem, st>>>(a);
-  else if (a.kx <= 8) resize_norm_kernel<T, 8><<<grid, 256, smem, st>>>(a);
-  else if (a.kx <= 16) resize_norm_kernel<T, 16><<<grid, 256, smem, st>>>(a);
-  else resize_norm_kernel<T, 32><<<grid, 256, smem, st>>>(a);
+template <typename T, int GPL>
+static int launch_resize_g(const ResizeArgs& a, dim3 grid, size_t smem, cudaStream_t st) {
+#define WITW_RESIZE_LAUNCH(K)                                                                                             \
+  do {                                                                                                                    \
+    if (smem > 48 * 1024)                                                                                                 \
+      WITW_CUDA(cudaFuncSetAttribute(resize_norm_kernel<T, K, GPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    resize_norm_kernel<T, K, GPL><<<grid, 256, smem, st>>>(a);                                                            \
+  } while (0)
+  // the x pass runs exactly K taps per column (zero weights past a column's own count)
+  if (a.kx <= 2) WITW_RESIZE_LAUNCH(2);
+  else if (a.kx <= 3) WITW_RESIZE_LAUNCH(3);
+  else if (a.kx <= 5) WITW_RESIZE_LAUNCH(5);
+  else if (a.kx <= 7) WITW_RESIZE_LAUNCH(7);
+  else if (a.kx <= 9) WITW_RESIZE_LAUNCH(9);
+  else if (a.kx <= 16) WITW_RESIZE_LAUNCH(16);
+  else WITW_RESIZE_LAUNCH(32);
+#undef WITW_RESIZE_LAUNCH
   WITW_LAUNCH_CHECK();
   return WITW_OK;
+}
+
+template <typename T>
+static int launch_resize(const ResizeArgs& a, int gpl, dim3 grid, size_t smem, cudaStream_t st) {
+  if (gpl == 1) return launch_resize_g<T, 1>(a, grid, smem, st);
+  if (gpl == 2) return launch_resize_g<T, 2>(a, grid, smem, st);
+  return launch_resize_g<T, 3>(a, grid, smem, st);
 }
 
 }  // namespace witw
@@ -224,26 +387,38 @@ extern "C" int witw_resize_plan_build(int in_h, int in_w, int out_h, int out_w, 
   float* wy = reinterpret_cast<float*>(base + h.off_wy);
   axis_taps(in_w, out_w, antialias, h.kx, sx, cx, wx);
   axis_taps(in_h, out_h, antialias, h.ky, sy, cy, wy);
-  // rows per CTA: the largest of 32, 16, ... 1 whose source-row span fits the shared-memory tile
-  int tile_rows = 32, span = 0;
-  for (;; tile_rows /= 2) {
-    span = 0;
-    for (int y0 = 0; y0 < out_h; y0 += tile_rows) {
-      const int y1 = (y0 + tile_rows < out_h ? y0 + tile_rows : out_h) - 1;
-      int lo = sy[y0], hi = sy[y1] + cy[y1];
-      for (int y = y0; y <= y1; ++y) {     // the tables are monotone; do not rely on it
-        if (sy[y] < lo) lo = sy[y];
-        if (sy[y] + cy[y] > hi) hi = sy[y] + cy[y];
-      }
-      WITW_REQUIRE(lo == sy[y0] && hi == sy[y1] + cy[y1], WITW_ERR_UNSUPPORTED, "witw_resize_plan_build: non-monotone row taps");
-      if (hi - lo > span) span = hi - lo;
-    }
-    if (span <= kMaxSpanRows || tile_rows == 1) break;
+  // the kernel takes a tile's source rectangle from its first and last row / column: the tables must be monotone
+  for (int i = 1; i < out_w; ++i)
+    WITW_REQUIRE(sx[i] >= sx[i - 1] && sx[i] + cx[i] >= sx[i - 1] + cx[i - 1], WITW_ERR_UNSUPPORTED, "witw_resize_plan_build: non-monotone column taps");
+  for (int i = 1; i < out_h; ++i)
+    WITW_REQUIRE(sy[i] >= sy[i - 1] && sy[i] + cy[i] >= sy[i - 1] + cy[i - 1], WITW_ERR_UNSUPPORTED, "witw_resize_plan_build: non-monotone row taps");
+  int cols_max = 0;
+  for (int x0 = 0; x0 < out_w; x0 += kTileCols) {
+    const int x1 = (x0 + kTileCols < out_w ? x0 + kTileCols : out_w) - 1;
+    const int n = sx[x1] + cx[x1] - sx[x0];
+    if (n > cols_max) cols_max = n;
   }
-  WITW_REQUIRE(span <= kMaxSpanRows, WITW_ERR_UNSUPPORTED, "witw_resize_plan_build: one output row needs %d source rows (height %d -> %d); at most %d",
-               span, in_h, out_h, kMaxSpanRows);
-  h.tile_rows = tile_rows;
-  h.span_max = span;
+  h.cols_max = cols_max;
+  // rows per CTA: the largest of 32, 16, ... 1 whose tile fits the preferred shared-memory size, else the limit
+  for (int t = 0; t < 2; ++t) {
+    const int esz = t == 0 ? 1 : 4;
+    int fallback_rows = 0, fallback_span = 0;
+    for (int tile_rows = 32; tile_rows >= 1; tile_rows /= 2) {
+      int span = 0;
+      for (int y0 = 0; y0 < out_h; y0 += tile_rows) {
+        const int y1 = (y0 + tile_rows < out_h ? y0 + tile_rows : out_h) - 1;
+        const int n = sy[y1] + cy[y1] - sy[y0];
+        if (n > span) span = n;
+      }
+      const size_t need = tile_smem_bytes(span, tile_rows, cols_max, esz);
+      if (need <= kSmemPreferred) { h.tile_rows[t] = tile_rows; h.span[t] = span; break; }
+      if (need <= kSmemLimit && fallback_rows == 0) { fallback_rows = tile_rows; fallback_span = span; }
+    }
+    if (h.tile_rows[t] == 0) { h.tile_rows[t] = fallback_rows; h.span[t] = fallback_span; }
+  }
+  WITW_REQUIRE(h.tile_rows[0] > 0 || h.tile_rows[1] > 0, WITW_ERR_UNSUPPORTED,
+               "witw_resize_plan_build: %dx%d -> %dx%d needs more than %zu KB of shared memory per output row tile", in_h, in_w, out_h, out_w,
+               kSmemLimit / 1024);
   std::memcpy(base, &h, sizeof(h));
   return WITW_OK;
 }
@@ -254,7 +429,11 @@ extern "C" int witw_resize_norm(const void* src_dev, int src_is_u8, float* dst_d
   WITW_REQUIRE(plan_host && plan_dev, WITW_ERR_INVALID, "witw_resize_norm: null plan");
   ResizePlanHeader h;
   std::memcpy(&h, plan_host, sizeof(h));
-  WITW_REQUIRE(h.magic == kResizeMagic && h.tile_rows > 0, WITW_ERR_INVALID, "witw_resize_norm: not a resize plan");
+  WITW_REQUIRE(h.magic == kResizeMagic, WITW_ERR_INVALID, "witw_resize_norm: not a resize plan");
+  const int t = src_is_u8 ? 0 : 1;
+  const int esz = src_is_u8 ? 1 : 4;
+  WITW_REQUIRE(h.tile_rows[t] > 0, WITW_ERR_UNSUPPORTED, "witw_resize_norm: %dx%d -> %dx%d does not fit shared memory for %s sources", h.in_h,
+               h.in_w, h.out_h, h.out_w, src_is_u8 ? "uint8" : "fp32");
   WITW_REQUIRE(n_planes >= 0 && n_ch >= 1, WITW_ERR_INVALID, "witw_resize_norm: bad plane count");
   WITW_REQUIRE(col_start >= 0 && col_start < h.out_w && col_count >= 1 && col_count <= h.out_w, WITW_ERR_INVALID,
                "witw_resize_norm: column window [%d, +%d) outside the %d resized columns", col_start, col_count, h.out_w);
@@ -263,10 +442,13 @@ extern "C" int witw_resize_norm(const void* src_dev, int src_is_u8, float* dst_d
                "witw_resize_norm: normalisation needs divisor, mean and std for at most 8 channels (got %d)", n_ch);
   if (n_planes == 0) return WITW_OK;
   WITW_REQUIRE(src_dev && dst_dev, WITW_ERR_INVALID, "witw_resize_norm: null image pointer");
+  WITW_REQUIRE(reinterpret_cast<uintptr_t>(src_dev) % 16 == 0, WITW_ERR_INVALID, "witw_resize_norm: source images must be 16-byte aligned");
   const char* base = static_cast<const char*>(plan_dev);
   ResizeArgs a;
   std::memset(&a, 0, sizeof(a));
-  a.src = src_dev; a.dst = dst_dev; a.n_planes = n_planes; a.n_ch = n_ch;
+  a.src = static_cast<const unsigned char*>(src_dev);
+  a.src_end16 = a.src + align16((size_t)n_planes * h.in_h * h.in_w * esz);
+  a.dst = dst_dev; a.n_planes = n_planes; a.n_ch = n_ch;
   a.in_h = h.in_h; a.in_w = h.in_w; a.out_h = h.out_h; a.out_cols = col_count; a.full_w = h.out_w; a.col_start = col_start;
   a.sx = reinterpret_cast<const int32_t*>(base + h.off_sx);
   a.cx = reinterpret_cast<const int32_t*>(base + h.off_cx);
@@ -276,12 +458,40 @@ extern "C" int witw_resize_norm(const void* src_dev, int src_is_u8, float* dst_d
   a.cy = reinterpret_cast<const int32_t*>(base + h.off_cy);
   a.wy = reinterpret_cast<const float*>(base + h.off_wy);
   a.ky = h.ky;
-  a.tile_rows = h.tile_rows;
-  a.normalize = normalize ? 1 : 0;
-  for (int c = 0; c < n_ch && normalize; ++c) { a.divisor[c] = divisor[c]; a.mean[c] = mean[c]; a.stdv[c] = stdv[c]; }
-  dim3 grid((unsigned)ceil_div(col_count, kTileCols), (unsigned)ceil_div(h.out_h, h.tile_rows),
-            (unsigned)(n_planes < 32768 ? n_planes : 32768));
-  const size_t smem = (size_t)h.span_max * kTileCols * sizeof(float);
+  a.tile_rows = h.tile_rows[t];
+  a.pitch_bytes = (int)land_pitch_bytes(h.cols_max, esz);
+  a.land_bytes = h.span[t] * a.pitch_bytes;
+  a.pitch_cols = (int)mid_pitch_cols(h.cols_max);
+  // behind an identity geometry this is ImageNormalization itself: keep torch's two divisions bit for bit
+  const bool identity = h.in_h == h.out_h && h.in_w == h.out_w;
+  a.normalize = !normalize ? 0 : (identity ? 1 : 2);
+  for (int c = 0; c < n_ch && normalize; ++c) {
+    a.divisor[c] = divisor[c]; a.mean[c] = mean[c]; a.stdv[c] = stdv[c];
+    a.scale[c] = (float)(1.0 / ((double)divisor[c] * (double)stdv[c]));
+    a.bias[c] = (float)(-(double)mean[c] / (double)stdv[c]);
+  }
+  // y pass: 2^lpr_shift lanes share an output row and each takes gpl adjacent four-column groups per pass.  Pick the split
+  // of a warp with the fewest instructions per output row on the widest tile: one pass of a lane costs about 15 + 13 gpl
+  // issue slots per tap (12 per group to convert and blend, gpl + 1 shared loads, the row bookkeeping)
+  int gpl = 1;
+  {
+    const int groups = (h.cols_max + 3) / 4;
+    double best = 1e30;
+    a.lpr_shift = 5;
+    for (int g = 3; g >= 1; --g)
+      for (int shift = 5; shift >= 3; --shift) {
+        const double cost = (double)ceil_div(groups, g << shift) * (15.0 + 13.0 * g) / (double)(32 >> shift);
+        if (cost < best - 1e-9) { best = cost; a.lpr_shift = shift; gpl = g; }
+      }
+  }
+  const unsigned gx = (unsigned)ceil_div(h.out_w, kTileCols), gy = (unsigned)ceil_div(h.out_h, a.tile_rows);
+  // a few resident waves of CTAs, each looping over planes: per-thread taps and tile geometry are set up once
+  int64_t gz = ceil_div<int64_t>((int64_t)sm_count() * 8, (int64_t)gx * gy);
+  if (gz > n_planes) gz = n_planes;
+  if (gz > 65535) gz = 65535;
+  if (gz < 1) gz = 1;
+  dim3 grid(gx, gy, (unsigned)gz);
+  const size_t smem = tile_smem_bytes(h.span[t], a.tile_rows, h.cols_max, esz);
   cudaStream_t st = as_stream(stream);
-  return src_is_u8 ? launch_resize<uint8_t>(a, grid, smem, st) : launch_resize<float>(a, grid, smem, st);
+  return src_is_u8 ? launch_resize<uint8_t>(a, gpl, grid, smem, st) : launch_resize<float>(a, gpl, grid, smem, st);
 }

@@ -317,6 +317,8 @@ def resize_normalize(images, out_h, out_w, antialias=True, mean=None, std=None, 
     if images.dim() < 3:
         raise ValueError("resize_normalize: expected [..., C, H, W] images")
     src = images.detach().contiguous()
+    if src.data_ptr() % 16:          # the kernel stages source rows with aligned 16-byte loads from the tensor's base
+        src = src.clone()
     c, in_h, in_w = src.shape[-3:]
     lead = tuple(src.shape[:-2])
     n_planes = int(np.prod(lead))

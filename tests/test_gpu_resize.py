@@ -94,6 +94,11 @@ def test_image_normalization_dropin_bit_exact(W):
     # float pixels, as the reference's datasets deliver them (cvig_fov.py:90-91)
     d = W.ImageNormalization()({"surface": su8.float().cuda(), "overhead": ov8[0].float().cuda()})
     assert torch.equal(d["surface"].cpu(), O.image_normalization(su8))
+    # a plane that is not a whole number of four-pixel groups takes the general kernel: same bits
+    odd = torch.randint(0, 256, (2, 3, 5, 7), generator=gen, dtype=torch.uint8)
+    d = W.ImageNormalization()({"surface": odd.cuda(), "overhead": odd.float().cuda()})
+    ref_odd = torch.stack([O.image_normalization(x) for x in odd])
+    assert torch.equal(d["surface"].cpu(), ref_odd) and torch.equal(d["overhead"].cpu(), ref_odd)
     # cvig_semantic.py:163-176: five channels, only the first three divided by 255
     mean, std = (0.485, 0.456, 0.406, 0.45, 0.45), (0.229, 0.224, 0.225, 0.22, 0.22)
     x = torch.rand(5, 128, 64, generator=gen) * torch.tensor([255, 255, 255, 1, 1.0]).view(5, 1, 1)

@@ -332,6 +332,38 @@ __global__ void __launch_bounds__(256) resize_norm_kernel(const ResizeArgs a) {
   }
 }
 
+// ImageNormalization alone (identity geometry): a streaming kernel, four pixels per thread and iteration.  uint8 pixels go
+// through a per-channel table of the 256 possible results held in shared memory (the same three IEEE operations, evaluated
+// once per table entry by each CTA); fp32 pixels are divided, shifted and divided in place.  Bit-identical to torch.
+template <typename T>
+__global__ void __launch_bounds__(256) normalize_kernel(const ResizeArgs a, long long plane_groups, long long n_groups_total) {
+  __shared__ float lut[8 * 256];
+  constexpr bool kU8 = sizeof(T) == 1;
+  if (kU8) {
+    for (int i = threadIdx.x; i < a.n_ch * 256; i += 256) {
+      const int c = i >> 8;
+      lut[i] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)(i & 255), a.divisor[c]), a.mean[c]), a.stdv[c]);
+    }
+    __syncthreads();
+  }
+  const long long stride = (long long)gridDim.x * 256;
+  for (long long g = (long long)blockIdx.x * 256 + threadIdx.x; g < n_groups_total; g += stride) {
+    const int c = (int)((g / plane_groups) % a.n_ch);       // a group of four pixels never straddles two planes
+    float4 o;
+    if (kU8) {
+      const uint32_t v = __ldcs(reinterpret_cast<const uint32_t*>(a.src) + g);
+      const float* t = lut + c * 256;
+      o = make_float4(t[v & 255u], t[(v >> 8) & 255u], t[(v >> 16) & 255u], t[v >> 24]);
+    } else {
+      const float4 v = __ldcs(reinterpret_cast<const float4*>(a.src) + g);
+      const float dv = a.divisor[c], mn = a.mean[c], sd = a.stdv[c];
+      o = make_float4(__fdiv_rn(__fsub_rn(__fdiv_rn(v.x, dv), mn), sd), __fdiv_rn(__fsub_rn(__fdiv_rn(v.y, dv), mn), sd),
+                      __fdiv_rn(__fsub_rn(__fdiv_rn(v.z, dv), mn), sd), __fdiv_rn(__fsub_rn(__fdiv_rn(v.w, dv), mn), sd));
+    }
+    __stcs(reinterpret_cast<float4*>(a.dst) + g, o);
+  }
+}
+
 template <typename T, int GPL>
 static int launch_resize_g(const ResizeArgs& a, dim3 grid, size_t smem, cudaStream_t st) {
 #define WITW_RESIZE_LAUNCH(K)                                                                                             \
@@ -484,6 +516,20 @@ extern "C" int witw_resize_norm(const void* src_dev, int src_is_u8, float* dst_d
         if (cost < best - 1e-9) { best = cost; a.lpr_shift = shift; gpl = g; }
       }
   }
+  cudaStream_t st = as_stream(stream);
+  // ImageNormalization on its own: no resampling, stream the pixels
+  const long long plane_px = (long long)h.in_h * h.in_w;
+  if (identity && normalize && col_start == 0 && col_count == h.out_w && plane_px % 4 == 0) {
+    const long long plane_groups = plane_px / 4, total = plane_groups * n_planes;
+    long long blocks = ceil_div<long long>(total, 256 * 8);             // about eight groups per thread
+    const long long cap = (long long)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    if (src_is_u8) normalize_kernel<uint8_t><<<(unsigned)blocks, 256, 0, st>>>(a, plane_groups, total);
+    else normalize_kernel<float><<<(unsigned)blocks, 256, 0, st>>>(a, plane_groups, total);
+    WITW_LAUNCH_CHECK();
+    return WITW_OK;
+  }
   const unsigned gx = (unsigned)ceil_div(h.out_w, kTileCols), gy = (unsigned)ceil_div(h.out_h, a.tile_rows);
   // a few resident waves of CTAs, each looping over planes: per-thread taps and tile geometry are set up once
   int64_t gz = ceil_div<int64_t>((int64_t)sm_count() * 8, (int64_t)gx * gy);
@@ -492,6 +538,5 @@ extern "C" int witw_resize_norm(const void* src_dev, int src_is_u8, float* dst_d
   if (gz < 1) gz = 1;
   dim3 grid(gx, gy, (unsigned)gz);
   const size_t smem = tile_smem_bytes(h.span[t], a.tile_rows, h.cols_max, esz);
-  cudaStream_t st = as_stream(stream);
   return src_is_u8 ? launch_resize<uint8_t>(a, gpl, grid, smem, st) : launch_resize<float>(a, gpl, grid, smem, st);
 }

@@ -317,6 +317,24 @@ def run_ours(args):
                 bufs[b][1].copy_(su_host, non_blocking=True)
             ready[b].record(copy_stream)
 
+    # results leave the device the same way: step i's ranks and top-k are copied into pinned host buffers on a third stream
+    # and read by the host while step i+1 is already running, so the launch latency of a step hides behind the previous one
+    d2h_stream = torch.cuda.Stream(device=device)
+    host_out = [None, None]
+    computed = [torch.cuda.Event() for _ in range(2)]
+    landed = [torch.cuda.Event() for _ in range(2)]
+
+    def download(b, tensors):
+        computed[b].record()
+        if host_out[b] is None:
+            host_out[b] = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in tensors]
+        with torch.cuda.stream(d2h_stream):
+            d2h_stream.wait_event(computed[b])
+            for h, t in zip(host_out[b], tensors):
+                h.copy_(t, non_blocking=True)
+                t.record_stream(d2h_stream)
+            landed[b].record(d2h_stream)
+
     def run_e2e(n):
         out = None
         upload(0)
@@ -327,18 +345,36 @@ def run_ours(args):
             torch.cuda.current_stream().wait_event(ready[b])
             if world > 1:
                 dist.broadcast(bufs[b][1], src=0)      # ... and reaches the other ranks over NVLink
+            if i >= 2:
+                landed[b].synchronize()                # the host buffers of step i-2 have been read below; reuse them
             if world == 1:
-                r, td, ti = W.evaluate_ranks(bufs[b][0], bufs[b][1], path="tc", topk=TOPK)
+                res = W.evaluate_ranks(bufs[b][0], bufs[b][1], path="tc", topk=TOPK)
             else:
-                r, td, ti = evaluate_ranks_sharded(bufs[b][0], bufs[b][1], g_offset, g_total, topk=TOPK)
+                res = evaluate_ranks_sharded(bufs[b][0], bufs[b][1], g_offset, g_total, topk=TOPK)
             free[b].record()
-            out = (r.cpu(), td.cpu(), ti.cpu())       # device -> host read of this step's result
+            download(b, res)                           # device -> host read of this step's result (ranks, top-k)
+            if i >= 1:
+                landed[b ^ 1].synchronize()            # step i-1 is on the host now
+                out = tuple(h.clone() for h in host_out[b ^ 1])
+        landed[(n - 1) % 2].synchronize()
+        out = tuple(h.clone() for h in host_out[(n - 1) % 2])
         return out
 
     run_e2e(2)
     e2e_ms, e2e_out = timed(lambda: run_e2e(steps), 1)
     clocks = sampler.stop() if rank == 0 else None      # sampled over both timed regions (device-resident and end-to-end)
     e2e_value = world * Q_TOTAL / (e2e_ms / steps / 1000.0)
+    # the same step's upload on an idle device: the PCIe floor under the end-to-end step time
+    torch.cuda.synchronize()
+    u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    u0.record()
+    for _ in range(3):
+        bufs[0][0].copy_(ov_host, non_blocking=True)
+        if rank == 0:
+            bufs[0][1].copy_(su_host, non_blocking=True)
+    u1.record()
+    torch.cuda.synchronize()
+    h2d_alone_ms = u0.elapsed_time(u1) / 3
     h2d = ov_host.numel() * 4 + su_host.numel() * 4     # rank 0; the other ranks upload their gallery shard only
     d2h = sum(t.numel() * t.element_size() for t in e2e_out)
 
@@ -386,7 +422,9 @@ def run_ours(args):
         },
         "roofline": roofline,
         "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / steps,
-                "note": "W.evaluate_ranks() on pinned-host inputs; H2D of step i+1 double-buffered on a copy stream behind step i"
+                "h2d_alone_ms": h2d_alone_ms, "h2d_alone_gbs": h2d / h2d_alone_ms / 1e6,
+                "note": "W.evaluate_ranks() on pinned-host inputs; H2D of step i+1 double-buffered on a copy stream behind step i, "
+                        "D2H of step i's ranks and top-k into pinned host memory on a third stream, read by the host during step i+1"
                         + ("" if world == 1 else "; every rank uploads its gallery shard, rank 0 also the replicated query set, which is then broadcast over NCCL")},
         # per step: gallery prep, crop_norm, query prep, (hankel: spectral_rows x2,) spectral_pairs (true match), the sweep,
         # topk_merge, spectral_pairs (re-check), recheck_apply, topk_refine_pairs, spectral_pairs (top-k), topk_refine_sort
@@ -394,7 +432,7 @@ def run_ours(args):
         "clocks": clocks,
         "recall": {k: float(v) for k, v in recall.items()},
     }
-    if world == 1:
+    if world == 1 and not args.no_extras:
         line["dense_sweep"] = dense_sweep_roofline(torch, ops, ov, su, peak)
         line["gallery_sweep"] = gallery_size_sweep(torch, ops, device, value)
         v, cores, sample = cpu_reference_queries_per_s(15.0)
@@ -416,6 +454,9 @@ def main():
                     help="tensor-core sweep: spectral (correlation theorem, default where supported) or hankel (dense contraction over the shifts)")
     ap.add_argument("--gallery-per-gpu", type=int, default=G_PER_GPU,
                     help="gallery items per GPU (default 10000 = BASELINE configs[1]; 125000 on 8 GPUs = configs[3], the 1M-tile gallery)")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the side measurements after the timed regions (dense-sweep roofline, gallery-size sweep): "
+                         "what the ncu launch list of the step is taken with")
     args = ap.parse_args()
     G_PER_GPU = args.gallery_per_gpu
     if args.impl == "reference":

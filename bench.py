@@ -242,6 +242,7 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # stdout carries the one JSON line only (NCCL_DEBUG=VERSION prints there)
         dist.init_process_group("nccl", device_id=device)
     steps, warmup = max(1, args.steps), max(3, args.warmup)
 

@@ -135,7 +135,7 @@ static bool plan_layout(int in_h, int in_w, int out_h, int out_w, int antialias,
 // ------------------------------------------------------------------------------------------
 struct ResizeArgs {
   const unsigned char* src;       // 16-byte aligned
-  const unsigned char* src_end16; // end of the source tensor rounded up to 16 bytes
+  const unsigned char* src_end;   // one past the last byte of the source tensor
   float* dst;
   long long n_planes;
   int n_ch;
@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(256) resize_norm_kernel(const ResizeArgs a) {
   for (int i = tid; i < a.tile_rows * pitch_cols + kMidPad; i += 256) mid[i] = 0.0f;
 
   // A: asynchronous copy of plane p's source rectangle [r_lo, r_hi) x [c_lo, c_hi) into landing buffer `buf`.
-  // Row rr lands from the aligned chunk that holds its first byte; chunks past the tensor's last chunk are skipped.
+  // Row rr lands from the aligned chunk that holds its first byte; chunks past the tensor's end are skipped.
   auto prefetch = [&](long long p, int buf) {
     const unsigned char* rect = a.src + (size_t)p * plane_bytes + ((size_t)r_lo * a.in_w + c_lo) * ESZ;
     unsigned char* land = smem + (size_t)buf * a.land_bytes;
@@ -265,7 +265,12 @@ __global__ void __launch_bounds__(256) resize_norm_kernel(const ResizeArgs a) {
       if (ch >= n_chunks) { ch -= n_chunks; ++rr; if (rr >= span) break; }
       const unsigned char* g = rect + (size_t)rr * row_bytes;
       const unsigned char* chunk = g - (reinterpret_cast<uintptr_t>(g) & 15) + 16 * ch;
-      if (chunk < a.src_end16) cp_async16(land + rr * pitch_bytes + 16 * ch, chunk);
+      unsigned char* dst = land + rr * pitch_bytes + 16 * ch;
+      if (chunk + 16 <= a.src_end) {
+        cp_async16(dst, chunk);
+      } else if (chunk < a.src_end) {                 // the tensor's last, partial chunk: nothing is read past its end
+        for (int k = 0; k < (int)(a.src_end - chunk); ++k) dst[k] = __ldg(chunk + k);
+      }
     }
     cp_async_commit();
   };
@@ -479,7 +484,7 @@ extern "C" int witw_resize_norm(const void* src_dev, int src_is_u8, float* dst_d
   ResizeArgs a;
   std::memset(&a, 0, sizeof(a));
   a.src = static_cast<const unsigned char*>(src_dev);
-  a.src_end16 = a.src + align16((size_t)n_planes * h.in_h * h.in_w * esz);
+  a.src_end = a.src + (size_t)n_planes * h.in_h * h.in_w * esz;
   a.dst = dst_dev; a.n_planes = n_planes; a.n_ch = n_ch;
   a.in_h = h.in_h; a.in_w = h.in_w; a.out_h = h.out_h; a.out_cols = col_count; a.full_w = h.out_w; a.col_start = col_start;
   a.sx = reinterpret_cast<const int32_t*>(base + h.off_sx);

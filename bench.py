@@ -33,7 +33,8 @@ G_PER_GPU = 10000
 Q_TOTAL = 10000
 FOV = 360
 TOPK = 10
-FLOP_PER_PAIR = 2 * 64 * 16 * 4 * 64  # 2*W*C*H*sw = 524 288 at 360 deg
+SW = 64                                # query columns: int(fov/360*512)//8 (cvig_fov.py:22, 8 image pixels per feature column)
+FLOP_PER_PAIR = 2 * 64 * 16 * 4 * SW   # 2*W*C*H*sw = 524 288 at 360 deg, 131 072 at 90 deg
 METRIC = "queries/sec vs gallery size (orientation-searched distance + top-k)"
 
 
@@ -54,12 +55,20 @@ class ClockSampler(object):
         self.index = index
         self.lines = []
         self.proc = None
+        self.first = 0
+
+    def mark(self):
+        """Samples taken before this call (sampler start-up, warm-up steps) are not reported."""
+        self.first = len(self.lines)
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
                                           "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
+            deadline = time.time() + 5.0                 # wait until it has attached to the driver and delivers samples
+            while not self.lines and time.time() < deadline and self.proc.poll() is None:
+                time.sleep(0.01)
         except OSError:
             self.proc = None
 
@@ -73,7 +82,7 @@ class ClockSampler(object):
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for ln in self.lines:
+        for ln in self.lines[self.first:]:
             parts = [p.strip() for p in ln.split(",")]
             if len(parts) < 7:
                 continue
@@ -125,7 +134,7 @@ def cpu_reference_queries_per_s(budget_s=15.0):
     t0 = time.perf_counter()
     O.rank_loop(ov, su, query_indices=list(range(n)))
     dt = time.perf_counter() - t0
-    return n / dt, cores, "first %d queries of the 10k-query set against the full 10k gallery (%.1f s)" % (n, dt)
+    return n / dt, cores, "first %d queries of the %d-query set against the full %d-item gallery (%.1f s)" % (n, Q_TOTAL, G_PER_GPU, dt)
 
 
 def run_reference(args):
@@ -145,7 +154,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
         "ms_per_step": 1000.0 * Q_TOTAL / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": "cvig_fov 360deg eval, 10k queries x 10k gallery, rank loop (BASELINE configs[1]); CPU port of the reference's PyTorch path",
+        "config": {"workload": "cvig_fov %ddeg eval, %d queries x %d gallery, rank loop (BASELINE %s); CPU port of the reference's PyTorch path"
+                               % (FOV, Q_TOTAL, G_PER_GPU, config_name(G_PER_GPU)),
                    "gallery": G_PER_GPU, "queries": Q_TOTAL, "fov": FOV},
         "cpu_baseline": {"value": value, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -159,25 +169,25 @@ def make_data(torch, device, n_gallery, n_query, seed, planted):
     gen = torch.Generator(device=device).manual_seed(seed)
     ov = torch.randn(n_gallery, 16, 4, 64, generator=gen, device=device) * 0.06
     qgen = torch.Generator(device=device).manual_seed(1234)
-    su = torch.randn(n_query, 16, 4, 64, generator=qgen, device=device) * 0.06
+    su = torch.randn(n_query, 16, 4, SW, generator=qgen, device=device) * 0.06
     if planted:
         n = min(n_gallery, n_query)
         shifts = torch.randint(0, 64, (n,), generator=qgen, device=device)
-        cols = (shifts.view(n, 1) + torch.arange(64, device=device).view(1, 64)) % 64
-        su[:n] = torch.gather(ov[:n], 3, cols.view(n, 1, 1, 64).expand(n, 16, 4, 64)) + 0.5 * su[:n]
+        cols = (shifts.view(n, 1) + torch.arange(SW, device=device).view(1, SW)) % 64
+        su[:n] = torch.gather(ov[:n], 3, cols.view(n, 1, 1, SW).expand(n, 16, 4, SW)) + 0.5 * su[:n]
     return ov, su
 
 
-def dense_sweep_roofline(torch, ops, ov, su, peak, iters=5):
+def dense_sweep_roofline(torch, ops, ov, su, peak, true_idx=None, iters=5):
     """The north star's kernel (2): the shift search as one dense bf16 contraction on tcgen05 (csrc/match_tc.cu), timed alone
     on the bench workload with CUDA events -- the tensor-pipe roofline figure that the spectral default cannot show, because
     the spectral sweep does 31x fewer tensor FLOPs per pair.  Outside the timed step; N=1 only."""
-    gallery = ops.GalleryIndex(ov, 64, impl="hankel")
+    gallery = ops.GalleryIndex(ov, SW, impl="hankel")
     queries = ops.QueryBatch(su, impl="hankel")
     evs = []
     for i in range(2 + iters):
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-        ops.evaluate_ranks_prepared(gallery, queries, topk=TOPK, events=ev)
+        ops.evaluate_ranks_prepared(gallery, queries, true_idx=true_idx, topk=TOPK, events=ev)
         if i >= 2:
             evs.append(ev)
     torch.cuda.synchronize()
@@ -186,8 +196,8 @@ def dense_sweep_roofline(torch, ops, ov, su, peak, iters=5):
     del gallery, queries
     return {"kernel": "match_tc_kernel", "bound": "tensor", "kernel_ms": ms, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
             "frac": achieved / peak, "launches": iters,
-            "note": "dense contraction over all 64 shifts, 524 288 tensor FLOP per pair as executed; same operands and epilogue outputs "
-                    "(rank count + top-k candidates) as the step's spectral sweep; ncu: profiles/match_tc_r1c.txt"}
+            "note": "dense contraction over all 64 shifts, %d tensor FLOP per pair as executed; same operands and epilogue outputs "
+                    "(rank count + top-k candidates) as the step's spectral sweep; ncu: profiles/match_tc_r1c.txt" % FLOP_PER_PAIR}
 
 
 def gallery_size_sweep(torch, ops, device, value_10k, sizes=(1000, 100000), iters=5):
@@ -198,11 +208,11 @@ def gallery_size_sweep(torch, ops, device, value_10k, sizes=(1000, 100000), iter
             ov, su = make_data(torch, device, g, Q_TOTAL, seed=7, planted=False)
             true_idx = torch.arange(Q_TOTAL, device=device) % g
             gen = torch.Generator(device=device).manual_seed(11)      # every query is a rolled, noised copy of its gallery item
-            cols = (torch.randint(0, 64, (Q_TOTAL, 1), generator=gen, device=device) + torch.arange(64, device=device).view(1, 64)) % 64
-            su = torch.gather(ov[true_idx], 3, cols.view(Q_TOTAL, 1, 1, 64).expand(Q_TOTAL, 16, 4, 64)) + 0.5 * su
+            cols = (torch.randint(0, 64, (Q_TOTAL, 1), generator=gen, device=device) + torch.arange(SW, device=device).view(1, SW)) % 64
+            su = torch.gather(ov[true_idx], 3, cols.view(Q_TOTAL, 1, 1, SW).expand(Q_TOTAL, 16, 4, SW)) + 0.5 * su
 
             def step():
-                return ops.evaluate_ranks_prepared(ops.GalleryIndex(ov, 64), ops.QueryBatch(su), true_idx=true_idx, topk=TOPK)
+                return ops.evaluate_ranks_prepared(ops.GalleryIndex(ov, SW), ops.QueryBatch(su), true_idx=true_idx, topk=TOPK)
 
             for _ in range(3):
                 step()
@@ -222,6 +232,18 @@ def gallery_size_sweep(torch, ops, device, value_10k, sizes=(1000, 100000), iter
         torch.cuda.empty_cache()
     rows.append({"gallery": G_PER_GPU, "queries": Q_TOTAL, "queries_per_s": value_10k, "note": "the timed step above"})
     return sorted(rows, key=lambda r: r["gallery"])
+
+
+def config_name(g_total):
+    if (FOV, Q_TOTAL, G_PER_GPU) == (360, 10000, 10000):
+        return "configs[1]"
+    if (FOV, Q_TOTAL, G_PER_GPU) == (90, 10000, 10000):
+        return "configs[2]"
+    if FOV == 360 and g_total == 1000000:
+        return "configs[3]"
+    if FOV == 90 and g_total == 100000:
+        return "configs[4], correlation-sweep half"
+    return "a variation of configs[1]"
 
 
 def run_ours(args):
@@ -251,15 +273,18 @@ def run_ours(args):
     g_total = world * G_PER_GPU
     sweep_events = []
 
+    # query i matches gallery item i; with more queries than gallery items the match indices wrap around
+    true_idx = None if Q_TOTAL <= g_total else torch.arange(Q_TOTAL, device=device) % g_total
+
     def step_device():
         """fp32 features in HBM -> ranks (+ top-k)."""
         if world == 1:
-            gallery = ops.GalleryIndex(ov, 64)
+            gallery = ops.GalleryIndex(ov, SW)
             queries = ops.QueryBatch(su)
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             sweep_events.append(ev)
-            return ops.evaluate_ranks_prepared(gallery, queries, topk=TOPK, events=ev)
-        return evaluate_ranks_sharded(ov, su, g_offset, g_total, topk=TOPK, local=timed_local)
+            return ops.evaluate_ranks_prepared(gallery, queries, true_idx=true_idx, topk=TOPK, events=ev)
+        return evaluate_ranks_sharded(ov, su, g_offset, g_total, true_idx=true_idx, topk=TOPK, local=timed_local)
 
     timed_local = W.sharded.CudaLocal(event_sink=sweep_events)
 
@@ -283,14 +308,16 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()), out
 
+    # the sampler starts before the warm-up: the first nvidia-smi on a fresh box takes a while to attach to the driver and
+    # stalls kernel launches while it does (seen once as 12.6 instead of 7.65 ms per step when it started with the timed region)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(warmup):
         out = step_device()
     torch.cuda.synchronize()
     sweep_events.clear()
-
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    sampler.mark()
     ms_total, out = timed(step_device, steps)
     ms_step = ms_total / steps
     value = world * Q_TOTAL / (ms_step / 1000.0)
@@ -349,9 +376,9 @@ def run_ours(args):
             if i >= 2:
                 landed[b].synchronize()                # the host buffers of step i-2 have been read below; reuse them
             if world == 1:
-                res = W.evaluate_ranks(bufs[b][0], bufs[b][1], path="tc", topk=TOPK)
+                res = W.evaluate_ranks(bufs[b][0], bufs[b][1], true_idx=true_idx, path="tc", topk=TOPK)
             else:
-                res = evaluate_ranks_sharded(bufs[b][0], bufs[b][1], g_offset, g_total, topk=TOPK)
+                res = evaluate_ranks_sharded(bufs[b][0], bufs[b][1], g_offset, g_total, true_idx=true_idx, topk=TOPK)
             free[b].record()
             download(b, res)                           # device -> host read of this step's result (ranks, top-k)
             if i >= 1:
@@ -386,9 +413,9 @@ def run_ours(args):
 
     peak, peak_src = measured_peaks()
     achieved = FLOP_PER_PAIR * float(G_PER_GPU) * float(Q_TOTAL) / (kernel_ms / 1000.0) / 1e12
-    sweep_impl = ops._pick_impl(None, 64, 64, 64)
+    sweep_impl = ops._pick_impl(None, 64, 64, SW)
     kernel = "match_spec_kernel" if sweep_impl == "spectral" else "match_tc_kernel"
-    traffic, traffic_src = measured_traffic(kernel)
+    traffic, traffic_src = measured_traffic(kernel) if (FOV == 360 and G_PER_GPU == 10000 and Q_TOTAL == 10000) else (None, None)
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
                 "traffic_source": traffic_src, "kernel": kernel, "kernel_ms": kernel_ms, "flop_per_pair": FLOP_PER_PAIR, "peak_source": peak_src}
     if sweep_impl == "spectral":
@@ -397,8 +424,8 @@ def run_ours(args):
         exec_tc = 2.0 * 128 * 16 * 16 * 256 / 1024.0          # FLOP per pair issued as tcgen05.mma (256 MMAs of 128x16x16 per 1024 pairs)
         smem_bytes = 2.0 * (256 * 4608) / 1024.0              # per pair: operand bytes written by TMA + read by the MMAs
         roofline.update({
-            "note": "frac > 1: achieved counts the direct form's 524 288 FLOP per pair; the kernel evaluates the same correlation "
-                    "through the correlation theorem with %d tensor FLOP + ~1 000 CUDA-core FLOP per pair" % int(exec_tc),
+            "note": "frac > 1: achieved counts the direct form's %d FLOP per pair; the kernel evaluates the same correlation "
+                    "through the correlation theorem with %d tensor FLOP + ~1 000 CUDA-core FLOP per pair" % (FLOP_PER_PAIR, int(exec_tc)),
             "executed_tensor_tflops": exec_tc * float(G_PER_GPU) * float(Q_TOTAL) / (kernel_ms / 1000.0) / 1e12,
             "bound_detail": "shared-memory bandwidth feeding N=16 UMMAs (query stage written once by TMA, read once per 8 gallery items)",
             "smem_gbs_per_sm": smem_bytes * float(G_PER_GPU) * float(Q_TOTAL) / 148.0 / (kernel_ms / 1000.0) / 1e9,
@@ -407,13 +434,13 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {
-            "workload": "cvig_fov 360deg eval: 10k queries x %d-item gallery per GPU, orientation-searched distance + rank count + top-%d "
-                        "(BASELINE %s%s)" % (G_PER_GPU, TOPK, "configs[1]" if G_PER_GPU == 10000 else "configs[3] when gallery_total = 1M",
+            "workload": "cvig_fov %ddeg eval: %d queries x %d-item gallery per GPU, orientation-searched distance + rank count + top-%d "
+                        "(BASELINE %s%s)" % (FOV, Q_TOTAL, G_PER_GPU, TOPK, config_name(g_total),
                                              "" if world == 1 else "; gallery sharded, one shard per GPU, NCCL count all-reduce + top-k all-gather"),
             "gallery_total": g_total, "gallery_per_gpu": G_PER_GPU, "queries": Q_TOTAL, "fov": FOV, "feature_shape": [16, 4, 64],
             "unit_note": "one unit = one query swept over one %d-item gallery shard; queries/s over the whole %d-item gallery = %.1f" % (G_PER_GPU, g_total, value / world),
-            "l2_policy": "inputs larger than L2 (fp32 features 328 MB + fp32 spectra 328 MB + bf16 operands %s per step vs 126 MB L2)"
-                         % ("240 MB" if sweep_impl == "spectral" else "1.3 GB"),
+            "l2_policy": "inputs larger than L2 (fp32 features %d MB + their fp32 spectra + the bf16 operands per step vs 126 MB L2)"
+                         % ((G_PER_GPU * 64 * 64 + Q_TOTAL * 64 * SW) * 4 // 1000000),
             "sweep": sweep_impl,
             "step": ("fp32 features in HBM -> operand prep (bf16 azimuth spectra in UMMA layout, norms, fp32 spectra) -> fp32 true-match distances -> "
                      "tcgen05 per-frequency products + in-register inverse FFT, argmax, distance, rank count, top-k -> fp32 re-check of near-threshold "
@@ -434,8 +461,9 @@ def run_ours(args):
         "recall": {k: float(v) for k, v in recall.items()},
     }
     if world == 1 and not args.no_extras:
-        line["dense_sweep"] = dense_sweep_roofline(torch, ops, ov, su, peak)
+        line["dense_sweep"] = dense_sweep_roofline(torch, ops, ov, su, peak, true_idx)
         line["gallery_sweep"] = gallery_size_sweep(torch, ops, device, value)
+    if world == 1:
         v, cores, sample = cpu_reference_queries_per_s(15.0)
         line["cpu_baseline"] = {"value": v, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample}
     print(json.dumps(line))
@@ -445,7 +473,7 @@ def run_ours(args):
 
 
 def main():
-    global G_PER_GPU
+    global G_PER_GPU, FOV, Q_TOTAL, SW, FLOP_PER_PAIR
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -455,11 +483,18 @@ def main():
                     help="tensor-core sweep: spectral (correlation theorem, default where supported) or hankel (dense contraction over the shifts)")
     ap.add_argument("--gallery-per-gpu", type=int, default=G_PER_GPU,
                     help="gallery items per GPU (default 10000 = BASELINE configs[1]; 125000 on 8 GPUs = configs[3], the 1M-tile gallery)")
+    ap.add_argument("--fov", type=int, default=FOV, help="field of view of the queries in degrees (default 360; 90 = BASELINE configs[2] / [4])")
+    ap.add_argument("--queries", type=int, default=Q_TOTAL, help="number of queries (default 10000)")
     ap.add_argument("--no-extras", action="store_true",
                     help="skip the side measurements after the timed regions (dense-sweep roofline, gallery-size sweep): "
                          "what the ncu launch list of the step is taken with")
     args = ap.parse_args()
     G_PER_GPU = args.gallery_per_gpu
+    FOV, Q_TOTAL = args.fov, args.queries
+    SW = int(FOV / 360 * 512) // 8
+    if not 1 <= SW <= 64:
+        raise SystemExit("bench.py: --fov must give 1..64 feature columns, got %d" % SW)
+    FLOP_PER_PAIR = 2 * 64 * 16 * 4 * SW
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)

@@ -14,9 +14,10 @@
 //      16-byte cp.async copies of aligned global chunks, while the current plane is computed.  Rows of an image whose row
 //      pitch is not a multiple of 16 bytes start at any byte offset inside their first chunk; the offset is a per-row
 //      constant that phase B applies (a funnel shift of two adjacent words on the rows that are not word aligned).
-//   B  y pass first (it shrinks the rows by the scale factor before the irregular x pass): a warp owns an output row, a
-//      lane four adjacent source columns -- one 32-bit shared load brings four uint8 pixels (a float4 for aligned fp32
-//      rows) per tap row, blended with packed f32x2 operations -- and writes the fp32 intermediate tile
+//   B  y pass first (it shrinks the rows by the scale factor before the irregular x pass): 8, 16 or 32 lanes share an output
+//      row and a lane owns one to three adjacent four-pixel groups (the host picks the split with the fewest instructions per
+//      row for the tile width) -- one 32-bit shared load brings four uint8 pixels (a float4 for aligned fp32 rows) per tap
+//      row, PRMT + packed FADD2 turn the bytes into floats, packed FFMA2 blends them -- and writes the fp32 intermediate tile
 //   C  x pass: a thread owns one output column (its taps live in registers), blends, normalises, stores 128-byte rows.
 // ATen runs the x pass first and rounds its intermediate to fp32; running y first moves results by an ulp or two of the
 // pixel scale (measured against the oracle in tests/test_gpu_resize.py), well inside the parity tolerance.
@@ -150,11 +151,6 @@ struct ResizeArgs {
   int normalize;                  // 0: resize only, 1: (v / divisor - mean) / std with IEEE divisions, 2: v * scale + bias
   float divisor[8], mean[8], stdv[8], scale[8], bias[8];
 };
-
-// uint8 -> fp32 without the conversion pipe: byte i of w becomes the mantissa of 2^23 + v
-__device__ __forceinline__ float byte_to_float(uint32_t w, int i) {
-  return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540u + i)) - 8388608.0f;
-}
 
 // phase B: one tap row of GPL adjacent four-column groups, accumulated with packed f32x2 operations (two columns per
 // instruction).  `row` points at the 4-byte word holding the row's first needed byte and `bs` is that byte's bit offset

@@ -154,6 +154,20 @@ int witw_l2_distance_backward_f32(const float* crop_dev, const float* su_dev, co
                                   float* grad_crop_dev, float* grad_su_dev, float* coef_scratch_dev,
                                   int64_t G, int64_t Q, int64_t K, witw_stream_t stream);
 
+/* The training slice of train() (cvig_fov.py:450-460) without the [G,Q,C,H,sw] crop: the forward is witw_match_f32
+ * (orientation + distance); this is the backward of distance = l2_distance(crop_overhead(ov, ori), su) with respect to
+ * both feature sets, from the features, the orientation and grad_dist [G,Q].  grad_ov [G,CH,W] / grad_su [Q,CH,sw]:
+ * either may be NULL; coef_scratch: [G,Q,3] fp32.  Deterministic (no atomics). */
+int witw_match_backward_f32(const float* ov_dev, const float* su_dev, const int64_t* ori_dev,
+                            const float* grad_dist_dev, float* grad_ov_dev, float* grad_su_dev,
+                            float* coef_scratch_dev, int64_t G, int64_t Q, int CH, int W, int sw,
+                            witw_stream_t stream);
+
+/* triplet_loss (cvig_fov.py:366-382): the soft-margin triplet loss of a [N,N] distance matrix whose diagonal holds the
+ * matching pairs, loss_dev[0], and (optionally) its gradient grad_dist_dev [N,N].  2 <= N <= 4096. */
+int witw_triplet_loss_f32(const float* dist_dev, int N, float alpha, float* loss_dev,
+                          float* grad_dist_dev, witw_stream_t stream);
+
 /* Tensor-core path (tcgen05, bf16 operands, fp32 accumulation in TMEM); W must be 64.
  * gallery_prep writes the gallery operand (pre-shifted 16-byte rows that a no-swizzle UMMA
  * descriptor reads as the Hankel matrix of all 64 azimuth shifts) and the table

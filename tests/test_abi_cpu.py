@@ -163,6 +163,16 @@ def test_install_rebinds_and_restores():
     assert hasattr(mod, "evaluate_ranks") and set(orig) >= {"correlation", "l2_distance"}
     W.uninstall(mod)
     assert mod.correlation is orig["correlation"] and not hasattr(mod, "evaluate_ranks")
+    assert not hasattr(mod, "triplet_loss") and not hasattr(mod, "Resize")
+    # the loss and the dataset transforms are rebound only where the module has them / on request
+    mod.triplet_loss, mod.Resize, mod.ImageNormalization = object(), object(), object()
+    orig = W.install(mod, transforms=True)
+    assert mod.triplet_loss is W.triplet_loss and mod.Resize is W.Resize and mod.ImageNormalization is W.ImageNormalization
+    W.uninstall(mod)
+    assert mod.triplet_loss is orig["triplet_loss"] and mod.Resize is orig["Resize"]
+    W.install(mod)
+    assert mod.Resize is orig["Resize"] and mod.triplet_loss is W.triplet_loss
+    W.uninstall(mod)
     with pytest.raises(AttributeError):
         W.install(types.ModuleType("not_cvig"))
 

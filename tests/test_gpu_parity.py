@@ -297,6 +297,59 @@ def test_train_step_gradients_match_reference_autograd(W):
         W.evaluate_ranks(ov_g, su_g)
 
 
+def test_fused_train_step_matches_reference_autograd(W):
+    """match_distance (no [G,Q,C,H,sw] crop in either direction) + the one-kernel triplet_loss against torch autograd through
+    the oracle's functions, fp32 and float64; and against the unfused rebound names, which share the arithmetic."""
+    def triplet_loss(distances, alpha=10.0):                     # cvig_fov.py:366-382
+        n = distances.shape[0]
+        m = torch.diagonal(distances)
+        a = torch.sum(torch.log(1.0 + torch.exp(alpha * (m - distances))))
+        b = torch.sum(torch.log(1.0 + torch.exp(alpha * (m.unsqueeze(1) - distances))))
+        return (a + b) / (2.0 * n * (n - 1))
+
+    def oracle_grads(ov, su, dtype, alpha):
+        o = ov.to(dtype).clone().requires_grad_(True)
+        s = su.to(dtype).clone().requires_grad_(True)
+        dist = O.l2_distance(O.crop_overhead(o, O.correlation(o, s), su.shape[3]), s)
+        loss = triplet_loss(dist, alpha)
+        loss.backward()
+        return dist.detach(), loss.item(), o.grad.double(), s.grad.double()
+
+    for fov, n, alpha in ((360, 16, 10.0), (90, 13, 10.0), (180, 8, 2.0)):
+        ov, su, _ = O.synth_features(n, n, fov=fov, noise=1.0, seed=fov + 7)
+        d32, l32, go32, gs32 = oracle_grads(ov, su, torch.float32, alpha)
+        d64, l64, go64, gs64 = oracle_grads(ov, su, torch.float64, alpha)
+        o, s = ov.cuda().requires_grad_(True), su.cuda().requires_grad_(True)
+        dist, ori = W.match_distance(o, s)
+        assert not ori.requires_grad and torch.equal(ori.cpu(), O.correlation(ov, su))
+        assert (dist.detach().cpu() - d32).abs().max().item() <= 5e-6
+        loss = W.triplet_loss(dist, alpha)
+        assert loss.dim() == 0 and abs(loss.item() - l64) <= 1e-5 * abs(l64)
+        loss.backward()
+        for got, r32, r64 in ((o.grad.cpu().double(), go32, go64), (s.grad.cpu().double(), gs32, gs64)):
+            allowed = max(3.0 * (r32 - r64).abs().max().item(), 1e-5 * r64.abs().max().item())
+            assert (got - r64).abs().max().item() <= allowed
+        # the loss kernel alone against torch on the same matrix (values and gradient), incl. a non-default alpha
+        # (float64 torch is the yardstick: fp32 autograd adds the diagonal's +-alpha/z halves to the small terms before they
+        # cancel and loses ~0.2 % of the diagonal gradient; the kernel never forms them)
+        dm = dist.detach().double().clone().requires_grad_(True)
+        triplet_loss(dm, alpha).backward()
+        dk = dist.detach().clone().requires_grad_(True)
+        lk = W.triplet_loss(dk, alpha)
+        (3.0 * lk).backward()                                     # a scaled upstream gradient
+        assert (dk.grad.double() - 3.0 * dm.grad).abs().max().item() <= 3e-6 * 3.0 * dm.grad.abs().max().item()
+        # gradient with respect to one side only
+        s2 = su.cuda().requires_grad_(True)
+        d2, _ = W.match_distance(ov.cuda(), s2)
+        d2.sum().backward()
+        assert s2.grad is not None and torch.isfinite(s2.grad).all()
+    # no gradient requested: plain forward
+    d3, o3 = W.match_distance(ov.cuda(), su.cuda())
+    assert not d3.requires_grad and torch.equal(o3.cpu(), O.correlation(ov, su))
+    with pytest.raises(ValueError):
+        W.triplet_loss(torch.zeros(3, 4, device="cuda"))
+
+
 # ----------------------------------------------------------------------------- f4: uint8 -> normalised polar
 def test_normalized_polar_exact_matches_reference_chain(W, golden):
     """exact=True: bit-identical to ImageNormalization -> PolarTransform of the unmodified reference (golden prep.npz)."""

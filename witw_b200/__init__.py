@@ -23,6 +23,7 @@ from .ops import (
     heatmap_scores,
     l2_distance,
     match,
+    match_distance,
     normalized_polar,
     polar_grid,
     polar_transform,
@@ -33,6 +34,7 @@ from .ops import (
     sweep_tc,
     tc_supported,
     topk_from_distances,
+    triplet_loss,
     true_match_distances,
 )
 from .install import install, uninstall
@@ -41,7 +43,7 @@ from .sharded import evaluate_ranks_sharded, shard_bounds
 __all__ = [
     "GalleryBuilder", "GalleryIndex", "ImageNormalization", "PolarTransform", "QueryBatch", "Resize", "WitwError", "baseline_ranks", "bilinear_interpolate", "correlation",
     "correlation_scores", "crop_overhead", "evaluate_ranks", "evaluate_ranks_prepared", "evaluate_ranks_sharded",
-    "heatmap_scores", "install", "l2_distance", "match", "normalized_polar", "polar_grid", "polar_transform", "prepare_pair", "rank_from_distances",
-    "recall_from_ranks", "resize_normalize", "shard_bounds", "sweep_tc", "tc_supported", "topk_from_distances", "true_match_distances",
+    "heatmap_scores", "install", "l2_distance", "match", "match_distance", "normalized_polar", "polar_grid", "polar_transform", "prepare_pair", "rank_from_distances",
+    "recall_from_ranks", "resize_normalize", "shard_bounds", "sweep_tc", "tc_supported", "topk_from_distances", "triplet_loss", "true_match_distances",
     "uninstall",
 ]

@@ -39,6 +39,9 @@ SIGNATURES = {
     "witw_l2_distance_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
     "witw_crop_backward_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p]),
     "witw_l2_distance_backward_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
+    "witw_match_backward_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int,
+                                        c_int, c_void_p]),
+    "witw_triplet_loss_f32": (c_int, [c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p]),
     "witw_gallery_operand_bytes": (c_size_t, [c_int64, c_int, c_int]),
     "witw_query_operand_bytes": (c_size_t, [c_int64, c_int, c_int]),
     "witw_gallery_prep": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),

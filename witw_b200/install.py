@@ -12,7 +12,9 @@ attributes on the imported module therefore swaps the hot path for every caller:
 from . import ops
 
 _REBOUND = ("bilinear_interpolate", "PolarTransform", "correlation", "crop_overhead", "l2_distance")
-_ADDED = ("match", "evaluate_ranks", "recall_from_ranks", "heatmap_scores", "polar_transform")
+# train() picks its loss up as a module global too (cvig_fov.py:413); rebound where the module defines it
+_REBOUND_IF_PRESENT = ("triplet_loss",)
+_ADDED = ("match", "match_distance", "evaluate_ranks", "recall_from_ranks", "heatmap_scores", "polar_transform")
 
 
 # the dataset transforms upstream of PolarTransform (cvig_fov.py:100-149); rebound only on request because the reference runs
@@ -32,6 +34,10 @@ def install(module, transforms=False):
             raise AttributeError("install: %s has no attribute %r -- not a WITW cvig module?" % (getattr(module, "__name__", module), name))
         originals[name] = getattr(module, name)
         setattr(module, name, getattr(ops, name))
+    for name in _REBOUND_IF_PRESENT:
+        if hasattr(module, name):
+            originals[name] = getattr(module, name)
+            setattr(module, name, getattr(ops, name))
     for name in _ADDED:
         if hasattr(module, name):
             originals[name] = getattr(module, name)
@@ -45,7 +51,7 @@ def uninstall(module):
     originals = getattr(module, "_witw_b200_originals", None)
     if originals is None:
         return
-    for name in _REBOUND + _TRANSFORMS + _ADDED:
+    for name in _REBOUND + _REBOUND_IF_PRESENT + _TRANSFORMS + _ADDED:
         if name in originals:
             setattr(module, name, originals[name])
         elif name in _ADDED and hasattr(module, name):

@@ -805,6 +805,73 @@ def l2_distance(overhead_cropped, surface_embed):
     return _l2_forward(_f32c(overhead_cropped), _f32c(surface_embed), g, q, k)
 
 
+class _MatchDistanceFn(torch.autograd.Function):
+    """correlation -> crop_overhead -> l2_distance as one differentiable op (cvig_fov.py:450-453): the forward is the exact
+    fp32 match kernel, the backward works from the features and the orientation -- no [G,Q,C,H,sw] crop in either direction
+    (64 MB per 64 x 64 batch at 360 degrees in the reference, plus the same again for its gradient)."""
+
+    @staticmethod
+    def forward(ctx, overhead_embed, surface_embed):
+        ori, dist = match(overhead_embed.detach(), surface_embed.detach(), path="fp32")
+        ctx.save_for_backward(_f32c(overhead_embed), _f32c(surface_embed), ori)
+        ctx.mark_non_differentiable(ori)
+        return dist, ori
+
+    @staticmethod
+    def backward(ctx, grad_dist, _grad_ori):
+        ov, su, ori = ctx.saved_tensors
+        g, c, h, w = ov.shape
+        q, _, _, sw = su.shape
+        need_ov, need_su = ctx.needs_input_grad
+        gd = _f32c(grad_dist)
+        with torch.cuda.device(gd.device):
+            grad_ov = torch.empty_like(ov) if need_ov else None
+            grad_su = torch.empty_like(su) if need_su else None
+            coef = torch.empty((max(g * q, 1), 3), dtype=torch.float32, device=gd.device)
+            _lib.call("witw_match_backward_f32", ov.data_ptr(), su.data_ptr(), ori.data_ptr(), gd.data_ptr(), _ptr(grad_ov), _ptr(grad_su),
+                      coef.data_ptr(), g, q, c * h, w, sw, _stream())
+        return grad_ov, grad_su
+
+
+def match_distance(overhead_embed, surface_embed):
+    """(distance fp32 [G,Q], orientation int64 [G,Q]) of the training step (cvig_fov.py:450-453:
+    ``l2_distance(crop_overhead(ov, correlation(ov, su), sw), su)``) as one differentiable call: gradients flow to both
+    feature sets through the distance, none through the orientation (an argmax, as in the reference)."""
+    _need_cuda("match_distance", overhead_embed, surface_embed, allow_grad=True)
+    _feature_dims("match_distance", overhead_embed, surface_embed)
+    if torch.is_grad_enabled() and (overhead_embed.requires_grad or surface_embed.requires_grad):
+        return _MatchDistanceFn.apply(overhead_embed, surface_embed)
+    ori, dist = match(overhead_embed, surface_embed, path="fp32")
+    return dist, ori
+
+
+class _TripletLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, distances, alpha):
+        d = _f32c(distances)
+        n = d.shape[0]
+        with torch.cuda.device(d.device):
+            loss = torch.empty(1, dtype=torch.float32, device=d.device)
+            grad = torch.empty_like(d) if ctx.needs_input_grad[0] else None
+            _lib.call("witw_triplet_loss_f32", d.data_ptr(), n, float(alpha), loss.data_ptr(), _ptr(grad), _stream())
+        ctx.save_for_backward(grad)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        (grad,) = ctx.saved_tensors
+        return (None if grad is None else grad * grad_loss), None
+
+
+def triplet_loss(distances, alpha=10.):
+    """Drop-in for cvig_fov.py:366-382: the soft-margin triplet loss of a [N,N] distance matrix with the matching pairs on
+    its diagonal (0-dim tensor); loss and gradient come out of one kernel."""
+    _need_cuda("triplet_loss", distances, allow_grad=True)
+    if distances.dim() != 2 or distances.shape[0] != distances.shape[1]:
+        raise ValueError("triplet_loss: expected a square [N,N] distance matrix, got %s" % (tuple(distances.shape),))
+    return _TripletLossFn.apply(distances, alpha)
+
+
 # ----------------------------------------------------------------------------- K4
 def true_match_distances(overhead_embed, surface_embed, true_idx=None):
     """Exact fp32 (distance [Q], orientation [Q]) of each query against its matching gallery item."""

@@ -164,3 +164,18 @@ def test_plan_driven_resample_tracks_oracle():
                     acc = (acc + t[:, j] * p["wx"][c, j]).astype(np.float32)
                 out[y0:y1, c] = acc
     assert np.abs(out - O.resize_bilinear(x, oh, ow, True).numpy()).max() <= RESIZE_TOL
+
+
+def test_resize_plan_cache_is_bounded(monkeypatch):
+    """Datasets with many raw image sizes must not grow the plan cache without bound: least recently used plans go first."""
+    from witw_b200 import ops
+
+    monkeypatch.setattr(ops, "RESIZE_CACHE_ENTRIES", 3)
+    monkeypatch.setattr(ops, "_resize_cache", {})
+    dev = torch.device("cpu")                     # the cache logic is device-agnostic; kernels are not involved
+    for i in range(5):
+        ops._resize_plan(10 + i, 10, 8, 8, True, dev)
+    assert [k[0] for k in ops._resize_cache] == [12, 13, 14]
+    first = ops._resize_plan(12, 10, 8, 8, True, dev)
+    assert [k[0] for k in ops._resize_cache] == [13, 14, 12]
+    assert ops._resize_plan(12, 10, 8, 8, True, dev) is first

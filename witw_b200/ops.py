@@ -295,12 +295,19 @@ def resize_plan_host(in_h, in_w, out_h, out_w, antialias):
     return host
 
 
+RESIZE_CACHE_ENTRIES = 256      # plans kept per process (datasets with many distinct raw image sizes); least recently used go first
+
+
 def _resize_plan(in_h, in_w, out_h, out_w, antialias, device):
     key = (int(in_h), int(in_w), int(out_h), int(out_w), bool(antialias), str(device))
-    if key not in _resize_cache:
+    plan = _resize_cache.pop(key, None)
+    if plan is None:
         host = resize_plan_host(in_h, in_w, out_h, out_w, antialias)
-        _resize_cache[key] = (host, torch.from_numpy(host).to(device))
-    return _resize_cache[key]
+        plan = (host, torch.from_numpy(host).to(device))
+        while len(_resize_cache) >= RESIZE_CACHE_ENTRIES:
+            _resize_cache.pop(next(iter(_resize_cache)))
+    _resize_cache[key] = plan       # (re)inserted last: dicts keep insertion order, so the first key is the oldest use
+    return plan
 
 
 def resize_normalize(images, out_h, out_w, antialias=True, mean=None, std=None, divisor=255.0, col_start=0, col_count=None):

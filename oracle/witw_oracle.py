@@ -117,7 +117,7 @@ def resize_taps(in_size, out_size, antialias):
     align_corners=False).  The arithmetic lives in torch (third party, not under /root/reference):
 
     * antialias=False -- what the reference's pinned torchvision 0.9.1 / torch 1.8.1 (model/requirements.txt) computes:
-      ``src = max(scale*(i+0.5)-0.5, 0)``, ``i0 = int(src)``, ``i1 = i0 + (i0 < in-1)``, ``l1 = src - i0``, ``l0 = 1 - l1``
+      ``src = max(fma(scale, i+0.5, -0.5), 0)``, ``i0 = int(src)``, ``i1 = i0 + (i0 < in-1)``, ``l1 = src - i0``, ``l0 = 1 - l1``
       (ATen upsample_bilinear2d, area_pixel_compute_source_index), all in fp32, ``scale = float(in)/out``.
     * antialias=True -- what torchvision >= 0.17 does by default, i.e. the reference as it runs in the build container:
       triangle filter of half-width ``support = max(scale, 1)`` around ``center = scale*(i+0.5)``; taps
@@ -135,7 +135,10 @@ def resize_taps(in_size, out_size, antialias):
             if in_size == out_size:     # ATen: a scale of exactly 1 is a plain copy
                 start[i], count[i], wts[i, 0] = i, 1, 1.0
                 continue
-            src = max(f32(scale * f32(i + 0.5)) - f32(0.5), f32(0.0))
+            # ATen's builds contract ``scale * (i + 0.5) - 0.5`` into one fused multiply-add (one rounding; measured on the
+            # torch of the build container: with an inexact scale such as 100/300 the separately rounded form is off by up
+            # to 4e-6 in the weight); the float64 product of two floats is exact, so this is that fma
+            src = max(f32(np.float64(scale) * (i + 0.5) - 0.5), f32(0.0))
             i0 = int(src)
             l1 = min(max(f32(src - f32(i0)), f32(0.0)), f32(1.0))
             start[i] = i0

@@ -179,3 +179,30 @@ def test_resize_plan_cache_is_bounded(monkeypatch):
     first = ops._resize_plan(12, 10, 8, 8, True, dev)
     assert [k[0] for k in ops._resize_cache] == [13, 14, 12]
     assert ops._resize_plan(12, 10, 8, 8, True, dev) is first
+
+
+def test_random_geometries_plan_oracle_torch_agree():
+    """Seeded random sizes (integer and awkward ratios, 1-pixel axes, up- and downsampling): the library's host tables equal
+    the oracle's bit for bit, and the oracle's resize tracks ATen's."""
+    import torch.nn.functional as F
+
+    from witw_b200 import ops
+
+    rng = np.random.default_rng(20261017)
+    sizes = [(1, 7, 3, 64), (12, 9, 1, 1), (300, 100, 100, 300), (96, 512, 32, 128), (2, 2, 255, 257), (511, 513, 128, 512)]
+    while len(sizes) < 36:
+        ih, iw = (int(v) for v in rng.integers(1, 400, 2))
+        oh, ow = (int(v) for v in rng.integers(1, 300, 2))
+        if max(ih / oh, iw / ow) < 15:          # the kernel's tap limit (32 per output column) is tested elsewhere
+            sizes.append((ih, iw, oh, ow))
+    gen = torch.Generator().manual_seed(17)
+    for (ih, iw, oh, ow) in sizes:
+        x = torch.randint(0, 256, (1, ih, iw), generator=gen).float()
+        for aa in (True, False):
+            p = parse_plan(ops.resize_plan_host(ih, iw, oh, ow, aa))
+            sx, cx, wx = O.resize_taps(iw, ow, aa)
+            sy, cy, wy = O.resize_taps(ih, oh, aa)
+            for name, ref in (("sx", sx), ("cx", cx), ("wx", wx), ("sy", sy), ("cy", cy), ("wy", wy)):
+                assert np.array_equal(p[name], ref), (ih, iw, oh, ow, aa, name)
+            ref = F.interpolate(x[None], size=(oh, ow), mode="bilinear", align_corners=False, antialias=aa)[0]
+            assert (O.resize_bilinear(x, oh, ow, aa) - ref).abs().max().item() <= RESIZE_TOL, (ih, iw, oh, ow, aa)

@@ -61,7 +61,7 @@ static void axis_taps(int in_size, int out_size, int antialias, int k, int32_t* 
         start[i] = i; count[i] = 1; w[(size_t)i * k] = 1.0f;
         continue;
       }
-      float src = scale * ((float)i + 0.5f) - 0.5f;
+      float src = std::fmaf(scale, (float)i + 0.5f, -0.5f);   // ATen's builds contract this into one fused multiply-add
       if (src < 0.0f) src = 0.0f;
       int i0 = (int)std::floor(src);
       if (i0 > in_size - 1) i0 = in_size - 1;

@@ -186,3 +186,37 @@ def test_shard_bounds_partition():
         assert all(spans[i][1] == spans[i + 1][0] for i in range(p - 1))
         sizes = [b - a for a, b in spans]
         assert max(sizes) - min(sizes) <= 1
+
+
+def test_argument_validation_needs_no_device():
+    """The C ABI's error behaviour (status code + witw_last_error message) for bad arguments, checked without a GPU: every
+    call below must be refused before any CUDA work is attempted."""
+    from witw_b200 import _lib, ops
+
+    lib = _lib.load()
+    INVALID, UNSUPPORTED = -1, -2
+    # Resize front end
+    assert lib.witw_resize_plan_bytes(0, 10, 4, 4, 1) == 0
+    assert lib.witw_resize_plan_build(10, 10, 4, 4, 1, None) == INVALID and "null plan" in _lib.last_error()
+    plan = ops.resize_plan_host(20, 30, 8, 12, True)
+    one = np.ones(3, np.float32)
+    assert lib.witw_resize_norm(None, 1, None, 1, 3, None, None, 0, 12, None, None, None, None) == INVALID
+    assert lib.witw_resize_norm(None, 1, None, 1, 3, plan.ctypes.data, plan.ctypes.data, 12, 12, None, None, None, None) == INVALID
+    assert "column window" in _lib.last_error()
+    assert lib.witw_resize_norm(None, 1, None, 1, 9, plan.ctypes.data, plan.ctypes.data, 0, 12, one.ctypes.data, one.ctypes.data,
+                                one.ctypes.data, None) == INVALID and "8 channels" in _lib.last_error()
+    bad = plan.copy()
+    bad[:4] = 0                                   # not a plan: wrong magic
+    assert lib.witw_resize_norm(None, 1, None, 1, 3, bad.ctypes.data, bad.ctypes.data, 0, 12, None, None, None, None) == INVALID
+    assert lib.witw_resize_norm(None, 1, None, 1, 3, plan.ctypes.data, plan.ctypes.data, 0, 12, None, None, None, None) == INVALID
+    assert "null image pointer" in _lib.last_error()
+    assert lib.witw_resize_norm(None, 1, None, 0, 3, plan.ctypes.data, plan.ctypes.data, 0, 12, None, None, None, None) == 0   # no planes: nothing to do
+    # training slice
+    assert lib.witw_triplet_loss_f32(None, 1, 10.0, None, None, None) == UNSUPPORTED and "batch size" in _lib.last_error()
+    assert lib.witw_triplet_loss_f32(None, 8, 10.0, None, None, None) == INVALID
+    assert lib.witw_match_backward_f32(None, None, None, None, None, None, None, 4, 4, 64, 64, 65, None) == INVALID
+    assert lib.witw_match_backward_f32(None, None, None, None, None, None, None, 4, 4, 64, 64, 16, None) == INVALID
+    assert "null pointer" in _lib.last_error()
+    # matching kernels: shapes the kernels do not cover are refused with a reason
+    assert lib.witw_spec_supported(64, 64, 64) == 1 and lib.witw_spec_supported(32, 64, 64) == 0 and lib.witw_spec_supported(64, 32, 16) == 0
+    assert lib.witw_gallery_operand_bytes(10, 64, 0) == 0

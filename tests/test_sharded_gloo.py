@@ -45,7 +45,7 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, packed=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.set_num_threads(1)
@@ -55,16 +55,18 @@ def _worker(rank, world, port, out):
     ov, su, _ = O.synth_features(23, 17, fov=90, noise=10.0, seed=99)
     true_idx = torch.arange(17).flip(0)  # a permutation, so owners differ from the trivial layout
     lo, hi = shard_bounds(23, world, rank)
-    ranks, td, ti = evaluate_ranks_sharded(ov[lo:hi], su, lo, 23, true_idx=true_idx, topk=4, local=OracleLocal())
+    ranks, td, ti = evaluate_ranks_sharded(ov[lo:hi], su, lo, 23, true_idx=true_idx, topk=4, local=OracleLocal(), packed=packed)
     if rank == 0:
         np.savez(out, ranks=ranks.numpy(), td=td.numpy(), ti=ti.numpy())
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_two_shards_equal_one(tmp_path):
+@pytest.mark.parametrize("packed", [False, True])
+def test_two_shards_equal_one(tmp_path, packed):
+    """packed: counts and top-k candidates travel in one all-gather instead of an all-reduce and two all-gathers."""
     out = str(tmp_path / "r0.npz")
-    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), out, packed), nprocs=2, join=True)
     got = np.load(out)
     ov, su, _ = O.synth_features(23, 17, fov=90, noise=10.0, seed=99)
     true_idx = torch.arange(17).flip(0)

@@ -13,6 +13,8 @@ every rank holds all queries.  One sweep needs three tiny exchanges over NCCL / 
 The local compute is pluggable so the exchange logic is testable on CPU (gloo) with the
 oracle standing in for the kernels; the default is the CUDA path of ops.py.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -94,11 +96,29 @@ class CudaLocal(object):
         return out_d, out_i
 
 
-def evaluate_ranks_sharded(ov_local, surface_embed, g_offset, n_gallery_total, true_idx=None, topk=0, group=None, local=None):
+# One all-gather of [counts | top-k distances | top-k indices] per rank instead of an all-reduce and two all-gathers
+# (two collective launches fewer per sweep).  The logic is covered by the gloo test; it has not been timed over NCCL yet,
+# so it is opt-in (WITW_PACKED_EXCHANGE=1 or packed=True).
+PACKED_EXCHANGE = os.environ.get("WITW_PACKED_EXCHANGE", "0") == "1"
+
+
+def _exchange_packed(counts, td, ti, world, group):
+    """counts int64 [Q], td fp32 [Q,k], ti int32 [Q,k] of this shard -> (summed counts, [P,Q,k] distances, [P,Q,k] indices)."""
+    q, k = td.shape
+    mine = torch.cat((counts.to(torch.int32).reshape(q, 1), td.contiguous().view(torch.int32), ti.contiguous()), dim=1).contiguous()
+    parts = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine, group=group)
+    allp = torch.stack(parts)                                   # [P, Q, 1 + 2k] int32
+    total = allp[:, :, 0].to(torch.int64).sum(dim=0)
+    return total, allp[:, :, 1:1 + k].contiguous().view(torch.float32), allp[:, :, 1 + k:].contiguous()
+
+
+def evaluate_ranks_sharded(ov_local, surface_embed, g_offset, n_gallery_total, true_idx=None, topk=0, group=None, local=None,
+                           packed=None):
     """Sharded evaluate_ranks: every rank passes its gallery slice [g_offset, g_offset+G_local) and all queries.
 
     Returns ranks int64 [Q] (identical on every rank), plus merged (topk_dist, topk_idx) when topk > 0.
-    Works without an initialised process group (world size 1).
+    Works without an initialised process group (world size 1).  packed: see PACKED_EXCHANGE.
     """
     local = local or CudaLocal()
     world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
@@ -126,6 +146,11 @@ def evaluate_ranks_sharded(ov_local, surface_embed, g_offset, n_gallery_total, t
 
     # (2) local sweep, then the count reduction
     counts, td, ti = local.sweep(ov_local, surface_embed, d_true, t_idx, g_offset, topk)
+    packed = PACKED_EXCHANGE if packed is None else packed
+    if world > 1 and topk and packed and q > 0:
+        counts, all_d, all_i = _exchange_packed(counts, td, ti, world, group)
+        td, ti = local.merge(all_d, all_i, topk)
+        return counts, td, ti
     if world > 1:
         dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
     if not topk:

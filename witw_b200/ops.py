@@ -23,7 +23,6 @@ cvig_fov.py:450-460); correlation is an argmax and carries no gradient, as in th
 the fused forms (match, evaluate_ranks, ...) are forward-only and refuse tensors that require
 grad under an enabled grad mode rather than silently detaching them.
 """
-import math
 
 import numpy as np
 import torch

@@ -360,7 +360,8 @@ class Resize(object):
     """Drop-in for cvig_fov.py:100-134 on CUDA tensors ([C,H,W] samples or [N,C,H,W] batches, uint8 or fp32):
     the surface image to 128 x 512 and a window of ``int(fov/360*512)`` columns from a random start with wrap-around
     (panoramas, 'cvusa'), or straight to 128 x that width ('witw'); the overhead image to 256 x 256.  The start column is
-    drawn exactly as the reference draws it (``torch.randint(0, 512, ())`` on the CPU generator)."""
+    drawn exactly as the reference draws it (``torch.randint(0, 512, ())`` on the CPU generator), once per call: the images
+    of a batch share their start column; call it per sample, or use ``resize_normalize(col_start=...)``, for one draw each."""
 
     def __init__(self, dataset, fov=360, random_orientation=True, antialias=True, device=None):
         self.fov = fov

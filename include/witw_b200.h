@@ -168,117 +168,146 @@ int witw_match_backward_f32(const float* ov_dev, const float* su_dev, const int6
 int witw_triplet_loss_f32(const float* dist_dev, int N, float alpha, float* loss_dev,
                           float* grad_dist_dev, witw_stream_t stream);
 
-/* Tensor-core path (tcgen05, bf16 operands, fp32 accumulation in TMEM); W must be 64.
- * gallery_prep writes the gallery operand (pre-shifted 16-byte rows that a no-swizzle UMMA
- * descriptor reads as the Hankel matrix of all 64 azimuth shifts) and the table
- * crop_inv_norm[g,s] = 1/||crop(ov_g,s)|| (fp32, from the fp32 inputs).  query_prep writes
- * the bf16 query operand [Q, CH*sw_pad] and q_inv_norm[q]. */
+/* ---- Whole-gallery sweeps on the tensor cores (tcgen05, fp16 operands, fp32 accumulation in TMEM); W must be 64 ----
+ *
+ * Two sweeps with one contract -- correlation -> crop_overhead -> l2_distance of cvig_fov.py:297-363 for every (gallery
+ * item, query) pair, the rank rule of cvig_fov.py:552 and a per-query top-k fused behind it:
+ *   witw_match_spec  (csrc/match_spec.cu, needs C*H == 64) evaluates the circular correlation through the correlation
+ *        theorem, corr[g,q,:] = irfft( sum_r O[g,r,f] conj(S[q,r,f]) ): 33 bins x 64 feature rows of complex MACs on
+ *        tcgen05 (16.9 kFLOP per pair instead of 524 kFLOP at 360 degrees), the 64-point inverse real FFT, the argmax
+ *        over the shift and everything after it in the epilogue, register-local.
+ *   witw_match_tc    (csrc/match_tc.cu) is the same search as one dense contraction over all 64 shifts; the gallery
+ *        operand is a set of pre-shifted 16-byte rows that a no-swizzle UMMA descriptor reads as the Hankel matrix.
+ *
+ * Operands (csrc/sweep_common.cuh).  Features are scaled to unit norm before they are rounded to fp16, so an accumulator is
+ * acc[s] = unit * corr[g,q,s] / (||ov_g|| ||su_q||) and
+ *        dist = 2 - 2 * acc[s*] * gal_scale[g,s*] * qry_aux[q][0].
+ * The prep functions write, per gallery item: the operand, gal_scale [G_pad,64], gal_aux [G_pad,4] = (max and spread of
+ * gal_scale[g,:], the item's rounding scale, the operand's scale) and -- optional, for the fp32 finish -- crop_inv_norm
+ * [G_pad,64] = 1/||crop(ov_g,s)||; per query: the operand, qry_aux [Q,2] = (1, or NaN for a zero-norm query; the query's
+ * rounding scale) and q_inv_norm [Q].  G_pad = G rounded up to 4 (dense) / 8 (spectral); the tables of a call start at its
+ * first item.  witw_spec_gallery_prep: g_first = index of ov[0] inside the operand (a multiple of 8 unless it continues a
+ * partial group), so an encode loop (cvig_fov.py:519-532) can append batch by batch.  spec_out (optional): the fp32
+ * spectra of the same rows in the layout of witw_spectral_rows_f32 -- the operands of the fp32 finish, from the same pass. */
 size_t witw_gallery_operand_bytes(int64_t G, int CH, int sw);
 size_t witw_query_operand_bytes(int64_t Q, int CH, int sw);
-int witw_gallery_prep(const float* ov_dev, int64_t G, int CH, int W, int sw, void* gal_op_dev,
-                      float* crop_inv_norm_dev /* [G_pad4,64], G_pad4 = G rounded up to 4 */,
-                      witw_stream_t stream);
-int witw_query_prep(const float* su_dev, int64_t Q, int CH, int sw, void* qry_op_dev,
-                    float* q_inv_norm_dev /* [Q] */, witw_stream_t stream);
+int witw_gallery_prep(const float* ov_dev, int64_t G, int CH, int W, int sw, void* gal_op_dev, float* gal_scale_dev,
+                      float* gal_aux_dev, float* crop_inv_norm_dev /* optional */, witw_stream_t stream);
+int witw_query_prep(const float* su_dev, int64_t Q, int CH, int sw, void* qry_op_dev, float* qry_aux_dev,
+                    float* q_inv_norm_dev, witw_stream_t stream);
+int witw_spec_supported(int CH, int W, int sw);
+size_t witw_spec_gallery_operand_bytes(int64_t G, int CH);
+size_t witw_spec_query_operand_bytes(int64_t Q, int CH);
+int witw_spec_gallery_prep(const float* ov_dev, int64_t G, int64_t g_first, int CH, int W, int sw, void* gal_op_dev,
+                           float* gal_scale_dev, float* gal_aux_dev, float* crop_inv_norm_dev /* optional */,
+                           float* spec_out_dev /* optional */, witw_stream_t stream);
+int witw_spec_query_prep(const float* su_dev, int64_t Q, int CH, int sw, void* qry_op_dev, float* qry_aux_dev,
+                         float* q_inv_norm_dev, float* spec_out_dev /* optional */, witw_stream_t stream);
 
-/* One sweep of Q queries over G gallery items.  Optional outputs (NULL to skip):
+/* One sweep of Q queries over G gallery items.  All pointers are device pointers; every output is optional (NULL).
  *   dist [G,Q] fp32, ori [G,Q] uint8
- *   rank_count [Q] int32 += #{g : dist[g,q] <= d_true[q]}   (needs d_true [Q]; the rank rule
- *        of cvig_fov.py:552; the caller zeroes rank_count, shards add into it).  true_idx [Q]
- *        (optional, global gallery index of each query's match): that item is counted iff
- *        d_true[q] is not NaN, whatever its bf16 distance -- d[idx] <= d[idx] in the reference
- *   topk_dist/topk_idx [n_slots,Q,topk]: per-query k smallest (distance, gallery index +
- *        g_index_offset) candidates of each of n_slots gallery slices, ascending; n_slots from
- *        witw_match_tc_topk_slots(); merge them with witw_topk_merge(). topk <= 16.
- */
+ *   rank_count [Q] int32 += #{g : dist[g,q] <= d_true[q]}  (needs d_true [Q]; the rank rule of cvig_fov.py:552; the caller
+ *        zeroes rank_count, shards add into it).  true_idx [Q] (optional, global gallery index of each query's match):
+ *        that item is counted iff d_true[q] is not NaN -- d[idx] <= d[idx] in the reference.
+ *   topk_key / topk_idx [n_slots,Q,topk]: per query the topk smallest (key, gallery index + g_index_offset) candidates
+ *        of each of n_slots gallery slices, ascending; n_slots from witw_match_*_topk_slots(); merge with
+ *        witw_topk_merge().  topk <= 16.
+ * err_sigmas > 0 bounds what the fp16 operands can have done to a result (err_sigmas standard deviations of the
+ * accumulated rounding error, per pair; 5 is the library's default) and changes three things: a top-k key is
+ * dist - slack, a lower bound of the pair's fp32 distance; a rank decision within slack of d_true is not taken but
+ * deferred; and for the matrix outputs, pairs whose argmax is not certain or whose slack exceeds fix_rel * dist are
+ * deferred for an fp32 overwrite.  Deferred pairs go to per-query lists: list_n [Q] (zeroed by the caller) counts them,
+ * list_g [Q,list_cap] holds the local gallery index with bit 31 set when the rank decision is pending.  A count above
+ * list_cap means the query's list is incomplete: witw_finish_spec_f32 flags it and the caller re-does that query with
+ * witw_match_columns_spec_f32.  err_sigmas == 0: keys are the fp16 distances and every decision is taken from them. */
+typedef struct witw_sweep_args {
+  const void* gal_op;
+  const float* gal_scale;
+  const float* gal_aux;
+  const void* qry_op;
+  const float* qry_aux;
+  int64_t G, Q;
+  int32_t CH, sw;
+  int32_t g_index_offset;
+  int32_t topk;
+  float* dist;
+  uint8_t* ori;
+  const float* d_true;
+  const int32_t* true_idx;
+  int32_t* rank_count;
+  float* topk_key;
+  int32_t* topk_idx;
+  int32_t* list_g;
+  int32_t* list_n;
+  int32_t list_cap;
+  float err_sigmas;
+  float fix_rel;
+} witw_sweep_args;
 int witw_match_tc_topk_slots(int64_t G, int64_t Q);
-int witw_match_tc(const void* gal_op_dev, const float* crop_inv_norm_dev, const void* qry_op_dev,
-                  const float* q_inv_norm_dev, int64_t G, int64_t Q, int CH, int sw,
-                  float* dist_dev, uint8_t* ori_dev, const float* d_true_dev,
-                  const int32_t* true_idx_dev, int32_t* rank_count_dev, int topk,
-                  float* topk_dist_dev, int32_t* topk_idx_dev, int32_t g_index_offset,
-                  float recheck_band, int64_t* recheck_g_dev, int64_t* recheck_q_dev,
-                  int32_t* recheck_count_dev, int32_t recheck_capacity, witw_stream_t stream);
+int witw_match_tc(const witw_sweep_args* args, witw_stream_t stream);
+int witw_match_spec_topk_slots(int64_t G, int64_t Q);
+int witw_match_spec(const witw_sweep_args* args, witw_stream_t stream);
 
-/* Exact finish of the tensor-core rank count.  With recheck_capacity > 0 witw_match_tc does not
- * count pairs whose bf16 distance is within recheck_band of d_true[q]; it appends them (local gallery
- * index, query) to the lists and bumps recheck_count_dev[0] (recheck_count_dev[1] counts pairs that did
- * not fit and were decided in bf16; the caller zeroes both).  witw_recheck_apply_f32 recomputes the
- * listed pairs in exact fp32 and adds d_exact <= d_true[q] to rank_count -- so the ranks are those of
- * the fp32 reference chain (cvig_fov.py:547-552) unless the list overflowed.  scratch: [capacity] fp32. */
-int witw_recheck_apply_f32(const float* ov_dev, const float* su_dev, const int64_t* recheck_g_dev,
-                           const int64_t* recheck_q_dev, const int32_t* recheck_count_dev,
-                           int32_t capacity, int CH, int W, int sw, const float* d_true_dev,
-                           int32_t* rank_count_dev, float* scratch_dev, witw_stream_t stream);
-
-/* Exact re-ranking of top-k candidates: cand_idx [Q,kc] (global indices, -1 = empty) of a gallery
- * [G,...] whose first item has global index g_index_offset; distances are recomputed in fp32 and the
- * k_out best kept, ascending, ties by lower index.  kc <= 32.  scratch: witw_topk_refine_scratch_bytes(). */
-size_t witw_topk_refine_scratch_bytes(int64_t Q, int kc);
-int witw_topk_refine_f32(const float* ov_dev, const float* su_dev, int64_t G, int64_t Q, int CH, int W,
-                         int sw, const int32_t* cand_idx_dev, int kc, int32_t g_index_offset, int k_out,
-                         float* topk_dist_dev, int32_t* topk_idx_dev, void* scratch_dev,
-                         witw_stream_t stream);
-
-/* The same finishes in the azimuth-frequency domain (csrc/spectral.cu).  The circular correlation of
- * cvig_fov.py:297-312 is evaluated through the correlation theorem on packed 64-point spectra of the
- * feature rows: ~13k MACs per pair instead of 262k, and in fp32 closer to the float64 value than a
- * 4096-term fp32 dot product.  W must be 64; narrower query rows are zero-padded.
- *   witw_spectral_rows_f32: x [n_rows,row_len] fp32 -> spec [n_rows,64] fp32 (32 float2 slots per row:
- *        slot f = (Re X_f, Im X_f) for f = 1..31, slot 0 = (X_0, X_32)).  Gallery: n_rows = G*CH,
- *        row_len = 64; queries: n_rows = Q*CH, row_len = sw.
- *   witw_match_pairs_spec_f32: exact (dist [n_pairs], ori [n_pairs] int64) of explicit pairs;
- *        crop_inv_norm [G,64] and q_inv_norm [Q] are the fp32 tables of witw_gallery_prep / witw_query_prep.
- *   witw_recheck_apply_spec_f32 / witw_topk_refine_spec_f32: as the _f32 forms above, on spectra. */
+/* ---- fp32 evaluation in the azimuth-frequency domain (csrc/spectral.cu, csrc/finish.cu) ----
+ * The circular correlation of cvig_fov.py:297-312 through the correlation theorem on packed 64-point spectra of the
+ * feature rows: ~13k MACs per pair instead of 262k, and in fp32 closer to the float64 value than a 4096-term fp32 dot
+ * product.  W must be 64; narrower query rows are zero-padded.
+ *   witw_spectral_rows_f32: x [n_rows,row_len] fp32 -> spec [n_rows,64] fp32 (32 float2 slots per row: slot f =
+ *        (Re X_f, Im X_f) for f = 1..31, slot 0 = (X_0, X_32)).  Gallery: n_rows = G*CH, row_len = 64; queries:
+ *        n_rows = Q*CH, row_len = sw.
+ *   witw_match_pairs_spec_f32: (dist [n_pairs], ori [n_pairs] int64) of explicit pairs; crop_inv_norm [G,64] and
+ *        q_inv_norm [Q] are the fp32 tables of the prep functions.  The true-match distances of the rank rule.
+ *   witw_match_columns_spec_f32: the distances / orientations of F selected queries (q_sel [F], NULL = 0..F-1) against
+ *        every gallery item: element (g, column) at [g*ld + column], column = the query index when col_is_q, else
+ *        0..F-1; ori as int64 and / or uint8; count_out [F] += #{g : d <= d_true[q]} (the match itself, true_idx[q] -
+ *        g_index_offset, counted by index).  The whole answer for a few queries (heat map, cvig_fov.py:545-552 one query
+ *        at a time) and the fallback for queries witw_finish_spec_f32 flags.
+ *   witw_finish_spec_f32: the fp32 finish of a sweep run with err_sigmas > 0, one CTA per query: evaluates the
+ *        query's deferred pairs (pending rank decisions are added to rank_count, matrix entries overwritten) and
+ *        re-ranks the sweep's merged top-k candidates cand_key / cand_idx [Q,kc] (ascending keys) into out_dist /
+ *        out_idx [Q,k_out] -- exact distances, ties by lower index.  qflag [Q] / n_flagged [1] (zeroed by the caller):
+ *        bit 0 = the query's list overflowed, bit 1 = the keys do not prove that no item outside the candidate list
+ *        belongs to the top k_out; flagged queries must be re-done with witw_match_columns_spec_f32. */
 int witw_spectral_rows_f32(const float* x_dev, int64_t n_rows, int row_len, float* spec_dev,
                            witw_stream_t stream);
 int witw_match_pairs_spec_f32(const float* gal_spec_dev, const float* crop_inv_norm_dev,
                               const float* qry_spec_dev, const float* q_inv_norm_dev,
                               const int64_t* pair_g_dev, const int64_t* pair_q_dev, int64_t n_pairs, int CH,
                               float* dist_dev, int64_t* ori_dev, witw_stream_t stream);
-int witw_recheck_apply_spec_f32(const float* gal_spec_dev, const float* crop_inv_norm_dev,
-                                const float* qry_spec_dev, const float* q_inv_norm_dev,
-                                const int64_t* recheck_g_dev, const int64_t* recheck_q_dev,
-                                const int32_t* recheck_count_dev, int32_t capacity, int CH,
-                                const float* d_true_dev, int32_t* rank_count_dev, float* scratch_dev,
-                                witw_stream_t stream);
-int witw_topk_refine_spec_f32(const float* gal_spec_dev, const float* crop_inv_norm_dev,
-                              const float* qry_spec_dev, const float* q_inv_norm_dev, int64_t G, int64_t Q,
-                              int CH, const int32_t* cand_idx_dev, int kc, int32_t g_index_offset, int k_out,
-                              float* topk_dist_dev, int32_t* topk_idx_dev, void* scratch_dev,
-                              witw_stream_t stream);
-
-/* The whole-gallery sweep in the azimuth-frequency domain (csrc/match_spec.cu): the same contract as
- * witw_match_tc -- correlation -> crop_overhead -> l2_distance of cvig_fov.py:297-363, the rank rule of :552 and a
- * per-query top-k -- but the circular correlation is evaluated through the correlation theorem:
- *     corr[g,q,:] = irfft( sum_r O[g,r,f] conj(S[q,r,f]) )
- * The per-frequency products (33 bins x 64 feature rows of complex MACs, 16.9 kFLOP per pair instead of 524 kFLOP at
- * 360 degrees) run on tcgen05 with bf16 spectra and fp32 accumulation in TMEM; the 64-point inverse real FFT, the
- * argmax over the shift and everything after it run in the epilogue, register-local.  Needs C*H == 64 and W == 64.
- *   witw_spec_gallery_prep: ov [G,64,64] fp32 -> bf16 spectra in the operand layout (16 KB per item, groups of 8
- *        items) and crop_inv_norm [G rounded up to 8, 64].  g_first = index of ov[0] inside the operand (a multiple
- *        of 8 unless it continues a partial group), so an encode loop can append batch by batch.
- *   witw_spec_query_prep: su [Q,64,sw] fp32 -> bf16 spectra of the zero-padded rows, scaled by 1/64 (8 KB per
- *        query, laid out per tile of 128 queries), and q_inv_norm [Q].
- *   spec_out (both, optional): the fp32 spectra of the same rows in the layout of witw_spectral_rows_f32
- *        ([G*64,64] / [Q*64,64]) -- the operands of the exact finish, produced in the same pass.
- *   witw_match_spec: arguments as witw_match_tc; top-k candidate lists: witw_match_spec_topk_slots(). */
-int witw_spec_supported(int CH, int W, int sw);
-size_t witw_spec_gallery_operand_bytes(int64_t G, int CH);
-size_t witw_spec_query_operand_bytes(int64_t Q, int CH);
-int witw_spec_gallery_prep(const float* ov_dev, int64_t G, int64_t g_first, int CH, int W, int sw,
-                           void* gal_op_dev, float* crop_inv_norm_dev, float* spec_out_dev /* optional */,
-                           witw_stream_t stream);
-int witw_spec_query_prep(const float* su_dev, int64_t Q, int CH, int sw, void* qry_op_dev,
-                         float* q_inv_norm_dev, float* spec_out_dev /* optional */, witw_stream_t stream);
-int witw_match_spec_topk_slots(int64_t G, int64_t Q);
-int witw_match_spec(const void* gal_op_dev, const float* crop_inv_norm_dev, const void* qry_op_dev,
-                    const float* q_inv_norm_dev, int64_t G, int64_t Q, int CH, int sw,
-                    float* dist_dev, uint8_t* ori_dev, const float* d_true_dev,
-                    const int32_t* true_idx_dev, int32_t* rank_count_dev, int topk,
-                    float* topk_dist_dev, int32_t* topk_idx_dev, int32_t g_index_offset,
-                    float recheck_band, int64_t* recheck_g_dev, int64_t* recheck_q_dev,
-                    int32_t* recheck_count_dev, int32_t recheck_capacity, witw_stream_t stream);
+int witw_match_columns_spec_f32(const float* gal_spec_dev, const float* crop_inv_norm_dev, const float* qry_spec_dev,
+                                const float* q_inv_norm_dev, int64_t G, int CH, const int32_t* q_sel_dev, int64_t F,
+                                float* dist_dev, int64_t* ori64_dev, uint8_t* ori8_dev, int64_t ld, int col_is_q,
+                                const float* d_true_dev, const int32_t* true_idx_dev, int32_t g_index_offset,
+                                int32_t* count_out_dev, witw_stream_t stream);
+typedef struct witw_finish_args {
+  const float* gal_spec;
+  const float* crop_inv_norm;
+  const float* qry_spec;
+  const float* q_inv_norm;
+  int64_t G, Q;
+  int32_t CH;
+  int32_t g_index_offset;
+  const int32_t* list_g;
+  const int32_t* list_n;
+  int32_t list_cap;
+  int32_t kc;
+  const float* d_true;
+  int32_t* rank_count;
+  float* dist;
+  uint8_t* ori;
+  const float* cand_key;
+  const int32_t* cand_idx;
+  float* out_dist;
+  int32_t* out_idx;
+  int32_t k_out;
+  int32_t reserved;
+  int32_t* qflag;
+  int32_t* n_flagged;
+} witw_finish_args;
+int witw_finish_spec_f32(const witw_finish_args* args, witw_stream_t stream);
+/* sizeof(witw_sweep_args) / sizeof(witw_finish_args) as this library was built: a binding checks its own declaration. */
+size_t witw_sizeof_sweep_args(void);
+size_t witw_sizeof_finish_args(void);
 
 /* ------------------------------------------------------------------------------------------
  * K4  rank / top-k               replaces model/cvig_fov.py:550-552 and

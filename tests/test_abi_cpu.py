@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), "missing export " + n
     # the ctypes table covers exactly the header
     assert sorted(_lib.SIGNATURES) == names
-    assert _lib.load().witw_version() >= 100
+    assert _lib.load().witw_version() >= 200
 
 
 def test_host_grid_and_lut_match_oracle():
@@ -220,3 +220,70 @@ def test_argument_validation_needs_no_device():
     # matching kernels: shapes the kernels do not cover are refused with a reason
     assert lib.witw_spec_supported(64, 64, 64) == 1 and lib.witw_spec_supported(32, 64, 64) == 0 and lib.witw_spec_supported(64, 32, 16) == 0
     assert lib.witw_gallery_operand_bytes(10, 64, 0) == 0
+
+
+@pytest.mark.parametrize("name", ["cvig_fov", "cvig_semantic"])
+def test_install_on_the_real_reference_module(name):
+    """install() against the unmodified reference module (build container only): every rebound callable accepts the
+    reference's own positional arguments under the reference's own parameter names (cvig_fov.py:156, 186, 297, 318, 346, 366)."""
+    import inspect
+
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("reference tree not mounted")
+    import witw_b200 as W
+
+    mod = ref_loader.load(name)
+    ref_sigs = {n: inspect.signature(getattr(mod, n)) for n in ("bilinear_interpolate", "correlation", "crop_overhead", "l2_distance", "triplet_loss")}
+    ref_call = inspect.signature(mod.PolarTransform.__call__)
+    ref_init = inspect.signature(mod.PolarTransform.__init__)
+    originals = W.install(mod)
+    try:
+        assert mod.correlation is W.correlation and mod.PolarTransform is W.PolarTransform and mod.triplet_loss is W.triplet_loss
+        for n, ref in ref_sigs.items():
+            ours = inspect.signature(getattr(mod, n))
+            ref_names = list(ref.parameters)
+            assert list(ours.parameters)[: len(ref_names)] == ref_names, (n, ours, ref)
+            for p in list(ours.parameters.values())[len(ref_names):]:      # anything extra must be optional
+                assert p.default is not inspect.Parameter.empty, (n, p)
+            for pn, p in ref.parameters.items():                           # the reference's defaults are kept
+                if p.default is not inspect.Parameter.empty:
+                    assert ours.parameters[pn].default == p.default, (n, pn)
+        assert list(inspect.signature(mod.PolarTransform.__call__).parameters) == list(ref_call.parameters)
+        mod.PolarTransform()                                               # the reference constructs it without arguments
+        assert all(p.default is not inspect.Parameter.empty for k, p in inspect.signature(mod.PolarTransform.__init__).parameters.items()
+                   if k not in ref_init.parameters)
+        # heatmap.py and train()/test() also read these; install() must leave them alone
+        assert mod.Globals is not None and hasattr(mod, "FOV_DSM") and mod.Resize is not W.Resize
+        # the drop-ins refuse CPU tensors loudly (no CPU fallback), as the reference's CPU callers would find out at once
+        import torch
+        with pytest.raises(RuntimeError):
+            mod.correlation(torch.zeros(2, 16, 4, 64), torch.zeros(1, 16, 4, 64))
+    finally:
+        W.uninstall(mod)
+    assert mod.correlation is originals["correlation"] and mod.PolarTransform is originals["PolarTransform"]
+    W.install(mod, polar=False)
+    assert mod.PolarTransform is originals["PolarTransform"] and mod.correlation is W.correlation
+    W.uninstall(mod)
+
+
+def test_polar_drop_in_explains_itself_inside_a_dataloader_worker():
+    """A CPU tensor inside a forked DataLoader worker: a clear error, not 'Cannot re-initialize CUDA in forked subprocess'."""
+    import torch
+    import torch.utils.data
+
+    import witw_b200 as W
+
+    class Tiles(torch.utils.data.Dataset):
+        def __len__(self):
+            return 2
+
+        def __getitem__(self, i):
+            try:
+                W.PolarTransform()({"overhead": torch.zeros(3, 256, 256)})
+            except RuntimeError as exc:
+                return str(exc)
+            return "no error"
+
+    msgs = list(torch.utils.data.DataLoader(Tiles(), batch_size=1, num_workers=1))
+    assert all("DataLoader worker" in m[0] and "num_workers=0" in m[0] for m in msgs), msgs

@@ -38,6 +38,21 @@ def test_reference_arm_line(bench, monkeypatch):
     assert d["cpu_baseline"]["cores"] >= 1 and "queries" in d["cpu_baseline"]["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["vs_baseline"] is None and d["n_gpus"] == 1 and d["steps"] == 1
+    # both arms describe the workload with the same object (the driver compares them)
+    assert d["config"] == bench.workload_config(1) and {"workload", "gallery_total", "gallery_per_gpu", "queries", "fov"} <= set(d["config"])
+
+
+def test_cpu_sample_reports_ranks_and_ties(bench):
+    """The CPU leg doubles as the bench line's parity check: ranks of the first queries and, per query, how many gallery
+    items tie the threshold within fp32 round-off."""
+    import numpy as np
+
+    from oracle import witw_oracle as O
+    ov, su = bench.synth_cpu(64, 8, noise=20.0, seed=3)
+    qps, cores, ranks, ties, dt = bench.cpu_rank_sample(ov, su, budget_s=5.0, max_queries=8)
+    assert qps > 0 and cores >= 1 and len(ranks) == len(ties) >= 2
+    assert np.array_equal(ranks, O.rank_loop(ov, su, query_indices=list(range(len(ranks)))))
+    assert (ties >= 0).all()
 
 
 def test_reference_arm_other_ranks_stay_silent(bench, monkeypatch):

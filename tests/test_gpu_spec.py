@@ -1,12 +1,16 @@
-"""GPU parity tests of the spectral tensor-core sweep (csrc/match_spec.cu: per-frequency products on tcgen05 with bf16
-spectra, inverse FFT + argmax + distance + rank count + top-k in the epilogue) against the oracle."""
+"""GPU parity tests of the spectral tensor-core sweep (csrc/match_spec.cu: per-frequency products on tcgen05 with fp16
+spectra of the norm-scaled features, inverse FFT + argmax + distance + rank count + top-k in the epilogue) and of its
+fp32 finish (csrc/finish.cu) against the oracle."""
 import numpy as np
 import pytest
 import torch
 
 from oracle import witw_oracle as O
+from parity_helpers import assert_orientation_is_the_references, check_exact_results, hard_features_cuda, reference_columns
 
 pytestmark = pytest.mark.gpu
+
+KAPPA = 16.0     # csrc/sweep_common.cuh: kSpecKappa
 
 
 @pytest.fixture(scope="module")
@@ -22,98 +26,127 @@ def _spectral_sweep(W):
     W.ops.TC_IMPL = "spectral"          # also for widths where "auto" would pick the dense contraction
     yield
     W.ops.TC_IMPL = "auto"
+    W.ops.DEFERRAL_CAP = None
 
 
 def spec_model(ov, su):
-    """What the kernel computes, in float64: spectra of the fp32 rows rounded to bf16 (the query's scaled by 1/64),
-    per-frequency products summed over the feature rows, inverse real FFT; norms of the fp32 inputs."""
+    """What the raw sweep computes, in float64: spectra of the fp32 rows scaled by 16 / norm and rounded to fp16,
+    per-frequency products summed over the feature rows, inverse real FFT; norms of the fp32 inputs.
+    Returns (normalised correlation [G,Q,64], orientation, distance)."""
     G, Q, sw = ov.shape[0], su.shape[0], su.shape[3]
     pad = torch.zeros(Q, su.shape[1], su.shape[2], 64, dtype=torch.float64)
     pad[..., :sw] = su.double()
-    So = torch.fft.rfft(ov.double(), dim=3).reshape(G, -1, 33)
-    Sq = torch.fft.rfft(pad, dim=3).reshape(Q, -1, 33) / 64.0
+    gn = ov.double().reshape(G, -1).norm(dim=1)
+    qn = su.double().reshape(Q, -1).norm(dim=1)
+    So = torch.fft.rfft(ov.double(), dim=3).reshape(G, -1, 33) * (KAPPA / gn).view(G, 1, 1)
+    Sq = torch.fft.rfft(pad, dim=3).reshape(Q, -1, 33) * (KAPPA / qn).view(Q, 1, 1)
 
     def rnd(z):
-        return torch.complex(z.real.float().bfloat16().double(), z.imag.float().bfloat16().double())
+        return torch.complex(z.real.float().half().double(), z.imag.float().half().double())
 
     So, Sq = rnd(So), rnd(Sq)
     P = torch.einsum("grf,qrf->gqf", So, Sq.conj())
-    corr = torch.fft.irfft(P, n=64, dim=2) * 64.0                    # irfft divides by 64; the 1/64 is already in Sq
+    corr = torch.fft.irfft(P, n=64, dim=2) / KAPPA ** 2             # corr / (||ov|| ||su||)
     ori = torch.argmax(corr, -1)
-    w = 64
-    shift = (torch.arange(w).view(w, 1) + torch.arange(sw).view(1, sw)) % w
+    shift = (torch.arange(64).view(64, 1) + torch.arange(sw).view(1, sw)) % 64
     cn = torch.sqrt((ov.double() ** 2).sum((1, 2))[:, shift].sum(-1))
-    qn = su.double().reshape(Q, -1).norm(dim=1)
     best = torch.gather(corr, 2, ori.unsqueeze(-1)).squeeze(-1)
-    dist = 2 - 2 * best / (torch.gather(cn, 1, ori.reshape(G, -1)).reshape(ori.shape) * qn.unsqueeze(0))
-    return corr, ori, dist
+    ratio = gn.view(G, 1) / torch.gather(cn, 1, ori.reshape(G, -1)).reshape(ori.shape)
+    return corr, ori, 2 - 2 * best * ratio
 
 
 @pytest.mark.parametrize("fov,G,Q", [(360, 203, 300), (180, 36, 16), (90, 130, 70), (70, 64, 257), (6, 20, 9), (360, 8, 128), (360, 1, 1)])
 def test_spec_match_vs_oracle(W, fov, G, Q):
     ov, su, _ = O.synth_features(G, Q, fov=fov, noise=1.0, seed=fov + G)
-    ori, dist = W.match(ov.cuda(), su.cuda(), path="tc")
+    # tier 1: the raw fp16 sweep against the float64 model of the same arithmetic: fp32 transform / accumulation round-off only
+    ori, dist = W.match(ov.cuda(), su.cuda(), path="tc16")
     ori, dist = ori.cpu(), dist.cpu()
     assert tuple(ori.shape) == (G, Q) and ori.dtype == torch.int64
-    # tier 1: against the float64 model of the same arithmetic (bf16 spectra): fp32 transform round-off only
     corr, m_ori, m_dist = spec_model(ov, su)
     diff = ori != m_ori
     a = torch.gather(corr, 2, ori.unsqueeze(-1)).squeeze(-1)
     b = torch.gather(corr, 2, m_ori.unsqueeze(-1)).squeeze(-1)
-    assert bool((((a - b).abs() <= 1e-4 * corr.abs().amax(-1)) | ~diff).all())
-    assert diff.float().mean().item() <= 0.01
-    assert (dist.double() - m_dist)[~diff].abs().max().item() <= 2e-4
-    # tier 2: against the fp32 reference chain -> north-star tolerance where the orientation agrees
+    assert bool((((a - b).abs() <= 4e-6) | ~diff).all())            # differs only between shifts the model itself ties
+    assert (dist.double() - m_dist)[~diff].abs().max().item() <= 2e-5
+    # tier 2: the finished sweep against the fp32 reference chain: the reference's orientation, distances within the
+    # north star's 1e-3 relative at every field of view, on every pair
     ref_ori, ref = O.match(ov, su)
-    same = ori == ref_ori
+    ori, dist = W.match(ov.cuda(), su.cuda(), path="tc")
+    ori, dist = ori.cpu(), dist.cpu()
+    same = assert_orientation_is_the_references(ov, su, ori, ref_ori)
     rel = ((dist - ref).abs() / ref.abs())[same]
-    assert rel.max().item() <= (1e-3 if fov == 360 else 4e-3), rel.max().item()
-    assert (dist - ref).abs()[same].max().item() <= (2e-3 if su.shape[3] >= 8 else 4e-3)   # one-column queries: flat spectra
-    assert same.float().mean().item() >= 0.98
-    c32 = O.fused_fp64(ov, su)[0]
-    a = torch.gather(c32, 2, ori.unsqueeze(-1)).squeeze(-1)
-    b = torch.gather(c32, 2, ref_ori.unsqueeze(-1)).squeeze(-1)
-    assert bool((((a - b).abs() <= 2e-2 * c32.abs().amax(-1)) | same).all())
+    assert rel.max().item() <= 1e-3, rel.max().item()
+    assert (dist - ref)[same].abs().max().item() <= (6e-4 if su.shape[3] >= 8 else 1.5e-3)
+    if G * Q >= 1000:
+        assert same.float().mean().item() >= 0.995
 
 
 @pytest.mark.parametrize("fov,n,noise", [(360, 300, 25.0), (180, 260, 12.0), (90, 260, 10.0)])
-def test_spec_evaluate_ranks_vs_oracle(W, fov, n, noise):
+def test_spec_raw_sweep_ranks_and_topk(W, fov, n, noise):
+    """exact=False: the raw fp16 decisions.  Ranks differ from the reference only by pairs within 3e-4 of the threshold;
+    the fused top-k is a sort of the kernel's own distance matrix."""
     ov, su, _ = O.synth_features(n, n, fov=fov, noise=noise, seed=17)
     ranks, td, ti = W.evaluate_ranks(ov.cuda(), su.cuda(), path="tc", topk=5, exact=False)
     ranks = ranks.cpu().numpy()
     ref_ori, ref = O.match(ov, su)
     want = (ref <= torch.diagonal(ref).unsqueeze(0)).sum(0).numpy()
     assert len(set(want.tolist())) > 5
-    band = ((ref - torch.diagonal(ref).unsqueeze(0)).abs() <= 2e-3).sum(0).numpy() - 1
+    band = ((ref - torch.diagonal(ref).unsqueeze(0)).abs() <= (3e-4 if fov == 360 else 1.2e-2)).sum(0).numpy() - 1
     assert np.all(np.abs(ranks - want) <= band)
-    assert np.mean(ranks == want) >= 0.8
-    # fused top-k agrees with a sort of the kernel's own distance matrix
-    _, dist = W.match(ov.cuda(), su.cuda(), path="tc")
+    assert np.mean(ranks == want) >= 0.9
+    _, dist = W.match(ov.cuda(), su.cuda(), path="tc16")
     sd = torch.sort(dist.t().cpu(), dim=1, stable=True)
     assert torch.equal(td.cpu(), sd.values[:, :5]) and torch.equal(ti.cpu().long(), sd.indices[:, :5])
 
 
-@pytest.mark.parametrize("fov,n,noise", [(360, 300, 25.0), (180, 280, 12.0), (90, 260, 10.0)])
+@pytest.mark.parametrize("fov,n,noise", [(360, 300, 25.0), (180, 280, 12.0), (90, 260, 10.0), (45, 300, 6.0)])
 def test_spec_exact_finish_matches_fp32_reference(W, fov, n, noise):
     """exact=True on the spectral sweep: ranks and top-k are the fp32 reference's (cvig_fov.py:547-552)."""
     ov, su, _ = O.synth_features(n, n, fov=fov, noise=noise, seed=23)
     ranks, td, ti = W.evaluate_ranks(ov.cuda(), su.cuda(), path="tc", topk=5)
-    ranks = ranks.cpu().numpy()
     ref_ori, ref = O.match(ov, su)
-    thr = torch.diagonal(ref).unsqueeze(0)
-    want = (ref <= thr).sum(0).numpy()
+    want = check_exact_results(ref, ranks.cpu().numpy(), td, ti, 5)
     assert len(set(want.tolist())) > 5
-    tie = ((ref - thr).abs() <= 3e-6).sum(0).numpy() - 1
-    assert np.all(np.abs(ranks - want) <= tie)
-    assert np.mean(ranks == want) >= 0.98
-    appended, dropped = W.ops.evaluate_ranks_prepared.last_recheck.cpu().tolist()
-    assert dropped == 0 and appended > 0
-    tdc, tic = td.cpu(), ti.cpu().long()
-    assert (tdc - torch.gather(ref.t(), 1, tic)).abs().max().item() <= 5e-6
-    assert bool((tdc[:, 1:] >= tdc[:, :-1]).all())
+    stats = W.ops.evaluate_ranks_prepared.last_stats
+    deferred = stats["deferred"].cpu()
+    assert int(deferred.max()) <= stats["list_cap"] and int(deferred.sum()) > 0 and stats["flagged"] == 0
+    # the deferral is sparse: the error bound of the fp16 operands is ~1e-4 of a distance
+    assert int(deferred.sum()) <= 0.03 * n * n
+
+
+@pytest.mark.parametrize("fov", [360, 90])
+def test_spec_exact_finish_survives_list_overflow(W, fov):
+    """Deferral lists that are too small (forced here: 2 entries per query) must not cost exactness: the overflowing
+    queries are re-done entirely in fp32 (the re-check list used to overflow silently)."""
+    n = 400
+    ov, su, _ = O.synth_features(n, n, fov=fov, noise=25.0 if fov == 360 else 10.0, seed=31)
+    W.ops.DEFERRAL_CAP = 2
+    ranks, td, ti = W.evaluate_ranks(ov.cuda(), su.cuda(), path="tc", topk=5)
+    stats = W.ops.evaluate_ranks_prepared.last_stats
+    assert stats["flagged"] > 0 and int(stats["deferred"].max()) > 2
+    ref_ori, ref = O.match(ov, su)
+    check_exact_results(ref, ranks.cpu().numpy(), td, ti, 5)
+    # the matrix outputs take the same way out
+    ori, dist = W.match(ov.cuda(), su.cuda(), path="tc")
+    assert int(W.ops.match.last_flagged) > 0
+    same = assert_orientation_is_the_references(ov, su, ori.cpu(), ref_ori)
+    assert ((dist.cpu() - ref).abs() / ref.abs())[same].max().item() <= 1e-3
+
+
+def test_spec_topk_with_duplicate_items_is_proven_or_redone(W):
+    """Twenty identical gallery items tie exactly: the 16 candidate keys cannot prove the top 5 complete, the query is
+    flagged and re-done in fp32, and the result is the stable sort's (lowest indices first)."""
+    ov, su, _ = O.synth_features(200, 40, fov=360, noise=0.5, seed=8)
+    ov[100:120] = ov[3]
+    ranks, td, ti = W.evaluate_ranks(ov.cuda(), su.cuda(), path="tc", topk=5)
+    assert W.ops.evaluate_ranks_prepared.last_stats["flagged"] >= 1
+    ref = O.match(ov, su)[1]
     sd = torch.sort(ref.t(), dim=1, stable=True)
-    assert torch.equal(tic[:, 0], sd.indices[:, 0])
-    assert (tic == sd.indices[:, :5]).float().mean().item() >= (0.99 if fov == 360 else 0.9)
+    tic = ti.cpu().long()
+    assert torch.equal(tic[3], sd.indices[3, :5]) and tic[3].tolist() == [3, 100, 101, 102, 103]
+    check_exact_results(ref, ranks.cpu().numpy(), td, ti, 5)
+    with pytest.raises(ValueError):
+        W.evaluate_ranks(ov.cuda(), su.cuda(), path="tc", topk=13)
 
 
 def test_spec_properties_at_scale(W):
@@ -128,8 +161,8 @@ def test_spec_properties_at_scale(W):
     assert torch.equal(torch.diagonal(ori[:Q]).cpu(), sh)
     ori2, dist2 = W.match(torch.roll(ovc, 5, dims=3), suc, path="tc")
     flips = ori2 != (ori + 5) % 64
-    assert flips.float().mean().item() <= 0.02                        # the rolled spectra round differently
-    assert (dist2 - dist)[~flips].abs().max().item() <= 2e-3
+    assert flips.float().mean().item() <= 1e-4                        # only exact fp32 near-ties may land elsewhere
+    assert (dist2 - dist)[~flips].abs().max().item() <= 4e-4
     d_true, _ = W.true_match_distances(ovc, suc)
     parts = []
     t32 = torch.arange(Q, dtype=torch.int32, device="cuda")
@@ -142,16 +175,34 @@ def test_spec_properties_at_scale(W):
     assert torch.equal(parts[0] + parts[1], whole)
 
 
+@pytest.mark.parametrize("fov,noise", [(360, 25.0), (90, 10.0)])
+def test_spec_baseline_size_hard_data_equals_the_oracle(W, fov, noise):
+    """BASELINE configs[1] / configs[2] at full size, 10k x 10k, on data where ranks are non-trivial: the ranks and the
+    top-10 of a 64-query subset equal the oracle's rank loop (cvig_fov.py:545-552, oracle.rank_loop / oracle.match run on the
+    host against the whole gallery) except where fp32 distances tie to 3e-6; nothing was dropped on the way."""
+    G = Q = 10000
+    sw = int(fov / 360 * 512) // 8
+    ov, su, _ = hard_features_cuda(G, Q, sw, noise, seed=5)
+    ranks, td, ti = W.evaluate_ranks(ov, su, path="tc", topk=10)
+    stats = W.ops.evaluate_ranks_prepared.last_stats
+    deferred = stats["deferred"].cpu()
+    assert int(deferred.max()) <= stats["list_cap"] and stats["flagged"] == 0
+    assert 0 < int(deferred.sum()) <= 0.02 * G * Q
+    r = ranks.cpu().numpy()
+    assert len(set(r.tolist())) > 1000 and r.max() > 2000              # ranks all over the gallery
+    sub = torch.arange(0, Q, Q // 64)[:64]
+    ovh, suh = ov.cpu(), su.cpu()
+    ref = reference_columns(ovh, suh, sub)
+    check_exact_results(ref, r[sub.numpy()], td[sub.cuda()], ti[sub.cuda()], 10, true_rows=sub)
+    assert np.array_equal(O.rank_loop(ovh, suh, query_indices=sub.tolist()[:4]), (ref <= ref[sub, torch.arange(64)].unsqueeze(0)).sum(0).numpy()[:4])
+
+
 def test_spec_baseline_size_10k_x_10k(W):
     """BASELINE configs[1] at full size through size-independent properties: every (gallery, query) pair is visited
     exactly once, planted matches are rank 1 / top-1 with the planted orientation, distances are finite and in [0, 4]."""
     G = Q = 10000
     sw = 64
-    gen = torch.Generator(device="cuda").manual_seed(11)
-    ov = torch.randn(G, 16, 4, 64, device="cuda", generator=gen) * 0.06
-    shifts = torch.randint(0, 64, (Q,), device="cuda", generator=gen)
-    cols = (shifts.view(Q, 1) + torch.arange(sw, device="cuda").view(1, sw)) % 64
-    su = torch.gather(ov, 3, cols.view(Q, 1, 1, sw).expand(Q, 16, 4, sw)) + 0.03 * torch.randn(Q, 16, 4, sw, device="cuda", generator=gen)
+    ov, su, shifts = hard_features_cuda(G, Q, sw, 0.5, seed=11)
     gal, qry = W.GalleryIndex(ov, sw), W.QueryBatch(su)
     assert gal.impl == "spectral" and qry.impl == "spectral"
     inf = torch.full((Q,), float("inf"), device="cuda")
@@ -168,15 +219,15 @@ def test_spec_baseline_size_10k_x_10k(W):
     assert float(td.min()) >= 0.0 and float(td.max()) <= 4.0
     d_true, o_true = W.true_match_distances(ov, su)
     assert torch.equal(o_true, shifts)
-    # the bf16 sweep's own orientation and distance on the matches, from a strip of the matrix
+    # the sweep's own orientation and distance on the matches, from a strip of the matrix
     res = W.sweep_tc(W.GalleryIndex(ov[:512], sw), W.QueryBatch(su[:512]), want_dist=True, want_ori=True)
     assert torch.equal(torch.diagonal(res["ori"]).long(), shifts[:512])
-    assert (torch.diagonal(res["dist"]) - d_true[:512]).abs().max().item() <= 2e-3
+    assert (torch.diagonal(res["dist"]) - d_true[:512]).abs().max().item() <= 2e-4
 
 
 def test_spec_gallery_builder_matches_one_shot_prep(W):
     """Encode-loop plumbing (cvig_fov.py:519-532) on the spectral operand: batches appended one by one give the same
-    operand, crop norms and ranks as preparing the concatenated gallery at once."""
+    operand, tables and ranks as preparing the concatenated gallery at once."""
     ov, su, _ = O.synth_features(158, 158, fov=180, noise=6.0, seed=21)
     ovc, suc = ov.cuda(), su.cuda()
     whole = W.GalleryIndex(ovc, 32)
@@ -187,7 +238,9 @@ def test_spec_gallery_builder_matches_one_shot_prep(W):
     built = b.finish()
     assert built.G == 158
     assert torch.equal(built.operand[: whole.operand.numel()], whole.operand)
-    assert torch.equal(built.crop_inv_norm[: 160 * 64], whole.crop_inv_norm[: 160 * 64])
+    for name, width in (("scale", 64), ("aux", 4), ("crop_inv_norm", 64)):
+        assert torch.equal(getattr(built, name)[: 160 * width], getattr(whole, name)[: 160 * width]), name
+    assert torch.equal(built.spec, whole.spec)
     r1 = W.evaluate_ranks_prepared(whole, W.QueryBatch(suc))
     r2 = W.evaluate_ranks_prepared(built, W.QueryBatch(suc))
     assert torch.equal(r1, r2)
@@ -195,29 +248,55 @@ def test_spec_gallery_builder_matches_one_shot_prep(W):
         b.append(ovc[:8])
 
 
+def test_spec_operands_do_not_depend_on_the_feature_scale(W):
+    """The operands are norm-scaled before they are rounded to fp16: features a million times larger or smaller (fp16 would
+    overflow / flush them) give the same orientations and distances."""
+    ov, su, _ = O.synth_features(96, 130, fov=90, noise=2.0, seed=6)
+    base = W.match(ov.cuda(), su.cuda(), path="tc16")
+    for k_ov, k_su in ((1e6, 1e-6), (2.0 ** -20, 2.0 ** 12)):
+        ori, dist = W.match((ov * k_ov).cuda(), (su * k_su).cuda(), path="tc16")
+        assert (ori != base[0]).float().mean().item() <= 2e-3
+        assert (dist - base[1])[ori == base[0]].abs().max().item() <= 1e-4
+
+
 def test_spec_nan_and_zero_inputs(W):
-    """A zero-norm query gives NaN distances (no epsilon in cvig_fov.py:351-361) and rank 0; other queries are unaffected."""
+    """A zero-norm query / gallery item gives NaN distances (no epsilon in cvig_fov.py:351-361), orientation 0 and rank
+    contributions of 0; other pairs are unaffected."""
     ov, su, _ = O.synth_features(64, 40, fov=360, noise=1.0, seed=2)
     su[7] = 0.0
-    ori, dist = W.match(ov.cuda(), su.cuda(), path="tc")
+    ov[11] = 0.0
     ref_ori, ref = O.match(ov, su)
-    assert bool(torch.isnan(dist[:, 7]).all()) and bool(torch.isnan(ref[:, 7]).all())
-    keep = torch.ones(40, dtype=torch.bool)
-    keep[7] = False
-    assert (dist.cpu()[:, keep] - ref[:, keep]).abs().max().item() <= 2e-3
+    for path in ("tc16", "tc"):
+        ori, dist = W.match(ov.cuda(), su.cuda(), path=path)
+        ori, dist = ori.cpu(), dist.cpu()
+        assert bool(torch.isnan(dist[:, 7]).all()) and bool(torch.isnan(ref[:, 7]).all())
+        assert bool(torch.isnan(dist[11]).all()) and bool(torch.isnan(ref[11]).all())
+        assert bool((ori[11] == ref_ori[11]).all()) and bool((ori[:, 7] == ref_ori[:, 7]).all())
+        keep = torch.ones(64, 40, dtype=torch.bool)
+        keep[:, 7] = False
+        keep[11] = False
+        assert (dist[keep] - ref[keep]).abs().max().item() <= 3e-4
+    ranks = W.evaluate_ranks(ov.cuda(), su.cuda(), path="tc").cpu().numpy()
+    want = (ref <= torch.diagonal(ref[:40]).unsqueeze(0)).sum(0).numpy()
+    assert np.array_equal(ranks, want) and ranks[7] == 0 and ranks[11] == 0
 
 
 def test_spec_heatmap_sweep_one_query_many_tiles(W):
-    """tools/heatmap/heatmap.py:171-177 shape on the spectral sweep: one photo against a swept grid of tiles."""
+    """tools/heatmap/heatmap.py:171-177 shape: one photo against a swept grid of tiles -- evaluated entirely in fp32
+    (witw_match_columns_spec_f32), so orientation, dissimilarity and score are the reference's."""
     ov, su, sh = O.synth_features(1200, 1, fov=70, noise=0.3, seed=3)
     rdeg, rdis, rscore = O.heatmap_scores(ov, su)
-    deg, dis, score = W.heatmap_scores(ov.cuda(), su.cuda(), path="tc")
+    deg, dis, score = W.heatmap_scores(ov.cuda(), su.cuda())
     assert tuple(deg.shape) == (1200,) and tuple(dis.shape) == (1200,)
-    same = deg.cpu() == rdeg
-    assert same.float().mean().item() >= 0.98
-    assert (dis.cpu() - rdis)[same].abs().max().item() <= 2e-3
-    assert (score.cpu() - rscore)[same].abs().max().item() <= 2e-2 * float(rscore.max())
+    ori = ((deg.cpu() + 180) * 64 / 360).round().long().view(-1, 1)
+    same = assert_orientation_is_the_references(ov, su, ori, O.correlation(ov, su)).view(-1)
+    assert same.float().mean().item() >= 0.999
+    assert (dis.cpu() - rdis)[same].abs().max().item() <= 5e-6
+    assert ((score.cpu() - rscore)[same].abs() <= 1e-4 * rscore[same].abs()).all()
     assert int(torch.argmin(dis)) == 0 and float(deg[0]) == float(sh[0]) * 360 / 64 - 180
+    # the finished tensor-core sweep gives the same picture
+    deg2, dis2, _ = W.heatmap_scores(ov.cuda(), su.cuda(), path="tc")
+    assert (deg2.cpu() == rdeg)[same].all() and (dis2.cpu() - rdis)[same].abs().max().item() <= 6e-4
 
 
 def test_spec_sharded_single_process_matches_unsharded(W):
@@ -244,7 +323,7 @@ def test_spec_sharded_single_process_matches_unsharded(W):
 
 def test_spec_random_shapes_against_oracle(W):
     """Seeded random problem shapes (gallery not a multiple of 8, queries not a multiple of 128, several work chunks, query
-    widths 8..64): distances / orientations of the sweep and exact-finish ranks against the fp32 reference chain."""
+    widths 8..64): distances / orientations of the finished sweep and exact-finish ranks against the fp32 reference chain."""
     rng = np.random.default_rng(2024)
     for trial in range(10):
         G = int(rng.integers(9, 1200))
@@ -259,12 +338,8 @@ def test_spec_random_shapes_against_oracle(W):
         su[:n] = torch.gather(ov[:n], 3, cols.view(n, 1, 1, sw).expand(n, 16, 4, sw)) + 6.0 * su[:n]
         ref_ori, ref = O.match(ov, su)
         ori, dist = W.match(ov.cuda(), su.cuda(), path="tc")
-        same = ori.cpu() == ref_ori
-        assert same.float().mean().item() >= 0.97, (G, Q, sw)
-        assert (dist.cpu() - ref)[same].abs().max().item() <= 3e-3, (G, Q, sw)
+        same = assert_orientation_is_the_references(ov, su, ori.cpu(), ref_ori)
+        assert ((dist.cpu() - ref).abs() / ref.abs())[same].max().item() <= 1e-3, (G, Q, sw)
         if Q <= G:
             ranks = W.evaluate_ranks(ov.cuda(), su.cuda(), path="tc").cpu().numpy()
-            thr = torch.diagonal(ref[:Q]).unsqueeze(0)
-            want = (ref <= thr).sum(0).numpy()
-            tie = ((ref - thr).abs() <= 3e-6).sum(0).numpy() - 1
-            assert np.all(np.abs(ranks - want) <= tie), (G, Q, sw)
+            check_exact_results(ref, ranks, None, None, 0)

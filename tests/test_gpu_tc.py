@@ -1,11 +1,15 @@
-"""GPU parity tests of the tcgen05 path (bf16 operands, fp32 accumulation) against the oracle."""
+"""GPU parity tests of the dense tcgen05 sweep (csrc/match_tc.cu: fp16 operands of the norm-scaled features, fp32
+accumulation) and of its fp32 finish against the oracle."""
 import numpy as np
 import pytest
 import torch
 
 from oracle import witw_oracle as O
+from parity_helpers import assert_orientation_is_the_references, check_exact_results, hard_features_cuda, reference_columns
 
 pytestmark = pytest.mark.gpu
+
+KAPPA = 256.0    # csrc/sweep_common.cuh: kDenseKappa
 
 
 @pytest.fixture(scope="module")
@@ -22,62 +26,68 @@ def _hankel_sweep(W):
     W.ops.TC_IMPL = "hankel"
     yield
     W.ops.TC_IMPL = "auto"
+    W.ops.DEFERRAL_CAP = None
 
 
-def bf16_model(ov, su):
-    """What the kernel computes, in float64: correlation of bf16-rounded operands, norms of the fp32 inputs."""
-    corr = O.fused_fp64(ov.bfloat16().float(), su.bfloat16().float())[0]
+def fp16_model(ov, su):
+    """What the raw sweep computes, in float64: correlation of the features scaled by 256 / norm and rounded to fp16,
+    norms of the fp32 inputs.  Returns (normalised correlation, orientation, distance)."""
+    G, Q = ov.shape[0], su.shape[0]
+    gn = ov.double().reshape(G, -1).norm(dim=1)
+    qn = su.double().reshape(Q, -1).norm(dim=1)
+    o16 = (ov.double() * (KAPPA / gn).view(G, 1, 1, 1)).float().half().float()
+    s16 = (su.double() * (KAPPA / qn).view(Q, 1, 1, 1)).float().half().float()
+    corr = O.fused_fp64(o16, s16)[0] / KAPPA ** 2
     ori = torch.argmax(corr, -1)
     w, sw = ov.shape[3], su.shape[3]
     shift = (torch.arange(w).view(w, 1) + torch.arange(sw).view(1, sw)) % w
     cn = torch.sqrt((ov.double() ** 2).sum((1, 2))[:, shift].sum(-1))                       # [G,W]
-    qn = su.double().reshape(su.shape[0], -1).norm(dim=1)
     best = torch.gather(corr, 2, ori.unsqueeze(-1)).squeeze(-1)
-    dist = 2 - 2 * best / (torch.gather(cn, 1, ori.reshape(ov.shape[0], -1)).reshape(ori.shape) * qn.unsqueeze(0))
-    return corr, ori, dist
+    ratio = gn.view(G, 1) / torch.gather(cn, 1, ori.reshape(G, -1)).reshape(ori.shape)
+    return corr, ori, 2 - 2 * best * ratio
 
 
 @pytest.mark.parametrize("fov,G,Q", [(360, 203, 300), (90, 130, 70), (70, 64, 257), (180, 36, 16), (6, 20, 9)])
 def test_tc_match_vs_oracle(W, fov, G, Q):
     ov, su, _ = O.synth_features(G, Q, fov=fov, noise=1.0, seed=fov)
-    ori, dist = W.match(ov.cuda(), su.cuda(), path="tc")
+    # tier 1: the raw fp16 sweep against the float64 model of the same arithmetic -> only accumulation-order noise
+    ori, dist = W.match(ov.cuda(), su.cuda(), path="tc16")
     ori, dist = ori.cpu(), dist.cpu()
     assert tuple(ori.shape) == (G, Q) and ori.dtype == torch.int64
-    # tier 1: against the float64 model of the same arithmetic -> only accumulation-order noise
-    corr, m_ori, m_dist = bf16_model(ov, su)
+    corr, m_ori, m_dist = fp16_model(ov, su)
     diff = ori != m_ori
     a = torch.gather(corr, 2, ori.unsqueeze(-1)).squeeze(-1)
     b = torch.gather(corr, 2, m_ori.unsqueeze(-1)).squeeze(-1)
-    assert bool((((a - b).abs() <= 2e-6 * corr.abs().amax(-1)) | ~diff).all())
+    assert bool((((a - b).abs() <= 4e-6) | ~diff).all())
     assert (dist.double() - m_dist)[~diff].abs().max().item() <= 2e-5
-    # tier 2: against the fp32 reference chain -> within 1e-3 relative where the orientation agrees;
-    # orientation flips only between shifts whose fp32 scores are within bf16 rounding of each other
+    # tier 2: the finished sweep against the fp32 reference chain: the reference's orientation (up to fp32 ties), distances
+    # within the north star's 1e-3 relative at every field of view
     ref_ori, ref = O.match(ov, su)
-    same = ori == ref_ori
+    ori, dist = W.match(ov.cuda(), su.cuda(), path="tc")
+    ori, dist = ori.cpu(), dist.cpu()
+    same = assert_orientation_is_the_references(ov, su, ori, ref_ori)
     rel = ((dist - ref).abs() / ref.abs())[same]
-    assert rel.max().item() <= (1e-3 if fov == 360 else 4e-3), rel.max().item()
-    assert (dist - ref).abs()[same].max().item() <= 2e-3
-    assert same.float().mean().item() >= 0.98
-    c32 = O.fused_fp64(ov, su)[0]
-    a = torch.gather(c32, 2, ori.unsqueeze(-1)).squeeze(-1)
-    b = torch.gather(c32, 2, ref_ori.unsqueeze(-1)).squeeze(-1)
-    assert bool((((a - b).abs() <= 2e-2 * c32.abs().amax(-1)) | same).all())
+    assert rel.max().item() <= 1e-3, rel.max().item()
+    assert (dist - ref)[same].abs().max().item() <= (6e-4 if su.shape[3] >= 8 else 1.5e-3)
+    if G * Q >= 1000:
+        assert same.float().mean().item() >= 0.995
 
 
 @pytest.mark.parametrize("fov,n,noise", [(360, 300, 25.0), (90, 260, 10.0)])
-def test_tc_evaluate_ranks_vs_oracle(W, fov, n, noise):
+def test_tc_raw_sweep_ranks_and_topk(W, fov, n, noise):
+    """exact=False: the raw fp16 decisions."""
     ov, su, _ = O.synth_features(n, n, fov=fov, noise=noise, seed=17)
     ranks, td, ti = W.evaluate_ranks(ov.cuda(), su.cuda(), path="tc", topk=5, exact=False)
     ranks = ranks.cpu().numpy()
     ref_ori, ref = O.match(ov, su)
     want = (ref <= torch.diagonal(ref).unsqueeze(0)).sum(0).numpy()
     assert len(set(want.tolist())) > 5                                   # non-degenerate ranks
-    # identical counts except for gallery items whose fp32 distance ties the threshold within tolerance
-    band = ((ref - torch.diagonal(ref).unsqueeze(0)).abs() <= 2e-3).sum(0).numpy() - 1
+    # identical counts except for gallery items whose fp32 distance ties the threshold within the fp16 error
+    band = ((ref - torch.diagonal(ref).unsqueeze(0)).abs() <= (3e-4 if fov == 360 else 1.2e-2)).sum(0).numpy() - 1
     assert np.all(np.abs(ranks - want) <= band)
-    assert np.mean(ranks == want) >= 0.8
+    assert np.mean(ranks == want) >= 0.9
     # fused top-k agrees with a sort of the kernel's own distance matrix
-    _, dist = W.match(ov.cuda(), su.cuda(), path="tc")
+    _, dist = W.match(ov.cuda(), su.cuda(), path="tc16")
     sd = torch.sort(dist.t().cpu(), dim=1, stable=True)
     assert torch.equal(td.cpu(), sd.values[:, :5]) and torch.equal(ti.cpu().long(), sd.indices[:, :5])
 
@@ -91,12 +101,13 @@ def test_tc_properties_at_scale(W):
     ovc, suc = ov.cuda(), su.cuda()
     ranks = W.evaluate_ranks(ovc, suc, path="tc")
     assert int((ranks != 1).sum()) == 0
-    ori, dist = W.match(ovc, suc, path="tc")
+    ori, dist = W.match(ovc, suc, path="tc16")
     assert torch.equal(torch.diagonal(ori[:Q]).cpu(), sh)
     rolled = torch.roll(ovc, 5, dims=3)
-    ori2, dist2 = W.match(rolled, suc, path="tc")
-    assert torch.equal(ori2, (ori + 5) % 64)
-    assert torch.equal(dist2, dist)                                       # same products, same order
+    ori2, dist2 = W.match(rolled, suc, path="tc16")
+    flips = ori2 != (ori + 5) % 64                                        # same products in the same order; the item norms are summed in
+    assert flips.float().mean().item() <= 1e-4                            # another order, which can move an operand element by an fp16 ulp
+    assert (dist2 - dist)[~flips].abs().max().item() <= 1e-5
     d_true, _ = W.true_match_distances(ovc, suc)
     parts = []
     t32 = torch.arange(Q, dtype=torch.int32, device="cuda")
@@ -114,12 +125,9 @@ def test_tc_baseline_size_10k_x_10k(W, fov):
     planted matches are rank 1 / top-1 with the planted orientation, distances are finite and in [0, 4]."""
     G = Q = 10000
     sw = int(fov / 360 * 512) // 8
-    gen = torch.Generator(device="cuda").manual_seed(11)
-    ov = torch.randn(G, 16, 4, 64, device="cuda", generator=gen) * 0.06
-    shifts = torch.randint(0, 64, (Q,), device="cuda", generator=gen)
-    cols = (shifts.view(Q, 1) + torch.arange(sw, device="cuda").view(1, sw)) % 64
-    su = torch.gather(ov, 3, cols.view(Q, 1, 1, sw).expand(Q, 16, 4, sw)) + 0.03 * torch.randn(Q, 16, 4, sw, device="cuda", generator=gen)
+    ov, su, shifts = hard_features_cuda(G, Q, sw, 0.5, seed=11)
     gal, qry = W.GalleryIndex(ov, sw), W.QueryBatch(su)
+    assert gal.impl == "hankel"
     inf = torch.full((Q,), float("inf"), device="cuda")
     cnt = torch.zeros(Q, dtype=torch.int32, device="cuda")
     W.sweep_tc(gal, qry, d_true=inf, rank_count=cnt)
@@ -134,9 +142,24 @@ def test_tc_baseline_size_10k_x_10k(W, fov):
     assert float(td.min()) >= 0.0 and float(td.max()) <= 4.0
     d_true, o_true = W.true_match_distances(ov, su)
     assert torch.equal(o_true, shifts)
-    assert (td[:, 0] - d_true).abs().max().item() <= 2e-3                 # bf16 sweep vs exact fp32 on the matches
+    assert (td[:, 0] - d_true).abs().max().item() <= 5e-6                 # the finish's fp32 distances on the matches
     rec = W.recall_from_ranks(ranks)
     assert rec["top_one"] == 100.0 and rec["top_percent"] == 100.0 and rec["count"] == Q
+
+
+def test_tc_baseline_size_hard_data_equals_the_oracle(W):
+    """The dense sweep at 10k x 10k, 90 degrees, on data with ranks all over the gallery: ranks and top-10 of a 32-query
+    subset equal the oracle's (cvig_fov.py:545-552) except where fp32 distances tie to 3e-6; nothing dropped."""
+    G = Q = 10000
+    ov, su, _ = hard_features_cuda(G, Q, 16, 10.0, seed=5)
+    ranks, td, ti = W.evaluate_ranks(ov, su, path="tc", topk=10)
+    stats = W.ops.evaluate_ranks_prepared.last_stats
+    assert int(stats["deferred"].max()) <= stats["list_cap"] and stats["flagged"] == 0
+    r = ranks.cpu().numpy()
+    assert len(set(r.tolist())) > 1000
+    sub = torch.arange(0, Q, Q // 32)[:32]
+    ref = reference_columns(ov.cpu(), su.cpu(), sub)
+    check_exact_results(ref, r[sub.numpy()], td[sub.cuda()], ti[sub.cuda()], 10, true_rows=sub)
 
 
 def test_tc_semantic_config_shapes(W):
@@ -167,7 +190,9 @@ def test_gallery_builder_matches_one_shot_prep(W):
     built = b.finish()
     assert built.G == 158
     assert torch.equal(built.operand[: whole.operand.numel()], whole.operand)
-    assert torch.equal(built.crop_inv_norm[: 160 * 64], whole.crop_inv_norm[: 160 * 64])
+    for name, width in (("scale", 64), ("aux", 4), ("crop_inv_norm", 64)):
+        assert torch.equal(getattr(built, name)[: 160 * width], getattr(whole, name)[: 160 * width]), name
+    assert torch.equal(built.spec, whole.spec)
     r1 = W.evaluate_ranks_prepared(whole, W.QueryBatch(suc))
     r2 = W.evaluate_ranks_prepared(built, W.QueryBatch(suc))
     assert torch.equal(r1, r2)
@@ -176,16 +201,17 @@ def test_gallery_builder_matches_one_shot_prep(W):
 
 
 def test_heatmap_sweep_one_query_many_tiles(W):
-    """tools/heatmap/heatmap.py:171-177 shape: one photo against a swept grid of tiles, both paths."""
+    """tools/heatmap/heatmap.py:171-177 shape: one photo against a swept grid of tiles, every path."""
     ov, su, sh = O.synth_features(1200, 1, fov=70, noise=0.3, seed=3)
     rdeg, rdis, rscore = O.heatmap_scores(ov, su)
-    for path in ("fp32", "tc"):
+    ref_ori = O.correlation(ov, su)
+    for path in ("fp32", "auto", "tc"):
         deg, dis, score = W.heatmap_scores(ov.cuda(), su.cuda(), path=path)
         assert tuple(deg.shape) == (1200,) and tuple(dis.shape) == (1200,)
-        tol = 5e-6 if path == "fp32" else 2e-3
-        same = deg.cpu() == rdeg
-        assert same.float().mean().item() >= (1.0 if path == "fp32" else 0.98)
-        assert (dis.cpu() - rdis)[same].abs().max().item() <= tol
+        ori = ((deg.cpu() + 180) * 64 / 360).round().long().view(-1, 1)
+        same = assert_orientation_is_the_references(ov, su, ori, ref_ori).view(-1)
+        assert same.float().mean().item() >= 0.999
+        assert (dis.cpu() - rdis)[same].abs().max().item() <= (6e-4 if path == "tc" else 5e-6)
         assert int(torch.argmin(dis)) == 0 and float(deg[0]) == float(sh[0]) * 360 / 64 - 180
 
 
@@ -228,47 +254,28 @@ def test_spectral_pair_distances_vs_oracle(W, fov, G, Q):
     assert diff.float().mean().item() <= 1e-3
 
 
-def test_spectral_and_direct_finish_agree(W):
-    """The two implementations of the exact finish give the same ranks and the same top-k."""
-    ov, su, _ = O.synth_features(280, 280, fov=90, noise=10.0, seed=5)
-    out = {}
-    for impl in ("spectral", "direct"):
-        W.ops.EXACT_IMPL = impl
-        try:
-            out[impl] = W.evaluate_ranks(ov.cuda(), su.cuda(), path="tc", topk=5)
-        finally:
-            W.ops.EXACT_IMPL = "spectral"
-    ref = O.match(ov, su)[1]
-    tie = ((ref - torch.diagonal(ref).unsqueeze(0)).abs() <= 3e-6).sum(0) - 1
-    assert bool(((out["spectral"][0] - out["direct"][0]).abs().cpu() <= tie).all())
-    assert (out["spectral"][1] - out["direct"][1]).abs().max().item() <= 5e-6
-    assert (out["spectral"][2] == out["direct"][2]).float().mean().item() >= 0.995
-
-
 @pytest.mark.parametrize("fov,n,noise", [(360, 300, 25.0), (90, 260, 10.0), (70, 200, 8.0)])
 def test_tc_exact_finish_matches_fp32_reference(W, fov, n, noise):
-    """exact=True: near-threshold rank decisions are re-taken in fp32 and the top-k re-ranked in fp32, so ranks and top-k
-    are the fp32 reference's (cvig_fov.py:547-552) -- differences only where fp32 distances themselves tie to round-off."""
+    """exact=True: rank decisions the fp16 operands cannot settle are taken in fp32 and the top-k re-ranked in fp32, so
+    ranks and top-k are the fp32 reference's (cvig_fov.py:547-552) -- differences only where fp32 distances themselves tie."""
     ov, su, _ = O.synth_features(n, n, fov=fov, noise=noise, seed=23)
     ranks, td, ti = W.evaluate_ranks(ov.cuda(), su.cuda(), path="tc", topk=5)       # exact=True is the default
-    ranks = ranks.cpu().numpy()
     ref_ori, ref = O.match(ov, su)
-    thr = torch.diagonal(ref).unsqueeze(0)
-    want = (ref <= thr).sum(0).numpy()
+    want = check_exact_results(ref, ranks.cpu().numpy(), td, ti, 5)
     assert len(set(want.tolist())) > 5
-    tie = ((ref - thr).abs() <= 3e-6).sum(0).numpy() - 1                            # fp32 round-off ties only
-    assert np.all(np.abs(ranks - want) <= tie)
-    assert np.mean(ranks == want) >= 0.98
-    appended, dropped = W.ops.evaluate_ranks_prepared.last_recheck.cpu().tolist()
-    assert dropped == 0 and appended > 0
-    # top-k: the returned distances are the exact fp32 distances of the returned items, ascending; the match is first;
-    # the item set is the reference's wherever the bf16 candidate list (k + margin deep) reaches far enough
-    tdc, tic = td.cpu(), ti.cpu().long()
-    assert (tdc - torch.gather(ref.t(), 1, tic)).abs().max().item() <= 5e-6
-    assert bool((tdc[:, 1:] >= tdc[:, :-1]).all())
-    sd = torch.sort(ref.t(), dim=1, stable=True)
-    assert torch.equal(tic[:, 0], sd.indices[:, 0])
-    assert (tic == sd.indices[:, :5]).float().mean().item() >= (0.99 if fov == 360 else 0.9)
+    stats = W.ops.evaluate_ranks_prepared.last_stats
+    deferred = stats["deferred"].cpu()
+    assert int(deferred.max()) <= stats["list_cap"] and int(deferred.sum()) > 0 and stats["flagged"] == 0
+    assert int(deferred.sum()) <= 0.03 * n * n
+
+
+def test_tc_exact_finish_survives_list_overflow(W):
+    n = 400
+    ov, su, _ = O.synth_features(n, n, fov=90, noise=10.0, seed=31)
+    W.ops.DEFERRAL_CAP = 2
+    ranks, td, ti = W.evaluate_ranks(ov.cuda(), su.cuda(), path="tc", topk=5)
+    assert W.ops.evaluate_ranks_prepared.last_stats["flagged"] > 0
+    check_exact_results(O.match(ov, su)[1], ranks.cpu().numpy(), td, ti, 5)
 
 
 def test_sharded_cuda_local_single_process(W):
@@ -298,7 +305,7 @@ def test_sharded_cuda_local_single_process(W):
 
 def test_tc_random_shapes_exact_finish_against_oracle(W):
     """Seeded random problem shapes on the dense sweep, narrow to full query widths: exact-finish ranks equal the fp32
-    reference chain's up to fp32 round-off ties (the re-check band widens as 0.4 / sw for cropped queries)."""
+    reference chain's up to fp32 round-off ties."""
     rng = np.random.default_rng(77)
     for trial in range(8):
         G = int(rng.integers(40, 900))
@@ -312,9 +319,4 @@ def test_tc_random_shapes_exact_finish_against_oracle(W):
         su = torch.gather(ov[:Q], 3, cols.view(Q, 1, 1, sw).expand(Q, 16, 4, sw)) + 6.0 * su
         ref = O.match(ov, su)[1]
         ranks = W.evaluate_ranks(ov.cuda(), su.cuda(), path="tc").cpu().numpy()
-        appended, dropped = W.ops.evaluate_ranks_prepared.last_recheck.cpu().tolist()
-        assert dropped == 0, (G, Q, sw, appended)
-        thr = torch.diagonal(ref[:Q]).unsqueeze(0)
-        want = (ref <= thr).sum(0).numpy()
-        tie = ((ref - thr).abs() <= 3e-6).sum(0).numpy() - 1
-        assert np.all(np.abs(ranks - want) <= tie), (G, Q, sw)
+        check_exact_results(ref, ranks, None, None, 0)

@@ -7,6 +7,7 @@ hand-written CUDA in libwitw_b200.so (C ABI: include/witw_b200.h).  No CPU fallb
 from . import _lib, ops
 from ._lib import WitwError
 from .ops import (
+    Deferral,
     GalleryBuilder,
     GalleryIndex,
     ImageNormalization,
@@ -20,6 +21,8 @@ from .ops import (
     crop_overhead,
     evaluate_ranks,
     evaluate_ranks_prepared,
+    exact_columns,
+    finish_tc,
     heatmap_scores,
     l2_distance,
     match,
@@ -41,7 +44,7 @@ from .install import install, uninstall
 from .sharded import evaluate_ranks_sharded, shard_bounds
 
 __all__ = [
-    "GalleryBuilder", "GalleryIndex", "ImageNormalization", "PolarTransform", "QueryBatch", "Resize", "WitwError", "baseline_ranks", "bilinear_interpolate", "correlation",
+    "Deferral", "exact_columns", "finish_tc", "GalleryBuilder", "GalleryIndex", "ImageNormalization", "PolarTransform", "QueryBatch", "Resize", "WitwError", "baseline_ranks", "bilinear_interpolate", "correlation",
     "correlation_scores", "crop_overhead", "evaluate_ranks", "evaluate_ranks_prepared", "evaluate_ranks_sharded",
     "heatmap_scores", "install", "l2_distance", "match", "match_distance", "normalized_polar", "polar_grid", "polar_transform", "prepare_pair", "rank_from_distances",
     "recall_from_ranks", "resize_normalize", "shard_bounds", "sweep_tc", "tc_supported", "topk_from_distances", "triplet_loss", "true_match_distances",

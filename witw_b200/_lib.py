@@ -44,33 +44,26 @@ SIGNATURES = {
     "witw_triplet_loss_f32": (c_int, [c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p]),
     "witw_gallery_operand_bytes": (c_size_t, [c_int64, c_int, c_int]),
     "witw_query_operand_bytes": (c_size_t, [c_int64, c_int, c_int]),
-    "witw_gallery_prep": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
-    "witw_query_prep": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "witw_gallery_prep": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "witw_query_prep": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "witw_match_tc_topk_slots": (c_int, [c_int64, c_int64]),
-    "witw_match_tc": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p,
-                              c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int32, c_float, c_void_p, c_void_p,
-                              c_void_p, c_int32, c_void_p]),
-    "witw_recheck_apply_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int, c_int, c_int, c_void_p,
-                                       c_void_p, c_void_p, c_void_p]),
-    "witw_topk_refine_scratch_bytes": (c_size_t, [c_int64, c_int]),
-    "witw_topk_refine_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p, c_int, c_int32, c_int,
-                                     c_void_p, c_void_p, c_void_p, c_void_p]),
+    "witw_match_tc": (c_int, [c_void_p, c_void_p]),
     "witw_spectral_rows_f32": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "witw_match_pairs_spec_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p,
                                           c_void_p]),
-    "witw_recheck_apply_spec_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int,
-                                            c_void_p, c_void_p, c_void_p, c_void_p]),
-    "witw_topk_refine_spec_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_int, c_int32,
-                                          c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "witw_match_columns_spec_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int64, c_void_p, c_void_p,
+                                            c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int32, c_void_p, c_void_p]),
+    "witw_finish_spec_f32": (c_int, [c_void_p, c_void_p]),
+    "witw_sizeof_sweep_args": (c_size_t, []),
+    "witw_sizeof_finish_args": (c_size_t, []),
     "witw_spec_supported": (c_int, [c_int, c_int, c_int]),
     "witw_spec_gallery_operand_bytes": (c_size_t, [c_int64, c_int]),
     "witw_spec_query_operand_bytes": (c_size_t, [c_int64, c_int]),
-    "witw_spec_gallery_prep": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "witw_spec_query_prep": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "witw_spec_gallery_prep": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                       c_void_p]),
+    "witw_spec_query_prep": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "witw_match_spec_topk_slots": (c_int, [c_int64, c_int64]),
-    "witw_match_spec": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p,
-                                c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int32, c_float, c_void_p, c_void_p,
-                                c_void_p, c_int32, c_void_p]),
+    "witw_match_spec": (c_int, [c_void_p, c_void_p]),
     "witw_rank_from_dist_f32": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
     "witw_l2_rank_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "witw_topk_slices": (c_int, [c_int64, c_int64]),
@@ -79,6 +72,29 @@ SIGNATURES = {
     "witw_topk_select_f32": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_int32, c_void_p, c_void_p]),
     "witw_topk_merge": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
 }
+
+
+class SweepArgs(ctypes.Structure):
+    """witw_sweep_args of include/witw_b200.h (field for field)."""
+    _fields_ = [
+        ("gal_op", c_void_p), ("gal_scale", c_void_p), ("gal_aux", c_void_p), ("qry_op", c_void_p), ("qry_aux", c_void_p),
+        ("G", c_int64), ("Q", c_int64), ("CH", c_int32), ("sw", c_int32), ("g_index_offset", c_int32), ("topk", c_int32),
+        ("dist", c_void_p), ("ori", c_void_p), ("d_true", c_void_p), ("true_idx", c_void_p), ("rank_count", c_void_p),
+        ("topk_key", c_void_p), ("topk_idx", c_void_p), ("list_g", c_void_p), ("list_n", c_void_p),
+        ("list_cap", c_int32), ("err_sigmas", c_float), ("fix_rel", c_float),
+    ]
+
+
+class FinishArgs(ctypes.Structure):
+    """witw_finish_args of include/witw_b200.h (field for field)."""
+    _fields_ = [
+        ("gal_spec", c_void_p), ("crop_inv_norm", c_void_p), ("qry_spec", c_void_p), ("q_inv_norm", c_void_p),
+        ("G", c_int64), ("Q", c_int64), ("CH", c_int32), ("g_index_offset", c_int32),
+        ("list_g", c_void_p), ("list_n", c_void_p), ("list_cap", c_int32), ("kc", c_int32),
+        ("d_true", c_void_p), ("rank_count", c_void_p), ("dist", c_void_p), ("ori", c_void_p),
+        ("cand_key", c_void_p), ("cand_idx", c_void_p), ("out_dist", c_void_p), ("out_idx", c_void_p),
+        ("k_out", c_int32), ("reserved", c_int32), ("qflag", c_void_p), ("n_flagged", c_void_p),
+    ]
 
 
 class WitwError(RuntimeError):
@@ -100,6 +116,8 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
+    if lib.witw_sizeof_sweep_args() != ctypes.sizeof(SweepArgs) or lib.witw_sizeof_finish_args() != ctypes.sizeof(FinishArgs):
+        raise ImportError("witw_b200: %s was built from another include/witw_b200.h (argument structures differ); rebuild it" % LIB_PATH)
     _lib = lib
     return lib
 

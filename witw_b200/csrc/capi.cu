@@ -29,7 +29,11 @@ int sm_count() {
 
 extern "C" const char* witw_last_error(void) { return witw::g_err; }
 
-extern "C" int witw_version(void) { return 100; }
+extern "C" int witw_version(void) { return 200; }
+
+// sizes of the argument structures, so that a binding can check its own declaration of them
+extern "C" size_t witw_sizeof_sweep_args(void) { return sizeof(witw_sweep_args); }
+extern "C" size_t witw_sizeof_finish_args(void) { return sizeof(witw_finish_args); }
 
 extern "C" int witw_device_check(void) {
   int dev = 0, major = 0;

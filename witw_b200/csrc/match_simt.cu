@@ -411,136 +411,6 @@ extern "C" int witw_match_pairs_f32(const float* ov, const float* su, const int6
   return launch_pairs(ov, su, pair_g, pair_q, n_pairs, nullptr, CH, W, sw, dist, ori, stream);
 }
 
-namespace witw {
-__global__ void __launch_bounds__(256)
-recheck_apply_kernel(const float* __restrict__ exact, const int64_t* __restrict__ list_q, const int32_t* __restrict__ count, int cap,
-                     const float* __restrict__ d_true, int32_t* __restrict__ rank_count) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int n = min(*count, cap);
-  if (i >= n) return;
-  const int64_t q = list_q[i];
-  if (exact[i] <= d_true[q]) atomicAdd(rank_count + q, 1);
-}
-
-__global__ void __launch_bounds__(128)
-topk_refine_sort_kernel(const float* __restrict__ exact, const int32_t* __restrict__ cand_idx, int64_t Q, int kc, int k_out,
-                        float* __restrict__ out_d, int32_t* __restrict__ out_i) {
-  // thread per query: selection sort of its kc exact distances (ties by lower gallery index), first k_out kept
-  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= Q) return;
-  const float inf = __int_as_float(0x7f800000);
-  unsigned used = 0;  // kc <= 32
-  for (int j = 0; j < k_out; ++j) {
-    float best = inf;
-    int32_t best_i = -1;
-    int best_p = -1;
-    for (int p = 0; p < kc; ++p) {
-      if (used & (1u << p)) continue;
-      const int32_t i = cand_idx[q * kc + p];
-      if (i < 0) continue;
-      const float d = exact[q * kc + p];
-      if (!(d == d)) continue;
-      if (best_p < 0 || d < best || (d == best && i < best_i)) { best = d; best_i = i; best_p = p; }
-    }
-    if (best_p >= 0) used |= 1u << best_p;
-    out_d[q * k_out + j] = best_p >= 0 ? best : inf;
-    out_i[q * k_out + j] = best_i;
-  }
-}
-
-__global__ void __launch_bounds__(256)
-topk_refine_pairs_kernel(const int32_t* __restrict__ cand_idx, int64_t n, int kc, int32_t g_offset, int64_t G, int64_t* __restrict__ pg,
-                         int64_t* __restrict__ pq) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  int64_t g = (int64_t)cand_idx[i] - g_offset;
-  if (g < 0 || g >= G) g = 0;  // padding slot: any valid pair, its result is ignored (index stays -1)
-  pg[i] = g;
-  pq[i] = i / kc;
-}
-}  // namespace witw
-
-extern "C" int witw_recheck_apply_f32(const float* ov, const float* su, const int64_t* recheck_g, const int64_t* recheck_q,
-                                      const int32_t* recheck_count, int32_t capacity, int CH, int W, int sw, const float* d_true,
-                                      int32_t* rank_count, float* scratch, witw_stream_t stream) {
-  int rc = check_match_shape("witw_recheck_apply_f32", 1, 1, CH, W, sw);
-  if (rc != WITW_OK) return rc;
-  if (capacity == 0) return WITW_OK;
-  WITW_REQUIRE(capacity > 0 && ov && su && recheck_g && recheck_q && recheck_count && d_true && rank_count && scratch, WITW_ERR_INVALID,
-               "witw_recheck_apply_f32: bad arguments");
-  // one CTA per list slot; CTAs past the device-side count exit at once, so no host round trip is needed
-  rc = launch_pairs(ov, su, recheck_g, recheck_q, capacity, recheck_count, CH, W, sw, scratch, nullptr, stream);
-  if (rc != WITW_OK) return rc;
-  recheck_apply_kernel<<<(unsigned)ceil_div<int64_t>(capacity, 256), 256, 0, as_stream(stream)>>>(scratch, recheck_q, recheck_count, capacity, d_true,
-                                                                                           rank_count);
-  WITW_LAUNCH_CHECK();
-  return WITW_OK;
-}
-
-extern "C" size_t witw_topk_refine_scratch_bytes(int64_t Q, int kc) { return (size_t)std::max<int64_t>(Q, 1) * kc * (8 + 8 + 4); }
-
-extern "C" int witw_topk_refine_f32(const float* ov, const float* su, int64_t G, int64_t Q, int CH, int W, int sw, const int32_t* cand_idx,
-                                    int kc, int32_t g_offset, int k_out, float* out_dist, int32_t* out_idx, void* scratch,
-                                    witw_stream_t stream) {
-  int rc = check_match_shape("witw_topk_refine_f32", G, Q, CH, W, sw);
-  if (rc != WITW_OK) return rc;
-  WITW_REQUIRE(kc >= 1 && kc <= 32 && k_out >= 1 && k_out <= kc, WITW_ERR_INVALID, "witw_topk_refine_f32: need 1 <= k_out <= kc <= 32");
-  if (Q == 0) return WITW_OK;
-  WITW_REQUIRE(G > 0 && ov && su && cand_idx && out_dist && out_idx && scratch, WITW_ERR_INVALID, "witw_topk_refine_f32: bad arguments");
-  const int64_t n = Q * kc;
-  WITW_REQUIRE(n < (1ll << 31), WITW_ERR_UNSUPPORTED, "witw_topk_refine_f32: too many candidates");
-  int64_t* pg = reinterpret_cast<int64_t*>(scratch);
-  int64_t* pq = pg + n;
-  float* exact = reinterpret_cast<float*>(pq + n);
-  topk_refine_pairs_kernel<<<(unsigned)ceil_div<int64_t>(n, 256), 256, 0, as_stream(stream)>>>(cand_idx, n, kc, g_offset, G, pg, pq);
-  WITW_LAUNCH_CHECK();
-  rc = launch_pairs(ov, su, pg, pq, n, nullptr, CH, W, sw, exact, nullptr, stream, kc);  // the kc candidates of a query share one CTA
-  if (rc != WITW_OK) return rc;
-  topk_refine_sort_kernel<<<(unsigned)ceil_div<int64_t>(Q, 128), 128, 0, as_stream(stream)>>>(exact, cand_idx, Q, kc, k_out, out_dist, out_idx);
-  WITW_LAUNCH_CHECK();
-  return WITW_OK;
-}
-
-// Same two finishes on packed azimuth spectra (spectral.cu): ~20x fewer MACs per pair than the direct fp32 kernels.
-extern "C" int witw_recheck_apply_spec_f32(const float* gal_spec, const float* crop_inv_norm, const float* qry_spec,
-                                           const float* q_inv_norm, const int64_t* recheck_g, const int64_t* recheck_q,
-                                           const int32_t* recheck_count, int32_t capacity, int CH, const float* d_true,
-                                           int32_t* rank_count, float* scratch, witw_stream_t stream) {
-  WITW_REQUIRE(CH > 0 && capacity >= 0, WITW_ERR_INVALID, "witw_recheck_apply_spec_f32: bad shape");
-  if (capacity == 0) return WITW_OK;
-  WITW_REQUIRE(gal_spec && crop_inv_norm && qry_spec && q_inv_norm && recheck_g && recheck_q && recheck_count && d_true && rank_count && scratch,
-               WITW_ERR_INVALID, "witw_recheck_apply_spec_f32: null pointer");
-  int rc = launch_pairs_spec(gal_spec, crop_inv_norm, qry_spec, q_inv_norm, recheck_g, recheck_q, capacity, recheck_count, CH, scratch, nullptr, stream);
-  if (rc != WITW_OK) return rc;
-  recheck_apply_kernel<<<(unsigned)ceil_div<int64_t>(capacity, 256), 256, 0, as_stream(stream)>>>(scratch, recheck_q, recheck_count, capacity, d_true,
-                                                                                           rank_count);
-  WITW_LAUNCH_CHECK();
-  return WITW_OK;
-}
-
-extern "C" int witw_topk_refine_spec_f32(const float* gal_spec, const float* crop_inv_norm, const float* qry_spec,
-                                         const float* q_inv_norm, int64_t G, int64_t Q, int CH, const int32_t* cand_idx, int kc,
-                                         int32_t g_offset, int k_out, float* out_dist, int32_t* out_idx, void* scratch,
-                                         witw_stream_t stream) {
-  WITW_REQUIRE(G >= 0 && Q >= 0 && CH > 0, WITW_ERR_INVALID, "witw_topk_refine_spec_f32: bad shape");
-  WITW_REQUIRE(kc >= 1 && kc <= 32 && k_out >= 1 && k_out <= kc, WITW_ERR_INVALID, "witw_topk_refine_spec_f32: need 1 <= k_out <= kc <= 32");
-  if (Q == 0) return WITW_OK;
-  WITW_REQUIRE(G > 0 && gal_spec && crop_inv_norm && qry_spec && q_inv_norm && cand_idx && out_dist && out_idx && scratch, WITW_ERR_INVALID,
-               "witw_topk_refine_spec_f32: bad arguments");
-  const int64_t n = Q * kc;
-  WITW_REQUIRE(n < (1ll << 31), WITW_ERR_UNSUPPORTED, "witw_topk_refine_spec_f32: too many candidates");
-  int64_t* pg = reinterpret_cast<int64_t*>(scratch);
-  int64_t* pq = pg + n;
-  float* exact = reinterpret_cast<float*>(pq + n);
-  topk_refine_pairs_kernel<<<(unsigned)ceil_div<int64_t>(n, 256), 256, 0, as_stream(stream)>>>(cand_idx, n, kc, g_offset, G, pg, pq);
-  WITW_LAUNCH_CHECK();
-  int rc = launch_pairs_spec(gal_spec, crop_inv_norm, qry_spec, q_inv_norm, pg, pq, n, nullptr, CH, exact, nullptr, stream);
-  if (rc != WITW_OK) return rc;
-  topk_refine_sort_kernel<<<(unsigned)ceil_div<int64_t>(Q, 128), 128, 0, as_stream(stream)>>>(exact, cand_idx, Q, kc, k_out, out_dist, out_idx);
-  WITW_LAUNCH_CHECK();
-  return WITW_OK;
-}
-
 extern "C" int witw_crop_gather_f32(const float* ov, const int64_t* ori, float* out, int64_t G, int64_t Q, int CH, int W, int sw,
                                     witw_stream_t stream) {
   WITW_REQUIRE(G >= 0 && Q >= 0 && CH > 0 && W > 0 && sw > 0 && sw <= W, WITW_ERR_INVALID, "witw_crop_gather_f32: bad shape");

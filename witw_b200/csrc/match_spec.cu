@@ -28,8 +28,12 @@
 // by the MMAs (256 MMAs x 4.6 KB), 2.33 MB at 128 B/cycle = 9.3 us; the kernel runs at 91 % of that.
 // Measured and dropped: multicasting the query stage over a cluster (2/4/8 CTAs) -- L2 is not the limiter, the
 // lock-step costs up to 20 %.
+//
+// Operands are fp16 spectra of the norm-scaled features (sweep_common.cuh): 8x finer than bf16 at the same cost, and
+// with a per-pair bound on what the rounding can do to a result, so that the epilogue knows which decisions it may
+// take itself and which it must defer to the fp32 finish (finish.cu).
 #include <cuda.h>
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -37,12 +41,15 @@
 #include "common.cuh"
 #include "ifft64_gen.cuh"
 #include "row_fft.cuh"
+#include "sweep_common.cuh"
 #include "tc_common.cuh"
 
 namespace witw {
 
 void* get_encode_tiled();                                                                         // polar.cu
-int launch_crop_norm(const float* ov, int64_t G, int64_t G_pad, int CH, int sw, float* crop_inv_norm, witw_stream_t stream);  // match_tc.cu
+// match_tc.cu: per-item norms, crop-norm tables and operand scale (gal_aux[g] = (max scale, spread, 0, kappa / ||ov_g||))
+int launch_item_stats(const float* ov, int64_t G, int64_t G_pad, int CH, int sw, float kappa, float unit, float dense_sigma,
+                      float* gal_scale, float* gal_aux, float* crop_inv_norm, witw_stream_t stream);
 
 constexpr int kSpThreads = 512;
 constexpr int kSpStages = 6;           // even: producer / issuer warp p owns the stages of parity p
@@ -51,31 +58,67 @@ constexpr int kSpBBytes = 2 * 16 * 128;   // 2 K halves x 8 items x (Re, Im) x 6
 constexpr int kSpSlots = 32;
 constexpr int kSpItems = 8;            // gallery items per tile (= per operand group)
 constexpr int kSpCH = 64;              // feature rows (C*H) the operand layout is built for
-constexpr int kSpTopkMax = 16;
+constexpr int kSpTopkMax = kSweepTopk;
 constexpr int kSpMaxChunks = 32;       // two candidate lists per chunk; witw_topk_merge takes up to 64
 
-// Timing experiments only (wrong results): WITW_SPEC_DEBUG bit 0 = no inverse FFT, bit 1 = no TMEM loads in the epilogue,
-// bit 2 = no tcgen05.mma (barriers only), bit 3 = no query-stage loads, bit 4 = chunk-major work order.
+// Timing experiments (wrong results by design) exist only in builds with -DWITW_DEBUG_HOOKS (tools/ probes): WITW_SPEC_DEBUG
+// bit 0 = no inverse FFT, bit 1 = no TMEM loads in the epilogue, bit 2 = no tcgen05.mma (barriers only), bit 3 = no
+// query-stage loads, bit 4 = chunk-major work order.  The shipped library never reads the environment.
+#ifdef WITW_DEBUG_HOOKS
 static int spec_debug() {
   static int v = -1;
   if (v < 0) { const char* e = std::getenv("WITW_SPEC_DEBUG"); v = e ? std::atoi(e) : 0; }
   return v;
 }
+#define SPEC_DBG(P, bit) (((P).debug & (bit)) != 0)
+#else
+static int spec_debug() { return 0; }
+#define SPEC_DBG(P, bit) false
+#endif
 
 // ------------------------------------------------------------------------------------------
 // operand preparation
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint2 pack4_bf16(float a, float b, float c, float d) {
-  const __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+__device__ __forceinline__ uint2 pack4_f16(float a, float b, float c, float d) {
+  const __half2 lo = __floats2half2_rn(a, b), hi = __floats2half2_rn(c, d);
   return make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
 }
 
+// sum over the threads of a 256-thread CTA; red: 8 floats of shared memory
+__device__ __forceinline__ float block_sum_256(float v, float* red) {
+  for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) t += red[w];
+  return t;
+}
+
+// sum over the packed half spectrum (32 slots x 64 rows in shared memory) of |X|^4; slot 0 holds the two real bins
+__device__ __forceinline__ float spectrum_quartic(const float (*sre)[kSpCH + 1], const float (*sim)[kSpCH + 1]) {
+  float s4 = 0.f;
+  for (int idx = threadIdx.x; idx < kSpSlots * kSpCH; idx += 256) {
+    const int slot = idx >> 6, row = idx & 63;
+    const float re = sre[slot][row], im = sim[slot][row];
+    if (slot == 0) {
+      s4 += re * re * re * re + im * im * im * im;
+    } else {
+      const float m2 = re * re + im * im;
+      s4 += m2 * m2;
+    }
+  }
+  return s4;
+}
+
 // CTA = one gallery item: 64 warp-level row FFTs, then the item's 128 operand rows of 128 bytes
-// (slot, K half, Re/Im) are written into its group's tiles.
+// (slot, K half, Re/Im) are written into its group's tiles, scaled by gal_aux[g].w = kappa / ||ov_g|| (launch_item_stats).
 __global__ void __launch_bounds__(256)
-spec_gallery_prep_kernel(const float* __restrict__ ov, int64_t G, int64_t g_first, __nv_bfloat16* __restrict__ out,
+spec_gallery_prep_kernel(const float* __restrict__ ov, int64_t G, int64_t g_first, __half* __restrict__ out, float4* __restrict__ gal_aux,
                          float* __restrict__ spec_out) {
   __shared__ float sre[kSpSlots][kSpCH + 1], sim[kSpSlots][kSpCH + 1];  // [slot][feature row]
+  __shared__ float red[8];
   const int64_t g_local = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   RowFft fft;
@@ -92,6 +135,10 @@ spec_gallery_prep_kernel(const float* __restrict__ ov, int64_t G, int64_t g_firs
     float2* dst = reinterpret_cast<float2*>(spec_out + g_local * (kSpCH * 64));
     for (int idx = threadIdx.x; idx < kSpCH * 32; idx += 256) dst[idx] = make_float2(sre[idx & 31][idx >> 5], sim[idx & 31][idx >> 5]);
   }
+  const float scale = gal_aux[g_local].w;     // 0 for a zero-norm item and past G: a zero operand
+  // rounding scale of the item (sweep_common.cuh): 4-norm of the normalised half spectrum
+  const float s4 = block_sum_256(spectrum_quartic(sre, sim), red);
+  if (threadIdx.x == 0) gal_aux[g_local].z = kRoundSigma * (2.0f / 64.0f) * kSpecUnit * sqrtf(sqrtf(s4)) * (scale / kSpecKappa);
   const int64_t g = g_first + g_local;
   const int64_t group = g >> 3;
   const int i = (int)(g & 7);
@@ -102,31 +149,31 @@ spec_gallery_prep_kernel(const float* __restrict__ ov, int64_t G, int64_t g_firs
     float v[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float re = sre[slot][r0 + j], im = sim[slot][r0 + j];
+      const float re = sre[slot][r0 + j] * scale, im = sim[slot][r0 + j] * scale;
       if (slot == 0) v[j] = (half == c) ? (half == 0 ? re : im) : 0.f;   // [O_0 | 0] and [0 | O_32]
       else v[j] = half == 0 ? (c == 0 ? re : im) : (c == 0 ? im : -re);  // [Re | Im] and [Im | -Re]
     }
     const int64_t row = ((group * kSpSlots + slot) * 2 + half) * 16 + 4 * (i >> 1) + 2 * c + (i & 1);
-    *reinterpret_cast<uint2*>(out + row * 64 + r0) = pack4_bf16(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<uint2*>(out + row * 64 + r0) = pack4_f16(v[0], v[1], v[2], v[3]);
   }
 }
 
-// CTA = one query: spectra of the zero-padded rows scaled by 1/64 (the inverse transform's normalisation, exact in
-// bf16) and the fp32 inverse norm of the query.  Operand layout: [query tile of 128][slot][K half: Re(r) | Im(r)][query
-// row][64 bf16], so the two K-major tiles of one slot of one query tile are 32 contiguous KB (one TMA box).  Queries past Q
-// in the last tile are written as zeros.
+// CTA = one query: spectra of the zero-padded rows scaled by kappa / ||su_q||, the fp32 inverse norm of the query and its
+// sweep constants qry_aux[q] = (1 or NaN, 4-norm of the normalised half spectrum).  Operand layout: [query tile of
+// 128][slot][K half: Re(r) | Im(r)][query row][64 fp16], so the two K-major tiles of one slot of one query tile are 32
+// contiguous KB (one TMA box).  Queries past Q in the last tile are written as zeros.
 __global__ void __launch_bounds__(256)
-spec_query_prep_kernel(const float* __restrict__ su, int64_t Q, int sw, __nv_bfloat16* __restrict__ out, float* __restrict__ q_inv_norm,
-                       float* __restrict__ spec_out) {
+spec_query_prep_kernel(const float* __restrict__ su, int64_t Q, int sw, __half* __restrict__ out, float2* __restrict__ qry_aux,
+                       float* __restrict__ q_inv_norm, float* __restrict__ spec_out) {
   __shared__ float sre[kSpSlots][kSpCH + 1], sim[kSpSlots][kSpCH + 1];
   __shared__ float red[8];
   const int64_t q = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool live = q < Q;
+  float e = 0.f;
   if (live) {
     RowFft fft;
     fft.init(lane);
-    float e = 0.f;
     for (int row = warp; row < kSpCH; row += 8) {
       const float* r = su + (q * kSpCH + row) * sw;
       const int j = 2 * lane;
@@ -139,25 +186,26 @@ spec_query_prep_kernel(const float* __restrict__ su, int64_t Q, int sw, __nv_bfl
       sre[lane][row] = X.x;
       sim[lane][row] = X.y;
     }
-    for (int m = 16; m > 0; m >>= 1) e += __shfl_xor_sync(0xffffffffu, e, m);
-    if (lane == 0) red[warp] = e;
   }
-  __syncthreads();
-  if (live && threadIdx.x == 0) {
-    float t = 0.f;
-    for (int w = 0; w < 8; ++w) t += red[w];
-    q_inv_norm[q] = 1.0f / sqrtf(t);
+  const float energy = block_sum_256(e, red);     // also the barrier between the transforms and their readers
+  const float norm = sqrtf(energy);
+  const float scale = (live && norm > 0.f) ? kSpecKappa / norm : 0.f;
+  if (live) {
+    const float s4 = block_sum_256(spectrum_quartic(sre, sim), red);
+    if (threadIdx.x == 0) {
+      q_inv_norm[q] = 1.0f / norm;
+      qry_aux[q] = make_float2(norm > 0.f ? 1.0f : __int_as_float(0x7fc00000), sqrtf(sqrtf(s4)) * (scale / kSpecKappa));
+    }
+    if (spec_out != nullptr) {
+      float2* dst = reinterpret_cast<float2*>(spec_out + q * (kSpCH * 64));
+      for (int idx = threadIdx.x; idx < kSpCH * 32; idx += 256) dst[idx] = make_float2(sre[idx & 31][idx >> 5], sim[idx & 31][idx >> 5]);
+    }
   }
-  if (spec_out != nullptr && live) {
-    float2* dst = reinterpret_cast<float2*>(spec_out + q * (kSpCH * 64));
-    for (int idx = threadIdx.x; idx < kSpCH * 32; idx += 256) dst[idx] = make_float2(sre[idx & 31][idx >> 5], sim[idx & 31][idx >> 5]);
-  }
-  __nv_bfloat16* tile = out + (q >> 7) * (int64_t)(2 * kSpSlots * 128 * 64) + (q & 127) * 64;
+  __half* tile = out + (q >> 7) * (int64_t)(2 * kSpSlots * 128 * 64) + (q & 127) * 64;
   for (int idx = threadIdx.x; idx < kSpSlots * 2 * 16; idx += 256) {
     const int slot = idx >> 5, half = (idx >> 4) & 1, r0 = (idx & 15) * 4;
     const float* s = half == 0 ? &sre[slot][r0] : &sim[slot][r0];
-    const float k = 1.0f / 64.0f;
-    const uint2 v = live ? pack4_bf16(s[0] * k, s[1] * k, s[2] * k, s[3] * k) : make_uint2(0u, 0u);
+    const uint2 v = live ? pack4_f16(s[0] * scale, s[1] * scale, s[2] * scale, s[3] * scale) : make_uint2(0u, 0u);
     *reinterpret_cast<uint2*>(tile + (int64_t)(2 * slot + half) * (128 * 64) + r0) = v;
   }
 }
@@ -170,32 +218,16 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t& a, uint32_t& 
 }
 
 struct SpParams {
-  const float* crop_inv_norm;    // [G_pad8][64]
-  const float* q_inv_norm;       // [Q]
-  float* dist;                   // [G][Q] or null
-  uint8_t* ori;                  // [G][Q] or null
-  const float* d_true;           // [Q] or null
-  const int32_t* true_idx;       // [Q] or null
-  int32_t* rank_count;           // [Q] or null
-  float* topk_dist;              // [2 * n_chunks][Q][topk] or null
-  int32_t* topk_idx;
-  int64_t G, Q;
-  int topk;
-  int32_t g_offset;
+  SweepOut out;
   int n_qtiles, n_chunks, groups_per_chunk, n_groups;
   int debug;
-  float band;
-  int64_t* recheck_g;
-  int64_t* recheck_q;
-  int32_t* recheck_count;
-  int32_t recheck_cap;
 };
 
 __global__ void __launch_bounds__(kSpThreads, 1)
 match_spec_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant__ CUtensorMap g_map, const SpParams P) {
   constexpr uint32_t kTmemCols = 512;
-  // kind::f16: D fp32, A/B bf16, both K-major, N = 16, M = 128
-  constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  // kind::f16: D fp32 (bit 4), A and B fp16 (format fields 0), both K-major, N = 16, M = 128
+  constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* a_base = smem;                                  // kSpStages x 32 KB, 1024-aligned
@@ -210,7 +242,7 @@ match_spec_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_consta
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int unit = blockIdx.x, n_units = gridDim.x;
   const int n_work = P.n_chunks * P.n_qtiles;
-  const bool chunk_major = (P.debug & 16) != 0;
+  const bool chunk_major = SPEC_DBG(P, 16);
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&q_map) : "memory");
@@ -236,9 +268,10 @@ match_spec_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_consta
   const uint32_t tmem_base = *tmem_holder;
 
   // 512 threads start with 128 registers each; the eight control warps give theirs up so that an epilogue thread can
-  // hold the 128 accumulators of two items plus the transform's temporaries (256 x 40 + 256 x 216 = 64 K registers)
-  if (warp < 8) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-  else asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+  // hold the 128 accumulators of two items plus the transform's temporaries (256 x 48 + 256 x 208 = 64 K registers; at 40 the
+  // control loops spill their loop counters)
+  if (warp < 8) asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+  else asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
 
   if (warp < 2) {
     // ===================== TMA producers: warp p loads the slots of parity p into the stages of parity p =====================
@@ -256,7 +289,7 @@ match_spec_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_consta
           bar_wait(s2u(&empty[s]), ph ^ 1);
           if (elect_one()) {
             const uint32_t fb = s2u(&full[s]);
-            if (P.debug & 8) {
+            if (SPEC_DBG(P, 8)) {
               bar_expect_tx(fb, (uint32_t)kSpBBytes);
             } else {
               bar_expect_tx(fb, (uint32_t)(kSpABytes + kSpBBytes));
@@ -292,7 +325,7 @@ match_spec_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_consta
       tc_fence_after();
       if (elect_one()) {
         const uint32_t tmem_d = tmem_base + slot * 16u;
-        if (!(P.debug & 4)) {
+        if (!SPEC_DBG(P, 4)) {
 #pragma unroll
           for (int h = 0; h < 2; ++h)    // K halves: tiles of 16 KB (queries) / 2 KB (items)
 #pragma unroll
@@ -307,6 +340,7 @@ match_spec_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_consta
     }
   } else {
     // ===================== epilogue: warps 8-11 items 0-3, warps 12-15 items 4-7 of each tile =====================
+    const SweepOut& S = P.out;
     const int wq = warp & 3;
     const int ihalf = (warp - 8) >> 2;
     const int row = wq * 32 + lane;
@@ -316,11 +350,8 @@ match_spec_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_consta
       const int qt = chunk_major ? w % P.n_qtiles : w / P.n_chunks;
       const int chunk = chunk_major ? w / P.n_qtiles : w - qt * P.n_chunks;
       const int64_t q = (int64_t)qt * 128 + row;
-      const bool q_ok = q < P.Q;
-      const float qin = q_ok ? P.q_inv_norm[q] : 0.f;
-      const float dtrue = (q_ok && P.d_true) ? P.d_true[q] : __int_as_float(0x7fc00000);
-      // the match itself always counts (d[idx] <= d[idx] in cvig_fov.py:552) unless its distance is NaN
-      const int32_t self_g = (q_ok && P.true_idx) ? P.true_idx[q] - P.g_offset : -1;
+      SweepQuery qc;
+      qc.load(S, q);
       int cnt = 0;
       float td[kSpTopkMax];
       int32_t ti[kSpTopkMax];
@@ -331,14 +362,18 @@ match_spec_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_consta
       for (int grp = grp0; grp < grp1; ++grp, ++tile_it) {
         bar_wait(s2u(tmem_full), tile_it & 1);
         tc_fence_after();
-        float bestv[4], cinv[4];
-        int argv[4];
+        float bestv[4], sclv[4];
+        int argv[4];   // bit 8: another shift lies within 2e of the maximum
 #pragma unroll 1
         for (int pp = 0; pp < 2; ++pp) {
           const int i0 = ihalf * 4 + pp * 2;      // items i0 and i0 + 1 in the .x / .y halves
+          const int64_t g0 = (int64_t)grp * kSpItems + i0;
+          // rounding scales of the two items (broadcast loads, consumed after the transform); rows past G are zeros
+          const float ag0 = __ldg(reinterpret_cast<const float*>(S.gal_aux + g0) + 2);
+          const float ag1 = __ldg(reinterpret_cast<const float*>(S.gal_aux + g0 + 1) + 2);
           float2 re[32], im[32], x[64];
           const uint32_t t0 = tmem_base + lane_field + (uint32_t)(2 * i0);
-          if (P.debug & 2) {
+          if (SPEC_DBG(P, 2)) {
 #pragma unroll
             for (int f = 0; f < 32; ++f) { re[f] = make_float2((float)(f + lane), (float)f); im[f] = make_float2((float)(f - pp), 1.f); }
           } else {
@@ -356,7 +391,7 @@ match_spec_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_consta
             __syncwarp();
             if (lane == 0) bar_arrive_local(s2u(tmem_empty));
           }
-          if (P.debug & 1) {
+          if (SPEC_DBG(P, 1)) {
 #pragma unroll
             for (int f = 0; f < 32; ++f) { x[2 * f] = re[f]; x[2 * f + 1] = im[f]; }
           } else {
@@ -369,59 +404,44 @@ match_spec_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_consta
             if (x[sft].x > best[0]) { best[0] = x[sft].x; arg[0] = sft; }
             if (x[sft].y > best[1]) { best[1] = x[sft].y; arg[1] = sft; }
           }
+          if (S.need_amb) {  // how many shifts could be the exact argmax (the maximum itself is one of them)
+            const float thr0 = best[0] - 2.0f * sweep_err(S, ag0, qc), thr1 = best[1] - 2.0f * sweep_err(S, ag1, qc);
+            int n0 = 0, n1 = 0;
 #pragma unroll
-          for (int e = 0; e < 2; ++e) {  // the crop-norm gather is issued now and consumed after the other pair's transform
-            const int64_t g = (int64_t)grp * kSpItems + i0 + e;
-            const float cin = (g < P.G) ? __ldg(P.crop_inv_norm + g * 64 + arg[e]) : 0.f;
+            for (int sft = 0; sft < 64; ++sft) {
+              n0 += (x[sft].x >= thr0) ? 1 : 0;
+              n1 += (x[sft].y >= thr1) ? 1 : 0;
+            }
+            arg[0] |= (n0 > 1) ? 256 : 0;
+            arg[1] |= (n1 > 1) ? 256 : 0;
+          }
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {  // the scale gather is issued now and consumed after the other pair's transform
+            const int64_t g = g0 + e;
+            const float scl = (g < S.G) ? __ldg(S.gal_scale + g * 64 + (arg[e] & 63)) : 0.f;
             // static indices (the pair loop is not unrolled: two copies of the transform would not fit the registers)
-            if (pp == 0) { bestv[e] = best[e]; argv[e] = arg[e]; cinv[e] = cin; }
-            else { bestv[2 + e] = best[e]; argv[2 + e] = arg[e]; cinv[2 + e] = cin; }
+            if (pp == 0) { bestv[e] = best[e]; argv[e] = arg[e]; sclv[e] = scl; }
+            else { bestv[2 + e] = best[e]; argv[2 + e] = arg[e]; sclv[2 + e] = scl; }
           }
         }
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int64_t g = (int64_t)grp * kSpItems + ihalf * 4 + e;
-          if (g < P.G && q_ok) {
-            const float d = 2.0f * (1.0f - bestv[e] * cinv[e] * qin);
-            if (P.dist) P.dist[g * P.Q + q] = d;
-            if (P.ori) P.ori[g * P.Q + q] = (uint8_t)argv[e];
-            if ((int32_t)g == self_g) {
-              cnt += (dtrue == dtrue) ? 1 : 0;
-            } else if (P.recheck_cap > 0 && fabsf(d - dtrue) <= P.band) {
-              const int32_t pos = atomicAdd(P.recheck_count, 1);
-              if (pos < P.recheck_cap) {
-                P.recheck_g[pos] = g;
-                P.recheck_q[pos] = q;
-              } else {  // list full: fall back to the bf16 decision and say so
-                atomicAdd(P.recheck_count + 1, 1);
-                cnt += (d <= dtrue) ? 1 : 0;
-              }
-            } else {
-              cnt += (d <= dtrue) ? 1 : 0;
-            }
-            if (P.topk > 0 && d < td[kSpTopkMax - 1]) {
-              float cd = d;
-              int32_t ci = (int32_t)g + P.g_offset;
-#pragma unroll
-              for (int j = 0; j < kSpTopkMax; ++j) {
-                if (cd < td[j]) {
-                  const float t0f = td[j]; const int32_t t1 = ti[j];
-                  td[j] = cd; ti[j] = ci; cd = t0f; ci = t1;
-                }
-              }
-            }
+          if (g < S.G && qc.ok) {
+            const float err = sweep_err(S, __ldg(reinterpret_cast<const float*>(S.gal_aux + g) + 2), qc);   // L1-resident by now
+            sweep_pair(S, qc, g, q, bestv[e], argv[e] & 63, (argv[e] & 256) != 0, sclv[e], err, cnt, td, ti);
           }
         }
       }
-      if (q_ok) {
-        if (P.rank_count && cnt) atomicAdd(P.rank_count + q, cnt);
-        if (P.topk > 0) {
+      if (qc.ok) {
+        if (S.rank_count && cnt) atomicAdd(S.rank_count + q, cnt);
+        if (S.topk > 0) {
           const int64_t slot = (int64_t)chunk * 2 + ihalf;
-          float* od = P.topk_dist + (slot * P.Q + q) * P.topk;
-          int32_t* oi = P.topk_idx + (slot * P.Q + q) * P.topk;
+          float* od = S.topk_key + (slot * S.Q + q) * S.topk;
+          int32_t* oi = S.topk_idx + (slot * S.Q + q) * S.topk;
 #pragma unroll
           for (int j = 0; j < kSpTopkMax; ++j)
-            if (j < P.topk) { od[j] = td[j]; oi[j] = ti[j]; }
+            if (j < S.topk) { od[j] = td[j]; oi[j] = ti[j]; }
         }
       }
     }
@@ -499,54 +519,54 @@ extern "C" size_t witw_spec_query_operand_bytes(int64_t Q, int CH) {
 }
 
 extern "C" int witw_spec_gallery_prep(const float* ov, int64_t G, int64_t g_first, int CH, int W, int sw, void* gal_op,
-                                      float* crop_inv_norm, float* spec_out, witw_stream_t stream) {
+                                      float* gal_scale, float* gal_aux, float* crop_inv_norm, float* spec_out, witw_stream_t stream) {
   WITW_REQUIRE(witw_spec_supported(CH, W, sw), WITW_ERR_UNSUPPORTED, "witw_spec_gallery_prep: needs C*H == 64, W == 64, 1 <= sw <= 64 (got %d, %d, %d)", CH, W, sw);
   WITW_REQUIRE(G >= 0 && g_first >= 0, WITW_ERR_INVALID, "witw_spec_gallery_prep: negative size");
   if (G == 0) return WITW_OK;
-  WITW_REQUIRE(ov && gal_op && crop_inv_norm, WITW_ERR_INVALID, "witw_spec_gallery_prep: null pointer");
-  WITW_REQUIRE(((uintptr_t)gal_op & 127) == 0 && ((uintptr_t)ov & 7) == 0, WITW_ERR_INVALID, "witw_spec_gallery_prep: operand must be 128-byte, features 8-byte aligned");
+  WITW_REQUIRE(ov && gal_op && gal_scale && gal_aux, WITW_ERR_INVALID, "witw_spec_gallery_prep: null pointer");
+  WITW_REQUIRE(((uintptr_t)gal_op & 127) == 0 && ((uintptr_t)ov & 7) == 0 && ((uintptr_t)gal_aux & 15) == 0, WITW_ERR_INVALID,
+               "witw_spec_gallery_prep: operand must be 128-byte, gal_aux 16-byte, features 8-byte aligned");
   // items up to the end of the last group are written (zeros past G) so a partial group never exposes stale bytes
   const int64_t g_end = ceil_div<int64_t>(g_first + G, kSpItems) * kSpItems;
   const int64_t n = g_end - g_first;
   WITW_REQUIRE(n < (1ll << 31), WITW_ERR_INVALID, "witw_spec_gallery_prep: too many items in one call");
   WITW_REQUIRE(((uintptr_t)spec_out & 7) == 0, WITW_ERR_INVALID, "witw_spec_gallery_prep: spectra must be 8-byte aligned");
-  spec_gallery_prep_kernel<<<(unsigned)n, 256, 0, as_stream(stream)>>>(ov, G, g_first, reinterpret_cast<__nv_bfloat16*>(gal_op), spec_out);
+  int rc = launch_item_stats(ov, G, n, CH, sw, kSpecKappa, kSpecUnit, 0.f, gal_scale, gal_aux, crop_inv_norm, stream);
+  if (rc != WITW_OK) return rc;
+  spec_gallery_prep_kernel<<<(unsigned)n, 256, 0, as_stream(stream)>>>(ov, G, g_first, reinterpret_cast<__half*>(gal_op),
+                                                                     reinterpret_cast<float4*>(gal_aux), spec_out);
   WITW_LAUNCH_CHECK();
-  return launch_crop_norm(ov, G, n, CH, sw, crop_inv_norm, stream);
+  return WITW_OK;
 }
 
-extern "C" int witw_spec_query_prep(const float* su, int64_t Q, int CH, int sw, void* qry_op, float* q_inv_norm, float* spec_out,
-                                    witw_stream_t stream) {
+extern "C" int witw_spec_query_prep(const float* su, int64_t Q, int CH, int sw, void* qry_op, float* qry_aux, float* q_inv_norm,
+                                    float* spec_out, witw_stream_t stream) {
   WITW_REQUIRE(witw_spec_supported(CH, 64, sw), WITW_ERR_UNSUPPORTED, "witw_spec_query_prep: needs C*H == 64 and 1 <= sw <= 64 (got %d, %d)", CH, sw);
   WITW_REQUIRE(Q >= 0 && Q < (1ll << 31), WITW_ERR_INVALID, "witw_spec_query_prep: bad query count");
   if (Q == 0) return WITW_OK;
-  WITW_REQUIRE(su && qry_op && q_inv_norm, WITW_ERR_INVALID, "witw_spec_query_prep: null pointer");
-  WITW_REQUIRE(((uintptr_t)qry_op & 127) == 0, WITW_ERR_INVALID, "witw_spec_query_prep: operand must be 128-byte aligned");
+  WITW_REQUIRE(su && qry_op && qry_aux && q_inv_norm, WITW_ERR_INVALID, "witw_spec_query_prep: null pointer");
+  WITW_REQUIRE(((uintptr_t)qry_op & 127) == 0 && ((uintptr_t)qry_aux & 7) == 0, WITW_ERR_INVALID,
+               "witw_spec_query_prep: operand must be 128-byte, qry_aux 8-byte aligned");
   const int64_t q_pad = ceil_div<int64_t>(Q, 128) * 128;
   WITW_REQUIRE(((uintptr_t)spec_out & 7) == 0, WITW_ERR_INVALID, "witw_spec_query_prep: spectra must be 8-byte aligned");
-  spec_query_prep_kernel<<<(unsigned)q_pad, 256, 0, as_stream(stream)>>>(su, Q, sw, reinterpret_cast<__nv_bfloat16*>(qry_op), q_inv_norm, spec_out);
+  spec_query_prep_kernel<<<(unsigned)q_pad, 256, 0, as_stream(stream)>>>(su, Q, sw, reinterpret_cast<__half*>(qry_op),
+                                                                        reinterpret_cast<float2*>(qry_aux), q_inv_norm, spec_out);
   WITW_LAUNCH_CHECK();
   return WITW_OK;
 }
 
 extern "C" int witw_match_spec_topk_slots(int64_t G, int64_t Q) { return make_spec_schedule(G, Q).n_chunks * 2; }
 
-extern "C" int witw_match_spec(const void* gal_op, const float* crop_inv_norm, const void* qry_op, const float* q_inv_norm, int64_t G,
-                               int64_t Q, int CH, int sw, float* dist, uint8_t* ori, const float* d_true, const int32_t* true_idx,
-                               int32_t* rank_count, int topk, float* topk_dist, int32_t* topk_idx, int32_t g_offset, float recheck_band,
-                               int64_t* recheck_g, int64_t* recheck_q, int32_t* recheck_count, int32_t recheck_capacity,
-                               witw_stream_t stream) {
-  WITW_REQUIRE(G >= 0 && Q >= 0 && witw_spec_supported(CH, 64, sw), WITW_ERR_UNSUPPORTED, "witw_match_spec: unsupported CH=%d sw=%d", CH, sw);
+extern "C" int witw_match_spec(const witw_sweep_args* a, witw_stream_t stream) {
+  WITW_REQUIRE(a != nullptr, WITW_ERR_INVALID, "witw_match_spec: null arguments");
+  const int64_t G = a->G, Q = a->Q;
+  WITW_REQUIRE(G >= 0 && Q >= 0 && witw_spec_supported(a->CH, 64, a->sw), WITW_ERR_UNSUPPORTED, "witw_match_spec: unsupported CH=%d sw=%d", a->CH, a->sw);
   if (G == 0 || Q == 0) return WITW_OK;
-  WITW_REQUIRE(gal_op && crop_inv_norm && qry_op && q_inv_norm, WITW_ERR_INVALID, "witw_match_spec: null operand");
-  WITW_REQUIRE(topk >= 0 && topk <= kSpTopkMax, WITW_ERR_UNSUPPORTED, "witw_match_spec: fused top-k supports k <= %d (got %d)", kSpTopkMax, topk);
-  WITW_REQUIRE(topk == 0 || (topk_dist && topk_idx), WITW_ERR_INVALID, "witw_match_spec: top-k buffers missing");
-  WITW_REQUIRE(!rank_count || d_true, WITW_ERR_INVALID, "witw_match_spec: rank_count needs d_true");
-  WITW_REQUIRE(recheck_capacity >= 0 && (recheck_capacity == 0 || (rank_count && recheck_g && recheck_q && recheck_count && recheck_band >= 0.f)),
-               WITW_ERR_INVALID, "witw_match_spec: re-check list needs rank_count, both index buffers, the counter and a band >= 0");
-  WITW_REQUIRE(G < (1ll << 31) && Q < (1ll << 31), WITW_ERR_INVALID, "witw_match_spec: sizes exceed 2^31");
-  WITW_REQUIRE(((uintptr_t)qry_op & 127) == 0 && ((uintptr_t)gal_op & 127) == 0, WITW_ERR_INVALID, "witw_match_spec: operands must be 128-byte aligned");
-  int rc = witw_device_check();
+  SweepOut out;
+  int rc = fill_sweep_out("witw_match_spec", a, kSpecUnit, &out);
+  if (rc != WITW_OK) return rc;
+  WITW_REQUIRE(((uintptr_t)a->qry_op & 127) == 0 && ((uintptr_t)a->gal_op & 127) == 0, WITW_ERR_INVALID, "witw_match_spec: operands must be 128-byte aligned");
+  rc = witw_device_check();
   if (rc != WITW_OK) return rc;
 
   const SpSchedule sch = make_spec_schedule(G, Q);
@@ -556,36 +576,33 @@ extern "C" int witw_match_spec(const void* gal_op, const float* crop_inv_norm, c
   auto encode = reinterpret_cast<EncodeTiledFn>(get_encode_tiled());
   WITW_REQUIRE(encode != nullptr, WITW_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   const cuuint32_t estr[2] = {1, 1};
-  // query spectra: [query tiles x 32 slots x 2 K halves x 128 rows][64] bf16; one box = the 256 rows of one slot of one tile
+  // query spectra: [query tiles x 32 slots x 2 K halves x 128 rows][64] fp16; one box = the 256 rows of one slot of one tile
   CUtensorMap qmap;
   const int64_t q_rows = ceil_div<int64_t>(Q, 128) * (2 * kSpSlots * 128);
   WITW_REQUIRE(q_rows < (1ll << 31), WITW_ERR_UNSUPPORTED, "witw_match_spec: %lld queries are too many for one sweep", (long long)Q);
   const cuuint64_t qdims[2] = {64, (cuuint64_t)q_rows};
   const cuuint64_t qstrides[1] = {128};
   const cuuint32_t qbox[2] = {64, 256};
-  CUresult cr = encode(&qmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(qry_op), qdims, qstrides, qbox, estr,
+  CUresult cr = encode(&qmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(a->qry_op), qdims, qstrides, qbox, estr,
                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   WITW_REQUIRE(cr == CUDA_SUCCESS, WITW_ERR_CUDA, "cuTensorMapEncodeTiled(query spectra) failed with CUresult %d", (int)cr);
-  // gallery spectra: [groups x 32 slots x 2 K halves x 16 rows][64] bf16; one box = the 32 rows of one slot
+  // gallery spectra: [groups x 32 slots x 2 K halves x 16 rows][64] fp16; one box = the 32 rows of one slot
   CUtensorMap gmap;
   const int64_t total_rows = (int64_t)sch.n_groups * kSpSlots * 32;
   WITW_REQUIRE(total_rows < (1ll << 31), WITW_ERR_UNSUPPORTED, "witw_match_spec: gallery of %lld items is too large for one sweep", (long long)G);
   const cuuint64_t gdims[2] = {64, (cuuint64_t)total_rows};
   const cuuint64_t gstrides[1] = {128};
   const cuuint32_t gbox[2] = {64, 32};
-  cr = encode(&gmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(gal_op), gdims, gstrides, gbox, estr,
+  cr = encode(&gmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(a->gal_op), gdims, gstrides, gbox, estr,
               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   WITW_REQUIRE(cr == CUDA_SUCCESS, WITW_ERR_CUDA, "cuTensorMapEncodeTiled(gallery spectra) failed with CUresult %d", (int)cr);
 
   SpParams P;
   std::memset(&P, 0, sizeof(P));
-  P.crop_inv_norm = crop_inv_norm; P.q_inv_norm = q_inv_norm;
-  P.dist = dist; P.ori = ori; P.d_true = d_true; P.true_idx = true_idx; P.rank_count = rank_count;
-  P.topk_dist = topk_dist; P.topk_idx = topk_idx; P.G = G; P.Q = Q; P.topk = topk; P.g_offset = g_offset;
+  P.out = out;
   P.n_qtiles = sch.n_qtiles; P.n_chunks = sch.n_chunks; P.groups_per_chunk = sch.groups_per_chunk; P.n_groups = sch.n_groups;
-  P.band = recheck_band; P.recheck_g = recheck_g; P.recheck_q = recheck_q; P.recheck_count = recheck_count; P.recheck_cap = recheck_capacity;
   P.debug = spec_debug();
   const size_t smem = (size_t)kSpStages * (kSpABytes + kSpBBytes) + (2 * kSpStages + 2) * 8 + 16;
   WITW_CUDA(cudaFuncSetAttribute(match_spec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

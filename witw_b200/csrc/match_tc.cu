@@ -18,16 +18,19 @@
 //   dist = 2 - 2 * corr_max * crop_inv_norm[g, s*] * q_inv_norm[q]
 // and, optionally, the rank count against the true-match distance and a per-query top-k.
 //
+// Operands are fp16, norm-scaled, and the epilogue defers what fp16 cannot settle (sweep_common.cuh).
+//
 // cta_group::2 (default): a CTA pair computes a 256-query x 4-item tile per accumulator stage
 // (UMMA 256x256x16); each CTA stages its own 128 queries and 2 items.  Warp roles per CTA:
 // 0 TMA producer (cta_group::2 copies signal the leader's barrier), 1 MMA issuer (leader), 2 TMEM allocator,
 // 4-7 epilogue.  Two accumulator stages (2 x 256 TMEM columns) overlap epilogue and MMA.
 #include <cuda.h>
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
+#include "sweep_common.cuh"
 #include "tc_common.cuh"
 
 namespace witw {
@@ -50,6 +53,9 @@ struct TcGeom {
   int kblocks;  // CH * sw_pad / 64
 };
 
+// Layout / CTA-mode experiments exist only in builds with -DWITW_DEBUG_HOOKS (tools/ probes); the shipped library never
+// reads the environment: Hankel operand layout, cta_group::2.
+#ifdef WITW_DEBUG_HOOKS
 static bool full_b_layout() {
   static int v = -1;
   if (v < 0) { const char* e = std::getenv("WITW_TC_FULL_B"); v = (e && e[0] == '1') ? 1 : 0; }
@@ -60,6 +66,10 @@ static int cta_group_mode() {
   if (v < 0) { const char* e = std::getenv("WITW_TC_CG"); v = (e && e[0] == '1') ? 1 : 2; }
   return v;
 }
+#else
+static bool full_b_layout() { return false; }
+static int cta_group_mode() { return 2; }
+#endif
 
 static bool make_geom(int CH, int sw, TcGeom* g) {
   if (sw < 1 || sw > 64 || CH < 1) return false;
@@ -83,10 +93,12 @@ static bool make_geom(int CH, int sw, TcGeom* g) {
 constexpr int kPrepRows = 16;  // feature rows of one item pair per CTA
 
 __global__ void __launch_bounds__(256)
-gallery_blocks_kernel(const float* __restrict__ ov, int64_t G, int CH, int bpc, int full, uint4* __restrict__ out) {
-  // CTA = (item pair, 16 feature rows).  Phase 1: the 2 x 16 rows are read once (coalesced float4), rounded to bf16
-  // once and laid out twice over in shared memory (circular wrap).  Phase 2: every 16-byte row of every block is
-  // eight consecutive bf16 of one of those rows; the stores are one contiguous run of the operand.
+gallery_blocks_kernel(const float* __restrict__ ov, int64_t G, int CH, int bpc, int full, const float4* __restrict__ gal_aux,
+                      uint4* __restrict__ out) {
+  // CTA = (item pair, 16 feature rows).  Phase 1: the 2 x 16 rows are read once (coalesced float4), scaled by the item's
+  // kappa / ||ov_g|| (gal_aux[g].w, launch_item_stats), rounded to fp16 once and laid out twice over in shared memory
+  // (circular wrap).  Phase 2: every 16-byte row of every block is eight consecutive fp16 of one of those rows; the
+  // stores are one contiguous run of the operand.
   __shared__ __align__(16) unsigned short e[2][kPrepRows][136];  // [item][row][0..127 = row twice over]
   const int64_t pair = blockIdx.y;
   const int ch0 = blockIdx.x * kPrepRows;
@@ -97,8 +109,12 @@ gallery_blocks_kernel(const float* __restrict__ ov, int64_t G, int CH, int bpc, 
     const int row = rem >> 4, c4 = rem & 15;
     const int64_t item = 2 * pair + item_l;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (item < G && row < n_rows) v = __ldg(reinterpret_cast<const float4*>(ov + (item * CH + ch0 + row) * kW) + c4);
-    const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    if (item < G && row < n_rows) {
+      v = __ldg(reinterpret_cast<const float4*>(ov + (item * CH + ch0 + row) * kW) + c4);
+      const float sc = __ldg(reinterpret_cast<const float*>(gal_aux + item) + 3);
+      v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
+    }
+    const __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
     const uint2 w = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
     *reinterpret_cast<uint2*>(&e[item_l][row][4 * c4]) = w;
     *reinterpret_cast<uint2*>(&e[item_l][row][64 + 4 * c4]) = w;
@@ -121,69 +137,99 @@ gallery_blocks_kernel(const float* __restrict__ ov, int64_t G, int CH, int bpc, 
   }
 }
 
+// Per-item tables (both sweeps; CTA = one item, thread = one azimuth column):
+//   crop_inv_norm[g,s] = 1 / ||crop(ov_g, s)||                       -- the fp32 finish (cvig_fov.py:351)
+//   gal_scale[g,s]     = ||ov_g|| / (||crop(ov_g, s)|| unit)          -- the sweeps (sweep_common.cuh)
+//   gal_aux[g]         = (max_s gal_scale, max - min, rounding scale, kappa / ||ov_g||)
+// The rounding scale is written here for the dense operand (dense_sigma > 0: 4-norm of the normalised features); the
+// spectral prep kernel writes its own.  Items past G get zeros.  A zero-norm item: operand scale 0, gal_scale NaN.
 __global__ void __launch_bounds__(64)
-crop_norm_kernel(const float* __restrict__ ov, int64_t G, int CH, int sw, float* __restrict__ crop_inv_norm) {
+item_stats_kernel(const float* __restrict__ ov, int64_t G, int CH, int sw, float kappa, float unit, float dense_sigma,
+                  float* __restrict__ gal_scale, float4* __restrict__ gal_aux, float* __restrict__ crop_inv_norm) {
   __shared__ float col_e[kW];
+  __shared__ float red[3][2];
   const int64_t g = blockIdx.x;
   const int j = threadIdx.x;
-  float e = 0.f;
-  if (g < G)
-    for (int ch = 0; ch < CH; ++ch) { const float v = ov[(g * CH + ch) * kW + j]; e = fmaf(v, v, e); }
+  if (g >= G) {
+    gal_scale[g * kW + j] = 0.f;
+    if (crop_inv_norm) crop_inv_norm[g * kW + j] = 0.f;
+    if (j == 0) gal_aux[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
+  float e = 0.f, f4 = 0.f;
+  for (int ch = 0; ch < CH; ++ch) {
+    const float v = ov[(g * CH + ch) * kW + j];
+    const float v2 = v * v;
+    e += v2;
+    f4 = fmaf(v2, v2, f4);
+  }
   col_e[j] = e;
+  float te = e, t4 = f4;
+  for (int m = 16; m > 0; m >>= 1) { te += __shfl_xor_sync(0xffffffffu, te, m); t4 += __shfl_xor_sync(0xffffffffu, t4, m); }
+  if ((j & 31) == 0) { red[0][j >> 5] = te; red[1][j >> 5] = t4; }
   __syncthreads();
+  const float norm = sqrtf(red[0][0] + red[0][1]);
   float c = 0.f;
   for (int k = 0; k < sw; ++k) c += col_e[(j + k) & 63];
-  crop_inv_norm[g * kW + j] = g < G ? 1.0f / sqrtf(c) : 0.f;
+  const float cin = 1.0f / sqrtf(c);
+  const float scl = norm * cin / unit;
+  gal_scale[g * kW + j] = scl;
+  if (crop_inv_norm) crop_inv_norm[g * kW + j] = cin;
+  float hi = scl, lo = scl;
+  for (int m = 16; m > 0; m >>= 1) { hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, m)); lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, m)); }
+  __syncthreads();
+  if ((j & 31) == 0) { red[0][j >> 5] = hi; red[2][j >> 5] = lo; }
+  __syncthreads();
+  if (j == 0) {
+    hi = fmaxf(red[0][0], red[0][1]);
+    lo = fminf(red[2][0], red[2][1]);
+    const float quart = sqrtf(sqrtf(red[1][0] + red[1][1]));
+    const bool live = norm > 0.f;
+    gal_aux[g] = make_float4(hi, hi - lo, live ? dense_sigma * unit * quart / norm : 0.f, live ? kappa / norm : 0.f);
+  }
 }
 
+// CTA = one query: K-major fp16 rows of the norm-scaled features, zero-padded to sw_pad columns; q_inv_norm[q] for the fp32
+// finish and qry_aux[q] = (1 or NaN, 4-norm of the normalised features) for the sweep.
 __global__ void __launch_bounds__(128)
-query_prep_kernel(const float* __restrict__ su, int64_t Q, int CH, int sw, int sw_pad, __nv_bfloat16* __restrict__ out,
-                  float* __restrict__ q_inv_norm) {
-  __shared__ float red[4];
+query_prep_kernel(const float* __restrict__ su, int64_t Q, int CH, int sw, int sw_pad, __half* __restrict__ out,
+                  float2* __restrict__ qry_aux, float* __restrict__ q_inv_norm) {
+  __shared__ float red[2][4];
   const int64_t q = blockIdx.x;
   const float* src = su + q * CH * sw;
-  __nv_bfloat16* dst = out + q * CH * sw_pad;
-  float e = 0.f;
+  __half* dst = out + q * CH * sw_pad;
+  float e = 0.f, f4 = 0.f;
+  for (int i = threadIdx.x; i < CH * sw; i += blockDim.x) {
+    const float v2 = src[i] * src[i];
+    e += v2;
+    f4 = fmaf(v2, v2, f4);
+  }
+  for (int m = 16; m > 0; m >>= 1) { e += __shfl_xor_sync(0xffffffffu, e, m); f4 += __shfl_xor_sync(0xffffffffu, f4, m); }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = e; red[1][threadIdx.x >> 5] = f4; }
+  __syncthreads();
+  const float norm = sqrtf(red[0][0] + red[0][1] + red[0][2] + red[0][3]);
+  const float scale = norm > 0.f ? kDenseKappa / norm : 0.f;
   for (int i = threadIdx.x; i < CH * sw_pad; i += blockDim.x) {
     const int ch = i / sw_pad, k = i - ch * sw_pad;
-    const float v = k < sw ? src[ch * sw + k] : 0.f;
-    e = fmaf(v, v, e);
-    dst[i] = __float2bfloat16_rn(v);
+    dst[i] = __float2half_rn(k < sw ? src[ch * sw + k] * scale : 0.f);
   }
-  for (int m = 16; m > 0; m >>= 1) e += __shfl_xor_sync(0xffffffffu, e, m);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = e;
-  __syncthreads();
-  if (threadIdx.x == 0) q_inv_norm[q] = 1.0f / sqrtf(red[0] + red[1] + red[2] + red[3]);
+  if (threadIdx.x == 0) {
+    q_inv_norm[q] = 1.0f / norm;
+    const float quart = sqrtf(sqrtf(red[1][0] + red[1][1] + red[1][2] + red[1][3]));
+    qry_aux[q] = make_float2(norm > 0.f ? 1.0f : __int_as_float(0x7fc00000), norm > 0.f ? quart / norm : 0.f);
+  }
 }
 
-constexpr int kTopkMax = 16;
+constexpr int kTopkMax = kSweepTopk;
 
 struct TcParams {
-  const float* crop_inv_norm;    // [G_pad4][64]
-  const float* q_inv_norm;       // [Q]
-  float* dist;                   // [G][Q] or null
-  uint8_t* ori;                  // [G][Q] or null
-  const float* d_true;           // [Q] or null
-  const int32_t* true_idx;       // [Q] global gallery index of each query's match, or null
-  int32_t* rank_count;           // [Q] or null
-  float* topk_dist;              // [n_chunks][Q][topk] or null
-  int32_t* topk_idx;
-  int64_t G, Q;
-  int topk;
-  int32_t g_offset;
+  SweepOut out;
   int n_qtiles, n_chunks, groups_per_chunk, n_groups;
   int kblocks, cpb, bpc, nkap;
   int sbo, lbo, kstep, b_bytes;
   int pair_rows;                 // CH * bpc: 128-byte blocks per item pair
   int stage_rows;                // cpb * bpc: blocks per K block per CTA
   int n_stages;                  // depth of the operand ring (<= kTcMaxStages)
-  // fp32 re-check of rank decisions the bf16 sweep cannot be trusted with: pairs whose distance is within
-  // `band` of the threshold are not counted here but appended to (recheck_g, recheck_q) for witw_recheck_apply_f32
-  float band;
-  int64_t* recheck_g;            // [recheck_cap] local gallery index
-  int64_t* recheck_q;            // [recheck_cap]
-  int32_t* recheck_count;        // [2]: pairs appended (may exceed the capacity), pairs dropped for lack of room
-  int32_t recheck_cap;
 };
 
 template <int CG>
@@ -193,7 +239,8 @@ match_tc_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant
   constexpr int UN = 128 * CG;           // UMMA N  (= accumulator columns per stage)
   constexpr int IG = 2 * CG;             // gallery items per group
   constexpr uint32_t kTmemCols = 2 * UN;
-  constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(UN >> 3) << 17) | ((uint32_t)(UM >> 4) << 24);
+  // kind::f16: D fp32 (bit 4), A and B fp16 (format fields 0), both K-major
+  constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(UN >> 3) << 17) | ((uint32_t)(UM >> 4) << 24);
 
   extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t b_stride = (uint32_t)((P.b_bytes + 127) & ~127);
@@ -319,6 +366,7 @@ match_tc_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant
     }
   } else if (warp >= 4) {
     // ===================== epilogue: 4 warps = 128 TMEM lanes = 128 queries =====================
+    const SweepOut& S = P.out;
     const int wq = warp & 3;
     const int row = wq * 32 + lane;
     const uint32_t lane_field = (uint32_t)(wq * 32) << 16;
@@ -326,12 +374,8 @@ match_tc_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant
     for (int item = unit; item < n_items; item += n_units) {
       const int qt = item / P.n_chunks, chunk = item - qt * P.n_chunks;
       const int64_t q = (int64_t)qt * UM + cta_rank * 128 + row;
-      const bool q_ok = q < P.Q;
-      const float qin = q_ok ? P.q_inv_norm[q] : 0.f;
-      const float dtrue = (q_ok && P.d_true) ? P.d_true[q] : __int_as_float(0x7fc00000);
-      // the match itself always counts (d[idx] <= d[idx] in cvig_fov.py:552) unless its distance is NaN;
-      // deciding it from the bf16 distance against the fp32 threshold would be a coin flip
-      const int32_t self_g = (q_ok && P.true_idx) ? P.true_idx[q] - P.g_offset : -1;
+      SweepQuery qc;
+      qc.load(S, q);
       int cnt = 0;
       float td[kTopkMax];
       int32_t ti[kTopkMax];
@@ -343,10 +387,10 @@ match_tc_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant
         const uint32_t acc = acc_it & 1, acc_ph = (acc_it >> 1) & 1;
         bar_wait(s2u(&tmem_full[acc]), acc_ph);
         tc_fence_after();
-        float best[IG];
+        float best[IG], second[IG];   // second: the largest accumulator of any other shift (the ambiguity test needs it)
         int arg[IG];
 #pragma unroll
-        for (int i = 0; i < IG; ++i) { best[i] = -__int_as_float(0x7f800000); arg[i] = 0; }
+        for (int i = 0; i < IG; ++i) { best[i] = -__int_as_float(0x7f800000); second[i] = best[i]; arg[i] = 0; }
 #pragma unroll
         for (int c = 0; c < UN / 32; ++c) {  // 32 columns = 16 shifts x 2 items
           uint32_t v[32];
@@ -360,6 +404,7 @@ match_tc_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant
             for (int gi = 0; gi < 2; ++gi) {
               const float x = __uint_as_float(v[2 * ds + gi]);
               const int i = 2 * h + gi;
+              if (S.need_amb) second[i] = fmaxf(second[i], fminf(x, best[i]));
               if (x > best[i]) { best[i] = x; arg[i] = s0 + ds; }  // strict '>' in ascending shift order: first maximum
             }
           }
@@ -374,48 +419,21 @@ match_tc_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant
 #pragma unroll
         for (int i = 0; i < IG; ++i) {
           const int64_t g = (int64_t)grp * IG + i;
-          if (g < P.G && q_ok) {
-            const float cin = P.crop_inv_norm[g * kW + arg[i]];
-            const float d = 2.0f * (1.0f - best[i] * cin * qin);
-            if (P.dist) P.dist[g * P.Q + q] = d;
-            if (P.ori) P.ori[g * P.Q + q] = (uint8_t)arg[i];
-            if ((int32_t)g == self_g) {
-              cnt += (dtrue == dtrue) ? 1 : 0;
-            } else if (P.recheck_cap > 0 && fabsf(d - dtrue) <= P.band) {
-              const int32_t pos = atomicAdd(P.recheck_count, 1);
-              if (pos < P.recheck_cap) {
-                P.recheck_g[pos] = g;
-                P.recheck_q[pos] = q;
-              } else {  // list full: fall back to the bf16 decision and say so
-                atomicAdd(P.recheck_count + 1, 1);
-                cnt += (d <= dtrue) ? 1 : 0;
-              }
-            } else {
-              cnt += (d <= dtrue) ? 1 : 0;
-            }
-            if (P.topk > 0 && d < td[kTopkMax - 1]) {
-              // insertion into the ascending register list (strict '<': earlier index wins ties)
-              float cd = d;
-              int32_t ci = (int32_t)g + P.g_offset;
-#pragma unroll
-              for (int j = 0; j < kTopkMax; ++j) {
-                if (cd < td[j]) {
-                  const float t0 = td[j]; const int32_t t1 = ti[j];
-                  td[j] = cd; ti[j] = ci; cd = t0; ci = t1;
-                }
-              }
-            }
+          if (g < S.G && qc.ok) {
+            const float e = sweep_err(S, __ldg(reinterpret_cast<const float*>(S.gal_aux + g) + 2), qc);
+            const bool amb = S.need_amb && second[i] >= best[i] - 2.0f * e;
+            sweep_pair(S, qc, g, q, best[i], arg[i], amb, __ldg(S.gal_scale + g * kW + arg[i]), e, cnt, td, ti);
           }
         }
       }
-      if (q_ok) {
-        if (P.rank_count && cnt) atomicAdd(P.rank_count + q, cnt);
-        if (P.topk > 0) {
-          float* od = P.topk_dist + ((int64_t)chunk * P.Q + q) * P.topk;
-          int32_t* oi = P.topk_idx + ((int64_t)chunk * P.Q + q) * P.topk;
+      if (qc.ok) {
+        if (S.rank_count && cnt) atomicAdd(S.rank_count + q, cnt);
+        if (S.topk > 0) {
+          float* od = S.topk_key + ((int64_t)chunk * S.Q + q) * S.topk;
+          int32_t* oi = S.topk_idx + ((int64_t)chunk * S.Q + q) * S.topk;
 #pragma unroll
           for (int j = 0; j < kTopkMax; ++j)
-            if (j < P.topk) { od[j] = td[j]; oi[j] = ti[j]; }
+            if (j < S.topk) { od[j] = td[j]; oi[j] = ti[j]; }
         }
       }
     }
@@ -437,9 +455,11 @@ match_tc_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant
   }
 }
 
-// crop_inv_norm[g,s] for G_pad >= G items (zeros past G); also used by the spectral sweep's prep (match_spec.cu).
-int launch_crop_norm(const float* ov, int64_t G, int64_t G_pad, int CH, int sw, float* crop_inv_norm, witw_stream_t stream) {
-  crop_norm_kernel<<<(unsigned)G_pad, 64, 0, as_stream(stream)>>>(ov, G, CH, sw, crop_inv_norm);
+// Per-item tables for G_pad >= G items (zeros past G); also used by the spectral sweep's prep (match_spec.cu).
+int launch_item_stats(const float* ov, int64_t G, int64_t G_pad, int CH, int sw, float kappa, float unit, float dense_sigma,
+                      float* gal_scale, float* gal_aux, float* crop_inv_norm, witw_stream_t stream) {
+  item_stats_kernel<<<(unsigned)G_pad, 64, 0, as_stream(stream)>>>(ov, G, CH, sw, kappa, unit, dense_sigma, gal_scale,
+                                                                   reinterpret_cast<float4*>(gal_aux), crop_inv_norm);
   WITW_LAUNCH_CHECK();
   return WITW_OK;
 }
@@ -481,58 +501,58 @@ extern "C" size_t witw_query_operand_bytes(int64_t Q, int CH, int sw) {
   return (size_t)std::max<int64_t>(Q, 1) * CH * g.sw_pad * 2;
 }
 
-extern "C" int witw_gallery_prep(const float* ov, int64_t G, int CH, int W, int sw, void* gal_op, float* crop_inv_norm,
-                                 witw_stream_t stream) {
+extern "C" int witw_gallery_prep(const float* ov, int64_t G, int CH, int W, int sw, void* gal_op, float* gal_scale, float* gal_aux,
+                                 float* crop_inv_norm, witw_stream_t stream) {
   TcGeom g;
   WITW_REQUIRE(W == kW, WITW_ERR_UNSUPPORTED, "witw_gallery_prep: the tensor-core path needs W == 64 (got %d)", W);
   WITW_REQUIRE(G >= 0 && make_geom(CH, sw, &g), WITW_ERR_UNSUPPORTED, "witw_gallery_prep: unsupported CH=%d sw=%d", CH, sw);
   if (G == 0) return WITW_OK;
-  WITW_REQUIRE(ov && gal_op && crop_inv_norm, WITW_ERR_INVALID, "witw_gallery_prep: null pointer");
-  WITW_REQUIRE(((uintptr_t)gal_op & 127) == 0, WITW_ERR_INVALID, "witw_gallery_prep: operand buffer must be 128-byte aligned");
+  WITW_REQUIRE(ov && gal_op && gal_scale && gal_aux, WITW_ERR_INVALID, "witw_gallery_prep: null pointer");
+  WITW_REQUIRE(((uintptr_t)gal_op & 127) == 0 && ((uintptr_t)gal_aux & 15) == 0, WITW_ERR_INVALID,
+               "witw_gallery_prep: operand buffer must be 128-byte, gal_aux 16-byte aligned");
   const int64_t g4 = ceil_div<int64_t>(G, 4) * 4;
   WITW_REQUIRE(((uintptr_t)ov & 15) == 0, WITW_ERR_INVALID, "witw_gallery_prep: features must be 16-byte aligned");
+  int rc = launch_item_stats(ov, G, g4, CH, sw, kDenseKappa, kDenseUnit, kRoundSigma, gal_scale, gal_aux, crop_inv_norm, stream);
+  if (rc != WITW_OK) return rc;
   for (int64_t p0 = 0; p0 < g4 / 2; p0 += 65535) {  // gridDim.y limit
     const int64_t np = std::min<int64_t>(65535, g4 / 2 - p0);
     gallery_blocks_kernel<<<dim3((unsigned)ceil_div(CH, kPrepRows), (unsigned)np), 256, 0, as_stream(stream)>>>(
-        ov + p0 * 2 * CH * kW, G - 2 * p0, CH, g.bpc, full_b_layout() ? 1 : 0,
+        ov + p0 * 2 * CH * kW, G - 2 * p0, CH, g.bpc, full_b_layout() ? 1 : 0, reinterpret_cast<const float4*>(gal_aux) + 2 * p0,
         reinterpret_cast<uint4*>(gal_op) + p0 * CH * g.bpc * 8);
     WITW_LAUNCH_CHECK();
   }
-  crop_norm_kernel<<<(unsigned)g4, 64, 0, as_stream(stream)>>>(ov, G, CH, sw, crop_inv_norm);
-  WITW_LAUNCH_CHECK();
   return WITW_OK;
 }
 
-extern "C" int witw_query_prep(const float* su, int64_t Q, int CH, int sw, void* qry_op, float* q_inv_norm, witw_stream_t stream) {
+extern "C" int witw_query_prep(const float* su, int64_t Q, int CH, int sw, void* qry_op, float* qry_aux, float* q_inv_norm,
+                               witw_stream_t stream) {
   TcGeom g;
   WITW_REQUIRE(Q >= 0 && make_geom(CH, sw, &g), WITW_ERR_UNSUPPORTED, "witw_query_prep: unsupported CH=%d sw=%d", CH, sw);
   if (Q == 0) return WITW_OK;
-  WITW_REQUIRE(su && qry_op && q_inv_norm, WITW_ERR_INVALID, "witw_query_prep: null pointer");
-  WITW_REQUIRE(Q < (1ll << 31), WITW_ERR_INVALID, "witw_query_prep: too many queries");
-  query_prep_kernel<<<(unsigned)Q, 128, 0, as_stream(stream)>>>(su, Q, CH, sw, g.sw_pad, reinterpret_cast<__nv_bfloat16*>(qry_op), q_inv_norm);
+  WITW_REQUIRE(su && qry_op && qry_aux && q_inv_norm, WITW_ERR_INVALID, "witw_query_prep: null pointer");
+  WITW_REQUIRE(Q < (1ll << 31) && ((uintptr_t)qry_aux & 7) == 0, WITW_ERR_INVALID, "witw_query_prep: too many queries or qry_aux not 8-byte aligned");
+  query_prep_kernel<<<(unsigned)Q, 128, 0, as_stream(stream)>>>(su, Q, CH, sw, g.sw_pad, reinterpret_cast<__half*>(qry_op),
+                                                              reinterpret_cast<float2*>(qry_aux), q_inv_norm);
   WITW_LAUNCH_CHECK();
   return WITW_OK;
 }
 
 extern "C" int witw_match_tc_topk_slots(int64_t G, int64_t Q) { return make_schedule(G, Q).n_chunks; }
 
-extern "C" int witw_match_tc(const void* gal_op, const float* crop_inv_norm, const void* qry_op, const float* q_inv_norm, int64_t G,
-                             int64_t Q, int CH, int sw, float* dist, uint8_t* ori, const float* d_true, const int32_t* true_idx,
-                             int32_t* rank_count, int topk, float* topk_dist, int32_t* topk_idx, int32_t g_offset, float recheck_band,
-                             int64_t* recheck_g, int64_t* recheck_q, int32_t* recheck_count, int32_t recheck_capacity,
-                             witw_stream_t stream) {
+extern "C" int witw_match_tc(const witw_sweep_args* a, witw_stream_t stream) {
+  WITW_REQUIRE(a != nullptr, WITW_ERR_INVALID, "witw_match_tc: null arguments");
+  const int64_t G = a->G, Q = a->Q;
+  const int CH = a->CH, sw = a->sw;
   TcGeom geo;
   WITW_REQUIRE(G >= 0 && Q >= 0 && make_geom(CH, sw, &geo), WITW_ERR_UNSUPPORTED, "witw_match_tc: unsupported CH=%d sw=%d", CH, sw);
   if (G == 0 || Q == 0) return WITW_OK;
-  WITW_REQUIRE(gal_op && crop_inv_norm && qry_op && q_inv_norm, WITW_ERR_INVALID, "witw_match_tc: null operand");
-  WITW_REQUIRE(topk >= 0 && topk <= kTopkMax, WITW_ERR_UNSUPPORTED, "witw_match_tc: fused top-k supports k <= %d (got %d)", kTopkMax, topk);
-  WITW_REQUIRE(topk == 0 || (topk_dist && topk_idx), WITW_ERR_INVALID, "witw_match_tc: top-k buffers missing");
-  WITW_REQUIRE(!rank_count || d_true, WITW_ERR_INVALID, "witw_match_tc: rank_count needs d_true");
-  WITW_REQUIRE(recheck_capacity >= 0 && (recheck_capacity == 0 || (rank_count && recheck_g && recheck_q && recheck_count && recheck_band >= 0.f)),
-               WITW_ERR_INVALID, "witw_match_tc: re-check list needs rank_count, both index buffers, the counter and a band >= 0");
-  WITW_REQUIRE(G < (1ll << 31) && Q < (1ll << 31), WITW_ERR_INVALID, "witw_match_tc: sizes exceed 2^31");
+  SweepOut out;
+  int rc = fill_sweep_out("witw_match_tc", a, kDenseUnit, &out);
+  if (rc != WITW_OK) return rc;
+  const void* qry_op = a->qry_op;
+  const void* gal_op = a->gal_op;
   WITW_REQUIRE(((uintptr_t)qry_op & 15) == 0 && ((uintptr_t)gal_op & 15) == 0, WITW_ERR_INVALID, "witw_match_tc: operands must be 16-byte aligned");
-  int rc = witw_device_check();
+  rc = witw_device_check();
   if (rc != WITW_OK) return rc;
 
   const TcSchedule sch = make_schedule(G, Q);
@@ -547,12 +567,12 @@ extern "C" int witw_match_tc(const void* gal_op, const float* crop_inv_norm, con
   const cuuint64_t strides[1] = {(cuuint64_t)ktot * 2};
   const cuuint32_t box[2] = {64, 128};
   const cuuint32_t estr[2] = {1, 1};
-  CUresult cr = encode(&qmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(qry_op), dims, strides, box, estr,
+  CUresult cr = encode(&qmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(qry_op), dims, strides, box, estr,
                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   WITW_REQUIRE(cr == CUDA_SUCCESS, WITW_ERR_CUDA, "cuTensorMapEncodeTiled(query operand) failed with CUresult %d", (int)cr);
 
-  // gallery operand as a [total_blocks][64] bf16 matrix of 128-byte blocks; one box = the blocks of one K block
+  // gallery operand as a [total_blocks][64] fp16 matrix of 128-byte blocks; one box = the blocks of one K block
   const int64_t pairs = ceil_div<int64_t>(G, 4) * 2;
   const int64_t total_rows = pairs * CH * geo.bpc;
   WITW_REQUIRE(total_rows < (1ll << 31), WITW_ERR_UNSUPPORTED, "witw_match_tc: gallery of %lld items is too large for one sweep", (long long)G);
@@ -561,20 +581,17 @@ extern "C" int witw_match_tc(const void* gal_op, const float* crop_inv_norm, con
   const cuuint64_t gdims[2] = {64, (cuuint64_t)total_rows};
   const cuuint64_t gstrides[1] = {128};
   const cuuint32_t gbox[2] = {64, (cuuint32_t)(geo.cpb * geo.bpc)};
-  cr = encode(&gmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(gal_op), gdims, gstrides, gbox, estr,
+  cr = encode(&gmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(gal_op), gdims, gstrides, gbox, estr,
               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   WITW_REQUIRE(cr == CUDA_SUCCESS, WITW_ERR_CUDA, "cuTensorMapEncodeTiled(gallery operand) failed with CUresult %d", (int)cr);
 
   TcParams P;
   std::memset(&P, 0, sizeof(P));
-  P.crop_inv_norm = crop_inv_norm; P.q_inv_norm = q_inv_norm;
-  P.dist = dist; P.ori = ori; P.d_true = d_true; P.true_idx = true_idx; P.rank_count = rank_count;
-  P.topk_dist = topk_dist; P.topk_idx = topk_idx; P.G = G; P.Q = Q; P.topk = topk; P.g_offset = g_offset;
+  P.out = out;
   P.n_qtiles = sch.n_qtiles; P.n_chunks = sch.n_chunks; P.groups_per_chunk = sch.groups_per_chunk; P.n_groups = sch.n_groups;
   P.kblocks = geo.kblocks; P.cpb = geo.cpb; P.bpc = geo.bpc; P.nkap = geo.nkap;
   P.sbo = geo.sbo; P.lbo = geo.lbo; P.kstep = geo.kstep; P.b_bytes = geo.b_bytes;
-  P.band = recheck_band; P.recheck_g = recheck_g; P.recheck_q = recheck_q; P.recheck_count = recheck_count; P.recheck_cap = recheck_capacity;
   P.pair_rows = CH * geo.bpc;
   P.stage_rows = geo.cpb * geo.bpc;
 

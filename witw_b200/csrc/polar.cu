@@ -137,13 +137,19 @@ static bool polar_fast_supported(int h_s, int w_s, int s_o) {
 static int polar_patch_w() {
   // Lanes of a warp on a 2-D output patch touch a compact 2-D footprint of the staged source window, which
   // spreads over the shared-memory banks better than 32 samples along one arc (measured: profiles/).
+  // measured on B200, 1024x3 planes: 32 -> 5053 GB/s, 16 -> 5515 GB/s, 8 -> 5332 GB/s.  The width is a constant of the
+  // shipped library; only builds with -DWITW_DEBUG_HOOKS (tools/ probes) read it from the environment.
+#ifdef WITW_DEBUG_HOOKS
   static int v = -1;
   if (v < 0) {
     const char* e = std::getenv("WITW_POLAR_PW");
-    v = e ? std::atoi(e) : 16;  // measured on B200, 1024x3 planes: 32 -> 5053 GB/s, 16 -> 5515 GB/s, 8 -> 5332 GB/s
+    v = e ? std::atoi(e) : 16;
     if (v != 8 && v != 16 && v != 32) v = 16;
   }
   return v;
+#else
+  return 16;
+#endif
 }
 
 // pixel (row, col-in-quadrant) handled by thread t in iteration i: warps tile the quadrant with patch_w x 32/patch_w patches

@@ -18,6 +18,7 @@
 
 #include "common.cuh"
 #include "row_fft.cuh"
+#include "spectral_pair.cuh"
 
 namespace witw {
 
@@ -43,20 +44,14 @@ spectral_rows_kernel(const float* __restrict__ x, int64_t n_rows, int row_len, f
   }
 }
 
-// One warp per pair, lane = frequency slot.  P_f = sum_ch O_f conj(S_f); then every lane evaluates the
-// inverse transform at shifts `lane` and `lane + 32` from the 32 broadcast P_f; warp argmax (first maximum,
-// NaN is the maximum -- torch.argmax); distance from the fp32 norm tables of the prep kernels.
+// One warp per pair (spectral_pair_eval); distance from the fp32 norm tables of the prep kernels.
 __global__ void __launch_bounds__(256)
 spectral_pairs_kernel(const float2* __restrict__ gal_spec, const float* __restrict__ crop_inv_norm,
                       const float2* __restrict__ qry_spec, const float* __restrict__ q_inv_norm,
                       const int64_t* __restrict__ pair_g, const int64_t* __restrict__ pair_q, int64_t n_pairs,
                       const int32_t* __restrict__ n_pairs_dev, int CH, float* __restrict__ dist, int64_t* __restrict__ ori) {
-  __shared__ float2 tw[64];  // (cos, sin)(2 pi m / 64)
-  if (threadIdx.x < 64) {
-    float s, c;
-    sincospif((float)threadIdx.x / 32.0f, &s, &c);
-    tw[threadIdx.x] = make_float2(c, s);
-  }
+  __shared__ float2 tw[64];
+  spectral_twiddles(tw);
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int64_t p = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -64,43 +59,10 @@ spectral_pairs_kernel(const float2* __restrict__ gal_spec, const float* __restri
   if (n_pairs_dev != nullptr) n = min(n, (int64_t)*n_pairs_dev);
   if (p >= n) return;
   const int64_t g = pair_g[p], q = pair_q[p];
-  const float2* go = gal_spec + g * CH * 32 + lane;
-  const float2* qo = qry_spec + q * CH * 32 + lane;
-  float a = 0.f, b = 0.f, c = 0.f;  // sum o.x s.x, sum o.y s.y, sum (o.y s.x - o.x s.y)
-#pragma unroll 8
-  for (int ch = 0; ch < CH; ++ch) {
-    const float2 o = __ldg(go + ch * 32), s = __ldg(qo + ch * 32);
-    a = fmaf(o.x, s.x, a);
-    b = fmaf(o.y, s.y, b);
-    c = fmaf(o.y, s.x, c);
-    c = fmaf(-o.x, s.y, c);
-  }
-  const float p0 = __shfl_sync(0xffffffffu, a, 0), p32 = __shfl_sync(0xffffffffu, b, 0);
-  const float re = a + b, im = c;
-  const float base = p0 + ((lane & 1) ? -p32 : p32);
-  float lo = 0.f, hi = 0.f;
-#pragma unroll
-  for (int f = 1; f < 32; ++f) {
-    const float fr = __shfl_sync(0xffffffffu, re, f), fi = __shfl_sync(0xffffffffu, im, f);
-    const float2 t = tw[(f * lane) & 63];
-    const float term = fr * t.x - fi * t.y;
-    lo += term;
-    hi += (f & 1) ? -term : term;
-  }
-  const float c_lo = (base + 2.0f * lo) * (1.0f / 64.0f), c_hi = (base + 2.0f * hi) * (1.0f / 64.0f);
-  float best = c_lo;
-  int arg = lane;
-  if (c_hi > best || (c_hi != c_hi && best == best)) { best = c_hi; arg = lane + 32; }
-#pragma unroll
-  for (int m = 16; m > 0; m >>= 1) {
-    const float ob = __shfl_xor_sync(0xffffffffu, best, m);
-    const int oa = __shfl_xor_sync(0xffffffffu, arg, m);
-    const bool take = (ob > best) || (ob != ob && best == best) || (ob == best && oa < arg) || (ob != ob && best != best && oa < arg);
-    if (take) { best = ob; arg = oa; }
-  }
+  const PairMax r = spectral_pair_eval(gal_spec + g * CH * 32 + lane, qry_spec + q * CH * 32 + lane, CH, tw, lane);
   if (lane == 0) {
-    if (dist != nullptr) dist[p] = 2.0f * (1.0f - best * crop_inv_norm[g * 64 + arg] * q_inv_norm[q]);
-    if (ori != nullptr) ori[p] = arg;
+    if (dist != nullptr) dist[p] = 2.0f * (1.0f - r.best * crop_inv_norm[g * 64 + r.arg] * q_inv_norm[q]);
+    if (ori != nullptr) ori[p] = r.arg;
   }
 }
 

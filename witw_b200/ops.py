@@ -24,6 +24,8 @@ the fused forms (match, evaluate_ranks, ...) are forward-only and refuse tensors
 grad under an enabled grad mode rather than silently detaching them.
 """
 
+import ctypes
+
 import numpy as np
 import torch
 
@@ -62,9 +64,18 @@ def _pick_impl(impl, ch, w, sw):
     return impl
 
 
-# how the exact fp32 finish of the tensor-core sweep evaluates its pairs: "spectral" (correlation theorem on packed
-# azimuth spectra, csrc/spectral.cu) or "direct" (4096-term fp32 dot products per shift, csrc/match_simt.cu)
-EXACT_IMPL = "spectral"
+# Bounds on what the fp16 operands of the tensor-core sweeps can have done to a result (csrc/sweep_common.cuh): decisions
+# within ERR_SIGMAS standard deviations of the accumulated rounding error are deferred to the fp32 finish (csrc/finish.cu).
+ERR_SIGMAS = 5.0
+# matrix outputs of the sweep: a pair whose error bound exceeds this fraction of its distance (the near matches) is
+# overwritten with its fp32 distance, so every entry is within the north star's 1e-3 relative of the fp32 reference
+FIX_REL = 1e-3
+# test hook: a fixed capacity of the per-query deferral lists (None: sized from the gallery)
+DEFERRAL_CAP = None
+# at most this many queries: every pair is evaluated in fp32 from the spectra (heat map, the reference's one-query loop)
+EXACT_SMALL_Q = 8
+# the fused top-k keeps 16 candidates per query; the exact finish needs a few more candidates than results
+TOPK_EXACT_MAX = 12
 
 
 # ----------------------------------------------------------------------------- helpers
@@ -350,6 +361,7 @@ def _via_device(t, device, fn, *args, **kwargs):
     is copied to ``device`` (default: the current CUDA device), processed there and returned on the CPU.  No CPU arithmetic."""
     if t.is_cuda:
         return fn(t, *args, **kwargs)
+    _refuse_dataloader_worker(fn.__name__)
     if not torch.cuda.is_available():
         raise RuntimeError("%s: no CUDA device; witw_b200 has no CPU fallback" % fn.__name__)
     dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
@@ -433,6 +445,7 @@ class PolarTransform(object):
         if tile.is_cuda:
             data["polar"] = polar_transform(tile, *self.geom, exact=self.exact)
         else:
+            _refuse_dataloader_worker("PolarTransform")
             if not torch.cuda.is_available():
                 raise RuntimeError("PolarTransform: no CUDA device; witw_b200 has no CPU fallback")
             dev = torch.device(self.device) if self.device is not None else torch.device("cuda", torch.cuda.current_device())
@@ -440,10 +453,25 @@ class PolarTransform(object):
         return data
 
 
+def _refuse_dataloader_worker(name):
+    """The reference builds its transforms into the dataset and runs them inside forked DataLoader workers (num_workers=8 /
+    12, cvig_fov.py:385, 490, 506), where CUDA cannot be initialised.  Say so, instead of torch's 'Cannot re-initialize CUDA in
+    forked subprocess'."""
+    import torch.utils.data
+
+    info = torch.utils.data.get_worker_info()
+    if info is not None:
+        raise RuntimeError(
+            "%s: called on a CPU tensor inside DataLoader worker %d -- the witw_b200 drop-in runs on the GPU, and CUDA cannot be "
+            "used in the reference's forked worker processes.  Run the loader with num_workers=0 (or multiprocessing_context='spawn'), "
+            "or keep the reference's transform in the workers (witw_b200.install(module, polar=False)) and call "
+            "witw_b200.polar_transform on the batched data['overhead'] after the loader." % (name, info.id))
+
+
 # ----------------------------------------------------------------------------- K2/K3
 def spectral_rows(rows, row_len):
     """Packed 64-point azimuth spectra [n_rows,64] fp32 of contiguous fp32 feature rows (row_len <= 64 columns,
-    zero-padded): the operand of the exact fp32 finish (csrc/spectral.cu)."""
+    zero-padded): the operand of the fp32 finish (csrc/spectral.cu)."""
     n_rows = rows.numel() // row_len
     out = torch.empty((n_rows, 64), dtype=torch.float32, device=rows.device)
     with torch.cuda.device(rows.device):
@@ -451,8 +479,17 @@ def spectral_rows(rows, row_len):
     return out
 
 
+def _gallery_tables(n_items, device, zero=False):
+    """(gal_scale [n,64], gal_aux [n,4], crop_inv_norm [n,64]) of include/witw_b200.h for n (padded) items."""
+    make = torch.zeros if zero else torch.empty
+    return (make(n_items * 64, dtype=torch.float32, device=device), make(n_items * 4, dtype=torch.float32, device=device),
+            make(n_items * 64, dtype=torch.float32, device=device))
+
+
 class GalleryIndex(object):
-    """Gallery feature maps prepared for the tensor-core sweep (bf16 Hankel blocks + crop norms).
+    """Gallery feature maps prepared for the tensor-core sweeps and their fp32 finish: the fp16 operand of the norm-scaled
+    features (azimuth spectra, or Hankel blocks for the dense sweep), the per-item scale / error-bound tables, and -- with
+    keep_fp32 -- the fp32 azimuth spectra every exact evaluation works on (csrc/sweep_common.cuh, csrc/finish.cu).
 
     Built once per (gallery, query width); reused for every query batch.  ``g_offset`` is the
     global index of the first item when the gallery is one shard of a larger one.
@@ -466,37 +503,35 @@ class GalleryIndex(object):
         self.device, self.G, self.CH, self.W, self.sw = dev, g, c * h, w, int(surface_width)
         self.C, self.H = c, h
         self.g_offset = int(g_offset)
+        if w != 64:
+            raise _lib.WitwError("GalleryIndex: tensor-core path needs W == 64, got %d" % w)
         ov = _f32c(overhead_embed)
-        self.ov = ov if keep_fp32 else None
         self.spec = None
-        self.impl = _pick_impl(impl, self.CH, w, self.sw) if w == 64 else "hankel"
-        if self.impl == "spectral":
-            with torch.cuda.device(dev):
-                nbytes = _lib.load().witw_spec_gallery_operand_bytes(g, self.CH)
-                self.operand = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-                g8 = max((g + 7) // 8 * 8, 8)
-                self.crop_inv_norm = torch.empty(g8 * 64, dtype=torch.float32, device=dev)
-                if keep_fp32:       # the exact finish's fp32 spectra come out of the same pass over the features
-                    self.spec = torch.empty((g * self.CH, 64), dtype=torch.float32, device=dev)
-                _lib.call("witw_spec_gallery_prep", ov.data_ptr(), g, 0, self.CH, w, self.sw, self.operand.data_ptr(),
-                          self.crop_inv_norm.data_ptr(), _ptr(self.spec), _stream())
-            return
+        self.impl = _pick_impl(impl, self.CH, w, self.sw)
         with torch.cuda.device(dev):
+            if keep_fp32:
+                self.spec = torch.empty((g * self.CH, 64), dtype=torch.float32, device=dev)
+            if self.impl == "spectral":
+                self.operand = torch.empty(_lib.load().witw_spec_gallery_operand_bytes(g, self.CH), dtype=torch.uint8, device=dev)
+                self.scale, self.aux, self.crop_inv_norm = _gallery_tables(max((g + 7) // 8 * 8, 8), dev)
+                # the finish's fp32 spectra come out of the same pass over the features
+                _lib.call("witw_spec_gallery_prep", ov.data_ptr(), g, 0, self.CH, w, self.sw, self.operand.data_ptr(), self.scale.data_ptr(),
+                          self.aux.data_ptr(), self.crop_inv_norm.data_ptr(), _ptr(self.spec), _stream())
+                return
             nbytes = _lib.load().witw_gallery_operand_bytes(g, self.CH, self.sw)
-            if nbytes == 0 or w != 64:
-                raise _lib.WitwError("GalleryIndex: " + (_lib.last_error() if w == 64 else "tensor-core path needs W == 64, got %d" % w))
+            if nbytes == 0:
+                raise _lib.WitwError("GalleryIndex: " + _lib.last_error())
             self.operand = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-            g4 = (g + 3) // 4 * 4
-            self.crop_inv_norm = torch.empty(max(g4, 4) * 64, dtype=torch.float32, device=dev)
-            _lib.call("witw_gallery_prep", ov.data_ptr(), g, self.CH, w, self.sw, self.operand.data_ptr(),
-                      self.crop_inv_norm.data_ptr(), _stream())
+            self.scale, self.aux, self.crop_inv_norm = _gallery_tables(max((g + 3) // 4 * 4, 4), dev)
+            _lib.call("witw_gallery_prep", ov.data_ptr(), g, self.CH, w, self.sw, self.operand.data_ptr(), self.scale.data_ptr(),
+                      self.aux.data_ptr(), self.crop_inv_norm.data_ptr(), _stream())
+            if keep_fp32 and g:
+                _lib.call("witw_spectral_rows_f32", ov.data_ptr(), g * self.CH, w, self.spec.data_ptr(), _stream())
 
     def spectral(self):
-        """Packed azimuth spectra [G*CH,64] of the fp32 features (built on first use, then kept)."""
+        """Packed azimuth spectra [G*CH,64] of the fp32 features."""
         if self.spec is None:
-            if self.ov is None:
-                raise ValueError("GalleryIndex: the fp32 features were dropped (keep_fp32=False); no exact finish")
-            self.spec = spectral_rows(self.ov, self.W)
+            raise ValueError("GalleryIndex: the fp32 spectra were dropped (keep_fp32=False); no fp32 finish")
         return self.spec
 
 
@@ -504,10 +539,10 @@ class GalleryBuilder(object):
     """Incremental GalleryIndex for the encode loop of test() (cvig_fov.py:519-532).
 
     The reference grows ``overhead_embed`` with torch.cat per batch (O(n^2) copies).  Here each encoder
-    output batch is written once: fp32 features into a preallocated buffer (kept for the exact true-match
-    distances) and, through witw_gallery_prep, straight into its slot of the tensor-core operand.
-    Batches must hold a multiple of 4 items (8 for the spectral sweep: ``batch_multiple``), except the last one.  keep_fp32: keep what the exact fp32 finish needs
-    (the packed azimuth spectra of the features, 16 KB per item); keep_raw: also keep the raw fp32 features.
+    output batch is written once, straight into its slot of the preallocated tensor-core operand, its tables and
+    (keep_fp32) the fp32 spectra the exact finish needs (16 KB per item).
+    Batches must hold a multiple of 4 items (8 for the spectral sweep: ``batch_multiple``), except the last one.
+    keep_raw: also keep the raw fp32 features.
     """
 
     def __init__(self, capacity, surface_width, channels=16, height=4, width=64, device=None, g_offset=0, keep_fp32=True,
@@ -518,8 +553,10 @@ class GalleryBuilder(object):
         self.capacity, self.sw = int(capacity), int(surface_width)
         self.C, self.H, self.W, self.CH = channels, height, width, channels * height
         self.g_offset, self.count, self.closed = int(g_offset), 0, False
+        if width != 64:
+            raise _lib.WitwError("GalleryBuilder: tensor-core path needs W == 64")
         lib = _lib.load()
-        self.impl = _pick_impl(impl, self.CH, width, self.sw) if width == 64 else "hankel"
+        self.impl = _pick_impl(impl, self.CH, width, self.sw)
         self.batch_multiple = 8 if self.impl == "spectral" else 4
         with torch.cuda.device(self.device):
             if self.impl == "spectral":
@@ -527,12 +564,11 @@ class GalleryBuilder(object):
                 self.pair_bytes = 0
             else:
                 nbytes = lib.witw_gallery_operand_bytes(self.capacity, self.CH, self.sw)
-                if nbytes == 0 or width != 64:
-                    raise _lib.WitwError("GalleryBuilder: " + (_lib.last_error() if width == 64 else "tensor-core path needs W == 64"))
+                if nbytes == 0:
+                    raise _lib.WitwError("GalleryBuilder: " + _lib.last_error())
                 self.pair_bytes = lib.witw_gallery_operand_bytes(4, self.CH, self.sw) // 2
             self.operand = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
-            cap4 = max((self.capacity + 7) // 8 * 8, 8)
-            self.crop_inv_norm = torch.zeros(cap4 * 64, dtype=torch.float32, device=self.device)
+            self.scale, self.aux, self.crop_inv_norm = _gallery_tables(max((self.capacity + 7) // 8 * 8, 8), self.device, zero=True)
             self.ov = torch.empty((self.capacity, channels, height, width), dtype=torch.float32, device=self.device) if keep_raw else None
             self.spec = torch.empty((self.capacity * self.CH, 64), dtype=torch.float32, device=self.device) if keep_fp32 else None
 
@@ -553,15 +589,16 @@ class GalleryBuilder(object):
             if self.ov is not None:
                 self.ov[self.count: self.count + n].copy_(part)
             spec_ptr = 0 if self.spec is None else self.spec.data_ptr() + self.count * self.CH * 64 * 4
+            tables = (self.scale.data_ptr() + self.count * 64 * 4, self.aux.data_ptr() + self.count * 4 * 4,
+                      self.crop_inv_norm.data_ptr() + self.count * 64 * 4)
             if self.impl == "spectral":
                 _lib.call("witw_spec_gallery_prep", part.data_ptr(), n, self.count, self.CH, self.W, self.sw, self.operand.data_ptr(),
-                          self.crop_inv_norm.data_ptr() + self.count * 64 * 4, spec_ptr, _stream())
+                          tables[0], tables[1], tables[2], spec_ptr, _stream())
             else:
                 if spec_ptr:
                     _lib.call("witw_spectral_rows_f32", part.data_ptr(), n * self.CH, self.W, spec_ptr, _stream())
                 _lib.call("witw_gallery_prep", part.data_ptr(), n, self.CH, self.W, self.sw,
-                          self.operand.data_ptr() + (self.count // 2) * self.pair_bytes,
-                          self.crop_inv_norm.data_ptr() + self.count * 64 * 4, _stream())
+                          self.operand.data_ptr() + (self.count // 2) * self.pair_bytes, tables[0], tables[1], tables[2], _stream())
         self.count += n
         self.closed = n % self.batch_multiple != 0
         return self
@@ -571,46 +608,45 @@ class GalleryBuilder(object):
         idx = GalleryIndex.__new__(GalleryIndex)
         idx.device, idx.G, idx.CH, idx.W, idx.sw = self.device, self.count, self.CH, self.W, self.sw
         idx.C, idx.H, idx.g_offset, idx.impl = self.C, self.H, self.g_offset, self.impl
-        idx.ov = None if self.ov is None else self.ov[: self.count]
         idx.spec = None if self.spec is None else self.spec[: self.count * self.CH]
-        idx.operand, idx.crop_inv_norm = self.operand, self.crop_inv_norm
+        idx.operand, idx.scale, idx.aux, idx.crop_inv_norm = self.operand, self.scale, self.aux, self.crop_inv_norm
         return idx
 
 
 class QueryBatch(object):
-    """Query feature maps prepared for the tensor-core sweep (bf16 [Q, CH*sw_pad] + inverse norms)."""
+    """Query feature maps prepared for the tensor-core sweeps (fp16 operand of the norm-scaled features, per-query sweep
+    constants, inverse norms) and, with keep_fp32, their fp32 azimuth spectra for the exact finish."""
 
     def __init__(self, surface_embed, keep_fp32=True, impl=None):
         dev = _need_cuda("QueryBatch", surface_embed)
         q, c, h, sw = surface_embed.shape
         self.device, self.Q, self.CH, self.sw = dev, q, c * h, sw
         su = _f32c(surface_embed)
-        self.su = su if keep_fp32 else None
         self.spec = None
         self.impl = _pick_impl(impl, self.CH, 64, sw)
-        if self.impl == "spectral":
-            with torch.cuda.device(dev):
-                self.operand = torch.empty(_lib.load().witw_spec_query_operand_bytes(q, self.CH), dtype=torch.uint8, device=dev)
-                self.inv_norm = torch.empty(max(q, 1), dtype=torch.float32, device=dev)
-                if keep_fp32:
-                    self.spec = torch.empty((q * self.CH, 64), dtype=torch.float32, device=dev)
-                _lib.call("witw_spec_query_prep", su.data_ptr(), q, self.CH, sw, self.operand.data_ptr(), self.inv_norm.data_ptr(),
-                          _ptr(self.spec), _stream())
-            return
         with torch.cuda.device(dev):
+            self.inv_norm = torch.empty(max(q, 1), dtype=torch.float32, device=dev)
+            self.aux = torch.empty(max(q, 1) * 2, dtype=torch.float32, device=dev)
+            if keep_fp32:
+                self.spec = torch.empty((q * self.CH, 64), dtype=torch.float32, device=dev)
+            if self.impl == "spectral":
+                self.operand = torch.empty(_lib.load().witw_spec_query_operand_bytes(q, self.CH), dtype=torch.uint8, device=dev)
+                _lib.call("witw_spec_query_prep", su.data_ptr(), q, self.CH, sw, self.operand.data_ptr(), self.aux.data_ptr(),
+                          self.inv_norm.data_ptr(), _ptr(self.spec), _stream())
+                return
             nbytes = _lib.load().witw_query_operand_bytes(q, self.CH, sw)
             if nbytes == 0:
                 raise _lib.WitwError("QueryBatch: " + _lib.last_error())
             self.operand = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-            self.inv_norm = torch.empty(max(q, 1), dtype=torch.float32, device=dev)
-            _lib.call("witw_query_prep", su.data_ptr(), q, self.CH, sw, self.operand.data_ptr(), self.inv_norm.data_ptr(), _stream())
+            _lib.call("witw_query_prep", su.data_ptr(), q, self.CH, sw, self.operand.data_ptr(), self.aux.data_ptr(),
+                      self.inv_norm.data_ptr(), _stream())
+            if keep_fp32 and q:
+                _lib.call("witw_spectral_rows_f32", su.data_ptr(), q * self.CH, sw, self.spec.data_ptr(), _stream())
 
     def spectral(self):
-        """Packed azimuth spectra [Q*CH,64] of the zero-padded fp32 query rows (built on first use, then kept)."""
+        """Packed azimuth spectra [Q*CH,64] of the zero-padded fp32 query rows."""
         if self.spec is None:
-            if self.su is None:
-                raise ValueError("QueryBatch: the fp32 features were dropped (keep_fp32=False); no exact finish")
-            self.spec = spectral_rows(self.su, self.sw)
+            raise ValueError("QueryBatch: the fp32 spectra were dropped (keep_fp32=False); no fp32 finish")
         return self.spec
 
 
@@ -632,13 +668,31 @@ def _pick_path(path, g, q, ch, w, sw):
     return path
 
 
+class Deferral(object):
+    """Per-query lists of the (gallery, query) pairs a sweep defers to the fp32 finish (csrc/sweep_common.cuh): list_n [Q]
+    counts them, list_g [Q,cap] holds them; a count above cap marks the query for a full fp32 re-evaluation.  The int32
+    bookkeeping (rank counts, list_n, qflag, n_flagged) lives in one zero-filled buffer: one fill per evaluation."""
+
+    def __init__(self, n_queries, n_gallery, device, matrix=False, err_sigmas=None, fix_rel=None, cap=None):
+        cap = DEFERRAL_CAP if cap is None else cap
+        if cap is None:   # room for 3 % (12 % for matrix outputs, where every uncertain argmax is listed) of the gallery per query
+            cap = min(max(n_gallery // (8 if matrix else 32), 64), 8192)
+        self.cap = int(cap)
+        self.err_sigmas = float(ERR_SIGMAS if err_sigmas is None else err_sigmas)
+        self.fix_rel = float(FIX_REL if fix_rel is None else fix_rel) if matrix else 0.0
+        qp = (max(n_queries, 1) + 3) // 4 * 4
+        self.list_g = torch.empty(qp * self.cap, dtype=torch.int32, device=device)
+        book = torch.zeros(3 * qp + 4, dtype=torch.int32, device=device)
+        self.counts, self.list_n, self.qflag, self.n_flagged = book[:qp], book[qp: 2 * qp], book[2 * qp: 3 * qp], book[3 * qp: 3 * qp + 1]
+
+
 def sweep_tc(gallery, queries, want_dist=False, want_ori=False, d_true=None, true_idx=None, rank_count=None, topk=0, events=None,
-             recheck=None):
+             deferral=None):
     """One tensor-core sweep of a QueryBatch over a GalleryIndex.  Returns a dict with the requested outputs.
 
     events: optional (start, end) torch.cuda.Event pair recorded around the sweep kernel alone (bench.py's roofline timer).
-    recheck: optional RecheckList; rank decisions within its band of the threshold are deferred to it (see exact=True
-    of evaluate_ranks_prepared)."""
+    deferral: optional Deferral; what fp16 cannot settle is listed there for finish_tc() instead of being decided here, and the
+    top-k keys are lower bounds of the exact distances.  Without it: the plain fp16 results."""
     if gallery.CH != queries.CH or gallery.sw != queries.sw or gallery.device != queries.device:
         raise ValueError("sweep_tc: gallery and queries disagree (CH %d/%d, sw %d/%d)" % (gallery.CH, queries.CH, gallery.sw, queries.sw))
     if gallery.impl != queries.impl:
@@ -656,13 +710,17 @@ def sweep_tc(gallery, queries, want_dist=False, want_ori=False, d_true=None, tru
             tk_d = torch.empty((slots, q, topk), dtype=torch.float32, device=dev)
             tk_i = torch.empty((slots, q, topk), dtype=torch.int32, device=dev)
         if g > 0 and q > 0:
+            args = _lib.SweepArgs(
+                gal_op=gallery.operand.data_ptr(), gal_scale=gallery.scale.data_ptr(), gal_aux=gallery.aux.data_ptr(),
+                qry_op=queries.operand.data_ptr(), qry_aux=queries.aux.data_ptr(), G=g, Q=q, CH=gallery.CH, sw=gallery.sw,
+                g_index_offset=gallery.g_offset, topk=int(topk), dist=_ptr(dist), ori=_ptr(ori), d_true=_ptr(d_true), true_idx=_ptr(true_idx),
+                rank_count=_ptr(rank_count), topk_key=_ptr(tk_d), topk_idx=_ptr(tk_i),
+                list_g=_ptr(deferral.list_g) if deferral else 0, list_n=_ptr(deferral.list_n) if deferral else 0,
+                list_cap=deferral.cap if deferral else 0, err_sigmas=deferral.err_sigmas if deferral else 0.0,
+                fix_rel=deferral.fix_rel if deferral else 0.0)
             if events is not None:
                 events[0].record()
-            _lib.call(fn_sweep, gallery.operand.data_ptr(), gallery.crop_inv_norm.data_ptr(), queries.operand.data_ptr(),
-                      queries.inv_norm.data_ptr(), g, q, gallery.CH, gallery.sw, _ptr(dist), _ptr(ori), _ptr(d_true),
-                      _ptr(true_idx), _ptr(rank_count), int(topk), _ptr(tk_d), _ptr(tk_i), gallery.g_offset,
-                      float(recheck.band) if recheck else 0.0, _ptr(recheck.g) if recheck else 0, _ptr(recheck.q) if recheck else 0,
-                      _ptr(recheck.count) if recheck else 0, int(recheck.capacity) if recheck else 0, _stream())
+            _lib.call(fn_sweep, ctypes.addressof(args), _stream())
             if events is not None:
                 events[1].record()
         if topk:
@@ -675,18 +733,106 @@ def sweep_tc(gallery, queries, want_dist=False, want_ori=False, d_true=None, tru
     return out
 
 
+def finish_tc(gallery, queries, deferral, d_true=None, rank_count=None, dist=None, ori=None, cand_key=None, cand_idx=None, k_out=0):
+    """The fp32 finish of a sweep that ran with ``deferral`` (csrc/finish.cu): settles the deferred pairs (rank decisions
+    into rank_count, fp32 values into dist / ori) and re-ranks the merged top-k candidates.  Returns (topk_dist, topk_idx)
+    or None.  Queries it cannot finish are flagged in deferral.qflag / n_flagged (see redo_flagged)."""
+    dev, q = gallery.device, queries.Q
+    td = ti = None
+    with torch.cuda.device(dev):
+        kc = 0
+        if k_out:
+            kc = cand_idx.shape[1]
+            td = torch.empty((q, k_out), dtype=torch.float32, device=dev)
+            ti = torch.empty((q, k_out), dtype=torch.int32, device=dev)
+        if gallery.G > 0 and q > 0:
+            args = _lib.FinishArgs(
+                gal_spec=gallery.spectral().data_ptr(), crop_inv_norm=gallery.crop_inv_norm.data_ptr(), qry_spec=queries.spectral().data_ptr(),
+                q_inv_norm=queries.inv_norm.data_ptr(), G=gallery.G, Q=q, CH=gallery.CH, g_index_offset=gallery.g_offset,
+                list_g=deferral.list_g.data_ptr(), list_n=deferral.list_n.data_ptr(), list_cap=deferral.cap, kc=kc, d_true=_ptr(d_true),
+                rank_count=_ptr(rank_count), dist=_ptr(dist), ori=_ptr(ori), cand_key=_ptr(cand_key.contiguous() if k_out else None),
+                cand_idx=_ptr(cand_idx.contiguous() if k_out else None), out_dist=_ptr(td), out_idx=_ptr(ti), k_out=int(k_out), reserved=0,
+                qflag=deferral.qflag.data_ptr(), n_flagged=deferral.n_flagged.data_ptr())
+            _lib.call("witw_finish_spec_f32", ctypes.addressof(args), _stream())
+    return (td, ti) if k_out else None
+
+
+def exact_columns(gallery, queries, q_sel=None, dist=None, ori64=None, ori8=None, ld=None, col_is_q=False, d_true=None, true_idx=None,
+                  count_out=None):
+    """Exact fp32 distances / orientations of whole query columns from the fp32 spectra (witw_match_columns_spec_f32):
+    queries q_sel (int32 tensor, default all) against every item of the gallery."""
+    f = queries.Q if q_sel is None else int(q_sel.numel())
+    if f == 0 or gallery.G == 0:
+        return
+    with torch.cuda.device(gallery.device):
+        for lo in range(0, f, 65535):
+            n = min(65535, f - lo)
+            off = 0 if col_is_q else lo
+            sel_ptr = 0 if q_sel is None else q_sel.data_ptr() + 4 * lo
+            if q_sel is None and lo:
+                raise ValueError("exact_columns: more than 65535 columns need an explicit q_sel")
+            _lib.call("witw_match_columns_spec_f32", gallery.spectral().data_ptr(), gallery.crop_inv_norm.data_ptr(), queries.spectral().data_ptr(),
+                      queries.inv_norm.data_ptr(), gallery.G, gallery.CH, sel_ptr, n,
+                      0 if dist is None else dist.data_ptr() + 4 * off, 0 if ori64 is None else ori64.data_ptr() + 8 * off,
+                      0 if ori8 is None else ori8.data_ptr() + off, int(f if ld is None else ld), int(bool(col_is_q)), _ptr(d_true), _ptr(true_idx),
+                      gallery.g_offset, 0 if count_out is None else count_out.data_ptr() + 4 * lo, _stream())
+
+
+_index_cache = []          # [(key, GalleryIndex)]: the gallery of the reference's one-query loop is prepared once, not per query
+INDEX_CACHE_ENTRIES = 2
+
+
+def _cached_index(overhead_embed, sw):
+    key = (overhead_embed.data_ptr(), tuple(overhead_embed.shape), overhead_embed.dtype, overhead_embed._version, int(sw), str(overhead_embed.device))
+    for k, idx in _index_cache:
+        if k == key:
+            return idx
+    idx = GalleryIndex(overhead_embed, sw)
+    _index_cache.insert(0, (key, idx))
+    del _index_cache[INDEX_CACHE_ENTRIES:]
+    return idx
+
+
+def clear_cache():
+    """Drop the prepared galleries kept for repeated small-query calls (each holds ~33 KB of device memory per item)."""
+    del _index_cache[:]
+
+
 def match(overhead_embed, surface_embed, path="auto", impl=None):
     """(orientation int64 [G,Q], distance fp32 [G,Q]) = a3 -> a4 -> a5 fused (cvig_fov.py:547-549).
 
-    path 'fp32': exact fp32 kernel; 'tc': tcgen05 bf16 x bf16 -> fp32; 'auto': by problem size.
+    path 'fp32': exact fp32 kernels; 'tc': the tcgen05 sweep, with every entry fp16 cannot settle (uncertain argmax, small
+    distance) overwritten with its fp32 value -- orientations are the fp32 reference's except where fp32 correlations
+    themselves tie, distances within 1e-3 relative; 'tc16': the raw fp16 sweep; 'auto': by problem size (a few queries
+    against a large gallery -- the heat map, the reference's one-query loop -- are evaluated entirely in fp32 from the
+    gallery's spectra, which are prepared once and cached).
     """
     dev = _need_cuda("match", overhead_embed, surface_embed)
     g, q, ch, w, sw = _feature_dims("match", overhead_embed, surface_embed)
-    which = _pick_path(path, g, q, ch, w, sw)
+    raw = path == "tc16"
+    which = _pick_path("tc" if raw else path, g, q, ch, w, sw)
+    if path == "auto" and w == 64 and 0 < q <= EXACT_SMALL_Q and g * q >= 1024:
+        gallery = _cached_index(overhead_embed, sw)
+        queries = QueryBatch(surface_embed, impl=gallery.impl)
+        with torch.cuda.device(dev):
+            dist = torch.empty((g, q), dtype=torch.float32, device=dev)
+            ori = torch.empty((g, q), dtype=torch.int64, device=dev)
+            exact_columns(gallery, queries, dist=dist, ori64=ori, ld=q)
+        return ori, dist
     if which == "tc":
         impl = _pick_impl(impl, ch, w, sw)
-        res = sweep_tc(GalleryIndex(overhead_embed, sw, keep_fp32=False, impl=impl), QueryBatch(surface_embed, keep_fp32=False, impl=impl),
-                       want_dist=True, want_ori=True)
+        gallery = GalleryIndex(overhead_embed, sw, keep_fp32=not raw, impl=impl)
+        queries = QueryBatch(surface_embed, keep_fp32=not raw, impl=impl)
+        if raw:
+            res = sweep_tc(gallery, queries, want_dist=True, want_ori=True)
+            return res["ori"].to(torch.int64), res["dist"]
+        defer = Deferral(q, g, dev, matrix=True)
+        res = sweep_tc(gallery, queries, want_dist=True, want_ori=True, deferral=defer)
+        finish_tc(gallery, queries, defer, dist=res["dist"], ori=res["ori"])
+        if g and q and int(defer.n_flagged):       # lists that overflowed: those columns entirely in fp32
+            sel = torch.nonzero(defer.qflag[:q]).to(torch.int32).flatten().contiguous()
+            exact_columns(gallery, queries, q_sel=sel, dist=res["dist"], ori8=res["ori"], ld=q, col_is_q=True)
+        match.last_flagged = defer.n_flagged
         return res["ori"].to(torch.int64), res["dist"]
     ov, su = _f32c(overhead_embed), _f32c(surface_embed)
     with torch.cuda.device(dev):
@@ -694,6 +840,9 @@ def match(overhead_embed, surface_embed, path="auto", impl=None):
         ori = torch.empty((g, q), dtype=torch.int64, device=dev)
         _lib.call("witw_match_f32", ov.data_ptr(), su.data_ptr(), g, q, ch, w, sw, dist.data_ptr(), ori.data_ptr(), 0, _stream())
     return ori, dist
+
+
+match.last_flagged = None
 
 
 def correlation_scores(overhead_embed, surface_embed):
@@ -943,9 +1092,9 @@ def evaluate_ranks(overhead_embed, surface_embed, true_idx=None, path="auto", to
 
     Query i matches gallery item i (or true_idx[i]).  The true-match distances are computed in
     exact fp32; on the tensor-core path the gallery sweep counts d[g,q] <= d_true[q] in the GEMM
-    epilogue without materialising the [G,Q] matrix; with exact=True (default) decisions within bf16 error of the
-    threshold are re-taken in fp32 and the top-k is re-ranked in fp32, so the results are the fp32 reference's.
-    With topk > 0 also returns (topk_dist [Q,k], topk_idx [Q,k]).
+    epilogue without materialising the [G,Q] matrix; with exact=True (default) every decision the fp16 operands cannot
+    settle within their error bound is taken in fp32 and the top-k is re-ranked in fp32, so the results are the fp32
+    reference's (see evaluate_ranks_prepared).  With topk > 0 also returns (topk_dist [Q,k], topk_idx [Q,k]).
     """
     dev = _need_cuda("evaluate_ranks", overhead_embed, surface_embed)
     g, q, ch, w, sw = _feature_dims("evaluate_ranks", overhead_embed, surface_embed)
@@ -964,48 +1113,6 @@ def evaluate_ranks(overhead_embed, surface_embed, true_idx=None, path="auto", to
     return evaluate_ranks_prepared(gallery, queries, true_idx=true_idx, topk=topk, exact=exact)
 
 
-class RecheckList(object):
-    """Device buffers for the (gallery, query) pairs whose rank decision the bf16 sweep defers to exact fp32."""
-
-    def __init__(self, capacity, band, device):
-        self.capacity, self.band = int(capacity), float(band)
-        self.g = torch.empty(self.capacity, dtype=torch.int64, device=device)
-        self.q = torch.empty(self.capacity, dtype=torch.int64, device=device)
-        self.count = torch.zeros(2, dtype=torch.int32, device=device)   # [appended, dropped for lack of room]
-        self.scratch = torch.empty(self.capacity, dtype=torch.float32, device=device)
-
-
-# How far the bf16 sweep can move a distance.  Full panoramas: only the rounding of the correlation, < 1e-3.  Limited
-# field of view: the crop norm depends on the chosen shift, so a bf16 argmax flip between two near-tied shifts moves
-# the distance of a weakly correlated pair by up to ~6e-3 (measured, SURVEY section 7.2) -- hence the wider band there.
-RECHECK_BAND_FULL = 4e-3
-RECHECK_BAND_CROPPED = 1.2e-2
-TOPK_MARGIN = 6
-
-
-def recheck_band(sw, w=64):
-    """Half-width of the distance band around the fp32 threshold inside which a bf16 rank decision is re-taken in fp32.
-    Measured worst |d_bf16 - d_fp32| over all pairs (float64 models of both sweeps, tests/test_gpu_spec.py: spec_model,
-    tests/test_gpu_tc.py: bf16_model): 3e-4 at sw = 64; with a cropped query an argmax flip between near-tied shifts swaps
-    the crop norm, and the error grows as ~0.2 / sw (5e-3 at 32, 1.3e-2 at 16, 1.8e-2 at 12, 3.3e-2 at 8)."""
-    if sw >= w:
-        return RECHECK_BAND_FULL
-    return max(RECHECK_BAND_CROPPED, 0.4 / max(int(sw), 1))
-
-
-def _exact_mode(gallery, queries, exact):
-    """None (no exact finish), "spectral" or "direct" for this pair of operands."""
-    if not exact:
-        return None
-    g_spec = gallery.spec is not None or gallery.ov is not None
-    q_spec = queries.spec is not None or queries.su is not None
-    if EXACT_IMPL == "spectral" and gallery.W == 64 and g_spec and q_spec:
-        return "spectral"
-    if gallery.ov is not None and queries.su is not None:
-        return "direct"
-    return None
-
-
 def pair_distances_prepared(gallery, queries, pair_g, pair_q):
     """Exact fp32 (distance, orientation) of explicit (local gallery index, query index) pairs on prepared operands,
     through the packed azimuth spectra."""
@@ -1020,86 +1127,112 @@ def pair_distances_prepared(gallery, queries, pair_g, pair_q):
     return d, o
 
 
-def evaluate_ranks_prepared(gallery, queries, true_idx=None, topk=0, d_true=None, events=None, exact=True):
-    """evaluate_ranks on prepared operands (tensor-core path).
+FALLBACK_COLUMNS = 256      # flagged queries re-done per call of the column kernel (bounds the [G, n] fp32 scratch matrix)
 
-    exact=True (needs the fp32 features or their spectra kept in the operands): every rank decision whose bf16 distance
-    falls within the bf16 error band (RECHECK_BAND_*) of the fp32 threshold is re-taken in exact fp32, and the top-k is
-    re-ranked in fp32 from the best k + TOPK_MARGIN bf16 candidates -- so ranks and top-k are those of the fp32
-    reference chain, not bf16 approximations.  The fp32 pairs are evaluated per EXACT_IMPL.
-    ``evaluate_ranks_prepared.last_recheck`` holds the [appended, dropped] counters of the last call (device tensor).
-    """
+
+def redo_flagged(gallery, queries, deferral, d_true, t32, counts, topk=0, td=None, ti=None):
+    """Queries the finish flagged (deferral list overflowed, or the candidate keys do not prove the top-k complete) are
+    evaluated against the whole gallery in fp32: their counts, and their top-k, are replaced.  Returns how many there were."""
     dev = gallery.device
-    mode = _exact_mode(gallery, queries, True)
-    if d_true is None and mode is None:
-        raise ValueError("evaluate_ranks_prepared: fp32 features were dropped; pass d_true")
-    fin = mode if exact else None
-    with torch.cuda.device(dev):
-        if d_true is None:
+    sel_all = torch.nonzero(deferral.qflag[: queries.Q]).to(torch.int32).flatten().contiguous()
+    for lo in range(0, sel_all.numel(), FALLBACK_COLUMNS):
+        sel = sel_all[lo: lo + FALLBACK_COLUMNS].contiguous()
+        f = sel.numel()
+        cnt = torch.zeros(f, dtype=torch.int32, device=dev)
+        scratch = torch.empty((gallery.G, f), dtype=torch.float32, device=dev) if topk else None
+        exact_columns(gallery, queries, q_sel=sel, dist=scratch, ld=f, d_true=d_true, true_idx=t32, count_out=cnt)
+        counts[sel.long()] = cnt
+        if topk:
+            fd, fi = topk_from_distances(scratch, topk, g_offset=gallery.g_offset)
+            td[sel.long()] = fd
+            ti[sel.long()] = fi
+    return int(sel_all.numel())
+
+
+class RankEvaluation(object):
+    """evaluate_ranks on prepared operands (tensor-core path), in two halves: the constructor enqueues everything on the
+    current stream (true-match distances, the sweep, the top-k merge, the fp32 finish) and returns without waiting;
+    result() reads back how many queries the finish flagged -- 4 bytes, the one host synchronisation of an evaluation --
+    re-does those entirely in fp32, and returns ranks [, topk_dist, topk_idx].  A caller that pipelines evaluations (bench.py)
+    constructs step i+1 before it asks step i for its result.
+
+    exact=True (needs the fp32 spectra kept in the operands): the sweep knows, per pair, how far its fp16 operands can have
+    moved the distance (csrc/sweep_common.cuh).  Rank decisions inside that slack of the fp32 threshold are taken from the
+    fp32 spectra instead, the top-k candidates (kept under lower-bound keys) are re-ranked in fp32, and a query whose
+    deferral list overflowed or whose candidate list cannot be proven complete is re-done entirely in fp32 -- so ranks and
+    top-k are those of the fp32 reference chain (cvig_fov.py:547-552), not approximations, at any size.
+    exact=False: the raw fp16 sweep (ranks may differ where distances tie within ~1e-4).
+    """
+
+    def __init__(self, gallery, queries, true_idx=None, topk=0, d_true=None, events=None, exact=True):
+        dev = gallery.device
+        has_fp32 = gallery.spec is not None and queries.spec is not None
+        if d_true is None and not has_fp32:
+            raise ValueError("evaluate_ranks_prepared: the fp32 spectra were dropped; pass d_true")
+        if exact and not has_fp32:
+            raise ValueError("evaluate_ranks_prepared: exact=True needs the fp32 spectra (keep_fp32=True)")
+        if exact and topk > TOPK_EXACT_MAX:
+            raise ValueError("evaluate_ranks_prepared: the exact fused top-k covers k <= %d (got %d); use exact=False, or "
+                             "match() + topk_from_distances() for longer lists" % (TOPK_EXACT_MAX, topk))
+        self.gallery, self.queries, self.topk, self.exact = gallery, queries, int(topk), bool(exact)
+        self.td = self.ti = self.defer = None
+        self.flagged = 0
+        nq = queries.Q
+        with torch.cuda.device(dev):
+            pq = torch.arange(nq, dtype=torch.int64, device=dev)
             if true_idx is None:
-                if queries.Q > gallery.G:
-                    raise IndexError("evaluate_ranks_prepared: %d queries but only %d gallery items and no true_idx" % (queries.Q, gallery.G))
-                pg = torch.arange(queries.Q, dtype=torch.int64, device=dev)
-                pq = pg
+                if nq > gallery.G and d_true is None:
+                    raise IndexError("evaluate_ranks_prepared: %d queries but only %d gallery items and no true_idx" % (nq, gallery.G))
+                pg = pq
             else:
                 pg = true_idx.to(dev, torch.int64).contiguous()
-                if queries.Q and (int(pg.max()) >= gallery.G or int(pg.min()) < 0):
+            if d_true is None:
+                if true_idx is not None and nq and (int(pg.max()) >= gallery.G or int(pg.min()) < 0):
                     raise IndexError("evaluate_ranks_prepared: true index outside the gallery")
-                pq = torch.arange(queries.Q, dtype=torch.int64, device=dev)
-            if mode == "spectral":
                 d_true, _ = pair_distances_prepared(gallery, queries, pg, pq)
-            else:
-                ov4 = gallery.ov.view(gallery.G, gallery.C, gallery.H, gallery.W)
-                su4 = queries.su.view(queries.Q, gallery.C, gallery.H, queries.sw)
-                d_true, _ = true_match_distances(ov4, su4, true_idx)
-        counts = torch.zeros(max(queries.Q, 1), dtype=torch.int32, device=dev)
-        if true_idx is None:
-            t32 = torch.arange(gallery.g_offset, gallery.g_offset + queries.Q, dtype=torch.int32, device=dev)
-        else:
-            t32 = (true_idx.to(dev, torch.int64) + gallery.g_offset).to(torch.int32).contiguous()
-        recheck = RecheckList(max(4 * queries.Q, 1 << 16), recheck_band(gallery.sw, gallery.W), dev) if fin else None
-        kc = min(16, topk + TOPK_MARGIN) if (topk and fin) else topk
-        res = sweep_tc(gallery, queries, d_true=d_true, true_idx=t32, rank_count=counts, topk=kc, events=events, recheck=recheck)
-        if fin and gallery.G > 0 and queries.Q > 0:
-            if fin == "spectral":
-                _lib.call("witw_recheck_apply_spec_f32", gallery.spectral().data_ptr(), gallery.crop_inv_norm.data_ptr(),
-                          queries.spectral().data_ptr(), queries.inv_norm.data_ptr(), recheck.g.data_ptr(), recheck.q.data_ptr(),
-                          recheck.count.data_ptr(), recheck.capacity, gallery.CH, d_true.data_ptr(), counts.data_ptr(),
-                          recheck.scratch.data_ptr(), _stream())
-            else:
-                _lib.call("witw_recheck_apply_f32", gallery.ov.data_ptr(), queries.su.data_ptr(), recheck.g.data_ptr(), recheck.q.data_ptr(),
-                          recheck.count.data_ptr(), recheck.capacity, gallery.CH, gallery.W, gallery.sw, d_true.data_ptr(),
-                          counts.data_ptr(), recheck.scratch.data_ptr(), _stream())
-            evaluate_ranks_prepared.last_recheck = recheck.count
-        ranks = counts[: queries.Q].to(torch.int64)
-        if topk and fin and queries.Q > 0:
-            td, ti = refine_topk(gallery, queries, res["topk_idx"], topk, impl=fin)
-            return ranks, td, ti
-    if topk:
-        return ranks, res["topk_dist"], res["topk_idx"]
-    return ranks
+            self.d_true = d_true
+            self.t32 = (pg + gallery.g_offset).to(torch.int32)
+            if not self.exact:
+                self.counts = torch.zeros(max(nq, 1), dtype=torch.int32, device=dev)
+                res = sweep_tc(gallery, queries, d_true=d_true, true_idx=self.t32, rank_count=self.counts, topk=topk, events=events)
+                if topk:
+                    self.td, self.ti = res["topk_dist"], res["topk_idx"]
+                return
+            self.defer = Deferral(nq, gallery.G, dev)
+            self.counts = self.defer.counts
+            res = sweep_tc(gallery, queries, d_true=d_true, true_idx=self.t32, rank_count=self.counts, topk=16 if topk else 0, events=events,
+                           deferral=self.defer)
+            fin = finish_tc(gallery, queries, self.defer, d_true=d_true, rank_count=self.counts, cand_key=res.get("topk_dist"),
+                            cand_idx=res.get("topk_idx"), k_out=topk)
+            if topk:
+                self.td, self.ti = fin
+            self._n_host = torch.empty(1, dtype=torch.int32, pin_memory=True)
+            self._n_host.copy_(self.defer.n_flagged, non_blocking=True)
+            self._landed = torch.cuda.Event()
+            self._landed.record()
+
+    def result(self):
+        nq = self.queries.Q
+        if self.exact and self.defer is not None:
+            self._landed.synchronize()
+            n = int(self._n_host[0])
+            if n and self.gallery.G > 0 and nq > 0:
+                with torch.cuda.device(self.gallery.device):
+                    self.flagged = redo_flagged(self.gallery, self.queries, self.defer, self.d_true, self.t32, self.counts, self.topk, self.td, self.ti)
+            evaluate_ranks_prepared.last_stats = {"deferred": self.defer.list_n[:nq], "flagged": self.flagged, "list_cap": self.defer.cap}
+            self.defer = None
+        ranks = self.counts[:nq].to(torch.int64)
+        return (ranks, self.td, self.ti) if self.topk else ranks
 
 
-evaluate_ranks_prepared.last_recheck = None
+def evaluate_ranks_prepared(gallery, queries, true_idx=None, topk=0, d_true=None, events=None, exact=True):
+    """evaluate_ranks on prepared operands: ``RankEvaluation(...).result()`` (see there).
+    ``evaluate_ranks_prepared.last_stats`` = {"deferred": per-query deferral counts (device tensor), "flagged": queries re-done
+    entirely in fp32, "list_cap": capacity of a query's list} of the last exact evaluation."""
+    return RankEvaluation(gallery, queries, true_idx=true_idx, topk=topk, d_true=d_true, events=events, exact=exact).result()
 
 
-def refine_topk(gallery, queries, cand_idx, k, impl=None):
-    """Exact fp32 re-ranking of bf16 top-k candidates [Q,kc] (global indices) -> (dist [Q,k], idx [Q,k])."""
-    dev = gallery.device
-    q, kc = cand_idx.shape
-    impl = impl or _exact_mode(gallery, queries, True)
-    with torch.cuda.device(dev):
-        td = torch.empty((q, k), dtype=torch.float32, device=dev)
-        ti = torch.empty((q, k), dtype=torch.int32, device=dev)
-        scratch = torch.empty(_lib.load().witw_topk_refine_scratch_bytes(q, kc), dtype=torch.uint8, device=dev)
-        if impl == "spectral":
-            _lib.call("witw_topk_refine_spec_f32", gallery.spectral().data_ptr(), gallery.crop_inv_norm.data_ptr(),
-                      queries.spectral().data_ptr(), queries.inv_norm.data_ptr(), gallery.G, q, gallery.CH,
-                      cand_idx.contiguous().data_ptr(), kc, gallery.g_offset, int(k), td.data_ptr(), ti.data_ptr(), scratch.data_ptr(), _stream())
-        else:
-            _lib.call("witw_topk_refine_f32", gallery.ov.data_ptr(), queries.su.data_ptr(), gallery.G, q, gallery.CH, gallery.W, gallery.sw,
-                      cand_idx.contiguous().data_ptr(), kc, gallery.g_offset, int(k), td.data_ptr(), ti.data_ptr(), scratch.data_ptr(), _stream())
-    return td, ti
+evaluate_ranks_prepared.last_stats = None
 
 
 def baseline_ranks(overhead_embed, surface_embed, true_idx=None, return_distances=False):

@@ -39,6 +39,7 @@ class CudaLocal(object):
         self.event_sink = event_sink
         self._key = None
         self._prepared = None
+        self._dmat = None
 
     def _operands(self, ov_local, su):
         """Prepared (GalleryIndex, QueryBatch) of this shard, shared by true_distances() and sweep() of one evaluation."""
@@ -54,20 +55,27 @@ class CudaLocal(object):
 
     def true_distances(self, ov_local, su, local_idx):
         """Exact fp32 distance of query i to local gallery item local_idx[i]."""
-        if self._tc(ov_local, su) and ops.EXACT_IMPL == "spectral":
+        if self._tc(ov_local, su):
             gallery, queries = self._operands(ov_local, su)
             pq = torch.arange(su.shape[0], dtype=torch.int64, device=su.device)
             return ops.pair_distances_prepared(gallery, queries, local_idx.to(torch.int64).contiguous(), pq)[0]
         g = ov_local.shape[0]
         if int(local_idx.numel()) and (int(local_idx.max()) >= g or int(local_idx.min()) < 0):
             raise IndexError("true_distances: index outside the shard")
-        d, _ = ops.true_match_distances(ov_local, su, local_idx)
-        return d
+        # fp32 path: the threshold is read out of the same distance matrix the sweep will count over, so that the match
+        # compares equal to itself bit for bit (cvig_fov.py:552 takes both from one tensor); sweep() reuses the matrix
+        _, dmat = ops.match(ov_local, su, path="fp32")
+        self._dmat = (self._dmat_key(ov_local, su), dmat)
+        return dmat[local_idx.to(torch.int64), torch.arange(su.shape[0], device=su.device)]
+
+    @staticmethod
+    def _dmat_key(ov_local, su):
+        return (ov_local.data_ptr(), tuple(ov_local.shape), su.data_ptr(), tuple(su.shape), ov_local._version, su._version)
 
     def sweep(self, ov_local, su, d_true, true_idx, g_offset, topk):
         if self._tc(ov_local, su):
-            # exact finish inside the shard: fp32 re-check of near-threshold rank decisions and fp32 re-ranking of the
-            # shard's top-k candidates, so what is exchanged are already the reference's counts and distances
+            # exact finish inside the shard: fp32 decisions wherever fp16 cannot settle a rank decision and fp32 re-ranking of
+            # the shard's top-k candidates, so what is exchanged are already the reference's counts and distances
             gallery, queries = self._operands(ov_local, su)
             gallery.g_offset = int(g_offset)
             self._key = None   # one evaluation per preparation: the caller may overwrite the buffers in place
@@ -80,8 +88,14 @@ class CudaLocal(object):
             if topk:
                 return res
             return res, None, None
-        _, dmat = ops.match(ov_local, su, path="fp32")
-        counts = (dmat <= d_true.unsqueeze(0)).sum(dim=0).to(torch.int64)  # fp32 path: the match compares equal to itself
+        cached = self._dmat
+        if cached is not None and cached[0] == self._dmat_key(ov_local, su):
+            dmat = cached[1]
+        else:
+            _, dmat = ops.match(ov_local, su, path="fp32")
+        self._dmat = None
+        # the owner's d_true[q] is an element of dmat, so its match counts; NaN compares false as in the reference
+        counts = (dmat <= d_true.unsqueeze(0)).sum(dim=0).to(torch.int64)
         if topk:
             td, ti = ops.topk_from_distances(dmat, topk, g_offset=g_offset)
             return counts, td, ti

@@ -147,6 +147,8 @@ def workload_config(world):
                     "(BASELINE %s)" % (FOV, Q_TOTAL, G_PER_GPU, TOPK, config_name(g_total)),
         "gallery_total": g_total, "gallery_per_gpu": G_PER_GPU, "queries": Q_TOTAL, "fov": FOV, "feature_shape": [16, 4, 64],
         "planted_noise": NOISE,
+        "l2_policy": "inputs larger than L2: every step re-reads %d MB of fp32 features and re-writes their operands and fp32 spectra "
+                     "(126 MB L2); no flush between steps" % ((G_PER_GPU * 64 * 64 + Q_TOTAL * 64 * SW) * 4 // 1000000),
     }
 
 
@@ -610,12 +612,19 @@ def run_ours(args):
                 t.record_stream(d2h_stream)
             landed[b].record(d2h_stream)
 
+    trace = os.environ.get("WITW_BENCH_TRACE") == "1"
+
     def run_e2e(n):
         out = None
         upload(0)
         pending = None                                 # (buffer index, RankEvaluation) of the step enqueued last
+        t_prev = time.perf_counter()
         for i in range(n):
             b = i % 2
+            if trace:
+                now = time.perf_counter()
+                sys.stderr.write("e2e iter %d: %.2f ms host\n" % (i, 1e3 * (now - t_prev)))
+                t_prev = now
             if i + 1 < n:
                 upload(i + 1)
             torch.cuda.current_stream().wait_event(ready[b])
@@ -652,7 +661,7 @@ def run_ours(args):
         out = tuple(h.clone() for h in host_out[last])
         return out
 
-    run_e2e(2)
+    run_e2e(max(4, warmup))                             # untimed: fills the pipeline once (allocator pools, pinned buffers, all code paths)
     e2e_ms, e2e_out = timed(lambda: run_e2e(steps))
     clocks = sampler.stop() if rank == 0 else None      # sampled over both timed regions (device-resident and end-to-end)
     e2e_value = world * Q_TOTAL / (e2e_ms / steps / 1000.0)
@@ -720,8 +729,6 @@ def run_ours(args):
     detail.update({
         "unit_note": "one unit = one query swept over one %d-item gallery shard; queries/s over the whole %d-item gallery = %.1f, pairs/s = %.4g"
                      % (G_PER_GPU, g_total, value / world, value * G_PER_GPU),
-        "l2_policy": "inputs larger than L2 (fp32 features %d MB + their fp32 spectra + the fp16 operands per step vs 126 MB L2)"
-                     % ((G_PER_GPU * 64 * 64 + Q_TOTAL * 64 * SW) * 4 // 1000000),
         "sweep": sweep_impl,
         "step": "fp32 features in HBM -> operand prep (fp16 %s of the norm-scaled features, scale / error-bound tables, fp32 spectra) -> fp32 "
                 "true-match distances -> tcgen05 sweep (argmax, distance, rank count, top-k candidates; decisions inside the fp16 error bound "

@@ -416,11 +416,14 @@ match_tc_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant
           if (CG == 1 || leader) bar_arrive_local(s2u(&tmem_empty[acc]));
           else bar_arrive_cluster(s2u(&tmem_empty[acc]), 0);
         }
+        // pin the tail below the release of the accumulator stage (see match_spec.cu: the compiler otherwise delays the arrive)
+#pragma unroll
+        for (int i = 0; i < IG; ++i) asm volatile("" : "+f"(best[i]), "+f"(second[i]), "+r"(arg[i]));
 #pragma unroll
         for (int i = 0; i < IG; ++i) {
           const int64_t g = (int64_t)grp * IG + i;
           if (g < S.G && qc.ok) {
-            const float e = sweep_err(S, __ldg(reinterpret_cast<const float*>(S.gal_aux + g) + 2), qc);
+            const float e = sweep_err(S, __ldg(reinterpret_cast<const float*>(S.gal_aux + g) + 2), qc, best[i]);
             const bool amb = S.need_amb && second[i] >= best[i] - 2.0f * e;
             sweep_pair(S, qc, g, q, best[i], arg[i], amb, __ldg(S.gal_scale + g * kW + arg[i]), e, cnt, td, ti);
           }
@@ -547,7 +550,7 @@ extern "C" int witw_match_tc(const witw_sweep_args* a, witw_stream_t stream) {
   WITW_REQUIRE(G >= 0 && Q >= 0 && make_geom(CH, sw, &geo), WITW_ERR_UNSUPPORTED, "witw_match_tc: unsupported CH=%d sw=%d", CH, sw);
   if (G == 0 || Q == 0) return WITW_OK;
   SweepOut out;
-  int rc = fill_sweep_out("witw_match_tc", a, kDenseUnit, &out);
+  int rc = fill_sweep_out("witw_match_tc", a, kDenseUnit, kDenseAccRel, &out);
   if (rc != WITW_OK) return rc;
   const void* qry_op = a->qry_op;
   const void* gal_op = a->gal_op;

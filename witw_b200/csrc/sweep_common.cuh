@@ -17,10 +17,13 @@
 // <= (2^-20/12) * 2 * w^2 * ||o||_4^2 ||s||_4^2   (Cauchy-Schwarz; w = 2/64 for the half-spectrum sums, 1 for the
 // direct form).  The prep kernels store  gal_aux[g].z = sqrt(2 * 2^-20/12) * w * ||o_g||_4 * unit  and
 // qry_aux[q].y = ||s_q||_4 (4-norms of the normalised operands), and a pair's bound is
-//     e(g,q) = max( err_sigmas * gal_aux[g].z * qry_aux[q].y,  kAccFloor * unit )          [accumulator units]
+//     e(g,q) = max( err_sigmas * gal_aux[g].z * qry_aux[q].y,  kAccFloor * unit ) + acc_rel |acc|     [accumulator units]
 // gal_aux[g] = (max_s gal_scale[g,:], max - min of gal_scale[g,:], the rounding scale above, the operand's kappa / ||ov_g||).
 // err_sigmas standard deviations of a bound on the standard deviation (default 5; on Gaussian features the bound
-// itself is ~2.8x the measured deviation), floored for the fp32 accumulation and inverse transform.
+// itself is ~2.8x the measured deviation), floored for the fp32 inverse transform, plus a term for the tensor core's
+// fp32 accumulation: every accumulation step can lose an ulp of the running sum (measured on B200: the 256 sequential
+// steps of the dense sweep's K = 4096 move a strongly correlated pair by 1.7e-5 of its accumulator, always downwards --
+// truncation, not rounding; the spectral sweep accumulates 8 steps per frequency slot).
 //
 // Consequences.  Let s* be the sweep's argmax.  The exact argmax lies among the shifts with acc[s] >= acc[s*] - 2e.
 //   * unambiguous pair (no other shift in that window): |d_exact - d| <= 2 e gal_scale[g,s*] =: slack
@@ -47,7 +50,9 @@ constexpr float kSpecUnit = 64.0f * kSpecKappa * kSpecKappa;
 constexpr float kDenseKappa = 256.0f;                     // dense operands: typical element ~4, largest possible 256
 constexpr float kDenseUnit = kDenseKappa * kDenseKappa;
 constexpr float kRoundSigma = 3.9867e-4f;                 // sqrt(2 * 2^-20 / 12)
-constexpr float kAccFloor = 2e-6f;                        // fp32 accumulation + inverse transform, in units of c[s]
+constexpr float kAccFloor = 2e-6f;                        // fp32 inverse transform / table round-off, in units of c[s]
+constexpr float kSpecAccRel = 2e-6f;                      // accumulation loss relative to |acc|: 8 steps per slot, x4 margin
+constexpr float kDenseAccRel = 5e-5f;                     // 256 steps: measured 1.7e-5, x3 margin
 constexpr int kSweepTopk = 16;                            // register-resident candidates per query and gallery chunk
 
 constexpr uint32_t kTagRank = 0x80000000u;                // list entry: the rank decision of this pair is pending
@@ -73,6 +78,7 @@ struct SweepOut {
   int32_t list_cap;
   float err_sigmas;              // 0: no bounds -- every decision is taken from the fp16 result, keys are distances
   float acc_floor;               // kAccFloor * unit
+  float acc_rel;                 // accumulation loss of the tensor core relative to |acc|
   float fix_rel;
   int need_amb;                  // the epilogue must look for a second shift within 2e of the maximum
 };
@@ -92,9 +98,10 @@ struct SweepQuery {
   }
 };
 
-// Bound e on the error of an accumulator of the pair (item with rounding scale ag = gal_aux[g].z, this query).
-__device__ __forceinline__ float sweep_err(const SweepOut& P, float ag, const SweepQuery& qc) {
-  return fmaxf(P.err_sigmas * ag * qc.bq, P.acc_floor);
+// Bound e on the error of the accumulators of a pair (item with rounding scale ag = gal_aux[g].z, this query) whose
+// largest accumulator is acc.
+__device__ __forceinline__ float sweep_err(const SweepOut& P, float ag, const SweepQuery& qc, float acc) {
+  return fmaxf(P.err_sigmas * ag * qc.bq, P.acc_floor) + P.acc_rel * fabsf(acc);
 }
 
 __device__ __forceinline__ void sweep_list_append(const SweepOut& P, int64_t q, uint32_t entry) {
@@ -148,7 +155,7 @@ __device__ __forceinline__ void sweep_pair(const SweepOut& P, const SweepQuery& 
 }
 
 // Host: validate the arguments of a sweep and translate them for the kernels.  unit: see above.
-inline int fill_sweep_out(const char* fn, const witw_sweep_args* a, float unit, SweepOut* o) {
+inline int fill_sweep_out(const char* fn, const witw_sweep_args* a, float unit, float acc_rel, SweepOut* o) {
   WITW_REQUIRE(a->gal_op && a->gal_scale && a->gal_aux && a->qry_op && a->qry_aux, WITW_ERR_INVALID, "%s: null operand", fn);
   WITW_REQUIRE(a->topk >= 0 && a->topk <= kSweepTopk, WITW_ERR_UNSUPPORTED, "%s: fused top-k supports k <= %d (got %d)", fn, kSweepTopk, a->topk);
   WITW_REQUIRE(a->topk == 0 || (a->topk_key && a->topk_idx), WITW_ERR_INVALID, "%s: top-k buffers missing", fn);
@@ -164,7 +171,7 @@ inline int fill_sweep_out(const char* fn, const witw_sweep_args* a, float unit, 
   o->topk_key = a->topk_key; o->topk_idx = a->topk_idx;
   o->list_g = a->list_cap > 0 ? a->list_g : nullptr; o->list_n = a->list_n;
   o->G = a->G; o->Q = a->Q; o->topk = a->topk; o->g_offset = a->g_index_offset; o->list_cap = a->list_cap;
-  o->err_sigmas = a->err_sigmas; o->acc_floor = kAccFloor * unit; o->fix_rel = a->fix_rel;
+  o->err_sigmas = a->err_sigmas; o->acc_floor = kAccFloor * unit; o->acc_rel = acc_rel; o->fix_rel = a->fix_rel;
   o->need_amb = (a->err_sigmas > 0.f && (a->sw < 64 || a->ori != nullptr)) ? 1 : 0;
   return WITW_OK;
 }

@@ -262,8 +262,8 @@ int witw_match_spec(const witw_sweep_args* args, witw_stream_t stream);
  *        0..F-1; ori as int64 and / or uint8; count_out [F] += #{g : d <= d_true[q]} (the match itself, true_idx[q] -
  *        g_index_offset, counted by index).  The whole answer for a few queries (heat map, cvig_fov.py:545-552 one query
  *        at a time) and the fallback for queries witw_finish_spec_f32 flags.
- *   witw_finish_spec_f32: the fp32 finish of a sweep run with err_sigmas > 0, one CTA per query: evaluates the
- *        query's deferred pairs (pending rank decisions are added to rank_count, matrix entries overwritten) and
+ *   witw_finish_spec_f32: the fp32 finish of a sweep run with err_sigmas > 0: evaluates every query's deferred pairs
+ *        (pending rank decisions are added to rank_count, matrix entries overwritten) and
  *        re-ranks the sweep's merged top-k candidates cand_key / cand_idx [Q,kc] (ascending keys) into out_dist /
  *        out_idx [Q,k_out] -- exact distances, ties by lower index.  qflag [Q] / n_flagged [1] (zeroed by the caller):
  *        bit 0 = the query's list overflowed, bit 1 = the keys do not prove that no item outside the candidate list
@@ -303,7 +303,9 @@ typedef struct witw_finish_args {
   int32_t reserved;
   int32_t* qflag;
   int32_t* n_flagged;
+  void* scratch; /* witw_finish_scratch_bytes(Q, kc) bytes, 16-byte aligned */
 } witw_finish_args;
+size_t witw_finish_scratch_bytes(int64_t Q, int kc);
 int witw_finish_spec_f32(const witw_finish_args* args, witw_stream_t stream);
 /* sizeof(witw_sweep_args) / sizeof(witw_finish_args) as this library was built: a binding checks its own declaration. */
 size_t witw_sizeof_sweep_args(void);

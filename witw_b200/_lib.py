@@ -54,6 +54,7 @@ SIGNATURES = {
     "witw_match_columns_spec_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int64, c_void_p, c_void_p,
                                             c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int32, c_void_p, c_void_p]),
     "witw_finish_spec_f32": (c_int, [c_void_p, c_void_p]),
+    "witw_finish_scratch_bytes": (c_size_t, [c_int64, c_int]),
     "witw_sizeof_sweep_args": (c_size_t, []),
     "witw_sizeof_finish_args": (c_size_t, []),
     "witw_spec_supported": (c_int, [c_int, c_int, c_int]),
@@ -93,7 +94,7 @@ class FinishArgs(ctypes.Structure):
         ("list_g", c_void_p), ("list_n", c_void_p), ("list_cap", c_int32), ("kc", c_int32),
         ("d_true", c_void_p), ("rank_count", c_void_p), ("dist", c_void_p), ("ori", c_void_p),
         ("cand_key", c_void_p), ("cand_idx", c_void_p), ("out_dist", c_void_p), ("out_idx", c_void_p),
-        ("k_out", c_int32), ("reserved", c_int32), ("qflag", c_void_p), ("n_flagged", c_void_p),
+        ("k_out", c_int32), ("reserved", c_int32), ("qflag", c_void_p), ("n_flagged", c_void_p), ("scratch", c_void_p),
     ]
 
 

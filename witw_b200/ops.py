@@ -746,13 +746,14 @@ def finish_tc(gallery, queries, deferral, d_true=None, rank_count=None, dist=Non
             td = torch.empty((q, k_out), dtype=torch.float32, device=dev)
             ti = torch.empty((q, k_out), dtype=torch.int32, device=dev)
         if gallery.G > 0 and q > 0:
+            scratch = torch.empty(_lib.load().witw_finish_scratch_bytes(q, kc), dtype=torch.uint8, device=dev)
             args = _lib.FinishArgs(
                 gal_spec=gallery.spectral().data_ptr(), crop_inv_norm=gallery.crop_inv_norm.data_ptr(), qry_spec=queries.spectral().data_ptr(),
                 q_inv_norm=queries.inv_norm.data_ptr(), G=gallery.G, Q=q, CH=gallery.CH, g_index_offset=gallery.g_offset,
                 list_g=deferral.list_g.data_ptr(), list_n=deferral.list_n.data_ptr(), list_cap=deferral.cap, kc=kc, d_true=_ptr(d_true),
                 rank_count=_ptr(rank_count), dist=_ptr(dist), ori=_ptr(ori), cand_key=_ptr(cand_key.contiguous() if k_out else None),
                 cand_idx=_ptr(cand_idx.contiguous() if k_out else None), out_dist=_ptr(td), out_idx=_ptr(ti), k_out=int(k_out), reserved=0,
-                qflag=deferral.qflag.data_ptr(), n_flagged=deferral.n_flagged.data_ptr())
+                qflag=deferral.qflag.data_ptr(), n_flagged=deferral.n_flagged.data_ptr(), scratch=scratch.data_ptr())
             _lib.call("witw_finish_spec_f32", ctypes.addressof(args), _stream())
     return (td, ti) if k_out else None
 

@@ -535,9 +535,13 @@ def run_ours(args):
                     out = prev.result()
                 prev = cur
             return prev.result()
-        for _ in range(n):
-            out = evaluate_ranks_sharded(ov, su, g_offset, g_total, true_idx=true_idx, topk=TOPK, local=timed_local)
-        return out
+        prev = None
+        for _ in range(n):                             # same pipelining; the collectives of step i+1 are enqueued behind step i's
+            cur = W.ShardedEvaluation(ov, su, g_offset, g_total, true_idx=true_idx, topk=TOPK, local=timed_local)
+            if prev is not None:
+                out = prev.result()
+            prev = cur
+        return prev.result()
 
     def barrier():
         if world > 1:
@@ -735,7 +739,7 @@ def run_ours(args):
                 "deferred) -> top-k merge -> fp32 finish (deferred rank decisions, top-k re-rank, completeness proof)%s"
                 % ("azimuth spectra in UMMA layout" if sweep_impl == "spectral" else "Hankel blocks",
                    "" if world == 1 else "; gallery sharded, one shard per GPU, NCCL all-reduce of the thresholds + one all-gather of counts and top-k"),
-        "pipelining": "one step deep: step i+1 is enqueued before the host reads step i's 4-byte finish flag" if world == 1 else "none",
+        "pipelining": "one step deep: step i+1 is enqueued before the host reads step i's 4-byte finish flag",
     })
     line = {
         "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_step,
@@ -847,7 +851,7 @@ def multi_gpu_extras(torch, dist, W, ops, device, world, rank):
             def exch():
                 dist.all_reduce(d_true)
                 if packed:
-                    c, ad, ai = sharded._exchange_packed(counts, td, ti, world, None)
+                    c, ad, ai, _ = sharded._exchange_packed(counts, td, ti, world, None)
                 else:
                     c = counts.clone()
                     dist.all_reduce(c)

@@ -37,6 +37,34 @@ class OracleLocal(object):
         return td, torch.gather(i, 1, pos)
 
 
+class FlaggingLocal(OracleLocal):
+    """A local compute whose first answer is wrong on one rank and says so (flagged > 0), as a CUDA shard does when its fp32
+    finish has to re-do queries: the exchange must be repeated with the corrected results on every rank."""
+
+    def __init__(self, bad_rank):
+        self.bad_rank = bad_rank
+
+    def launch(self, ov_local, su, d_true, true_idx, g_offset, topk):
+        counts, td, ti = self.sweep(ov_local, su, d_true, true_idx, g_offset, topk)
+        local = self
+
+        class Handle(object):
+            def __init__(self):
+                self.bad = dist.get_rank() == local.bad_rank
+                self.finished = False
+
+            def provisional(self):
+                if self.bad and not self.finished:
+                    return counts + 5, td + 1.0, ti, torch.ones(1, dtype=torch.int32)
+                return counts, td, ti, torch.zeros(1, dtype=torch.int32)
+
+            def finish(self):
+                self.finished = True
+                return self.bad
+
+        return Handle()
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -45,7 +73,7 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, out, packed=False):
+def _worker(rank, world, port, out, packed=False, flagging=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.set_num_threads(1)
@@ -55,18 +83,20 @@ def _worker(rank, world, port, out, packed=False):
     ov, su, _ = O.synth_features(23, 17, fov=90, noise=10.0, seed=99)
     true_idx = torch.arange(17).flip(0)  # a permutation, so owners differ from the trivial layout
     lo, hi = shard_bounds(23, world, rank)
-    ranks, td, ti = evaluate_ranks_sharded(ov[lo:hi], su, lo, 23, true_idx=true_idx, topk=4, local=OracleLocal(), packed=packed)
+    local = FlaggingLocal(bad_rank=1) if flagging else OracleLocal()
+    ranks, td, ti = evaluate_ranks_sharded(ov[lo:hi], su, lo, 23, true_idx=true_idx, topk=4, local=local, packed=packed)
     if rank == 0:
         np.savez(out, ranks=ranks.numpy(), td=td.numpy(), ti=ti.numpy())
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("packed", [False, True])
-def test_two_shards_equal_one(tmp_path, packed):
-    """packed: counts and top-k candidates travel in one all-gather instead of an all-reduce and two all-gathers."""
+@pytest.mark.parametrize("packed,flagging", [(False, False), (True, False), (True, True), (False, True)])
+def test_two_shards_equal_one(tmp_path, packed, flagging):
+    """packed: counts and top-k candidates travel in one all-gather instead of an all-reduce and two all-gathers.
+    flagging: one rank's first results are provisional (its finish flagged queries); the exchange is repeated."""
     out = str(tmp_path / "r0.npz")
-    mp.spawn(_worker, args=(2, _free_port(), out, packed), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), out, packed, flagging), nprocs=2, join=True)
     got = np.load(out)
     ov, su, _ = O.synth_features(23, 17, fov=90, noise=10.0, seed=99)
     true_idx = torch.arange(17).flip(0)

@@ -43,10 +43,10 @@ from .ops import (
 )
 from .heatmap import heatmap_sweep, prefetch_to_device, prepare_tiles, streamed_polar
 from .install import install, uninstall
-from .sharded import evaluate_ranks_sharded, shard_bounds
+from .sharded import ShardedEvaluation, evaluate_ranks_sharded, shard_bounds
 
 __all__ = [
-    "heatmap_sweep", "prefetch_to_device", "prepare_tiles", "streamed_polar", "RankEvaluation", "Deferral", "exact_columns", "finish_tc", "GalleryBuilder", "GalleryIndex", "ImageNormalization", "PolarTransform", "QueryBatch", "Resize", "WitwError", "baseline_ranks", "bilinear_interpolate", "correlation",
+    "ShardedEvaluation", "heatmap_sweep", "prefetch_to_device", "prepare_tiles", "streamed_polar", "RankEvaluation", "Deferral", "exact_columns", "finish_tc", "GalleryBuilder", "GalleryIndex", "ImageNormalization", "PolarTransform", "QueryBatch", "Resize", "WitwError", "baseline_ranks", "bilinear_interpolate", "correlation",
     "correlation_scores", "crop_overhead", "evaluate_ranks", "evaluate_ranks_prepared", "evaluate_ranks_sharded",
     "heatmap_scores", "install", "l2_distance", "match", "match_distance", "normalized_polar", "polar_grid", "polar_transform", "prepare_pair", "rank_from_distances",
     "recall_from_ranks", "resize_normalize", "shard_bounds", "sweep_tc", "tc_supported", "topk_from_distances", "triplet_loss", "true_match_distances",

@@ -47,9 +47,6 @@
 namespace witw {
 
 void* get_encode_tiled();                                                                         // polar.cu
-// match_tc.cu: per-item norms, crop-norm tables and operand scale (gal_aux[g] = (max scale, spread, 0, kappa / ||ov_g||))
-int launch_item_stats(const float* ov, int64_t G, int64_t G_pad, int CH, int sw, float kappa, float unit, float dense_sigma,
-                      float* gal_scale, float* gal_aux, float* crop_inv_norm, witw_stream_t stream);
 
 constexpr int kSpThreads = 512;
 constexpr int kSpStages = 6;           // even: producer / issuer warp p owns the stages of parity p
@@ -112,33 +109,78 @@ __device__ __forceinline__ float spectrum_quartic(const float (*sre)[kSpCH + 1],
   return s4;
 }
 
-// CTA = one gallery item: 64 warp-level row FFTs, then the item's 128 operand rows of 128 bytes
-// (slot, K half, Re/Im) are written into its group's tiles, scaled by gal_aux[g].w = kappa / ||ov_g|| (launch_item_stats).
+// CTA = one gallery item.  One pass over the item's fp32 features gives everything the sweeps and the fp32 finish need:
+// the 64 row spectra (warp-level FFTs), the column energies behind crop_inv_norm[g,s] = 1/||crop(ov_g,s)|| and
+// gal_scale[g,s] = ||ov_g|| / (||crop(ov_g,s)|| unit), the item's norm (operand scale kappa / ||ov_g||), its rounding scale
+// (sweep_common.cuh), the fp32 spectra of the finish, and the item's 128 operand rows of 128 bytes (slot, K half, Re/Im)
+// in its group's tiles.  A warp loads its eight rows before it transforms the first one: with one 256-byte load in flight per
+// warp the kernel ran at 2.8 TB/s.  Items past G (the rest of the last group) get zeros.
 __global__ void __launch_bounds__(256)
-spec_gallery_prep_kernel(const float* __restrict__ ov, int64_t G, int64_t g_first, __half* __restrict__ out, float4* __restrict__ gal_aux,
+spec_gallery_prep_kernel(const float* __restrict__ ov, int64_t G, int64_t g_first, int sw, __half* __restrict__ out,
+                         float* __restrict__ gal_scale, float4* __restrict__ gal_aux, float* __restrict__ crop_inv_norm,
                          float* __restrict__ spec_out) {
   __shared__ float sre[kSpSlots][kSpCH + 1], sim[kSpSlots][kSpCH + 1];  // [slot][feature row]
+  __shared__ float col_part[8][64];
+  __shared__ float col_e[64];
   __shared__ float red[8];
+  __shared__ float stat[4];           // norm, max scale, min scale
   const int64_t g_local = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool live = g_local < G;
   RowFft fft;
   fft.init(lane);
-  for (int row = warp; row < kSpCH; row += 8) {
-    float2 z = make_float2(0.f, 0.f);
-    if (g_local < G) z = __ldg(reinterpret_cast<const float2*>(ov + (g_local * kSpCH + row) * 64) + lane);
-    const float2 X = fft.run(z, lane);
-    sre[lane][row] = X.x;
-    sim[lane][row] = X.y;
+  float2 z[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    z[i] = make_float2(0.f, 0.f);
+    if (live) z[i] = __ldg(reinterpret_cast<const float2*>(ov + (g_local * kSpCH + warp + 8 * i) * 64) + lane);
   }
+  float e0 = 0.f, e1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    e0 = fmaf(z[i].x, z[i].x, e0);
+    e1 = fmaf(z[i].y, z[i].y, e1);
+    const float2 X = fft.run(z[i], lane);
+    sre[lane][warp + 8 * i] = X.x;
+    sim[lane][warp + 8 * i] = X.y;
+  }
+  col_part[warp][2 * lane] = e0;
+  col_part[warp][2 * lane + 1] = e1;
   __syncthreads();
-  if (spec_out != nullptr && g_local < G) {  // the fp32 spectra the exact finish works on (layout of witw_spectral_rows_f32)
+  if (threadIdx.x < 64) {             // column energies, the item's norm
+    float e = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) e += col_part[w][threadIdx.x];
+    col_e[threadIdx.x] = e;
+    float t = e;
+    for (int m = 16; m > 0; m >>= 1) t += __shfl_xor_sync(0xffffffffu, t, m);
+    if (lane == 0) red[warp] = t;
+  }
+  if (spec_out != nullptr && live) {  // the fp32 spectra the exact finish works on (layout of witw_spectral_rows_f32)
     float2* dst = reinterpret_cast<float2*>(spec_out + g_local * (kSpCH * 64));
     for (int idx = threadIdx.x; idx < kSpCH * 32; idx += 256) dst[idx] = make_float2(sre[idx & 31][idx >> 5], sim[idx & 31][idx >> 5]);
   }
-  const float scale = gal_aux[g_local].w;     // 0 for a zero-norm item and past G: a zero operand
+  __syncthreads();
+  const float norm = sqrtf(red[0] + red[1]);
+  if (threadIdx.x < 64) {             // crop norms of the 64 shifts and the scale table of the sweep
+    const int j = threadIdx.x;
+    float c = 0.f;
+    for (int k = 0; k < sw; ++k) c += col_e[(j + k) & 63];
+    const float cin = live ? 1.0f / sqrtf(c) : 0.f;
+    const float scl = live ? norm * cin / kSpecUnit : 0.f;
+    gal_scale[g_local * 64 + j] = scl;
+    if (crop_inv_norm != nullptr) crop_inv_norm[g_local * 64 + j] = cin;
+    float hi = scl, lo = scl;
+    for (int m = 16; m > 0; m >>= 1) { hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, m)); lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, m)); }
+    if (lane == 0) { stat[warp] = hi; stat[2 + warp] = lo; }
+  }
+  const float scale = (live && norm > 0.f) ? kSpecKappa / norm : 0.f;     // a zero-norm item: a zero operand, NaN scale table
   // rounding scale of the item (sweep_common.cuh): 4-norm of the normalised half spectrum
-  const float s4 = block_sum_256(spectrum_quartic(sre, sim), red);
-  if (threadIdx.x == 0) gal_aux[g_local].z = kRoundSigma * (2.0f / 64.0f) * kSpecUnit * sqrtf(sqrtf(s4)) * (scale / kSpecKappa);
+  const float s4 = block_sum_256(spectrum_quartic(sre, sim), red);        // (its barriers also publish stat[])
+  if (threadIdx.x == 0) {
+    const float hi = fmaxf(stat[0], stat[1]), lo = fminf(stat[2], stat[3]);
+    gal_aux[g_local] = make_float4(hi, hi - lo, kRoundSigma * (2.0f / 64.0f) * kSpecUnit * sqrtf(sqrtf(s4)) * (scale / kSpecKappa), scale);
+  }
   const int64_t g = g_first + g_local;
   const int64_t group = g >> 3;
   const int i = (int)(g & 7);
@@ -174,17 +216,21 @@ spec_query_prep_kernel(const float* __restrict__ su, int64_t Q, int sw, __half* 
   if (live) {
     RowFft fft;
     fft.init(lane);
-    for (int row = warp; row < kSpCH; row += 8) {
-      const float* r = su + (q * kSpCH + row) * sw;
+    float2 z[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {     // all eight rows of this warp are in flight before the first transform
+      const float* r = su + (q * kSpCH + warp + 8 * i) * sw;
       const int j = 2 * lane;
-      float2 z;
-      z.x = j < sw ? r[j] : 0.f;
-      z.y = j + 1 < sw ? r[j + 1] : 0.f;
-      e = fmaf(z.x, z.x, e);
-      e = fmaf(z.y, z.y, e);
-      const float2 X = fft.run(z, lane);
-      sre[lane][row] = X.x;
-      sim[lane][row] = X.y;
+      z[i].x = j < sw ? __ldg(r + j) : 0.f;
+      z[i].y = j + 1 < sw ? __ldg(r + j + 1) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      e = fmaf(z[i].x, z[i].x, e);
+      e = fmaf(z[i].y, z[i].y, e);
+      const float2 X = fft.run(z[i], lane);
+      sre[lane][warp + 8 * i] = X.x;
+      sim[lane][warp + 8 * i] = X.y;
     }
   }
   const float energy = block_sum_256(e, red);     // also the barrier between the transforms and their readers
@@ -548,10 +594,8 @@ extern "C" int witw_spec_gallery_prep(const float* ov, int64_t G, int64_t g_firs
   const int64_t n = g_end - g_first;
   WITW_REQUIRE(n < (1ll << 31), WITW_ERR_INVALID, "witw_spec_gallery_prep: too many items in one call");
   WITW_REQUIRE(((uintptr_t)spec_out & 7) == 0, WITW_ERR_INVALID, "witw_spec_gallery_prep: spectra must be 8-byte aligned");
-  int rc = launch_item_stats(ov, G, n, CH, sw, kSpecKappa, kSpecUnit, 0.f, gal_scale, gal_aux, crop_inv_norm, stream);
-  if (rc != WITW_OK) return rc;
-  spec_gallery_prep_kernel<<<(unsigned)n, 256, 0, as_stream(stream)>>>(ov, G, g_first, reinterpret_cast<__half*>(gal_op),
-                                                                     reinterpret_cast<float4*>(gal_aux), spec_out);
+  spec_gallery_prep_kernel<<<(unsigned)n, 256, 0, as_stream(stream)>>>(ov, G, g_first, sw, reinterpret_cast<__half*>(gal_op), gal_scale,
+                                                                     reinterpret_cast<float4*>(gal_aux), crop_inv_norm, spec_out);
   WITW_LAUNCH_CHECK();
   return WITW_OK;
 }

@@ -181,22 +181,30 @@ spec_gallery_prep_kernel(const float* __restrict__ ov, int64_t G, int64_t g_firs
     const float hi = fmaxf(stat[0], stat[1]), lo = fminf(stat[2], stat[3]);
     gal_aux[g_local] = make_float4(hi, hi - lo, kRoundSigma * (2.0f / 64.0f) * kSpecUnit * sqrtf(sqrtf(s4)) * (scale / kSpecKappa), scale);
   }
+  // the item's 128 operand rows: thread = (slot, eight feature rows); its 8 spectrum values give 16 bytes of each of the four
+  // operand rows (K half x Re/Im output) of the slot, so every value is loaded, scaled and converted once
   const int64_t g = g_first + g_local;
   const int64_t group = g >> 3;
   const int i = (int)(g & 7);
-  for (int idx = threadIdx.x; idx < 128 * 16; idx += 256) {
-    const int seg = idx >> 4, part = idx & 15;
-    const int slot = seg >> 2, half = (seg >> 1) & 1, c = seg & 1;
-    const int r0 = part * 4;
-    float v[4];
+  {
+    const int slot = threadIdx.x >> 3, r0 = (threadIdx.x & 7) * 8;
+    float re[8], im[8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float re = sre[slot][r0 + j] * scale, im = sim[slot][r0 + j] * scale;
-      if (slot == 0) v[j] = (half == c) ? (half == 0 ? re : im) : 0.f;   // [O_0 | 0] and [0 | O_32]
-      else v[j] = half == 0 ? (c == 0 ? re : im) : (c == 0 ? im : -re);  // [Re | Im] and [Im | -Re]
-    }
-    const int64_t row = ((group * kSpSlots + slot) * 2 + half) * 16 + 4 * (i >> 1) + 2 * c + (i & 1);
-    *reinterpret_cast<uint2*>(out + row * 64 + r0) = pack4_f16(v[0], v[1], v[2], v[3]);
+    for (int j = 0; j < 8; ++j) { re[j] = sre[slot][r0 + j] * scale; im[j] = sim[slot][r0 + j] * scale; }
+    const int64_t row0 = (group * kSpSlots + slot) * 32 + 4 * (i >> 1) + (i & 1);   // K half 0, output 0; + 2 = output 1; + 16 = K half 1
+    uint4 w[4];   // [Re | Im] -> Re P,  [Im | -Re] -> Im P;  slot 0: [O_0 | 0] -> P_0,  [0 | O_32] -> P_32
+    const uint2 a0 = pack4_f16(re[0], re[1], re[2], re[3]), a1 = pack4_f16(re[4], re[5], re[6], re[7]);
+    const uint2 b0 = pack4_f16(im[0], im[1], im[2], im[3]), b1 = pack4_f16(im[4], im[5], im[6], im[7]);
+    const uint2 n0 = pack4_f16(-re[0], -re[1], -re[2], -re[3]), n1 = pack4_f16(-re[4], -re[5], -re[6], -re[7]);
+    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+    w[0] = make_uint4(a0.x, a0.y, a1.x, a1.y);                                      // half 0, output 0
+    w[1] = slot == 0 ? zero : make_uint4(b0.x, b0.y, b1.x, b1.y);                   // half 0, output 1
+    w[2] = slot == 0 ? zero : make_uint4(b0.x, b0.y, b1.x, b1.y);                   // half 1, output 0
+    w[3] = slot == 0 ? make_uint4(b0.x, b0.y, b1.x, b1.y) : make_uint4(n0.x, n0.y, n1.x, n1.y);   // half 1, output 1
+    *reinterpret_cast<uint4*>(out + (row0) * 64 + r0) = w[0];
+    *reinterpret_cast<uint4*>(out + (row0 + 2) * 64 + r0) = w[1];
+    *reinterpret_cast<uint4*>(out + (row0 + 16) * 64 + r0) = w[2];
+    *reinterpret_cast<uint4*>(out + (row0 + 18) * 64 + r0) = w[3];
   }
 }
 
@@ -248,11 +256,19 @@ spec_query_prep_kernel(const float* __restrict__ su, int64_t Q, int sw, __half* 
     }
   }
   __half* tile = out + (q >> 7) * (int64_t)(2 * kSpSlots * 128 * 64) + (q & 127) * 64;
-  for (int idx = threadIdx.x; idx < kSpSlots * 2 * 16; idx += 256) {
-    const int slot = idx >> 5, half = (idx >> 4) & 1, r0 = (idx & 15) * 4;
-    const float* s = half == 0 ? &sre[slot][r0] : &sim[slot][r0];
-    const uint2 v = live ? pack4_f16(s[0] * scale, s[1] * scale, s[2] * scale, s[3] * scale) : make_uint2(0u, 0u);
-    *reinterpret_cast<uint2*>(tile + (int64_t)(2 * slot + half) * (128 * 64) + r0) = v;
+  {   // thread = (slot, eight feature rows): 16 bytes of the slot's Re row and of its Im row
+    const int slot = threadIdx.x >> 3, r0 = (threadIdx.x & 7) * 8;
+    uint4 wr = make_uint4(0u, 0u, 0u, 0u), wi = wr;
+    if (live) {
+      const float* a = &sre[slot][r0];
+      const float* b = &sim[slot][r0];
+      const uint2 a0 = pack4_f16(a[0] * scale, a[1] * scale, a[2] * scale, a[3] * scale), a1 = pack4_f16(a[4] * scale, a[5] * scale, a[6] * scale, a[7] * scale);
+      const uint2 b0 = pack4_f16(b[0] * scale, b[1] * scale, b[2] * scale, b[3] * scale), b1 = pack4_f16(b[4] * scale, b[5] * scale, b[6] * scale, b[7] * scale);
+      wr = make_uint4(a0.x, a0.y, a1.x, a1.y);
+      wi = make_uint4(b0.x, b0.y, b1.x, b1.y);
+    }
+    *reinterpret_cast<uint4*>(tile + (int64_t)(2 * slot) * (128 * 64) + r0) = wr;
+    *reinterpret_cast<uint4*>(tile + (int64_t)(2 * slot + 1) * (128 * 64) + r0) = wi;
   }
 }
 

@@ -825,9 +825,9 @@ def run_ours(args):
                 "note": "gallery and queries uploaded from pinned host memory every step, W.GalleryIndex / QueryBatch / RankEvaluation on them; H2D of step "
                         "i+1 double-buffered on a copy stream behind step i, D2H of step i's ranks and top-k into pinned host memory on a third stream"
                         + ("" if world == 1 else "; every rank uploads its gallery shard, rank 0 also the replicated query set, which is then broadcast over NCCL")},
-        # per step: item_stats, gallery prep, query prep, spectral_pairs (true match), the sweep, topk_merge, finish
-        # (hankel: + spectral_rows x2)
-        "gpu_launches": (7 if sweep_impl == "spectral" else 9) * steps,
+        # per step: gallery prep, query prep, spectral_pairs (true match), the sweep, topk_merge, finish_scan / _pairs / _topk
+        # (hankel: item_stats + gallery_blocks instead of one gallery prep, + spectral_rows x2)
+        "gpu_launches": (8 if sweep_impl == "spectral" else 11) * steps,
         "clocks": clocks,
         "recall": {k: float(v) for k, v in recall.items()},
         "deferral": {"deferred_pairs": int(step_stats["deferred"].sum()), "queries_redone_in_fp32": int(step_stats["flagged"]),

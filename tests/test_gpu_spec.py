@@ -343,3 +343,27 @@ def test_spec_random_shapes_against_oracle(W):
         if Q <= G:
             ranks = W.evaluate_ranks(ov.cuda(), su.cuda(), path="tc").cpu().numpy()
             check_exact_results(ref, ranks, None, None, 0)
+
+
+def test_one_query_calls_reuse_the_prepared_gallery_safely(W):
+    """The reference's rank loop calls correlation(overhead_embed, one_query) once per query (cvig_fov.py:545-549): the
+    gallery is prepared on the first call and reused -- but never for other data: an in-place change or a new tensor (even
+    one that could have landed at the same address) is prepared afresh."""
+    ov, su, _ = O.synth_features(1500, 3, fov=90, noise=2.0, seed=13)
+    ov2, _, _ = O.synth_features(1500, 3, fov=90, noise=2.0, seed=14)
+    W.ops.clear_cache()
+    a = ov.cuda()
+    o1 = W.correlation(a, su[:1].cuda())
+    assert len(W.ops._index_cache) == 1
+    o1b = W.correlation(a, su[1:2].cuda())
+    assert len(W.ops._index_cache) == 1                                  # reused
+    assert torch.equal(o1.cpu(), O.correlation(ov, su[:1])) and torch.equal(o1b.cpu(), O.correlation(ov, su[1:2]))
+    a.copy_(ov2.cuda())                                                  # in place: same address, new version
+    o2 = W.correlation(a, su[:1].cuda())
+    assert torch.equal(o2.cpu(), O.correlation(ov2, su[:1]))
+    del a
+    b = ov.cuda()                                                        # a new tensor of the same shape
+    o3 = W.correlation(b, su[:1].cuda())
+    assert torch.equal(o3.cpu(), O.correlation(ov, su[:1]))
+    W.ops.clear_cache()
+    assert len(W.ops._index_cache) == 0

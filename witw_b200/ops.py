@@ -779,23 +779,28 @@ def exact_columns(gallery, queries, q_sel=None, dist=None, ori64=None, ori8=None
                       gallery.g_offset, 0 if count_out is None else count_out.data_ptr() + 4 * lo, _stream())
 
 
-_index_cache = []          # [(key, GalleryIndex)]: the gallery of the reference's one-query loop is prepared once, not per query
+_index_cache = []          # [(key, features, GalleryIndex)]: the gallery of the reference's one-query loop is prepared once, not per query
 INDEX_CACHE_ENTRIES = 2
 
 
 def _cached_index(overhead_embed, sw):
-    key = (overhead_embed.data_ptr(), tuple(overhead_embed.shape), overhead_embed.dtype, overhead_embed._version, int(sw), str(overhead_embed.device))
-    for k, idx in _index_cache:
+    """The prepared gallery of a feature tensor, built on first use.  The key is the tensor's storage address, shape, dtype and
+    version counter (in-place writes bump it); the entry keeps a reference to the tensor, so its storage cannot be freed and
+    the address handed to another tensor while the entry lives."""
+    key = (overhead_embed.data_ptr(), tuple(overhead_embed.shape), tuple(overhead_embed.stride()), overhead_embed.dtype,
+           overhead_embed._version, int(sw), str(overhead_embed.device))
+    for k, _, idx in _index_cache:
         if k == key:
             return idx
     idx = GalleryIndex(overhead_embed, sw)
-    _index_cache.insert(0, (key, idx))
+    _index_cache.insert(0, (key, overhead_embed, idx))
     del _index_cache[INDEX_CACHE_ENTRIES:]
     return idx
 
 
 def clear_cache():
-    """Drop the prepared galleries kept for repeated small-query calls (each holds ~33 KB of device memory per item)."""
+    """Drop the prepared galleries kept for repeated small-query calls (each holds ~33 KB of device memory per item, and a
+    reference to the feature tensor it was built from)."""
     del _index_cache[:]
 
 

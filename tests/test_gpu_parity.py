@@ -139,6 +139,11 @@ def test_empty_inputs(W):
     o, d = W.match(ov.cuda(), su[:0].cuda(), path="fp32")
     assert tuple(o.shape) == (4, 0)
     assert tuple(W.rank_from_distances(torch.zeros(0, 5).cuda()).shape) == (5,)
+    # the tensor-core path on empty sides: shapes as the reference's, nothing launched on nothing
+    o, d = W.match(ov.cuda(), su[:0].cuda(), path="tc")
+    assert tuple(o.shape) == (4, 0) and tuple(d.shape) == (4, 0)
+    o, d = W.match(ov[:0].cuda(), su.cuda(), path="tc")
+    assert tuple(o.shape) == (0, 3)
 
 
 def test_errors(W):

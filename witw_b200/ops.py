@@ -743,8 +743,12 @@ def finish_tc(gallery, queries, deferral, d_true=None, rank_count=None, dist=Non
         kc = 0
         if k_out:
             kc = cand_idx.shape[1]
-            td = torch.empty((q, k_out), dtype=torch.float32, device=dev)
-            ti = torch.empty((q, k_out), dtype=torch.int32, device=dev)
+            if gallery.G > 0:
+                td = torch.empty((q, k_out), dtype=torch.float32, device=dev)
+                ti = torch.empty((q, k_out), dtype=torch.int32, device=dev)
+            else:               # an empty gallery: no candidates
+                td = torch.full((q, k_out), float("inf"), dtype=torch.float32, device=dev)
+                ti = torch.full((q, k_out), -1, dtype=torch.int32, device=dev)
         if gallery.G > 0 and q > 0:
             scratch = torch.empty(_lib.load().witw_finish_scratch_bytes(q, kc), dtype=torch.uint8, device=dev)
             args = _lib.FinishArgs(

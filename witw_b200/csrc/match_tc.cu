@@ -289,9 +289,8 @@ match_tc_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant
   tc_fence_before();
   if constexpr (CG == 2) {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-  } else {
-    __syncthreads();
   }
+  __syncthreads();   // (with CG == 2 the cluster barrier already orders this; compute-sanitizer's racecheck only knows this one)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
 

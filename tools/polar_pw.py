@@ -3,6 +3,8 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
+from witw_b200 import _lib
+_lib.LIB_PATH = os.path.join(os.path.dirname(_lib.LIB_PATH), "libwitw_b200_hooks.so")   # the WITW_* switches exist only in the hooks build (make -C witw_b200/csrc HOOKS=1)
 import witw_b200 as W
 x = torch.randn(1024, 3, 256, 256, device="cuda")
 ref = W.polar_transform(x[:4], exact=True)

@@ -1,5 +1,7 @@
 #!/usr/bin/env python
-"""Sweep-kernel time of library variants on the bench workload (planted, noise 0.5), raw vs deferral mode."""
+"""Sweep-kernel time of library builds on the bench workload (planted, noise 0.5), raw vs deferral mode, with and without the fused
+top-k: every witw_b200/libwitw_*.so found (the shipped library, the hooks build, hand-built experiment variants) in its own
+subprocess.  This is how the code-generation trap of the spectral sweep's epilogue was found (profiles/sweep_codegen_r2c.jsonl)."""
 import glob, json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 

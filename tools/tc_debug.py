@@ -9,6 +9,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
 from oracle import witw_oracle as O
+from witw_b200 import _lib
+_lib.LIB_PATH = os.path.join(os.path.dirname(_lib.LIB_PATH), "libwitw_b200_hooks.so")   # the WITW_* switches exist only in the hooks build (make -C witw_b200/csrc HOOKS=1)
 import witw_b200 as W
 
 fov = int(sys.argv[1]) if len(sys.argv) > 1 else 360

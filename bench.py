@@ -562,6 +562,7 @@ def run_ours(args):
 
     if args.sweep != "auto":
         ops.TC_IMPL = args.sweep
+    ops.L2_WINDOW = bool(args.l2_window)
     world = env_int("WORLD_SIZE", 1)
     rank = env_int("RANK", 0)
     local_rank = env_int("LOCAL_RANK", 0)
@@ -813,6 +814,7 @@ def run_ours(args):
                 % ("azimuth spectra in UMMA layout" if sweep_impl == "spectral" else "Hankel blocks",
                    "" if world == 1 else "; gallery sharded, one shard per GPU, NCCL all-reduce of the thresholds + one all-gather of counts and top-k"),
         "pipelining": "one step deep: step i+1 is enqueued before the host reads step i's 4-byte finish flag",
+        "l2_window": bool(args.l2_window),
     })
     line = {
         "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_step,
@@ -969,6 +971,8 @@ def main():
     ap.add_argument("--fov", type=int, default=FOV, help="field of view of the queries in degrees (default 360; 90 = BASELINE configs[2] / [4])")
     ap.add_argument("--queries", type=int, default=Q_TOTAL, help="number of queries (default 10000)")
     ap.add_argument("--noise", type=float, default=NOISE, help="noise of the planted matches (default 0.5: every match is rank 1; see the `hard` key)")
+    ap.add_argument("--l2-window", action="store_true",
+                    help="experiment: an L2 access-policy window over the query operand while the sweep runs (ops.L2_WINDOW)")
     ap.add_argument("--no-extras", action="store_true",
                     help="skip the side measurements after the timed regions: what the ncu launch list of the step is taken with")
     args = ap.parse_args()

@@ -41,6 +41,11 @@ const char* witw_last_error(void);
 int witw_version(void);
 /* 0 when the current device is compute capability 10.x, WITW_ERR_DEVICE otherwise */
 int witw_device_check(void);
+/* Opt-in: keep [ptr, ptr + bytes) resident in L2 for the kernels launched on `stream` from now on (an access-policy window
+ * backed by the device's persisting-L2 set-aside, which the call raises -- a device-wide setting -- to what is needed, at most
+ * the device's maximum).  bytes == 0 removes the window.  Meant for the query operand of a sweep, which is re-read once per 8
+ * gallery items while uploads and the gallery operand stream through the same cache. */
+int witw_stream_l2_window(const void* ptr_dev, size_t bytes, witw_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * K1  polar transform            replaces model/cvig_fov.py:156-209

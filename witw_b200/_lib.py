@@ -18,6 +18,7 @@ SIGNATURES = {
     "witw_last_error": (c_char_p, []),
     "witw_version": (c_int, []),
     "witw_device_check": (c_int, []),
+    "witw_stream_l2_window": (c_int, [c_void_p, c_size_t, c_void_p]),
     "witw_polar_grid": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p]),
     "witw_bilinear_lut": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
     "witw_bilinear_gather_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int64, c_void_p]),

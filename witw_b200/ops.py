@@ -686,6 +686,12 @@ class Deferral(object):
         self.counts, self.list_n, self.qflag, self.n_flagged = book[:qp], book[qp: 2 * qp], book[2 * qp: 3 * qp], book[3 * qp: 3 * qp + 1]
 
 
+# Opt-in: an L2 access-policy window over the query operand while a sweep runs (the operand is re-read once per 8 gallery
+# items; uploads of the next batch and the gallery operand stream through the same cache).  Raises the device's persisting-L2
+# set-aside, a device-wide setting, hence off unless asked for.
+L2_WINDOW = False
+
+
 def sweep_tc(gallery, queries, want_dist=False, want_ori=False, d_true=None, true_idx=None, rank_count=None, topk=0, events=None,
              deferral=None):
     """One tensor-core sweep of a QueryBatch over a GalleryIndex.  Returns a dict with the requested outputs.
@@ -718,11 +724,15 @@ def sweep_tc(gallery, queries, want_dist=False, want_ori=False, d_true=None, tru
                 list_g=_ptr(deferral.list_g) if deferral else 0, list_n=_ptr(deferral.list_n) if deferral else 0,
                 list_cap=deferral.cap if deferral else 0, err_sigmas=deferral.err_sigmas if deferral else 0.0,
                 fix_rel=deferral.fix_rel if deferral else 0.0)
+            if L2_WINDOW:
+                _lib.call("witw_stream_l2_window", queries.operand.data_ptr(), queries.operand.numel(), _stream())
             if events is not None:
                 events[0].record()
             _lib.call(fn_sweep, ctypes.addressof(args), _stream())
             if events is not None:
                 events[1].record()
+            if L2_WINDOW:
+                _lib.call("witw_stream_l2_window", 0, 0, _stream())
         if topk:
             fin_d = torch.empty((q, topk), dtype=torch.float32, device=dev)
             fin_i = torch.empty((q, topk), dtype=torch.int32, device=dev)

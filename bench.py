@@ -638,8 +638,15 @@ def run_ours(args):
     # the sampler starts before the warm-up: the first nvidia-smi on a fresh box takes a while to attach to the driver and
     # stalls kernel launches while it does (seen once as 12.6 instead of 7.65 ms per step when it started with the timed region)
     sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and os.environ.get("WITW_BENCH_NO_SAMPLER") != "1":      # (debug: is a stall the sampler's doing?)
         sampler.start()
+    # Spin-up before the W warm-up steps: the first CUDA process on a box that has been idle sees one stall of 40 - 50 ms some
+    # 60 ms into its first stretch of continuous work, with or without the sampler (measured: one 49.6 ms step among 7.5 ms
+    # ones in the first process only; later processes on the same box never) -- a power-state transition of the idle GPU.
+    # A second of untimed steps puts it behind us.
+    t_spin = time.perf_counter()
+    while time.perf_counter() - t_spin < 1.0:
+        run_steps(5)
     run_steps(warmup)
     torch.cuda.synchronize()
     sweep_events.clear()

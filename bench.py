@@ -645,7 +645,12 @@ def run_ours(args):
     # ones in the first process only; later processes on the same box never) -- a power-state transition of the idle GPU.
     # A second of untimed steps puts it behind us.
     t_spin = time.perf_counter()
-    while time.perf_counter() - t_spin < 1.0:
+    run_steps(3)
+    torch.cuda.synchronize()
+    n_spin = torch.tensor([int(min(200, max(0, 1.0 / max((time.perf_counter() - t_spin) / 3, 1e-4))))], device=device)
+    if world > 1:
+        dist.broadcast(n_spin, src=0)                  # every rank must run the same number of steps: they hold collectives
+    for _ in range(int(n_spin.item()) // 5):
         run_steps(5)
     run_steps(warmup)
     torch.cuda.synchronize()

@@ -640,20 +640,28 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)
     if rank == 0 and os.environ.get("WITW_BENCH_NO_SAMPLER") != "1":      # (debug: is a stall the sampler's doing?)
         sampler.start()
-    # Spin-up before the W warm-up steps: the first CUDA process on a box that has been idle sees one stall of 40 - 50 ms some
+    # Spin-up before the W warm-up steps.  The first CUDA process on a box that has been idle sees one stall of 40 - 50 ms some
     # 60 ms into its first stretch of continuous work, with or without the sampler (measured: one 49.6 ms step among 7.5 ms
-    # ones in the first process only; later processes on the same box never) -- a power-state transition of the idle GPU.
-    # A second of untimed steps puts it behind us.
+    # ones, in the first process only; later processes on the same box never) -- a power-state transition of the idle GPU.  A
+    # second of untimed steps puts it behind us; the second of rest that follows lets the board's power average recover, so
+    # that the timed steps start from the state a fresh run starts from (after a second of continuous work the power cap
+    # lowers the SM clock and the sweep takes 7.1 instead of 6.8 ms: `spin_up.ms_per_step` reports that sustained figure).
     run_steps(3)                                       # first launches: module loads, allocator pools
     torch.cuda.synchronize()
     t_spin = time.perf_counter()
     run_steps(3)
     torch.cuda.synchronize()
-    n_spin = torch.tensor([int(min(200, max(0, 1.0 / max((time.perf_counter() - t_spin) / 3, 1e-4))))], device=device)
+    spin_s = float(os.environ.get("WITW_BENCH_SPIN", "1.0"))
+    n_spin = torch.tensor([int(min(200, max(0, spin_s / max((time.perf_counter() - t_spin) / 3, 1e-4))))], device=device)
     if world > 1:
         dist.broadcast(n_spin, src=0)                  # every rank must run the same number of steps: they hold collectives
-    for _ in range(int(n_spin.item()) // 5):
+    n_spin = (int(n_spin.item()) // 5) * 5
+    t_spin = time.perf_counter()
+    for _ in range(n_spin // 5):
         run_steps(5)
+    torch.cuda.synchronize()
+    spin_ms = 1e3 * (time.perf_counter() - t_spin) / max(n_spin, 1)
+    time.sleep(float(os.environ.get("WITW_BENCH_REST", "1.0")))
     run_steps(warmup)
     torch.cuda.synchronize()
     sweep_events.clear()
@@ -829,6 +837,9 @@ def run_ours(args):
                    "" if world == 1 else "; gallery sharded, one shard per GPU, NCCL all-reduce of the thresholds + one all-gather of counts and top-k"),
         "pipelining": "one step deep: step i+1 is enqueued before the host reads step i's 4-byte finish flag",
         "l2_window": bool(args.l2_window),
+        "spin_up": {"steps": n_spin, "ms_per_step": spin_ms, "rest_s": float(os.environ.get("WITW_BENCH_REST", "1.0")),
+                    "note": "untimed: ~1 s of continuous steps (its wall-clock rate is the sustained, power-capped figure), then ~1 s of rest, "
+                            "then the W warm-up steps and the timed steps"},
     })
     line = {
         "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_step,

@@ -232,7 +232,10 @@ struct TcParams {
   int n_stages;                  // depth of the operand ring (<= kTcMaxStages)
 };
 
-template <int CG>
+// AMB: the epilogue also tracks the runner-up accumulator of every pair (the ambiguity test of sweep_common.cuh: cropped
+// queries, orientation output).  Two more instructions per accumulator; compiled out of the plain variant, whose epilogue
+// must drain 256 columns per accumulator stage while the MMAs of the next stage run.
+template <int CG, bool AMB>
 __global__ void __launch_bounds__(kTcThreads, 1)
 match_tc_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant__ CUtensorMap g_map, const TcParams P) {
   constexpr int UM = 128 * CG;           // UMMA M
@@ -403,7 +406,7 @@ match_tc_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant
             for (int gi = 0; gi < 2; ++gi) {
               const float x = __uint_as_float(v[2 * ds + gi]);
               const int i = 2 * h + gi;
-              if (S.need_amb) second[i] = fmaxf(second[i], fminf(x, best[i]));
+              if constexpr (AMB) second[i] = fmaxf(second[i], fminf(x, best[i]));
               if (x > best[i]) { best[i] = x; arg[i] = s0 + ds; }  // strict '>' in ascending shift order: first maximum
             }
           }
@@ -423,7 +426,7 @@ match_tc_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant
           const int64_t g = (int64_t)grp * IG + i;
           if (g < S.G && qc.ok) {
             const float e = sweep_err(S, __ldg(reinterpret_cast<const float*>(S.gal_aux + g) + 2), qc, best[i]);
-            const bool amb = S.need_amb && second[i] >= best[i] - 2.0f * e;
+            const bool amb = AMB && second[i] >= best[i] - 2.0f * e;
             sweep_pair(S, qc, g, q, best[i], arg[i], amb, __ldg(S.gal_scale + g * kW + arg[i]), e, cnt, td, ti);
           }
         }
@@ -618,13 +621,10 @@ extern "C" int witw_match_tc(const witw_sweep_args* a, witw_stream_t stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (sch.cg == 2) {
-    WITW_CUDA(cudaFuncSetAttribute(match_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    WITW_CUDA(cudaLaunchKernelEx(&cfg, match_tc_kernel<2>, qmap, gmap, P));
-  } else {
-    WITW_CUDA(cudaFuncSetAttribute(match_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    WITW_CUDA(cudaLaunchKernelEx(&cfg, match_tc_kernel<1>, qmap, gmap, P));
-  }
+  auto kernel = sch.cg == 2 ? (out.need_amb ? match_tc_kernel<2, true> : match_tc_kernel<2, false>)
+                            : (out.need_amb ? match_tc_kernel<1, true> : match_tc_kernel<1, false>);
+  WITW_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  WITW_CUDA(cudaLaunchKernelEx(&cfg, kernel, qmap, gmap, P));
   WITW_LAUNCH_CHECK();
   return WITW_OK;
 }

@@ -392,6 +392,7 @@ extern "C" int witw_topk_from_dist_f32(const float* dist, int64_t G, int64_t Q, 
 // instead -- slow, exact.
 // ------------------------------------------------------------------------------------------
 constexpr int kFilterThreads = 128;
+constexpr int kStash = 4;           // per-thread, per-column survivor slots of the filter pass
 
 // Threshold of a column = max over k disjoint row groups of the group's minimum: k distinct elements lie at or below
 // it, so it bounds the k-th smallest distance from above -- from min / max reductions alone, no lists.  Sampled row
@@ -455,11 +456,24 @@ topk_filter_kernel(const float* __restrict__ dist, int64_t G, int64_t Q, const f
   }
   const int64_t g0 = (int64_t)blockIdx.y * rows_per_slice;
   const int64_t g1 = min(g0 + rows_per_slice, G);
+  // Survivors are first kept in the thread's own slots of shared memory (kStash per column; a slice holds one or two per
+  // column) and flushed with one atomic per column at the end: the atomic-per-survivor of the first version stalled the warp
+  // for the returned position on 78 % of the rows.  A column that fills its slots falls back to that path.
+  __shared__ float stash_d[kStash][4][kFilterThreads];
+  __shared__ int32_t stash_i[kStash][4][kFilterThreads];
+  int n[4] = {0, 0, 0, 0};
+  const int tid = threadIdx.x;
   auto keep = [&](int c, float d, int64_t g) {
-    const int32_t pos = atomicAdd(cnt + q0 + c, 1);
-    if (pos < cap) {
-      buf_d[(q0 + c) * cap + pos] = d;
-      buf_i[(q0 + c) * cap + pos] = (int32_t)g;
+    if (n[c] < kStash) {
+      stash_d[n[c]][c][tid] = d;
+      stash_i[n[c]][c][tid] = (int32_t)g;
+      ++n[c];
+    } else {
+      const int32_t pos = atomicAdd(cnt + q0 + c, 1);
+      if (pos < cap) {
+        buf_d[(q0 + c) * cap + pos] = d;
+        buf_i[(q0 + c) * cap + pos] = (int32_t)g;
+      }
     }
   };
   constexpr int U = 4;
@@ -484,6 +498,18 @@ topk_filter_kernel(const float* __restrict__ dist, int64_t G, int64_t Q, const f
     if (v.y < bound[1]) keep(1, v.y, g);
     if (v.z < bound[2]) keep(2, v.z, g);
     if (v.w < bound[3]) keep(3, v.w, g);
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    if (n[c] > 0) {
+      const int32_t pos = atomicAdd(cnt + q0 + c, n[c]);
+      for (int j = 0; j < n[c]; ++j) {
+        if (pos + j < cap) {
+          buf_d[(q0 + c) * cap + pos + j] = stash_d[j][c][tid];
+          buf_i[(q0 + c) * cap + pos + j] = stash_i[j][c][tid];
+        }
+      }
+    }
   }
 }
 

@@ -251,6 +251,10 @@ typedef struct witw_sweep_args {
 int witw_match_tc_topk_slots(int64_t G, int64_t Q);
 int witw_match_tc(const witw_sweep_args* args, witw_stream_t stream);
 int witw_match_spec_topk_slots(int64_t G, int64_t Q);
+/* How witw_match_spec tiles the sweep: 2 (default) = a CTA pair per 128-query x 16-item tile (tcgen05 cta_group::2: the pair
+ * shares the gallery operand, each CTA stages 64 queries), 1 = one CTA per 128-query x 8-item tile.  Same results; a
+ * process-wide setting meant for measurements (call before witw_match_spec_topk_slots). */
+int witw_match_spec_variant(int cta_group);
 int witw_match_spec(const witw_sweep_args* args, witw_stream_t stream);
 
 /* ---- fp32 evaluation in the azimuth-frequency domain (csrc/spectral.cu, csrc/finish.cu) ----

@@ -71,7 +71,15 @@ def test_sweep_schedules_stay_within_the_merge_width():
         for fn in (lib.witw_match_spec_topk_slots, lib.witw_match_tc_topk_slots):
             n = fn(g, q)
             assert 1 <= n <= 64, (g, q, n)
-    assert lib.witw_match_spec_topk_slots(10000, 10000) == 56       # 28 chunks x 2 lists: the best-balanced split
+    assert lib.witw_match_spec_topk_slots(10000, 10000) == 52       # CTA pairs: 13 chunks x 4 lists, the best-balanced split
+    try:                                                            # one CTA per tile: 28 chunks x 2 lists
+        assert lib.witw_match_spec_variant(1) == 0
+        assert lib.witw_match_spec_topk_slots(10000, 10000) == 56
+        for g, q in ((1, 1), (1000000, 1), (333, 100000)):
+            assert 1 <= lib.witw_match_spec_topk_slots(g, q) <= 64
+        assert lib.witw_match_spec_variant(3) != 0                   # rejected, setting unchanged
+    finally:
+        assert lib.witw_match_spec_variant(2) == 0
 
 
 def test_polar_plan_u8_structure():

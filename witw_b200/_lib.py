@@ -66,6 +66,7 @@ SIGNATURES = {
     "witw_spec_query_prep": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "witw_match_spec_topk_slots": (c_int, [c_int64, c_int64]),
     "witw_match_spec": (c_int, [c_void_p, c_void_p]),
+    "witw_match_spec_variant": (c_int, [c_int]),
     "witw_rank_from_dist_f32": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
     "witw_l2_rank_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "witw_topk_slices": (c_int, [c_int64, c_int64]),

@@ -49,18 +49,28 @@ namespace witw {
 void* get_encode_tiled();                                                                         // polar.cu
 
 constexpr int kSpThreads = 512;
-constexpr int kSpStages = 6;           // even: producer / issuer warp p owns the stages of parity p
-constexpr int kSpABytes = 2 * 128 * 128;  // 2 K halves x 128 queries x 64 bf16
-constexpr int kSpBBytes = 2 * 16 * 128;   // 2 K halves x 8 items x (Re, Im) x 64 bf16
+constexpr int kSpStages = 6;           // one CTA per tile: stages of 36 KB, one issuer warp per stage
+#ifndef SPEC_NS_PAIR
+#define SPEC_NS_PAIR 10
+#define SPEC_NP_PAIR 2
+#define SPEC_NI_PAIR 5
+#endif
+constexpr int kSpStagesPair = SPEC_NS_PAIR;   // CTA pairs: stages of 20 KB
+constexpr int kSpProducersPair = SPEC_NP_PAIR, kSpIssuersPair = SPEC_NI_PAIR;   // control warps; both counts divide the ring depth
+constexpr int kSpABytes = 2 * 128 * 128;  // 2 K halves x 128 queries x 64 fp16 (one CTA per tile)
+constexpr int kSpABytesPair = kSpABytes / 2;  // CTA pair: each CTA stages 64 of the tile's 128 queries
+constexpr int kSpBBytes = 2 * 16 * 128;   // 2 K halves x 8 items x (Re, Im) x 64 fp16
 constexpr int kSpSlots = 32;
 constexpr int kSpItems = 8;            // gallery items per tile (= per operand group)
 constexpr int kSpCH = 64;              // feature rows (C*H) the operand layout is built for
 constexpr int kSpTopkMax = kSweepTopk;
-constexpr int kSpMaxChunks = 32;       // two candidate lists per chunk; witw_topk_merge takes up to 64
+constexpr int kSpMaxChunks = 32;       // two candidate lists per chunk (four with CTA pairs); witw_topk_merge takes up to 64
 
 // Timing experiments (wrong results by design) exist only in builds with -DWITW_DEBUG_HOOKS (tools/ probes): WITW_SPEC_DEBUG
 // bit 0 = no inverse FFT, bit 1 = no TMEM loads in the epilogue, bit 2 = no tcgen05.mma (barriers only), bit 3 = no
-// query-stage loads, bit 4 = chunk-major work order.  The shipped library never reads the environment.
+// query-stage loads, bit 4 = chunk-major work order, bit 5 = no operand ring at all (the epilogue and the per-tile handshake
+// alone), bit 6 = stages are released by a plain mbarrier arrive instead of tcgen05.commit, bit 7 = no per-tile handshake and no
+// epilogue (the ring alone).  The shipped library never reads the environment.
 #ifdef WITW_DEBUG_HOOKS
 static int spec_debug() {
   static int v = -1;
@@ -165,7 +175,8 @@ spec_gallery_prep_kernel(const float* __restrict__ ov, int64_t G, int64_t g_firs
   if (threadIdx.x < 64) {             // crop norms of the 64 shifts and the scale table of the sweep
     const int j = threadIdx.x;
     float c = 0.f;
-    for (int k = 0; k < sw; ++k) c += col_e[(j + k) & 63];
+    const int j0 = sw == 64 ? 0 : j;    // a full panorama's crop is the whole item at every shift: one summation order, one value
+    for (int k = 0; k < sw; ++k) c += col_e[(j0 + k) & 63];
     const float cin = live ? 1.0f / sqrtf(c) : 0.f;
     const float scl = live ? norm * cin / kSpecUnit : 0.f;
     gal_scale[g_local * 64 + j] = scl;
@@ -275,6 +286,11 @@ spec_query_prep_kernel(const float* __restrict__ su, int64_t Q, int sw, __half* 
 // ------------------------------------------------------------------------------------------
 // PTX used only here
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float fmax3(float a, float b, float c) {   // FMNMX3; NaN operands are dropped like fmaxf drops them
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
 __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(taddr));
 }
@@ -286,24 +302,40 @@ struct SpParams {
   int one;                       // always 1; opaque to the compiler (see the epilogue)
 };
 
+// CG == 1: one CTA per 128-query x 8-item tile (tcgen05.mma.cta_group::1, M = 128, N = 16).
+// CG == 2: a CTA pair per 128-query x 16-item tile (cta_group::2, M = 128, N = 32): each CTA stages 64 queries (the A rows
+// of its half of M) and its own group of 8 items (its half of N, which the pair's MMA reads from both CTAs), and its TMEM holds
+// D[m, n] at lane m + 64 (n / 16), column n % 16 -- lanes 0-63 = its 64 queries x the leader's group, lanes 64-127 = the same
+// queries x the peer's group.  Still 1 024 pairs x 64 accumulators per CTA, but the ring carries 20 KB per slot instead of 36.
+// ARG: the epilogue tracks the shift of the maximum (orientation output, cropped queries: the crop norm depends on it).  Without
+// it -- full panoramas, distances / ranks / top-k only -- a third of the epilogue's comparisons and selects go away.
+template <int CG, bool ARG>
 __global__ void __launch_bounds__(kSpThreads, 1)
 match_spec_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant__ CUtensorMap g_map, const SpParams P) {
   constexpr uint32_t kTmemCols = 512;
-  // kind::f16: D fp32 (bit 4), A and B fp16 (format fields 0), both K-major, N = 16, M = 128
-  constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  constexpr int kA = CG == 2 ? kSpABytesPair : kSpABytes;   // query bytes per stage and CTA
+  constexpr int NS = CG == 2 ? kSpStagesPair : kSpStages;   // ring depth
+  constexpr int NP = CG == 2 ? kSpProducersPair : 2;        // producer warps; warp p owns the stages = p (mod NP)
+  constexpr int NI = CG == 2 ? kSpIssuersPair : kSpStages;  // issuer warps; warp k owns the stages = k (mod NI)
+  static_assert(NS % NP == 0 && NS % NI == 0 && NP + NI <= 8, "control warps own whole residue classes of the ring's stages");
+  // kind::f16: D fp32 (bit 4), A and B fp16 (format fields 0), both K-major, N = 16 per CTA, M = 128
+  constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)((16 * CG) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
   extern __shared__ __align__(1024) unsigned char smem[];
-  unsigned char* a_base = smem;                                  // kSpStages x 32 KB, 1024-aligned
-  unsigned char* b_base = smem + kSpStages * kSpABytes;          // kSpStages x 4 KB, 1024-aligned
-  uint64_t* bars = reinterpret_cast<uint64_t*>(b_base + kSpStages * kSpBBytes);
-  uint64_t* full = bars;                      // [kSpStages]
-  uint64_t* empty = bars + kSpStages;         // [kSpStages]
-  uint64_t* tmem_full = bars + 2 * kSpStages;
-  uint64_t* tmem_empty = tmem_full + 1;
+  unsigned char* a_base = smem;                                  // NS x kA, 1024-aligned
+  unsigned char* b_base = smem + NS * kA;                        // NS x 4 KB, 1024-aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_base + NS * kSpBBytes);
+  uint64_t* full = bars;                      // [NS]   (CG == 2: the leader's are used)
+  uint64_t* empty = bars + NS;                // [NS]
+  uint64_t* tmem_full = bars + 2 * NS;
+  uint64_t* tmem_empty = tmem_full + 1;       //               (CG == 2: the leader's is used)
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int unit = blockIdx.x, n_units = gridDim.x;
+  uint32_t cta_rank = 0;
+  if constexpr (CG == 2) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
+  const bool leader = cta_rank == 0;
+  const int unit = blockIdx.x / CG, n_units = gridDim.x / CG;
   const int n_work = P.n_chunks * P.n_qtiles;
   const bool chunk_major = SPEC_DBG(P, 16);
 
@@ -313,19 +345,27 @@ match_spec_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_consta
   }
   if (warp == 1 && lane == 0) {
     if (s2u(smem) & 1023u) __trap();  // SWIZZLE_128B operand tiles need a 1024-byte aligned base
-    for (uint32_t s = 0; s < kSpStages; ++s) {
+    for (uint32_t s = 0; s < NS; ++s) {
       bar_init(s2u(&full[s]), 1);
       bar_init(s2u(&empty[s]), 1);
     }
-    bar_init(s2u(tmem_full), kSpStages);   // one tcgen05.commit per issuing warp
-    bar_init(s2u(tmem_empty), 8);     // one arrive per epilogue warp
+    bar_init(s2u(tmem_full), NI);          // one tcgen05.commit per issuing warp
+    bar_init(s2u(tmem_empty), 8 * CG);     // one arrive per epilogue warp (of both CTAs)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s2u(tmem_holder)), "r"(kTmemCols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (CG == 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s2u(tmem_holder)), "r"(kTmemCols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s2u(tmem_holder)), "r"(kTmemCols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
+  if constexpr (CG == 2) {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  }
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
@@ -342,83 +382,102 @@ match_spec_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_consta
   if (warp < 8) asm volatile("setmaxnreg.dec.sync.aligned.u32 " SPEC_STR(SPEC_NREG_LO) ";");
   else asm volatile("setmaxnreg.inc.sync.aligned.u32 " SPEC_STR(SPEC_NREG_HI) ";");
 
-  if (warp < 2) {
-    // ===================== TMA producers: warp p loads the slots of parity p into the stages of parity p =====================
-    const int par = warp;
-    uint32_t k = 0, ph = 0;  // this warp's stage = 2k + par, k = 0..2
-    for (int w = unit; w < n_work; w += n_units) {
+  if (warp < NP) {
+    // ===================== TMA producers: warp p loads every NP-th slot of this CTA's slot sequence =====================
+    // CG == 2: every stage's bytes -- this CTA's 64 queries and 8 items, and the peer's -- are accounted on the LEADER's full
+    // barrier: the leader arms it with the pair's total, the peer only issues its copies.
+    const uint32_t par = (uint32_t)warp;
+    const uint32_t full0 = CG == 2 ? map_to_cta(s2u(&full[0]), 0) : s2u(&full[0]);
+    uint32_t c0 = 0;         // sequence number of the current tile's slot 0
+    for (int w = unit; w < n_work && !SPEC_DBG(P, 32); w += n_units) {
       const int qt = chunk_major ? w % P.n_qtiles : w / P.n_chunks;
       const int chunk = chunk_major ? w / P.n_qtiles : w - qt * P.n_chunks;
       const int q_row = qt * (2 * kSpSlots * 128);   // first operand row of this query tile
       const int grp0 = chunk * P.groups_per_chunk;
       const int grp1 = min(grp0 + P.groups_per_chunk, P.n_groups);
-      for (int grp = grp0; grp < grp1; ++grp) {
-        for (int slot = par; slot < kSpSlots; slot += 2) {
-          const uint32_t s = 2 * k + par;
+      for (int grp = grp0; grp < grp1; ++grp, c0 += kSpSlots) {
+        const int my_grp = grp * CG + (int)cta_rank;   // (past the last group: the copy delivers zeros)
+        for (uint32_t slot = (par + NP - c0 % NP) % NP; slot < kSpSlots; slot += NP) {
+          const uint32_t c = c0 + slot, s = c % NS, ph = (c / NS) & 1u;
           bar_wait(s2u(&empty[s]), ph ^ 1);
           if (elect_one()) {
-            const uint32_t fb = s2u(&full[s]);
+            const uint32_t fb = full0 + s * 8;
             if (SPEC_DBG(P, 8)) {
-              bar_expect_tx(fb, (uint32_t)kSpBBytes);
+              if (leader) bar_expect_tx(s2u(&full[s]), (uint32_t)(CG * kSpBBytes));
             } else {
-              bar_expect_tx(fb, (uint32_t)(kSpABytes + kSpBBytes));
-              tma_2d<1>(s2u(a_base) + s * kSpABytes, &q_map, fb, 0, q_row + 256 * slot);
+              if (leader) bar_expect_tx(s2u(&full[s]), (uint32_t)(CG * (kA + kSpBBytes)));
+              if constexpr (CG == 1) {
+                tma_2d<1>(s2u(a_base) + s * kA, &q_map, fb, 0, q_row + 256 * (int)slot);
+              } else {   // K halves of this CTA's 64 queries: rows [64 rank, +64) of each 128-row half
+                tma_2d<2>(s2u(a_base) + s * kA, &q_map, fb, 0, q_row + 256 * (int)slot + 64 * (int)cta_rank);
+                tma_2d<2>(s2u(a_base) + s * kA + kA / 2, &q_map, fb, 0, q_row + 256 * (int)slot + 128 + 64 * (int)cta_rank);
+              }
             }
-            tma_2d<1>(s2u(b_base) + s * kSpBBytes, &g_map, fb, 0, (grp * kSpSlots + slot) * 32);
+            tma_2d<CG>(s2u(b_base) + s * kSpBBytes, &g_map, fb, 0, (my_grp * kSpSlots + (int)slot) * 32);
           }
           __syncwarp();
-          if (++k == kSpStages / 2) { k = 0; ph ^= 1; }
         }
       }
     }
-  } else if (warp < 8) {
-    // ===================== MMA issuers: warp 2 + k owns stage k, i.e. every sixth slot of this CTA's slot sequence =====================
-    const uint32_t k = (uint32_t)(warp - 2);
+  } else if (warp < NP + NI) {
+    // ===================== MMA issuers: warp NP + k owns every NI-th slot of this CTA's slot sequence =====================
+    // (CG == 2: the leader's warps issue for the pair)
+    if (leader) {
+    const uint32_t k = (uint32_t)(warp - NP);
     uint32_t n_tiles = 0;
     for (int w = unit; w < n_work; w += n_units) {
       const int chunk = chunk_major ? w / P.n_qtiles : w % P.n_chunks;
       const int grp0 = chunk * P.groups_per_chunk;
       n_tiles += (uint32_t)(min(grp0 + P.groups_per_chunk, P.n_groups) - grp0);
     }
-    const uint64_t da = make_desc(s2u(a_base) + k * kSpABytes, 16, 1024, 2 /*SWIZZLE_128B*/);
-    const uint64_t db = make_desc(s2u(b_base) + k * kSpBBytes, 16, 1024, 2 /*SWIZZLE_128B*/);
-    const uint32_t full_k = s2u(&full[k]), empty_k = s2u(&empty[k]);
-    uint32_t ph = 0, seen_tile = 0xffffffffu;
-    for (uint32_t c = k; c < n_tiles * kSpSlots; c += kSpStages, ph ^= 1) {
+    const uint64_t da0 = make_desc(s2u(a_base), 16, 1024, 2 /*SWIZZLE_128B*/);
+    const uint64_t db0 = make_desc(s2u(b_base), 16, 1024, 2 /*SWIZZLE_128B*/);
+    const uint32_t full0 = s2u(&full[0]), empty0 = s2u(&empty[0]);
+    uint32_t seen_tile = 0xffffffffu;
+    for (uint32_t c = k; c < n_tiles * kSpSlots; c += NI) {
       const uint32_t tile_it = c / kSpSlots, slot = c % kSpSlots;
-      if (tile_it != seen_tile) {  // first slot of a new tile: the epilogue must have drained the previous one
+      const uint32_t stg = c % NS, ph = (c / NS) & 1u;
+      const uint32_t empty_k = empty0 + stg * 8;
+      const uint64_t da = da0 + (uint64_t)(stg * (kA >> 4)), db = db0 + (uint64_t)(stg * (kSpBBytes >> 4));
+      if (tile_it != seen_tile && !SPEC_DBG(P, 128)) {  // first slot of a new tile: the epilogue must have drained the previous one
         seen_tile = tile_it;
         bar_wait(s2u(tmem_empty), (tile_it & 1) ^ 1);
       }
-      bar_wait(full_k, ph);
+      if (!SPEC_DBG(P, 32)) bar_wait(full0 + stg * 8, ph);
       tc_fence_after();
       if (elect_one()) {
         const uint32_t tmem_d = tmem_base + slot * 16u;
-        if (!SPEC_DBG(P, 4)) {
+        if (!SPEC_DBG(P, 4 | 32)) {
 #pragma unroll
-          for (int h = 0; h < 2; ++h)    // K halves: tiles of 16 KB (queries) / 2 KB (items)
+          for (int h = 0; h < 2; ++h)    // K halves: tiles of kA / 2 (queries) / 2 KB (items)
 #pragma unroll
             for (int j = 0; j < 4; ++j)  // 32 bytes (2 descriptor units) along K per step inside the 128B-swizzled rows
-              umma_bf16<1>(tmem_d, da + (uint64_t)(h * (kSpABytes >> 5) + 2 * j), db + (uint64_t)(h * (kSpBBytes >> 5) + 2 * j), kIdesc,
-                           (h | j) != 0 ? 1u : 0u);
+              umma_bf16<CG>(tmem_d, da + (uint64_t)(h * (kA >> 5) + 2 * j), db + (uint64_t)(h * (kSpBBytes >> 5) + 2 * j), kIdesc,
+                            (h | j) != 0 ? 1u : 0u);
         }
-        umma_commit<1>(empty_k);
-        if ((c + kSpStages) / kSpSlots != tile_it) umma_commit<1>(s2u(tmem_full));  // this warp's last slot of the tile
+        if (SPEC_DBG(P, 64)) {   // (timing experiment: no tcgen05.commit on the stage's way back)
+          bar_arrive_local(empty_k);
+          if (CG == 2) bar_arrive_cluster(empty_k, 1);
+        } else if (!SPEC_DBG(P, 32)) umma_commit<CG>(empty_k);          // frees the stage (in both CTAs) when these MMAs retire
+        if ((c + NI) / kSpSlots != tile_it && !SPEC_DBG(P, 128)) umma_commit<CG>(s2u(tmem_full));  // this warp's last slot of the tile
       }
       __syncwarp();
     }
-  } else {
-    // ===================== epilogue: warps 8-11 items 0-3, warps 12-15 items 4-7 of each tile =====================
+    }
+  } else if (warp >= 8) {
+    // ===================== epilogue: warps 8-11 items 0-3, warps 12-15 items 4-7 of each group =====================
     const SweepOut& S = P.out;
     const int wq = warp & 3;
     const int ihalf = (warp - 8) >> 2;
     const int row = wq * 32 + lane;
+    const int qrow = CG == 2 ? (int)cta_rank * 64 + (row & 63) : row;   // query of this lane within the 128-query tile
+    const int gsel = CG == 2 ? row >> 6 : 0;                           // which group of the pair's two this lane holds
     const uint32_t lane_field = (uint32_t)(wq * 32) << 16;
     uint32_t tile_it = 0;
-    for (int w = unit; w < n_work; w += n_units) {
+    for (int w = unit; w < n_work && !SPEC_DBG(P, 128); w += n_units) {
       const int qt = chunk_major ? w % P.n_qtiles : w / P.n_chunks;
       const int chunk = chunk_major ? w / P.n_qtiles : w - qt * P.n_chunks;
-      const int64_t q = (int64_t)qt * 128 + row;
+      const int64_t q = (int64_t)qt * 128 + qrow;
       SweepQuery qc;
       qc.load(S, q);
       int cnt = 0;
@@ -436,11 +495,11 @@ match_spec_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_consta
 #pragma unroll 1
         for (int pp = 0; pp < 2; ++pp) {
           const int i0 = ihalf * 4 + pp * 2;      // items i0 and i0 + 1 in the .x / .y halves
-          const int64_t g0 = (int64_t)grp * kSpItems + i0;
+          const int64_t g0 = (int64_t)(grp * CG + gsel) * kSpItems + i0;
           // rounding scales of the two items for the ambiguity test (broadcast loads, consumed after the transform; rows past
           // G are zeros)
           float ag0 = 0.f, ag1 = 0.f;
-          if (S.need_amb) {
+          if (S.need_amb && (CG == 1 || g0 < S.G)) {   // (a pair's second group may lie past the tables)
             ag0 = __ldg(reinterpret_cast<const float*>(S.gal_aux + g0) + 2);
             ag1 = __ldg(reinterpret_cast<const float*>(S.gal_aux + g0 + 1) + 2);
           }
@@ -462,7 +521,10 @@ match_spec_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_consta
           if (pp == 1) {  // this warp's share of the accumulators is in registers: hand TMEM back to the MMA issuers
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) bar_arrive_local(s2u(tmem_empty));
+            if (lane == 0) {
+              if (CG == 1 || leader) bar_arrive_local(s2u(tmem_empty));
+              else bar_arrive_remote(s2u(tmem_empty), 0);
+            }
           }
           // The rest of the pair's work is pure arithmetic on the registers just loaded.  Left in the same basic block, ptxas
           // predicates the barrier arrive above and sinks it below the whole transform (nothing depends on it), so the MMA
@@ -478,12 +540,20 @@ match_spec_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_consta
           }
           float best[2] = {-__int_as_float(0x7f800000), -__int_as_float(0x7f800000)};
           int arg[2] = {0, 0};
+          if constexpr (ARG) {
 #pragma unroll
-          for (int sft = 0; sft < 64; ++sft) {  // strict '>' in ascending shift order: first maximum
-            if (x[sft].x > best[0]) { best[0] = x[sft].x; arg[0] = sft; }
-            if (x[sft].y > best[1]) { best[1] = x[sft].y; arg[1] = sft; }
+            for (int sft = 0; sft < 64; ++sft) {  // strict '>' in ascending shift order: first maximum
+              if (x[sft].x > best[0]) { best[0] = x[sft].x; arg[0] = sft; }
+              if (x[sft].y > best[1]) { best[1] = x[sft].y; arg[1] = sft; }
+            }
+          } else {   // full panorama, no orientation output: only the maximum matters (gal_scale[g,:] is constant) -- 3-input maxima
+#pragma unroll
+            for (int sft = 0; sft < 64; sft += 2) {
+              best[0] = fmax3(best[0], x[sft].x, x[sft + 1].x);
+              best[1] = fmax3(best[1], x[sft].y, x[sft + 1].y);
+            }
           }
-          if (S.need_amb) {  // how many shifts could be the exact argmax (the maximum itself is one of them)
+          if (ARG && S.need_amb) {  // how many shifts could be the exact argmax (the maximum itself is one of them)
             const float thr0 = best[0] - 2.0f * sweep_err(S, ag0, qc, best[0]), thr1 = best[1] - 2.0f * sweep_err(S, ag1, qc, best[1]);
             int n0 = 0, n1 = 0;
 #pragma unroll
@@ -505,7 +575,7 @@ match_spec_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_consta
         }
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const int64_t g = (int64_t)grp * kSpItems + ihalf * 4 + e;
+          const int64_t g = (int64_t)(grp * CG + gsel) * kSpItems + ihalf * 4 + e;
           if (g < S.G && qc.ok) {
             const float err = sweep_err(S, __ldg(reinterpret_cast<const float*>(S.gal_aux + g) + 2), qc, bestv[e]);   // L1-resident by now
             sweep_pair(S, qc, g, q, bestv[e], argv[e] & 63, (argv[e] & 256) != 0, sclv[e], err, cnt, td, ti);
@@ -515,7 +585,7 @@ match_spec_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_consta
       if (qc.ok) {
         if (S.rank_count && cnt) atomicAdd(S.rank_count + q, cnt);
         if (S.topk > 0) {
-          const int64_t slot = (int64_t)chunk * 2 + ihalf;
+          const int64_t slot = (int64_t)chunk * (2 * CG) + gsel * 2 + ihalf;
           float* od = S.topk_key + (slot * S.Q + q) * S.topk;
           int32_t* oi = S.topk_idx + (slot * S.Q + q) * S.topk;
 #pragma unroll
@@ -528,14 +598,24 @@ match_spec_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_consta
 
   // ===================== teardown =====================
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  } else {
+    __syncthreads();
+  }
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    if constexpr (CG == 1)
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
   }
 }
 
-struct SpSchedule { int n_units, n_qtiles, n_groups, groups_per_chunk, n_chunks; };
+struct SpSchedule { int cg, n_units, n_qtiles, n_groups, groups_per_chunk, n_chunks; };   // n_groups: groups of 8 * cg items
+
+// 2 = CTA pairs (the default), 1 = one CTA per tile; witw_match_spec_variant() switches (tools/, A/B measurements).
+static int g_spec_cg = 2;
 
 // Static schedule: work item w = (query tile, gallery chunk) goes to CTA w % n_units.  The number of chunks (<= 32: two
 // candidate lists per chunk, witw_topk_merge takes 64) is chosen so that the busiest CTA carries as little more than the
@@ -562,16 +642,18 @@ static double spec_balance(int n_groups, int n_qtiles, int n_chunks_want, int n_
 static SpSchedule make_spec_schedule(int64_t G, int64_t Q) {
   static thread_local int64_t memo_g = -1, memo_q = -1;
   static thread_local SpSchedule memo;
-  if (G == memo_g && Q == memo_q) return memo;
+  const int cg = (g_spec_cg == 2 && sm_count() >= 2) ? 2 : 1;
+  if (G == memo_g && Q == memo_q && memo.cg == cg) return memo;
   SpSchedule s;
-  s.n_units = std::max(1, sm_count());
+  s.cg = cg;
+  s.n_units = std::max(1, sm_count() / cg);
   s.n_qtiles = (int)ceil_div<int64_t>(std::max<int64_t>(Q, 1), 128);
-  s.n_groups = (int)ceil_div<int64_t>(std::max<int64_t>(G, 1), kSpItems);
+  s.n_groups = (int)ceil_div<int64_t>(std::max<int64_t>(G, 1), kSpItems * cg);
   double best = -1.0;
   s.groups_per_chunk = s.n_groups;
   s.n_chunks = 1;
   const int64_t n_work_cap = (int64_t)1 << 22;  // bound the search for huge query counts
-  for (int c = 1; c <= kSpMaxChunks && c <= s.n_groups; ++c) {
+  for (int c = 1; c <= kSpMaxChunks / cg && c <= s.n_groups; ++c) {
     if ((int64_t)c * s.n_qtiles > n_work_cap && c > 1) break;
     int gpc, nc;
     const double e = spec_balance(s.n_groups, s.n_qtiles, c, s.n_units, &gpc, &nc);
@@ -632,7 +714,16 @@ extern "C" int witw_spec_query_prep(const float* su, int64_t Q, int CH, int sw, 
   return WITW_OK;
 }
 
-extern "C" int witw_match_spec_topk_slots(int64_t G, int64_t Q) { return make_spec_schedule(G, Q).n_chunks * 2; }
+extern "C" int witw_match_spec_topk_slots(int64_t G, int64_t Q) {
+  const SpSchedule s = make_spec_schedule(G, Q);
+  return s.n_chunks * 2 * s.cg;
+}
+
+extern "C" int witw_match_spec_variant(int cta_group) {
+  WITW_REQUIRE(cta_group == 1 || cta_group == 2, WITW_ERR_INVALID, "witw_match_spec_variant: 1 (one CTA per tile) or 2 (CTA pairs), got %d", cta_group);
+  g_spec_cg = cta_group;
+  return WITW_OK;
+}
 
 extern "C" int witw_match_spec(const witw_sweep_args* a, witw_stream_t stream) {
   WITW_REQUIRE(a != nullptr, WITW_ERR_INVALID, "witw_match_spec: null arguments");
@@ -659,14 +750,14 @@ extern "C" int witw_match_spec(const witw_sweep_args* a, witw_stream_t stream) {
   WITW_REQUIRE(q_rows < (1ll << 31), WITW_ERR_UNSUPPORTED, "witw_match_spec: %lld queries are too many for one sweep", (long long)Q);
   const cuuint64_t qdims[2] = {64, (cuuint64_t)q_rows};
   const cuuint64_t qstrides[1] = {128};
-  const cuuint32_t qbox[2] = {64, 256};
+  const cuuint32_t qbox[2] = {64, sch.cg == 2 ? 64u : 256u};   // CTA pair: one K half of a CTA's 64 queries per copy
   CUresult cr = encode(&qmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(a->qry_op), qdims, qstrides, qbox, estr,
                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   WITW_REQUIRE(cr == CUDA_SUCCESS, WITW_ERR_CUDA, "cuTensorMapEncodeTiled(query spectra) failed with CUresult %d", (int)cr);
   // gallery spectra: [groups x 32 slots x 2 K halves x 16 rows][64] fp16; one box = the 32 rows of one slot
   CUtensorMap gmap;
-  const int64_t total_rows = (int64_t)sch.n_groups * kSpSlots * 32;
+  const int64_t total_rows = ceil_div<int64_t>(G, kSpItems) * kSpSlots * 32;
   WITW_REQUIRE(total_rows < (1ll << 31), WITW_ERR_UNSUPPORTED, "witw_match_spec: gallery of %lld items is too large for one sweep", (long long)G);
   const cuuint64_t gdims[2] = {64, (cuuint64_t)total_rows};
   const cuuint64_t gstrides[1] = {128};
@@ -682,10 +773,27 @@ extern "C" int witw_match_spec(const witw_sweep_args* a, witw_stream_t stream) {
   P.n_qtiles = sch.n_qtiles; P.n_chunks = sch.n_chunks; P.groups_per_chunk = sch.groups_per_chunk; P.n_groups = sch.n_groups;
   P.debug = spec_debug();
   P.one = 1;
-  const size_t smem = (size_t)kSpStages * (kSpABytes + kSpBBytes) + (2 * kSpStages + 2) * 8 + 16;
-  WITW_CUDA(cudaFuncSetAttribute(match_spec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int grid = std::min(sch.n_units, sch.n_chunks * sch.n_qtiles);
-  match_spec_kernel<<<grid, kSpThreads, smem, as_stream(stream)>>>(qmap, gmap, P);
+  const int ns = sch.cg == 2 ? kSpStagesPair : kSpStages;
+  const size_t smem = (size_t)ns * ((sch.cg == 2 ? kSpABytesPair : kSpABytes) + kSpBBytes) + (2 * ns + 2) * 8 + 16;
+  const int grid = std::min(sch.n_units, sch.n_chunks * sch.n_qtiles) * sch.cg;
+  const bool need_arg = a->sw < 64 || a->ori != nullptr;
+  auto kernel = sch.cg == 2 ? (need_arg ? match_spec_kernel<2, true> : match_spec_kernel<2, false>)
+                            : (need_arg ? match_spec_kernel<1, true> : match_spec_kernel<1, false>);
+  WITW_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg;
+  std::memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid, 1, 1);
+  cfg.blockDim = dim3(kSpThreads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = as_stream(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)sch.cg;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  WITW_CUDA(cudaLaunchKernelEx(&cfg, kernel, qmap, gmap, P));
   WITW_LAUNCH_CHECK();
   return WITW_OK;
 }

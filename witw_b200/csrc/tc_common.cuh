@@ -58,6 +58,14 @@ __device__ __forceinline__ void tma_2d(uint32_t dst, const CUtensorMap* map, uin
         : "memory");
   }
 }
+// The same arrive with the default (CTA-scope) release: no GPU-wide fence (MEMBAR.ALL.GPU, ~1 us).  For hand-offs whose payload is
+// not ordinary memory -- an accumulator stage whose tcgen05.ld have completed (tcgen05.wait::ld +
+// tcgen05.fence::before_thread_sync order those).
+__device__ __forceinline__ void bar_arrive_remote(uint32_t local_bar, uint32_t cta_rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_bar), "r"(cta_rank));
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
 __device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t cta_rank) {
   uint32_t remote;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(cta_rank));

@@ -45,8 +45,8 @@ HARD_NOISE = {64: 13.0, 16: 6.0}       # `hard` arm: noise at which about half o
 SW = 64                                # query columns: int(fov/360*512)//8 (cvig_fov.py:22, 8 image pixels per feature column)
 FLOP_PER_PAIR = 2 * 64 * 16 * 4 * SW   # 2*W*C*H*sw = 524 288 at 360 deg, 131 072 at 90 deg
 METRIC = "queries/sec vs gallery size (orientation-searched distance + top-k)"
-SPEC_TC_FLOP_PER_PAIR = 2.0 * 128 * 16 * 16 * 256 / 1024.0    # issued as tcgen05.mma: 256 MMAs of 128x16x16 per 1024 pairs
-SPEC_SMEM_BYTES_PER_PAIR = 2.0 * (256 * 4608) / 1024.0        # operand bytes written by TMA + read by the MMAs
+SPEC_TC_FLOP_PER_PAIR = 2.0 * 128 * 32 * 16 * 256 / 2048.0    # issued as tcgen05.mma: 256 MMAs of 128x32x16 per CTA pair and 2048 pairs
+SPEC_TMA_BYTES_PER_PAIR = 32.0 * 20480 / 1024.0               # operand bytes TMA delivers: 32 slots x (16 KB queries + 4 KB items) per 1024 pairs
 
 
 def env_int(name, default):
@@ -563,6 +563,8 @@ def run_ours(args):
     if args.sweep != "auto":
         ops.TC_IMPL = args.sweep
     ops.L2_WINDOW = bool(args.l2_window)
+    if args.no_peer_exchange:
+        W.sharded.PEER_EXCHANGE = False
     world = env_int("WORLD_SIZE", 1)
     rank = env_int("RANK", 0)
     local_rank = env_int("LOCAL_RANK", 0)
@@ -784,6 +786,12 @@ def run_ours(args):
     if world > 1 and not args.no_extras:
         extras.update(multi_gpu_extras(torch, dist, W, ops, device, world, rank))
 
+    if world > 1:
+        from witw_b200 import peer
+        peer_used = any(v is not None for v in peer._cache.values())
+        torch.cuda.synchronize()
+        dist.barrier()
+        peer.shutdown()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -797,22 +805,33 @@ def run_ours(args):
     traffic = profile_json("roofline_traffic.json")
     at_baseline = FOV == 360 and G_PER_GPU == 10000 and Q_TOTAL == 10000
     if sweep_impl == "spectral":
-        # What bounds the spectral sweep is the shared-memory operand ring: per 1024 pairs the ring is written once by TMA and
-        # read once by 256 N=16 MMAs (4.6 KB each).  Its roof is measured by tools/ring_roof.py (the kernel's own ring with
-        # the epilogue's work switched off); the tensor pipe is mostly idle by construction.
-        roof = profile_json("smem_ring_roof.json")
-        sm_clock = (clocks or {}).get("sm_mhz") or 1965.0
-        nominal = 128.0 * sm_clock * 1e6 / 1e9
-        peak = roof.get("gbs_per_sm", nominal)
-        achieved = SPEC_SMEM_BYTES_PER_PAIR * pairs / 148.0 / (kernel_ms / 1000.0) / 1e9
-        exec_tf = SPEC_TC_FLOP_PER_PAIR * pairs / (kernel_ms / 1000.0) / 1e12
+        # The spectral sweep is a three-stage pipeline per tile -- TMA: fp16 operands L2 -> shared memory; tcgen05.mma: 64
+        # accumulators per pair in TMEM; epilogue: inverse FFT + maximum + rank count + top-k on the CUDA cores -- and TMEM holds
+        # exactly one tile, so the first half of a tile's epilogue cannot overlap the next tile's MMAs.  Its roof is the slowest
+        # stage running alone, measured on the kernel itself (tools/ring_roof.py: the hooks build switches the other stages off):
+        # the operand ring, bound by the L2 -> SM delivery of 640 B per pair.  HBM and the tensor pipe are far from their peaks
+        # by construction (operands are L2-resident; the correlation theorem removed 97 % of the tensor work).
+        roof = profile_json("sweep_roof_r2.json")
+        stage = roof.get("kernel_ms", {})
+        ring_alone_ms = stage.get("ring_alone", 3.235)   # fallbacks: the round-2 measurement
+        sec = kernel_ms / 1000.0
+        achieved = SPEC_TMA_BYTES_PER_PAIR * pairs / sec / 1e9
+        peak = SPEC_TMA_BYTES_PER_PAIR * 1e8 / (ring_alone_ms / 1000.0) / 1e9
+        exec_tf = SPEC_TC_FLOP_PER_PAIR * pairs / sec / 1e12
         roofline = {
-            "bound": "smem", "kernel": kernel, "kernel_ms": kernel_ms, "achieved": achieved, "peak": peak, "unit": "GB/s per SM", "frac": achieved / peak,
-            "peak_source": roof.get("source", "nominal 128 B/clk x SM clock (no measured ring roof in profiles/smem_ring_roof.json)"),
-            "bound_detail": "shared-memory operand ring feeding N=16 UMMAs: %d B per pair written by TMA + read by the MMAs (query stage "
-                            "written once, read once per 8 gallery items; TMEM capacity fixes the 128 x 8 tile)" % int(SPEC_SMEM_BYTES_PER_PAIR),
+            "bound": "l2_to_sm_operand_delivery", "kernel": kernel, "kernel_ms": kernel_ms, "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak,
+            "peak_source": roof.get("source", "round-2 measurement quoted in DESIGN.md 4.2s (profiles/sweep_roof_r2.json not found)"),
+            "bound_detail": "%d B of fp16 operands per (query, item) pair delivered from L2 into the shared-memory ring by TMA (a CTA pair stages "
+                            "64 queries + 8 items per CTA and frequency slot for 1 024 pairs per CTA; TMEM capacity fixes the tile); peak = the same "
+                            "bytes over the time of the kernel's own TMA + MMA ring running alone at 10k x 10k" % int(SPEC_TMA_BYTES_PER_PAIR),
+            "stages_alone_ms": {k: stage.get(k) for k in ("ring_alone", "tma_alone", "mma_alone", "epilogue_alone", "full")},
+            "stages_note": "each stage of the kernel's pipeline timed alone on the 10k x 10k workload (hooks build); `full` is the hooks build's "
+                           "whole kernel.  The gap between the slowest stage and the kernel is the half of the epilogue that holds TMEM.",
             "traffic": traffic.get(kernel + "_10k_x_10k_fov360_dram_bytes") if at_baseline else None,
             "traffic_source": traffic.get(kernel + "_source", traffic.get("source")) if at_baseline else None,
+            "hbm": {"algorithmic_bytes": 2 * 10000 * 64 * 64 * 2 * 2, "note": "fp16 operands of both sides are read from HBM once (164 MB + tables); "
+                    "the sweep re-reads them from L2"},
             "tensor": {"executed_tflops": exec_tf, "peak": sustained, "frac": exec_tf / sustained, "flop_per_pair_executed": int(SPEC_TC_FLOP_PER_PAIR),
                        "note": "tensor pipe as executed; the roofline-bound tensor kernel of the path is `dense_sweep`"},
             "algorithmic_speedup": {"flop_per_pair_direct": FLOP_PER_PAIR, "flop_per_pair_executed": int(SPEC_TC_FLOP_PER_PAIR),
@@ -834,7 +853,9 @@ def run_ours(args):
                 "true-match distances -> tcgen05 sweep (argmax, distance, rank count, top-k candidates; decisions inside the fp16 error bound "
                 "deferred) -> top-k merge -> fp32 finish (deferred rank decisions, top-k re-rank, completeness proof)%s"
                 % ("azimuth spectra in UMMA layout" if sweep_impl == "spectral" else "Hankel blocks",
-                   "" if world == 1 else "; gallery sharded, one shard per GPU, NCCL all-reduce of the thresholds + one all-gather of counts and top-k"),
+                   "" if world == 1 else ("; gallery sharded, one shard per GPU; thresholds, counts and top-k exchanged over peer memory (NVLink stores "
+                                          "from the library's kernels + flags)" if peer_used else
+                                          "; gallery sharded, one shard per GPU, NCCL all-reduce of the thresholds + one all-gather of counts and top-k")),
         "pipelining": "one step deep: step i+1 is enqueued before the host reads step i's 4-byte finish flag",
         "l2_window": bool(args.l2_window),
         "spin_up": {"steps": n_spin, "ms_per_step": spin_ms, "rest_s": float(os.environ.get("WITW_BENCH_REST", "1.0")),
@@ -975,7 +996,33 @@ def multi_gpu_extras(torch, dist, W, ops, device, world, rank):
             ms = torch.tensor([t0.elapsed_time(t1) / 20], device=device)
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
             res[name + "_ms"] = float(ms.item())
-        res["note"] = "per step: all-reduce of [Q] thresholds + exchange of [Q] counts and [Q,%d] top-k + merge; packed = one all-gather (default)" % TOPK
+        # the same exchange over peer memory (witw_b200/peer.py): two kernels of the library, NVLink stores + flags
+        from witw_b200 import peer
+        px = peer.get(Q_TOTAL, TOPK, device=device) if sharded.PEER_EXCHANGE else None
+        if px is not None:
+            c32 = counts.to(torch.int32)
+            t_idx = torch.arange(Q_TOTAL, device=device) % (world * G_PER_GPU)
+            flagged = torch.zeros(1, dtype=torch.int32, device=device)
+
+            def exch_peer():
+                px.thresholds(d_true, t_idx, rank * G_PER_GPU, G_PER_GPU)
+                px.results(c32, td, ti, flagged)
+            for _ in range(3):
+                exch_peer()
+            dist.barrier()
+            torch.cuda.synchronize()
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+            for _ in range(20):
+                exch_peer()
+            t1.record()
+            torch.cuda.synchronize()
+            ms = torch.tensor([t0.elapsed_time(t1) / 20], device=device)
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            res["peer_ms"] = float(ms.item())
+        res["used"] = "peer" if px is not None else "packed"
+        res["note"] = ("per step: [Q] thresholds to every rank + exchange of [Q] counts and [Q,%d] top-k + merge; peer = NVLink stores from the library's "
+                       "own kernels + flags (default), packed = NCCL all-reduce + one all-gather, separate = all-reduce + all-reduce + two all-gathers" % TOPK)
         out["exchange"] = res
     except Exception as exc:
         out["exchange"] = {"error": "%s: %s" % (type(exc).__name__, str(exc)[:300])}
@@ -996,6 +1043,7 @@ def main():
     ap.add_argument("--fov", type=int, default=FOV, help="field of view of the queries in degrees (default 360; 90 = BASELINE configs[2] / [4])")
     ap.add_argument("--queries", type=int, default=Q_TOTAL, help="number of queries (default 10000)")
     ap.add_argument("--noise", type=float, default=NOISE, help="noise of the planted matches (default 0.5: every match is rank 1; see the `hard` key)")
+    ap.add_argument("--no-peer-exchange", action="store_true", help="N > 1: exchange over NCCL collectives instead of peer memory")
     ap.add_argument("--l2-window", action="store_true",
                     help="experiment: an L2 access-policy window over the query operand while the sweep runs (ops.L2_WINDOW)")
     ap.add_argument("--no-extras", action="store_true",

@@ -320,6 +320,32 @@ int witw_finish_spec_f32(const witw_finish_args* args, witw_stream_t stream);
 size_t witw_sizeof_sweep_args(void);
 size_t witw_sizeof_finish_args(void);
 
+/* ---- peer-memory exchange of a gallery-sharded evaluation (csrc/peer.cu; witw_b200/sharded.py) ----
+ * The reference evaluates on one GPU (cvig_fov.py:519-552); with the gallery sharded over the GPUs of a box the rank rule needs
+ * the true-match distances everywhere before the sweep and the sum of the rank counts / the merge of the top-k lists after it.
+ * Each rank owns one exchange buffer (witw_peer_alloc: cudaMalloc + a 64-byte CUDA IPC handle for the other ranks'
+ * witw_peer_open); peers_dev is a DEVICE array of `world` buffer addresses as this rank sees them, own buffer at [rank].
+ * Both calls store this rank's part into every rank's buffer over NVLink, signal, wait for every peer's signal of the same
+ * sequence number (seq = 1, 2, ... identical on all ranks, one per call) and finish locally:
+ *   witw_peer_thresholds: d_local [Q] holds the fp32 distance of query q to item true_idx[q] where this rank owns that item
+ *        (g_offset <= true_idx[q] < g_offset + g_local); d_true_out [Q] receives the complete vector.
+ *   witw_peer_results: counts [Q] int32, td / ti [Q,k] (k may be 0), flagged [1] or NULL of this shard -> total_out [Q] int64
+ *        (the summed counts), n_flag_out [1] (the summed flags; bit 30: a wait timed out), merged_dist / merged_idx [Q,k]
+ *        (witw_topk_merge over the ranks' lists in rank order).
+ * world <= 16; k the same in both calls of an evaluation. */
+size_t witw_peer_exchange_bytes(int64_t Q, int k, int world);
+int witw_peer_alloc(size_t bytes, void** buf_dev, void* ipc_handle_64);
+int witw_peer_open(const void* ipc_handle_64, void** buf_dev);
+int witw_peer_close(void* buf_dev);
+int witw_peer_free(void* buf_dev);
+int witw_peer_thresholds(const float* d_local_dev, const int64_t* true_idx_dev, int64_t g_offset, int64_t g_local,
+                         int64_t Q, int k, void* const* peers_dev, int world, int rank, uint32_t seq,
+                         float* d_true_out_dev, witw_stream_t stream);
+int witw_peer_results(const int32_t* counts_dev, const float* td_dev, const int32_t* ti_dev, const int32_t* flagged_dev,
+                      int64_t Q, int k, void* const* peers_dev, const void* own_buf_dev, int world, int rank,
+                      uint32_t seq, int64_t* total_out_dev, int32_t* n_flag_out_dev, float* merged_dist_dev,
+                      int32_t* merged_idx_dev, witw_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * K4  rank / top-k               replaces model/cvig_fov.py:550-552 and
  *                                model/cvig_baseline.py:456-460

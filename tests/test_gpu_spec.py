@@ -368,3 +368,33 @@ def test_one_query_calls_reuse_the_prepared_gallery_safely(W):
     assert same(W.correlation(b, su[:1].cuda()), ov, 0)
     W.ops.clear_cache()
     assert len(W.ops._index_cache) == 0
+
+
+@pytest.mark.parametrize("fov,G,Q", [(360, 9, 130), (360, 17, 64), (90, 1003, 129), (180, 4099, 515), (360, 8, 1), (360, 24, 200)])
+def test_spec_cta_pair_tiling_equals_one_cta_per_tile(W, fov, G, Q):
+    """The CTA-pair sweep (tcgen05 cta_group::2, a pair shares the gallery operand; csrc/match_spec.cu) and the one-CTA-per-tile
+    sweep run the same operands through the same accumulation order: every raw output is bit-identical -- on ragged sizes too
+    (an odd number of 8-item groups leaves the pair's second CTA a group of zeros past the operand's end)."""
+    from witw_b200 import _lib, ops
+
+    ov, su, _ = O.synth_features(G, Q, fov=fov, noise=3.0, seed=G + Q)
+    gal, qry = ops.GalleryIndex(ov.cuda(), su.shape[3]), ops.QueryBatch(su.cuda())
+    pq = torch.arange(Q, device="cuda") % G
+    d_true, _ = ops.pair_distances_prepared(gal, qry, pq, torch.arange(Q, device="cuda"))
+    outs = []
+    try:
+        for variant in (1, 2):
+            _lib.call("witw_match_spec_variant", variant)
+            for want_ori in (True, False):             # with / without the shift of the maximum (the two epilogues)
+                cnt = torch.zeros(Q, dtype=torch.int32, device="cuda")
+                r = ops.sweep_tc(gal, qry, want_dist=True, want_ori=want_ori, d_true=d_true, true_idx=pq.to(torch.int32), rank_count=cnt, topk=16)
+                torch.cuda.synchronize()
+                outs.append((r["dist"].view(torch.int32), r["ori"], cnt, r["topk_dist"].view(torch.int32), r["topk_idx"]))
+    finally:
+        _lib.call("witw_match_spec_variant", 2)
+    for a, b in ((outs[0], outs[2]), (outs[1], outs[3])):
+        for x, y in zip(a, b):
+            assert (x is None and y is None) or torch.equal(x, y)
+    # and the no-argmax epilogue of a full panorama gives the distances of the argmax epilogue
+    if su.shape[3] == 64:
+        assert torch.equal(outs[2][0], outs[3][0]) and torch.equal(outs[2][2], outs[3][2])

@@ -1,16 +1,24 @@
 #!/usr/bin/env python
-"""The measured roof of the spectral sweep's data flow (csrc/match_spec.cu): the shared-memory operand ring, written by TMA
-and read by N=16 UMMAs.  Runs the kernel's own ring at 10k x 10k with the epilogue's work switched off, piece by piece,
-through the WITW_SPEC_DEBUG switches of the hooks build (make -C witw_b200/csrc HOOKS=1 -> libwitw_b200_hooks.so; the
-switches give wrong results by design and do not exist in the shipped library):
+"""The measured roofs of the spectral sweep (csrc/match_spec.cu): each stage of the kernel's own pipeline running alone.
 
-    full      everything                                              the shipped kernel's time
-    ring      TMA writes + MMA reads, epilogue reduced to its barriers   the roof of the ring  (bits 0|1: no IFFT, no TMEM loads)
-    tma_only  TMA writes only                                         (bits 0|1|2: no tcgen05.mma)
-    mma_only  MMA reads + gallery loads only                          (bits 0|1|8: no query-stage loads)
+The kernel is a three-stage pipeline per tile (1 024 pairs per CTA): TMA brings the fp16 operands from L2 into the
+shared-memory ring, tcgen05.mma turns them into 64 accumulators per pair in TMEM, and the epilogue warps turn those into
+distances (inverse FFT, maximum, rank count, top-k) on the CUDA cores.  This tool runs that same kernel at 10k x 10k with parts
+of it switched off, through the WITW_SPEC_DEBUG switches of the hooks build (make -C witw_b200/csrc HOOKS=1 ->
+libwitw_b200_hooks.so; the switches give wrong results by design and do not exist in the shipped library):
 
-One subprocess per mode (the switches are read once per process).  Writes profiles/smem_ring_roof.json, which bench.py's
-`roofline.peak` quotes: bytes through the ring per SM per second in `ring` mode.
+    full            everything                                                          the kernel's time
+    ring_alone      TMA + MMAs, no epilogue, no per-tile TMEM hand-off (bits 0|1|7)      the operand ring's roof: what bounds it is
+                                                                                        the L2 -> SM delivery of the operands
+    tma_alone       TMA only (bits 0|1|2|7)                                             L2 -> shared memory at the ring's own depth
+    mma_alone       MMAs + gallery loads only (bits 0|1|3|7)                             the tensor pipe on N=16-per-CTA MMAs
+    epilogue_alone  the epilogue and the per-tile hand-off, no ring (bit 5)              the CUDA-core roof
+    ring            TMA + MMAs + per-tile hand-off with an (almost) empty epilogue (bits 0|1)
+    protocol_only   barriers and 4 KB gallery loads only (bits 0|1|2|3)
+
+One subprocess per mode (the switches are read once per process).  WITW_RING_VARIANT = 2 (CTA pairs, default) or 1.  Writes
+gpurun_out/sweep_roof_v<variant>.json; profiles/sweep_roof_r2.json is a copy of the variant-2 file and is what bench.py's
+`roofline.peak` quotes.
 """
 import json
 import os
@@ -18,10 +26,11 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-MODES = (("full", 0), ("ring", 3), ("tma_only", 7), ("mma_only", 11), ("epilogue_only", 12), ("epilogue_alone", 32), ("protocol_only", 15), ("protocol_nocommit", 15 + 64), ("tma_nocommit", 7 + 64), ("ring_nohandshake", 3 + 128), ("protocol_nohandshake", 15 + 128))
-# written by TMA + read by the MMAs, per (query, item) pair: one CTA per tile 36 + 36 KB per slot and 1 024 pairs; CTA pairs
-# 20 KB written, 16 KB of queries + 8 KB of items (its own, read by both tensor cores) read per CTA, slot and 1 024 pairs
-BYTES_PER_PAIR = {1: 2.0 * (256 * 4608) / 1024.0, 2: 32.0 * (20480 + 24576) / 1024.0}
+MODES = (("full", 0), ("ring_alone", 3 + 128), ("tma_alone", 7 + 128), ("mma_alone", 11 + 128), ("epilogue_alone", 32), ("ring", 3),
+         ("protocol_only", 15))
+# operand bytes TMA delivers per (query, item) pair: a CTA pair stages 16 KB of query spectra + 4 KB of gallery spectra per slot
+# and CTA for 1 024 pairs per CTA; one CTA per tile stages 32 + 4 KB
+TMA_BYTES_PER_PAIR = {1: 32.0 * 36864 / 1024.0, 2: 32.0 * 20480 / 1024.0}
 VARIANT = int(os.environ.get("WITW_RING_VARIANT", "2"))
 
 
@@ -60,21 +69,20 @@ def main():
     res = {}
     only = os.environ.get("WITW_RING_MODES")
     for name, bits in MODES:
-        if only and name not in only.split(",") and name not in ("full", "ring"):
+        if only and name not in only.split(",") and name != "full":
             continue
         env = dict(os.environ, WITW_SPEC_DEBUG=str(bits))
         out = subprocess.check_output([sys.executable, os.path.abspath(__file__), "--child"], env=env, text=True)
         res[name] = json.loads(out.strip().splitlines()[-1])["kernel_ms"]
     pairs = 1e8
-    bpp = BYTES_PER_PAIR[VARIANT]
-    gbs = {k: bpp * pairs / 148.0 / (v / 1000.0) / 1e9 for k, v in res.items()}
+    bpp = TMA_BYTES_PER_PAIR[VARIANT]
     rec = {"workload": "10k x 10k, 360 deg, spectral sweep, counts + top-16", "variant": VARIANT, "kernel_ms": res,
-           "ring_gbs_per_sm_at_that_time": gbs, "gbs_per_sm": gbs["ring"],
-           "bytes_per_pair": bpp,
-           "source": "tools/ring_roof.py on B200: match_spec_kernel's own TMA-write + UMMA-read ring with the epilogue arithmetic and TMEM loads "
-                     "switched off (hooks build, WITW_SPEC_DEBUG=3); full kernel %.3f ms, ring alone %.3f ms" % (res["full"], res["ring"])}
+           "tma_bytes_per_pair": bpp,
+           "operand_delivery_tbs": {k: bpp * pairs / (v / 1000.0) / 1e12 for k, v in res.items() if k in ("full", "ring_alone", "tma_alone")},
+           "source": "tools/ring_roof.py on B200: match_spec_kernel's own pipeline stages running alone (hooks build, WITW_SPEC_DEBUG); "
+                     + ", ".join("%s %.3f ms" % (k, v) for k, v in res.items())}
     print(json.dumps(rec, indent=1))
-    out_path = os.path.join(ROOT, "gpurun_out", "smem_ring_roof_v%d.json" % VARIANT)
+    out_path = os.path.join(ROOT, "gpurun_out", "sweep_roof_v%d.json" % VARIANT)
     os.makedirs(os.path.dirname(out_path), exist_ok=True)
     with open(out_path, "w") as f:
         json.dump(rec, f, indent=1)

@@ -1,4 +1,6 @@
 #!/bin/bash
 cd "$GRAFT_REPO_ROOT"
-timeout 300 python tools/spec_pair_ab.py > gpurun_out/pair_ab.log 2>&1; echo "ab rc=$?"; tail -8 gpurun_out/pair_ab.log
-timeout 900 python -m pytest tests/test_gpu_spec.py -x -q -m gpu 2>&1 | tail -5
+nvidia-smi -L
+timeout 400 python -m pytest tests/test_gpu_peer.py -x -q -m gpu 2>&1 | tail -15
+CUDA_VISIBLE_DEVICES=0 timeout 400 python -m pytest tests/test_gpu_peer.py -x -q -m gpu 2>&1 | tail -15
+bash tools/runs/multi_gpu.sh 2 r2n

@@ -6,7 +6,7 @@ raised.  Build the library with ``python -c "import __graft_entry__ as g; g.buil
 """
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_uint8, c_void_p
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_uint8, c_uint32, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libwitw_b200.so")
@@ -67,6 +67,14 @@ SIGNATURES = {
     "witw_match_spec_topk_slots": (c_int, [c_int64, c_int64]),
     "witw_match_spec": (c_int, [c_void_p, c_void_p]),
     "witw_match_spec_variant": (c_int, [c_int]),
+    "witw_peer_exchange_bytes": (c_size_t, [c_int64, c_int, c_int]),
+    "witw_peer_alloc": (c_int, [c_size_t, c_void_p, c_void_p]),
+    "witw_peer_open": (c_int, [c_void_p, c_void_p]),
+    "witw_peer_close": (c_int, [c_void_p]),
+    "witw_peer_free": (c_int, [c_void_p]),
+    "witw_peer_thresholds": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_int, c_int, c_uint32, c_void_p, c_void_p]),
+    "witw_peer_results": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int, c_int, c_uint32,
+                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "witw_rank_from_dist_f32": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
     "witw_l2_rank_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "witw_topk_slices": (c_int, [c_int64, c_int64]),

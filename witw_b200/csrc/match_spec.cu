@@ -69,8 +69,7 @@ constexpr int kSpMaxChunks = 32;       // two candidate lists per chunk (four wi
 // Timing experiments (wrong results by design) exist only in builds with -DWITW_DEBUG_HOOKS (tools/ probes): WITW_SPEC_DEBUG
 // bit 0 = no inverse FFT, bit 1 = no TMEM loads in the epilogue, bit 2 = no tcgen05.mma (barriers only), bit 3 = no
 // query-stage loads, bit 4 = chunk-major work order, bit 5 = no operand ring at all (the epilogue and the per-tile handshake
-// alone), bit 6 = stages are released by a plain mbarrier arrive instead of tcgen05.commit, bit 7 = no per-tile handshake and no
-// epilogue (the ring alone).  The shipped library never reads the environment.
+// alone), bit 7 = no per-tile handshake and no epilogue (the ring alone).  The shipped library never reads the environment.
 #ifdef WITW_DEBUG_HOOKS
 static int spec_debug() {
   static int v = -1;
@@ -455,10 +454,7 @@ match_spec_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_consta
               umma_bf16<CG>(tmem_d, da + (uint64_t)(h * (kA >> 5) + 2 * j), db + (uint64_t)(h * (kSpBBytes >> 5) + 2 * j), kIdesc,
                             (h | j) != 0 ? 1u : 0u);
         }
-        if (SPEC_DBG(P, 64)) {   // (timing experiment: no tcgen05.commit on the stage's way back)
-          bar_arrive_local(empty_k);
-          if (CG == 2) bar_arrive_cluster(empty_k, 1);
-        } else if (!SPEC_DBG(P, 32)) umma_commit<CG>(empty_k);          // frees the stage (in both CTAs) when these MMAs retire
+        if (!SPEC_DBG(P, 32)) umma_commit<CG>(empty_k);          // frees the stage (in both CTAs) when these MMAs retire
         if ((c + NI) / kSpSlots != tile_it && !SPEC_DBG(P, 128)) umma_commit<CG>(s2u(tmem_full));  // this warp's last slot of the tile
       }
       __syncwarp();

@@ -416,7 +416,7 @@ match_tc_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant
         __syncwarp();
         if (lane == 0) {
           if (CG == 1 || leader) bar_arrive_local(s2u(&tmem_empty[acc]));
-          else bar_arrive_cluster(s2u(&tmem_empty[acc]), 0);
+          else bar_arrive_remote(s2u(&tmem_empty[acc]), 0);   // (CTA-scope release: no GPU-wide fence per group)
         }
         // pin the tail below the release of the accumulator stage (see match_spec.cu: the compiler otherwise delays the arrive)
 #pragma unroll

@@ -37,11 +37,6 @@ __device__ __forceinline__ void bar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void bar_arrive_local(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void bar_arrive_cluster(uint32_t local_bar, uint32_t cta_rank) {
-  uint32_t remote;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_bar), "r"(cta_rank));
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
-}
 // Tile-mode TMA load.  CG == 2: both CTAs of the pair run this; the bytes land in the issuing CTA's shared
 // memory and complete_tx is signalled on the LEADER CTA's mbarrier (bar is a shared::cluster address).
 template <int CG>
@@ -58,9 +53,9 @@ __device__ __forceinline__ void tma_2d(uint32_t dst, const CUtensorMap* map, uin
         : "memory");
   }
 }
-// The same arrive with the default (CTA-scope) release: no GPU-wide fence (MEMBAR.ALL.GPU, ~1 us).  For hand-offs whose payload is
-// not ordinary memory -- an accumulator stage whose tcgen05.ld have completed (tcgen05.wait::ld +
-// tcgen05.fence::before_thread_sync order those).
+// Arrive on the peer CTA's barrier with the default (CTA-scope) release.  The payload of these hand-offs is not ordinary
+// memory -- an accumulator stage whose tcgen05.ld have completed (tcgen05.wait::ld + tcgen05.fence::before_thread_sync order
+// those) -- so the cluster-scope release of the first version, which compiles to MEMBAR.ALL.GPU (~1 us per arrive), is not needed.
 __device__ __forceinline__ void bar_arrive_remote(uint32_t local_bar, uint32_t cta_rank) {
   uint32_t remote;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_bar), "r"(cta_rank));

@@ -151,6 +151,11 @@ class _Pending(object):
         return self.ev.flagged > 0
 
 
+# The exchange over peer memory (witw_b200/peer.py, csrc/peer.cu): NVLink stores from the library's own kernels + flags instead of
+# NCCL collectives.  Used when the group's ranks are CUDA ranks of one node and every rank could open every buffer; the NCCL
+# path below is the fallback (and the gloo path of the CPU tests).
+PEER_EXCHANGE = True
+
 # One all-gather of [counts | top-k distances | top-k indices] per rank instead of an all-reduce and two all-gathers: two
 # collective launches fewer per sweep (bench.py's `exchange` key times both forms over NCCL).  packed=False keeps the
 # separate collectives.
@@ -193,6 +198,10 @@ class ShardedEvaluation(object):
         dev = surface_embed.device
         q = surface_embed.shape[0]
         g_local = ov_local.shape[0]
+        self.peer = None
+        if self.world > 1 and PEER_EXCHANGE and packed is None and surface_embed.is_cuda and q > 0:
+            from . import peer
+            self.peer = peer.get(q, self.topk, group=group, device=dev)
         if true_idx is None:
             if q > n_gallery_total:
                 raise IndexError("evaluate_ranks_sharded: %d queries but only %d gallery items and no true_idx" % (q, n_gallery_total))
@@ -208,7 +217,9 @@ class ShardedEvaluation(object):
             mine = (t_idx >= g_offset) & (t_idx < g_offset + g_local)
             d = self.local.true_distances(ov_local, surface_embed, (t_idx - g_offset).clamp(0, g_local - 1))
             d_true = torch.where(mine, d.to(torch.float32), d_true)
-        if self.world > 1:
+        if self.peer is not None:
+            d_true = self.peer.thresholds(d_true, t_idx, g_offset, g_local)     # the owners' values, stored into every rank's buffer
+        elif self.world > 1:
             dist.all_reduce(d_true, op=dist.ReduceOp.SUM, group=group)
         # (2) local sweep
         if hasattr(self.local, "launch"):
@@ -227,6 +238,14 @@ class ShardedEvaluation(object):
             self._local_flag = flagged is not None
             return
         q = counts.shape[0]
+        if self.peer is not None:
+            total, md, mi, n_flag = self.peer.results(counts.to(torch.int32), td if self.topk else None, ti if self.topk else None, flagged)
+            self.out = (total, md, mi)
+            self._n_host = torch.empty((), dtype=torch.int32, pin_memory=True)
+            self._n_host.copy_(n_flag[0], non_blocking=True)
+            self._flag_event = torch.cuda.Event()
+            self._flag_event.record()
+            return
         if self.packed and q > 0:
             total, all_d, all_i, n_flag = _exchange_packed(counts, td, ti, self.world, self.group, flagged)
         else:
@@ -262,6 +281,8 @@ class ShardedEvaluation(object):
         else:
             if self._flag_event is not None:
                 self._flag_event.synchronize()
+            if int(self._n_host) & (1 << 30):
+                raise RuntimeError("evaluate_ranks_sharded: the peer-memory exchange timed out waiting for another rank")
             if int(self._n_host) > 0:          # somebody's finish flagged a query: every rank re-does its own, then all exchange again
                 self.handle.finish()
                 self.handle = _Done(*self.handle.provisional()[:3])

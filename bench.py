@@ -687,12 +687,20 @@ def run_ours(args):
     free = [torch.cuda.Event() for _ in range(2)]
     copy_stream = torch.cuda.Stream(device=device)
 
+    # The replicated query set crosses PCIe once per step in the whole job: every rank uploads 1/N of it (with one rank uploading
+    # all of it that rank carries twice the bytes of the others and paces the job) and the slices are all-gathered over NVLink.
+    q_split = world > 1 and Q_TOTAL % world == 0
+    q_lo, q_hi = (rank * (Q_TOTAL // world), (rank + 1) * (Q_TOTAL // world)) if q_split else (0, Q_TOTAL)
+    q_part = [torch.empty_like(su[q_lo:q_hi]) for _ in range(2)] if q_split else None
+
     def upload(i):
         b = i % 2
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(free[b])            # the step that last used this buffer has finished with it
             bufs[b][0].copy_(ov_host, non_blocking=True)
-            if rank == 0:                              # the replicated query set crosses PCIe once, on rank 0 ...
+            if q_split:
+                q_part[b].copy_(su_host[q_lo:q_hi], non_blocking=True)
+            elif rank == 0:
                 bufs[b][1].copy_(su_host, non_blocking=True)
             ready[b].record(copy_stream)
 
@@ -730,8 +738,10 @@ def run_ours(args):
             if i + 1 < n:
                 upload(i + 1)
             torch.cuda.current_stream().wait_event(ready[b])
-            if world > 1:
-                dist.broadcast(bufs[b][1], src=0)      # ... and reaches the other ranks over NVLink
+            if q_split:
+                dist.all_gather_into_tensor(bufs[b][1], q_part[b])     # the other ranks' slices arrive over NVLink
+            elif world > 1:
+                dist.broadcast(bufs[b][1], src=0)
             if world == 1:
                 cur = ops.RankEvaluation(ops.GalleryIndex(bufs[b][0], SW), ops.QueryBatch(bufs[b][1]), true_idx=true_idx, topk=TOPK)
                 free[b].record()
@@ -773,12 +783,14 @@ def run_ours(args):
     u0.record()
     for _ in range(3):
         bufs[0][0].copy_(ov_host, non_blocking=True)
-        if rank == 0:
+        if q_split:
+            q_part[0].copy_(su_host[q_lo:q_hi], non_blocking=True)
+        elif rank == 0:
             bufs[0][1].copy_(su_host, non_blocking=True)
     u1.record()
     torch.cuda.synchronize()
     h2d_alone_ms = u0.elapsed_time(u1) / 3
-    h2d = ov_host.numel() * 4 + su_host.numel() * 4     # rank 0; the other ranks upload their gallery shard only
+    h2d = ov_host.numel() * 4 + (q_hi - q_lo) * su_host[0].numel() * 4     # per rank: its gallery shard + its slice of the queries
     d2h = sum(t.numel() * t.element_size() for t in e2e_out)
     del bufs
 
@@ -869,10 +881,11 @@ def run_ours(args):
         "config_detail": detail,
         "roofline": roofline,
         "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / steps,
-                "h2d_alone_ms": h2d_alone_ms, "h2d_alone_gbs": h2d / h2d_alone_ms / 1e6,
+                "h2d_alone_ms": h2d_alone_ms, "h2d_alone_gbs": h2d / h2d_alone_ms / 1e6, "h2d_bytes_per_step_all_ranks": h2d * world,
                 "note": "gallery and queries uploaded from pinned host memory every step, W.GalleryIndex / QueryBatch / RankEvaluation on them; H2D of step "
                         "i+1 double-buffered on a copy stream behind step i, D2H of step i's ranks and top-k into pinned host memory on a third stream"
-                        + ("" if world == 1 else "; every rank uploads its gallery shard, rank 0 also the replicated query set, which is then broadcast over NCCL")},
+                        + ("" if world == 1 else "; every rank uploads its gallery shard and 1/N of the replicated query set (h2d_bytes_per_step is per rank), "
+                           "the query slices are all-gathered over NCCL")},
         # per step: gallery prep, query prep, spectral_pairs (true match), the sweep, topk_merge, finish_scan / _pairs / _topk
         # (hankel: item_stats + gallery_blocks instead of one gallery prep, + spectral_rows x2)
         "gpu_launches": (8 if sweep_impl == "spectral" else 11) * steps,

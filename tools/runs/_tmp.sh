@@ -1,6 +1,3 @@
 #!/bin/bash
 cd "$GRAFT_REPO_ROOT"
-nvidia-smi -L
-timeout 400 python -m pytest tests/test_gpu_peer.py -x -q -m gpu 2>&1 | tail -15
-CUDA_VISIBLE_DEVICES=0 timeout 400 python -m pytest tests/test_gpu_peer.py -x -q -m gpu 2>&1 | tail -15
-bash tools/runs/multi_gpu.sh 2 r2n
+timeout 400 python tools/ring_roof.py > gpurun_out/ring_r2p.log 2>&1; echo "rc=$?"; tail -22 gpurun_out/ring_r2p.log

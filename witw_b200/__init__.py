@@ -43,6 +43,7 @@ from .ops import (
 )
 from .heatmap import heatmap_sweep, prefetch_to_device, prepare_tiles, streamed_polar
 from .install import install, uninstall
+from . import peer, sharded
 from .sharded import ShardedEvaluation, evaluate_ranks_sharded, shard_bounds
 
 __all__ = [

@@ -316,7 +316,7 @@ match_spec_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_consta
   constexpr int NS = CG == 2 ? kSpStagesPair : kSpStages;   // ring depth
   constexpr int NP = CG == 2 ? kSpProducersPair : 2;        // producer warps; warp p owns the stages = p (mod NP)
   constexpr int NI = CG == 2 ? kSpIssuersPair : kSpStages;  // issuer warps; warp k owns the stages = k (mod NI)
-  static_assert(NS % NP == 0 && NS % NI == 0 && NP + NI <= 8, "control warps own whole residue classes of the ring's stages");
+  static_assert(NP + NI <= 8, "eight control warps");
   // kind::f16: D fp32 (bit 4), A and B fp16 (format fields 0), both K-major, N = 16 per CTA, M = 128
   constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)((16 * CG) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 

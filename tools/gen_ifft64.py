@@ -5,9 +5,8 @@ Input: a Hermitian spectrum in the packed form of csrc/spectral.cu -- re[0] = P_
 (re[f], im[f]) = P_f for f = 1..31 -- already scaled by 1/64.  Output: x[s] = sum_{f=0}^{63} P_f e^{+2 pi i f s / 64},
 s = 0..63 (P_{64-f} = conj P_f), i.e. numpy.fft.irfft of the unscaled spectrum.
 
-Method: the 64 real outputs are the 32 complex points z[n] = x[2n] + i x[2n+1] of
-    Z[k] = (P_k + conj P_{32-k}) + i w^k (P_k - conj P_{32-k}),   w = e^{2 pi i / 64},
-followed by a 32-point radix-2 decimation-in-time inverse FFT with literal twiddles (trivial ones folded).
+Method: real-data split radix (hermitian_to_real below): 487 operations; the first version (the half-length complex sequence
+z[n] = x[2n] + i x[2n+1] through a 32-point radix-2 FFT) needed 612.
 The script checks the generated operation list in float32 against numpy.fft.irfft before writing the file.
 
 Usage: python tools/gen_ifft64.py   (rewrites the header in place; the header is committed)
@@ -84,67 +83,70 @@ class PackedEmitter(Emitter):
         return self._new("__ffma2_rn(%s, make_float2(%s, %s), %s)" % (a, self.lit(c), self.lit(c), b), v)
 
 
-def brev5(i):
-    return int("{:05b}".format(i)[::-1], 2)
+def cmul(e, v, ang):
+    """(v.re + i v.im) e^{i ang}: two multiplications and two fused multiply-adds."""
+    c, s = math.cos(ang), math.sin(ang)
+    p = e.mulc(v[1], -s)
+    re = e.fmac(v[0], c, p)              # v.re c - v.im s
+    q = e.mulc(v[1], c)
+    im = e.fmac(v[0], s, q)              # v.re s + v.im c
+    return (re, im)
+
+
+def hermitian_to_real(e, n, X):
+    """Unnormalised inverse DFT x[m] = sum_{k<n} X[k] e^{+2 pi i k m / n} of a Hermitian spectrum given as X[0..n/2] (pairs of
+    variable names; X[0] and X[n/2] are real: their second entry is None).  Real-data split radix, decimation in time of the
+    output: the even outputs are the half-size transform of X[k] + X[k + n/2], the outputs 4m+1 and 4m+3 the quarter-size
+    transforms of w^k (U + iV) and w^{3k} (U - iV), U = X[k] - X[k + n/2], V = X[k + n/4] - X[k + 3n/4], w = e^{2 pi i / n};
+    X[n - j] = conj X[j] brings every index back into 0..n/2.  n (5 n / 2 - 6 at the top level) fewer operations per level than
+    transforming the half-length complex sequence."""
+    if n == 1:
+        return [X[0][0]]
+    if n == 2:
+        return [e.add(X[0][0], X[1][0]), e.sub(X[0][0], X[1][0])]
+    h, q = n // 2, n // 4
+    E = [None] * (q + 1)
+    E[0] = (e.add(X[0][0], X[h][0]), None)
+    for k in range(1, q):
+        a, b = X[k], X[h - k]
+        E[k] = (e.add(a[0], b[0]), e.sub(a[1], b[1]))
+    E[q] = (e.mulc(X[q][0], 2.0), None)
+    even = hermitian_to_real(e, h, E)
+    # odd outputs
+    Y = [None] * (q // 2 + 1)
+    Z = [None] * (q // 2 + 1)
+    u0 = e.sub(X[0][0], X[h][0])                      # U real, iV = -2 Im X[n/4]
+    Y[0] = (e.fmac(X[q][1], -2.0, u0), None)
+    Z[0] = (e.fmac(X[q][1], 2.0, u0), None)
+    for k in range(1, q // 2):
+        a, b, c, d = X[k], X[h - k], X[k + q], X[q - k]
+        ur, ui = e.sub(a[0], b[0]), e.add(a[1], b[1])     # U = X[k] - conj X[n/2 - k]
+        vr, vi = e.sub(c[0], d[0]), e.add(c[1], d[1])     # V = X[k + n/4] - conj X[n/4 - k]
+        s_ = (e.sub(ur, vi), e.add(ui, vr))               # U + iV
+        t_ = (e.add(ur, vi), e.sub(ui, vr))               # U - iV
+        Y[k] = cmul(e, s_, 2 * math.pi * k / n)
+        Z[k] = cmul(e, t_, 2 * math.pi * 3 * k / n)
+    if q >= 2:                                            # k = n/8: V = -conj U, both results are real
+        k = q // 2
+        a, b = X[k], X[h - k]
+        ur, ui = e.sub(a[0], b[0]), e.add(a[1], b[1])
+        Y[k] = (e.mulc(e.sub(ur, ui), math.sqrt(2.0)), None)
+        Z[k] = (e.mulc(e.add(ur, ui), -math.sqrt(2.0)), None)
+    o1 = hermitian_to_real(e, q, Y)
+    o3 = hermitian_to_real(e, q, Z)
+    out = [None] * n
+    for m in range(h):
+        out[2 * m] = even[m]
+    for m in range(q):
+        out[4 * m + 1] = o1[m]
+        out[4 * m + 3] = o3[m]
+    return out
 
 
 def build(e, re, im):
     """re/im: lists of 32 input variable names.  Returns list of 64 output variable names."""
-    z = [None] * 32
-    # k = 0: (P0 + P32, P0 - P32)
-    z[0] = (e.add(re[0], im[0]), e.sub(re[0], im[0]))
-    # k = 16: (2 a16, -2 b16)
-    z[16] = (e.mulc(re[16], 2.0), e.mulc(im[16], -2.0))
-    for k in range(1, 16):
-        kk = 32 - k
-        ar = e.add(re[k], re[kk])
-        ai = e.sub(im[k], im[kk])
-        dr = e.sub(re[k], re[kk])
-        di = e.add(im[k], im[kk])
-        c, s = math.cos(2 * math.pi * k / 64), math.sin(2 * math.pi * k / 64)
-        # T = D * w^k
-        p = e.mulc(di, -s)
-        tr = e.fmac(dr, c, p)            # dr*c - di*s
-        q = e.mulc(di, c)
-        ti = e.fmac(dr, s, q)            # dr*s + di*c
-        # Z_k = A + iT = (ar - ti, ai + tr);  Z_{32-k} = conj(A) + i conj(T) = (ar + ti, tr - ai)
-        z[k] = (e.sub(ar, ti), e.add(ai, tr))
-        z[kk] = (e.add(ar, ti), e.sub(tr, ai))
-    x = [z[brev5(i)] for i in range(32)]
-    m = 2
-    while m <= 32:
-        half = m // 2
-        for base in range(0, 32, m):
-            for j in range(half):
-                u, v = x[base + j], x[base + j + half]
-                ang = 2 * math.pi * j / m
-                c, s = math.cos(ang), math.sin(ang)
-                if j == 0:
-                    o1 = (e.add(u[0], v[0]), e.add(u[1], v[1]))
-                    o2 = (e.sub(u[0], v[0]), e.sub(u[1], v[1]))
-                elif 4 * j == m:  # w = i: t = (-v.im, v.re)
-                    o1 = (e.sub(u[0], v[1]), e.add(u[1], v[0]))
-                    o2 = (e.add(u[0], v[1]), e.sub(u[1], v[0]))
-                elif abs(abs(c) - abs(s)) < 1e-12:
-                    sg = 1.0 if c * s > 0 else -1.0
-                    # t.re = c*(v.re - sg*v.im), t.im = c*(v.im + sg*v.re)
-                    d = e.sub(v[0], v[1]) if sg > 0 else e.add(v[0], v[1])
-                    f = e.add(v[1], v[0]) if sg > 0 else e.sub(v[1], v[0])
-                    o1 = (e.fmac(d, c, u[0]), e.fmac(f, c, u[1]))
-                    o2 = (e.fmac(d, -c, u[0]), e.fmac(f, -c, u[1]))
-                else:
-                    p = e.mulc(v[1], -s)
-                    tr = e.fmac(v[0], c, p)
-                    q = e.mulc(v[1], c)
-                    ti = e.fmac(v[0], s, q)
-                    o1 = (e.add(u[0], tr), e.add(u[1], ti))
-                    o2 = (e.sub(u[0], tr), e.sub(u[1], ti))
-                x[base + j], x[base + j + half] = o1, o2
-        m *= 2
-    out = []
-    for n in range(32):
-        out += [x[n][0], x[n][1]]
-    return out
+    X = [(re[0], None)] + [(re[f], im[f]) for f in range(1, 32)] + [(im[0], None)]
+    return hermitian_to_real(e, 64, X)
 
 
 def main():

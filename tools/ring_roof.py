@@ -15,6 +15,7 @@ libwitw_b200_hooks.so; the switches give wrong results by design and do not exis
     epilogue_alone  the epilogue and the per-tile hand-off, no ring (bit 5)              the CUDA-core roof
     ring            TMA + MMAs + per-tile hand-off with an (almost) empty epilogue (bits 0|1)
     protocol_only   barriers and 4 KB gallery loads only (bits 0|1|2|3)
+    epilogue_no_ldtm / _no_ifft / _neither   the epilogue alone without its TMEM loads / its inverse FFT / both
 
 One subprocess per mode (the switches are read once per process).  WITW_RING_VARIANT = 2 (CTA pairs, default) or 1.  Writes
 gpurun_out/sweep_roof_v<variant>.json; profiles/sweep_roof_r2.json is a copy of the variant-2 file and is what bench.py's
@@ -27,7 +28,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 MODES = (("full", 0), ("ring_alone", 3 + 128), ("tma_alone", 7 + 128), ("mma_alone", 11 + 128), ("epilogue_alone", 32), ("ring", 3),
-         ("protocol_only", 15))
+         ("protocol_only", 15), ("epilogue_no_ldtm", 2 + 32), ("epilogue_no_ifft", 1 + 32), ("epilogue_neither", 3 + 32))
 # operand bytes TMA delivers per (query, item) pair: a CTA pair stages 16 KB of query spectra + 4 KB of gallery spectra per slot
 # and CTA for 1 024 pairs per CTA; one CTA per tile stages 32 + 4 KB
 TMA_BYTES_PER_PAIR = {1: 32.0 * 36864 / 1024.0, 2: 32.0 * 20480 / 1024.0}

@@ -1,20 +1,4 @@
 #!/bin/bash
 cd "$GRAFT_REPO_ROOT"
-nvidia-smi topo -m 2>&1 | head -30
-lscpu | grep -i "numa\|socket\|^CPU(s)\|model name"
-python - <<'PY'
-import os, pynvml
-pynvml.nvmlInit()
-n = pynvml.nvmlDeviceGetCount()
-print("devices", n, "affinity of this process", len(os.sched_getaffinity(0)))
-for i in range(n):
-    h = pynvml.nvmlDeviceGetHandleByIndex(i)
-    words = (os.cpu_count() + 63) // 64
-    try:
-        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
-        cpus = [64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1]
-        print(i, "cpus", len(cpus), cpus[:4], "...", cpus[-4:])
-    except Exception as e:
-        print(i, "err", e)
-PY
-cat /sys/devices/system/node/node*/cpulist 2>/dev/null | head
+WITW_RING_MODES=epilogue_alone,epilogue_no_ldtm,epilogue_no_ifft,epilogue_neither timeout 400 python tools/ring_roof.py > gpurun_out/ring_x.log 2>&1; python -c "
+import json; d=json.load(open('gpurun_out/sweep_roof_v2.json')); print({k: round(v,3) for k,v in d['kernel_ms'].items()})"

@@ -16,7 +16,7 @@
 //   B_f[item,1]  = [ Im O_f(r) | -Re O_f(r) ]   -> Im P_f              (slot 0: [ 0 | O_32 ]  -> P_32)
 // M = 128 queries (TMEM lanes), N = 16 = 8 gallery items x (Re, Im), and the 32 slots fill the 512 TMEM columns:
 // column 16 f + 4 (item / 2) + 2 c + item % 2.  The 64 accumulators of one (query, item) pair are 64 columns of one
-// lane, so the inverse real FFT (ifft64_gen.cuh, 612 fp32 operations) and the argmax over the shift are
+// lane, so the inverse real FFT (ifft64_gen.cuh, 487 fp32 operations) and the argmax over the shift are
 // register-local; the epilogue transforms two items at once in the two halves of packed f32x2 operations.
 //
 // Per CTA (one per SM, persistent, 16 warps): warps 0-1 TMA producers (even / odd stages), warps 2-7 MMA issuers,

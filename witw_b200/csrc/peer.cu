@@ -172,6 +172,7 @@ extern "C" int witw_peer_alloc(size_t bytes, void** buf_dev, void* ipc_handle_64
   cudaError_t e = cudaIpcGetMemHandle(&h, p);
   if (e != cudaSuccess) {
     cudaFree(p);
+    cudaGetLastError();
     return set_error(WITW_ERR_CUDA, "witw_peer_alloc: cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
   }
   std::memcpy(ipc_handle_64, &h, 64);
@@ -184,7 +185,12 @@ extern "C" int witw_peer_open(const void* ipc_handle_64, void** buf_dev) {
   cudaIpcMemHandle_t h;
   std::memcpy(&h, ipc_handle_64, 64);
   void* p = nullptr;
-  WITW_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) {
+    cudaGetLastError();   // not sticky: the caller falls back to the collectives, later launch checks must not see this
+    return set_error(WITW_ERR_CUDA, "witw_peer_open: cudaIpcOpenMemHandle failed: %s (the exporting device must be visible to this process)",
+                     cudaGetErrorString(e));
+  }
   *buf_dev = p;
   return WITW_OK;
 }

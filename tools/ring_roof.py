@@ -28,7 +28,8 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 MODES = (("full", 0), ("ring_alone", 3 + 128), ("tma_alone", 7 + 128), ("mma_alone", 11 + 128), ("epilogue_alone", 32), ("ring", 3),
-         ("protocol_only", 15), ("epilogue_no_ldtm", 2 + 32), ("epilogue_no_ifft", 1 + 32), ("epilogue_neither", 3 + 32))
+         ("protocol_only", 15), ("epilogue_no_ldtm", 2 + 32), ("epilogue_no_ifft", 1 + 32), ("epilogue_neither", 3 + 32),
+         ("full_half_b", 256), ("ring_alone_half_b", 3 + 128 + 256))
 # operand bytes TMA delivers per (query, item) pair: a CTA pair stages 16 KB of query spectra + 4 KB of gallery spectra per slot
 # and CTA for 1 024 pairs per CTA; one CTA per tile stages 32 + 4 KB
 TMA_BYTES_PER_PAIR = {1: 32.0 * 36864 / 1024.0, 2: 32.0 * 20480 / 1024.0}

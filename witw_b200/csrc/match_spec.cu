@@ -69,7 +69,8 @@ constexpr int kSpMaxChunks = 32;       // two candidate lists per chunk (four wi
 // Timing experiments (wrong results by design) exist only in builds with -DWITW_DEBUG_HOOKS (tools/ probes): WITW_SPEC_DEBUG
 // bit 0 = no inverse FFT, bit 1 = no TMEM loads in the epilogue, bit 2 = no tcgen05.mma (barriers only), bit 3 = no
 // query-stage loads, bit 4 = chunk-major work order, bit 5 = no operand ring at all (the epilogue and the per-tile handshake
-// alone), bit 7 = no per-tile handshake and no epilogue (the ring alone).  The shipped library never reads the environment.
+// alone), bit 7 = no per-tile handshake and no epilogue (the ring alone), bit 8 = only half of every gallery stage is loaded.
+// The shipped library never reads the environment.
 #ifdef WITW_DEBUG_HOOKS
 static int spec_debug() {
   static int v = -1;
@@ -404,7 +405,7 @@ match_spec_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_consta
             if (SPEC_DBG(P, 8)) {
               if (leader) bar_expect_tx(s2u(&full[s]), (uint32_t)(CG * kSpBBytes));
             } else {
-              if (leader) bar_expect_tx(s2u(&full[s]), (uint32_t)(CG * (kA + kSpBBytes)));
+              if (leader) bar_expect_tx(s2u(&full[s]), (uint32_t)(CG * (kA + (SPEC_DBG(P, 256) ? kSpBBytes / 2 : kSpBBytes))));
               if constexpr (CG == 1) {
                 tma_2d<1>(s2u(a_base) + s * kA, &q_map, fb, 0, q_row + 256 * (int)slot);
               } else {   // K halves of this CTA's 64 queries: rows [64 rank, +64) of each 128-row half
@@ -757,7 +758,7 @@ extern "C" int witw_match_spec(const witw_sweep_args* a, witw_stream_t stream) {
   WITW_REQUIRE(total_rows < (1ll << 31), WITW_ERR_UNSUPPORTED, "witw_match_spec: gallery of %lld items is too large for one sweep", (long long)G);
   const cuuint64_t gdims[2] = {64, (cuuint64_t)total_rows};
   const cuuint64_t gstrides[1] = {128};
-  const cuuint32_t gbox[2] = {64, 32};
+  const cuuint32_t gbox[2] = {64, (spec_debug() & 256) ? 16u : 32u};   // (hooks build, bit 8: what would half the gallery bytes buy?)
   cr = encode(&gmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(a->gal_op), gdims, gstrides, gbox, estr,
               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -14,20 +14,20 @@
 //   A_f[q]       = [ Re S_f(r) | Im S_f(r) ] / 64                      (slot 0: [ S_0 | S_32 ] / 64)
 //   B_f[item,0]  = [ Re O_f(r) |  Im O_f(r) ]   -> Re P_f              (slot 0: [ O_0 | 0 ]   -> P_0)
 //   B_f[item,1]  = [ Im O_f(r) | -Re O_f(r) ]   -> Im P_f              (slot 0: [ 0 | O_32 ]  -> P_32)
-// M = 128 queries (TMEM lanes), N = 16 = 8 gallery items x (Re, Im), and the 32 slots fill the 512 TMEM columns:
-// column 16 f + 4 (item / 2) + 2 c + item % 2.  The 64 accumulators of one (query, item) pair are 64 columns of one
-// lane, so the inverse real FFT (ifft64_gen.cuh, 487 fp32 operations) and the argmax over the shift are
-// register-local; the epilogue transforms two items at once in the two halves of packed f32x2 operations.
+// Per slot a CTA's accumulator is 128 TMEM lanes x 16 columns, column 4 (item / 2) + 2 c + item % 2 of an 8-item group, and
+// the 32 slots fill the 512 TMEM columns: the 64 accumulators of one (query, item) pair are 64 columns of one lane, so the
+// inverse real FFT (ifft64_gen.cuh, 487 fp32 operations) and the maximum over the shift are register-local; the epilogue
+// transforms two items at once in the two halves of packed f32x2 operations.  TMEM holds 1 024 pairs: a CTA's tile.
 //
-// Per CTA (one per SM, persistent, 16 warps): warps 0-1 TMA producers (even / odd stages), warps 2-7 MMA issuers,
-// one per stage of the operand ring (a single issuing warp's barrier round trip, ~430 cycles per stage, paced the
-// first version; two issuers: 7.98 ms, six: 7.87 ms), warps 8-15 epilogue (two warps per TMEM lane quarter, four
-// items each).  Operand ring of 6 stages; a stage is one slot: 32 KB of query spectra (two 128-byte-swizzled K
-// halves, contiguous in the tile-major operand: one TMA box) + 4 KB of gallery spectra.
-// Roofline of this data flow: the shared-memory port.  Per tile the ring is written once by TMA (1.15 MB) and read once
-// by the MMAs (256 MMAs x 4.6 KB), 2.33 MB at 128 B/cycle = 9.3 us; the kernel runs at 91 % of that.
-// Measured and dropped: multicasting the query stage over a cluster (2/4/8 CTAs) -- L2 is not the limiter, the
-// lock-step costs up to 20 %.
+// Default tiling: CTA pairs (tcgen05 cta_group::2, M = 128, N = 32).  A CTA stages 64 queries (its half of M) and one 8-item
+// group (its half of N; the pair's MMA reads both CTAs' halves) per slot, 20 KB, and holds 64 queries x 16 items in TMEM --
+// 640 B of operands per pair instead of the 1 152 B of one CTA per 128-query x 8-item tile (kept as variant 1: same operand
+// layouts, bit-identical results).  Per CTA (persistent, 16 warps): warps 0-1 TMA producers, warps 2-6 MMA issuers in the
+// leader CTA (warp k owns every fifth slot; a single issuing warp's barrier round trip, ~430 cycles per stage, paced the
+// first version), warps 8-15 epilogue (two warps per TMEM lane quarter, four items each); 10-stage operand ring, a stage is
+// one slot.  What bounds it (measured with tools/ring_roof.py): TMA + MMAs alone 3.1 ms per 10k x 10k (the
+// L2 -> SM delivery of the operands), the epilogue alone 2.8 ms, the kernel 4.1 - 4.4 ms -- TMEM holds exactly one tile, so
+// the first half of a tile's epilogue cannot overlap the next tile's MMAs.
 //
 // Operands are fp16 spectra of the norm-scaled features (sweep_common.cuh): 8x finer than bf16 at the same cost, and
 // with a per-pair bound on what the rounding can do to a result, so that the epilogue knows which decisions it may

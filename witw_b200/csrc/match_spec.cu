@@ -777,8 +777,7 @@ extern "C" int witw_match_spec(const witw_sweep_args* a, witw_stream_t stream) {
   auto kernel = sch.cg == 2 ? (need_arg ? match_spec_kernel<2, true> : match_spec_kernel<2, false>)
                             : (need_arg ? match_spec_kernel<1, true> : match_spec_kernel<1, false>);
   WITW_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  cudaLaunchConfig_t cfg;
-  std::memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid, 1, 1);
   cfg.blockDim = dim3(kSpThreads, 1, 1);
   cfg.dynamicSmemBytes = smem;

@@ -608,8 +608,7 @@ extern "C" int witw_match_tc(const witw_sweep_args* a, witw_stream_t stream) {
   const size_t smem = (size_t)n_stages * (kABytes + b_stride) + fixed;
   const int n_items = sch.n_chunks * sch.n_qtiles;
   const int units = std::min(sch.n_units, n_items);
-  cudaLaunchConfig_t cfg;
-  std::memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(units * sch.cg));
   cfg.blockDim = dim3(kTcThreads);
   cfg.dynamicSmemBytes = smem;

@@ -14,8 +14,9 @@ crop-normalise, distance, rank count, top-k; decisions its fp16 operands cannot 
 correlation theorem (csrc/match_spec.cu: per-frequency tcgen05 products + in-register inverse FFT);
 --sweep hankel is the dense contraction over all 64 shifts (csrc/match_tc.cu).
 N > 1: the gallery is sharded, one 10k-item shard per GPU (weak scaling: gallery_total = N*10k),
-queries replicated; the exchange is an all-reduce of the [Q] true distances before the sweep and one
-all-gather of [counts | top-k] after it, over NCCL.  value = N*Q / t: queries swept per second, each
+queries replicated; the [Q] true distances before the sweep and [counts | top-k] after it are exchanged
+over peer memory (NVLink stores from the library's own kernels, witw_b200/peer.py; --no-peer-exchange: an
+NCCL all-reduce and one all-gather).  value = N*Q / t: queries swept per second, each
 against a 10k-item gallery shard (see config.unit_note for the whole-gallery figure).
 
 Next to the timed step the line carries side measurements (N = 1; --no-extras skips them): the same step on data

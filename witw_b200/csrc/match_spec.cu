@@ -307,9 +307,12 @@ struct SpParams {
 // of its half of M) and its own group of 8 items (its half of N, which the pair's MMA reads from both CTAs), and its TMEM holds
 // D[m, n] at lane m + 64 (n / 16), column n % 16 -- lanes 0-63 = its 64 queries x the leader's group, lanes 64-127 = the same
 // queries x the peer's group.  Still 1 024 pairs x 64 accumulators per CTA, but the ring carries 20 KB per slot instead of 36.
-// ARG: the epilogue tracks the shift of the maximum (orientation output, cropped queries: the crop norm depends on it).  Without
-// it -- full panoramas, distances / ranks / top-k only -- a third of the epilogue's comparisons and selects go away.
-template <int CG, bool ARG>
+// EPI: what the epilogue extracts from a pair's 64 correlations.  0: the maximum alone (full panoramas, distances / ranks / top-k
+// only: the crop is the whole item at every shift) -- 32 three-input maxima per item.  1: the maximum and its first shift
+// (orientation output or cropped queries -- the crop norm depends on the shift -- without error bounds): compare and two selects
+// per correlation.  2: with error bounds, the maximum, then one pass for the shifts within 2e of it (their count decides whether
+// the pair is ambiguous, the lowest of them is the shift).
+template <int CG, int EPI>
 __global__ void __launch_bounds__(kSpThreads, 1)
 match_spec_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant__ CUtensorMap g_map, const SpParams P) {
   constexpr uint32_t kTmemCols = 512;
@@ -537,26 +540,32 @@ match_spec_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_consta
           }
           float best[2] = {-__int_as_float(0x7f800000), -__int_as_float(0x7f800000)};
           int arg[2] = {0, 0};
-          if constexpr (ARG) {
+          if constexpr (EPI == 1) {
 #pragma unroll
             for (int sft = 0; sft < 64; ++sft) {  // strict '>' in ascending shift order: first maximum
               if (x[sft].x > best[0]) { best[0] = x[sft].x; arg[0] = sft; }
               if (x[sft].y > best[1]) { best[1] = x[sft].y; arg[1] = sft; }
             }
-          } else {   // full panorama, no orientation output: only the maximum matters (gal_scale[g,:] is constant) -- 3-input maxima
+          } else {   // the maximum alone: 3-input maxima
 #pragma unroll
             for (int sft = 0; sft < 64; sft += 2) {
               best[0] = fmax3(best[0], x[sft].x, x[sft + 1].x);
               best[1] = fmax3(best[1], x[sft].y, x[sft + 1].y);
             }
           }
-          if (ARG && S.need_amb) {  // how many shifts could be the exact argmax (the maximum itself is one of them)
+          if constexpr (EPI == 2) {
+            // Shift and ambiguity in one pass: the shifts within 2e of the maximum are the candidates for the exact argmax.  One
+            // candidate: it is the maximum's shift.  Several: the pair is ambiguous -- its slack covers every candidate's crop norm
+            // (sweep_common.cuh) and matrix outputs are overwritten in fp32 -- and the lowest candidate stands in for the shift.
             const float thr0 = best[0] - 2.0f * sweep_err(S, ag0, qc, best[0]), thr1 = best[1] - 2.0f * sweep_err(S, ag1, qc, best[1]);
             int n0 = 0, n1 = 0;
 #pragma unroll
-            for (int sft = 0; sft < 64; ++sft) {
-              n0 += (x[sft].x >= thr0) ? 1 : 0;
-              n1 += (x[sft].y >= thr1) ? 1 : 0;
+            for (int sft = 63; sft >= 0; --sft) {
+              const bool c0 = x[sft].x >= thr0, c1 = x[sft].y >= thr1;
+              n0 += c0 ? 1 : 0;
+              n1 += c1 ? 1 : 0;
+              arg[0] = c0 ? sft : arg[0];
+              arg[1] = c1 ? sft : arg[1];
             }
             arg[0] |= (n0 > 1) ? 256 : 0;
             arg[1] |= (n1 > 1) ? 256 : 0;
@@ -773,9 +782,9 @@ extern "C" int witw_match_spec(const witw_sweep_args* a, witw_stream_t stream) {
   const int ns = sch.cg == 2 ? kSpStagesPair : kSpStages;
   const size_t smem = (size_t)ns * ((sch.cg == 2 ? kSpABytesPair : kSpABytes) + kSpBBytes) + (2 * ns + 2) * 8 + 16;
   const int grid = std::min(sch.n_units, sch.n_chunks * sch.n_qtiles) * sch.cg;
-  const bool need_arg = a->sw < 64 || a->ori != nullptr;
-  auto kernel = sch.cg == 2 ? (need_arg ? match_spec_kernel<2, true> : match_spec_kernel<2, false>)
-                            : (need_arg ? match_spec_kernel<1, true> : match_spec_kernel<1, false>);
+  const int epi = (a->sw < 64 || a->ori != nullptr) ? (out.need_amb ? 2 : 1) : 0;
+  auto kernel = sch.cg == 2 ? (epi == 2 ? match_spec_kernel<2, 2> : epi == 1 ? match_spec_kernel<2, 1> : match_spec_kernel<2, 0>)
+                            : (epi == 2 ? match_spec_kernel<1, 2> : epi == 1 ? match_spec_kernel<1, 1> : match_spec_kernel<1, 0>);
   WITW_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid, 1, 1);

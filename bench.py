@@ -912,7 +912,7 @@ def run_ours(args):
         line["configs"] = {
             "configs[2] 90deg 10k x 10k": safe(config_step, torch, ops, device, 10000, 90),
             "configs[4] 90deg 100k gallery (sweep half)": safe(config_step, torch, ops, device, 100000, 90, iters=3),
-            "gallery 1k": safe(config_step, torch, ops, device, 1000, 360),
+            "gallery 1k": safe(config_step, torch, ops, device, 1000, 360, iters=20, warm=5),
             "gallery 100k": safe(config_step, torch, ops, device, 100000, 360, iters=3),
             "configs[3] 1M gallery on one GPU": safe(config_step, torch, ops, device, 1000000, 360, iters=2, warm=1),
         }

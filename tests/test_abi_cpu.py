@@ -225,6 +225,15 @@ def test_argument_validation_needs_no_device():
     assert lib.witw_match_backward_f32(None, None, None, None, None, None, None, 4, 4, 64, 64, 65, None) == INVALID
     assert lib.witw_match_backward_f32(None, None, None, None, None, None, None, 4, 4, 64, 64, 16, None) == INVALID
     assert "null pointer" in _lib.last_error()
+    # peer-memory exchange: sizes and argument checks
+    b2, b8 = lib.witw_peer_exchange_bytes(10000, 10, 2), lib.witw_peer_exchange_bytes(10000, 10, 8)
+    assert 0 < b2 < b8 and b2 % 256 == 0 and b8 % 256 == 0
+    assert b8 >= 2 * (10000 * 4 + 8 * 10000 * 4 + 2 * 8 * 10000 * 10 * 4)           # two copies of thresholds, counts, top-k of 8 ranks
+    assert lib.witw_peer_exchange_bytes(10000, 10, 17) == 0 and lib.witw_peer_exchange_bytes(-1, 10, 2) == 0
+    assert lib.witw_peer_thresholds(None, None, 0, 10, 100, 10, None, 2, 0, 1, None, None) == INVALID
+    assert lib.witw_peer_results(None, None, None, None, 100, 10, None, None, 1, 0, 1, None, None, None, None, None) == INVALID   # world of one
+    assert "world 1" in _lib.last_error()
+    assert lib.witw_peer_open(None, None) == INVALID
     # matching kernels: shapes the kernels do not cover are refused with a reason
     assert lib.witw_spec_supported(64, 64, 64) == 1 and lib.witw_spec_supported(32, 64, 64) == 0 and lib.witw_spec_supported(64, 32, 16) == 0
     assert lib.witw_gallery_operand_bytes(10, 64, 0) == 0

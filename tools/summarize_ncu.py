@@ -44,7 +44,7 @@ if only or len(seen) == 1:
         hdr = next(r for r in rows if "Source" in r and "Instructions Executed" in r)
         body = rows[rows.index(hdr) + 1:]
         ist, isrc, iex = hdr.index("Warp Stall Sampling (All Samples)"), hdr.index("Source"), hdr.index("Instructions Executed")
-        data = [(int(r[ist]) if r[ist].isdigit() else 0, r[isrc].strip(), r[iex]) for r in body if len(r) > ist]
+        data = [(int(r[ist]) if r[ist].isdigit() else 0, r[isrc].strip(), r[iex]) for r in body if len(r) > max(ist, isrc, iex)]
         tot = sum(d[0] for d in data) or 1
         print("\n# top warp-stall sample locations (SASS), %d samples" % tot)
         for d in sorted(data, reverse=True)[:16]:

@@ -131,7 +131,10 @@ def get(n_queries, k, group=None, device=None):
 
 
 def shutdown():
-    """Close every exchange buffer (before destroying the process group)."""
+    """Close every exchange buffer (before destroying the process group).  Every rank must have finished its evaluations: a peer
+    that still waits on this rank's flags would time out."""
+    if torch.cuda.is_available() and any(px is not None for px in _cache.values()):
+        torch.cuda.synchronize()
     for px in _cache.values():
         if px is not None:
             px.close()

@@ -63,3 +63,25 @@ def test_slot_gemm_layout_reproduces_correlation():
         for q in range(Q):
             x = _generated_ifft(D[g, q, :, 0], D[g, q, :, 1])
             assert np.abs(x - corr[g, q]).max() <= 3e-6 * np.abs(corr[g, q]).max()
+
+
+def test_split_radix_recursion_at_every_size():
+    """The real-data split-radix recursion behind the codelet (gen_ifft64.hermitian_to_real) against numpy's unnormalised inverse
+    real FFT at every power of two it passes through, with its operation counts (the 64-point one is what the epilogue issues)."""
+    rng = np.random.default_rng(3)
+    ops = {}
+    for n in (2, 4, 8, 16, 32, 64):
+        sig = rng.standard_normal(n)
+        spec = np.fft.rfft(sig) / n
+        e = gen_ifft64.Emitter()
+        X = []
+        for k in range(n // 2 + 1):
+            re = e.inp("re%d" % k, spec[k].real)
+            im = None if k in (0, n // 2) else e.inp("im%d" % k, spec[k].imag)
+            X.append((re, im))
+        out = gen_ifft64.hermitian_to_real(e, n, X)
+        got = np.array([e.vals[o] for o in out], dtype=np.float64)
+        assert np.abs(got - sig).max() <= 2e-6 * np.abs(sig).max(), n
+        ops[n] = e.ops
+    assert ops[64] == 487 and ops[2] == 2 and all(ops[2 * n] > 2 * ops[n] for n in (2, 4, 8, 16, 32))
+    assert ops[64] < 612          # the first codelet: a 32-point complex radix-2 transform of the folded spectrum
